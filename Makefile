@@ -1,0 +1,29 @@
+# Builds the product library (CUDA kernels + C-ABI + host C++ mirror) for sm_100a, in-tree.
+NVCC ?= /usr/local/cuda/bin/nvcc
+HOSTCXX := $(if $(wildcard /usr/bin/g++),/usr/bin/g++,g++)
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr -Xptxas -v
+LIBDIR := jpgenc_b200/lib
+CU := $(wildcard jpgenc_b200/csrc/*.cu)
+HOSTSRC := jpgenc_b200/host/huffman_build.cpp jpgenc_b200/host/jfif_writer.cpp jpgenc_b200/host/ppm_reader.cpp
+OBJ := $(patsubst jpgenc_b200/csrc/%.cu,build/%.o,$(CU)) $(patsubst jpgenc_b200/host/%.cpp,build/host_%.o,$(HOSTSRC))
+HDR := $(wildcard jpgenc_b200/csrc/*.cuh) $(wildcard jpgenc_b200/host/*.hpp) include/jpgenc_b200.h
+
+all: $(LIBDIR)/libjpgenc_b200.so
+
+build/%.o: jpgenc_b200/csrc/%.cu $(HDR)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+build/host_%.o: jpgenc_b200/host/%.cpp $(HDR)
+	@mkdir -p build
+	$(HOSTCXX) -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(LIBDIR)/libjpgenc_b200.so: $(OBJ)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJ)
+
+clean:
+	rm -rf build $(LIBDIR)/*.so
+
+.PHONY: all clean

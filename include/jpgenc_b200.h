@@ -1,0 +1,154 @@
+/*
+ * jpgenc_b200.h — C-ABI of the B200-native JPEG encode path that drops in behind Nuos/jpgEnc's C++ surface.
+ *
+ * The reference has no FFI: its "interface" for this path is the stage methods of `class Image`
+ * (reference include/Image.hpp:76-92) driven by Image::writeJPEG (reference src/Image.cpp:831-976).
+ * Each entry point below names the reference code it replaces.  Plain pointers and sizes only; no
+ * exceptions cross this boundary: every call returns JPGENC_OK (0) or a negative code and
+ * jpgenc_last_error() gives the text.  The C++ host mirror (jpgenc_b200/host/) rethrows failures as
+ * std::runtime_error, which is what the reference throws (src/Image.cpp:428,450).
+ *
+ * Ownership: the caller owns every host pointer; the context owns all device memory and one CUDA
+ * stream.  Threading: one context per host thread / GPU; independent contexts may run concurrently
+ * (this is how a batch of images is sharded over GPUs).  There is no CPU fallback: without a CUDA
+ * device jpgenc_create fails.
+ *
+ * Device layouts (DESIGN.md "Data layout in HBM"):
+ *   rgb     u8  interleaved R,G,B, real_w*real_h*3, exactly the P6 payload (src/Image.cpp:411-418)
+ *   coef    i16 MCU-ordered: per 16x16 MCU the blocks Y00,Y01,Y10,Y11,Cb,Cr (the order of
+ *           src/Image.cpp:959-967), 64 coefficients each in ZIGZAG order, DC not differenced
+ *   scan    u8  entropy-coded segment: MCU-interleaved, 1-padded, FF->FF00 stuffed
+ */
+#ifndef JPGENC_B200_H
+#define JPGENC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPGENC_OK             0
+#define JPGENC_ERR_CUDA      -1   /* a CUDA runtime call failed (text in jpgenc_last_error) */
+#define JPGENC_ERR_ARG       -2   /* bad argument / call out of pipeline order */
+#define JPGENC_ERR_NO_DEVICE -3   /* no usable CUDA device: there is no CPU fallback */
+#define JPGENC_ERR_FORMAT    -4   /* not a P3/P6 PPM (reference: std::runtime_error, src/Image.cpp:449-450) */
+#define JPGENC_ERR_IO        -5   /* file could not be opened (reference: src/Image.cpp:427-428) */
+#define JPGENC_ERR_CAPACITY  -6   /* caller's output buffer too small */
+
+typedef struct jpgenc_ctx jpgenc_ctx;
+
+/* Table ids everywhere: 0 = Y_DC, 1 = Y_AC, 2 = C_DC, 3 = C_AC (src/Image.cpp:908-912, 946-949). */
+typedef struct {
+    uint32_t code_msb[256];   /* Code::code, MSB-aligned (include/Huffman.hpp:21-46) */
+    uint8_t  length[256];     /* 0 = symbol absent */
+    uint8_t  counts[16];      /* DHT: codes per length 1..16 (JpegSegments.hpp:188-218) */
+    uint8_t  symbols[256];    /* DHT: symbols in the reference's SymbolsPerLength order */
+    int32_t  nsymbols;
+} jpgenc_huff_table;
+
+typedef struct {
+    uint32_t real_w, real_h;      /* as in the PPM header */
+    uint32_t mcu_w, mcu_h;        /* padded to x16 (src/Image.cpp:479-489) */
+    uint64_t n_blocks;            /* mcu_w*mcu_h*6 */
+    uint64_t refined_blocks;      /* blocks re-done in exact FP64 because an FP32 quotient sat on a rounding boundary */
+    uint64_t scan_bits;           /* entropy-coded bits before padding */
+    uint64_t scan_bytes;          /* after 1-padding and FF00 stuffing */
+    uint64_t stuffed_ff;          /* number of 0xFF bytes that received a 0x00 */
+    float    ms_forward;          /* CUDA-event time of the last K1 (+ refine) */
+    float    ms_stats;            /* last K2 */
+    float    ms_entropy;          /* last K3 + K4 */
+    float    ms_h2d, ms_d2h;
+} jpgenc_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+int  jpgenc_create(int device, jpgenc_ctx** out);
+void jpgenc_destroy(jpgenc_ctx* ctx);
+/* ctx may be NULL: text of the last failure of jpgenc_create on this thread */
+const char* jpgenc_last_error(const jpgenc_ctx* ctx);
+/* the context's cudaStream_t, so a caller can record its own CUDA events around the stage calls */
+void* jpgenc_stream(jpgenc_ctx* ctx);
+int  jpgenc_synchronize(jpgenc_ctx* ctx);
+int  jpgenc_get_stats(jpgenc_ctx* ctx, jpgenc_stats* out);
+
+/* ---- parameters the reference hard-codes in writeJPEG --------------------------------------------- */
+/* natural (row-major) order, as in src/Image.cpp:850-869; defaults are those Annex-K tables */
+int jpgenc_set_qtables(jpgenc_ctx* ctx, const uint8_t qy[64], const uint8_t qc[64]);
+/* AAN constants a1..a5, s0..s7 evaluated by the HOST with the reference's expressions
+ * (include/Dct.hpp:21-43) so the exact path uses bit-identical doubles; optional (the library computes
+ * the same expressions itself when this is never called) */
+int jpgenc_set_dct_constants(jpgenc_ctx* ctx, const double a[5], const double s[8]);
+
+/* ---- input: replaces loadPPM's pixel path (src/Image.cpp:411-418, 465, 479-532) -------------------- */
+/* H2D of raw samples (P6 payload or parsed P3), maxval < 256.  Scaling by 255/maxval and the x16
+ * edge-replication padding happen on the device.  host_rgb should be pinned for full PCIe speed. */
+int jpgenc_upload_rgb(jpgenc_ctx* ctx, const uint8_t* host_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval);
+/* same, for pixels that already live in device memory (no copy is made; the pointer must stay valid) */
+int jpgenc_bind_device_rgb(jpgenc_ctx* ctx, const void* dev_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval);
+
+/* ---- K1: convertToColorSpace(YCbCr) + applySubsampling(S420_m) + applyDCT(Arai) + applyQuantization
+ *      + zigzag (src/Image.cpp:112-148, 198-235, 540-595, 597-636; Dct.hpp:47-215; Coding.hpp:57-97) -- */
+int jpgenc_color_dct_quant(jpgenc_ctx* ctx);
+/* test hooks: read the coefficients back (n_blocks*64 int16, MCU order) / feed the REFERENCE's planar
+ * natural-order int32 arrays QY,QCb,QCr (Image.hpp:112) so K2-K4 can be checked independently of K1 */
+int jpgenc_get_coefficients(jpgenc_ctx* ctx, int16_t* dst);
+int jpgenc_set_coefficients(jpgenc_ctx* ctx, const int32_t* q_y, const int32_t* q_cb, const int32_t* q_cr,
+                            uint32_t mcu_w, uint32_t mcu_h);
+/* feed MCU-ordered zigzag int16 coefficients directly */
+int jpgenc_set_coefficients_mcu(jpgenc_ctx* ctx, const int16_t* coef, uint32_t mcu_w, uint32_t mcu_h);
+
+/* ---- K2: applyDCdifferenceCoding + doRLEandCategoryCoding + the symbol texts
+ *      (src/Image.cpp:638-735, 888-906; Coding.hpp:148-283) reduced to what the table build needs ----- */
+/* count[t][s] = occurrences of symbol s in table t's text; first_pos[t][s] = an order-preserving key of
+ * its first occurrence in that text (UINT64_MAX if absent): (block index in text order)*64 + ordinal */
+int jpgenc_symbol_stats(jpgenc_ctx* ctx, uint32_t count[4][256], uint64_t first_pos[4][256]);
+
+/* ---- host: generateHuffmanCode from the statistics (src/Huffman.cpp:3-66, Huffman.hpp:114-174) ----- */
+int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
+
+/* ---- K3 + K4: doHuffmanEncoding, MCU interleave, fill(), FF00 stuffing
+ *      (src/Image.cpp:737-829, 957-971; BitstreamGeneric.hpp:182-195, 213-224, 242-248) ------------- */
+int jpgenc_entropy_encode(jpgenc_ctx* ctx, const jpgenc_huff_table tables[4], uint64_t* scan_bytes);
+int jpgenc_download_scan(jpgenc_ctx* ctx, uint8_t* dst, uint64_t cap);
+
+/* ---- whole image: what Image::writeJPEG does after loadPPM ----------------------------------------- */
+/* headers SOI..SOS (src/Image.cpp:933-954, JpegSegments.hpp); returns the length, dst may be NULL */
+size_t jpgenc_write_headers(uint32_t real_w, uint32_t real_h, const uint8_t qy[64], const uint8_t qc[64],
+                            const jpgenc_huff_table tables[4], uint8_t* dst);
+/* runs K1..K4 on the pixels bound/uploaded and assembles headers + scan + EOI into dst */
+int jpgenc_encode_bound(jpgenc_ctx* ctx, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);
+/* upload + encode (host pixels in, JPEG bytes out) */
+int jpgenc_encode_rgb(jpgenc_ctx* ctx, const uint8_t* host_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval,
+                      uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);
+/* main.cpp:8-32 — PPM file in, JPEG file out */
+int jpgenc_encode_ppm_file(jpgenc_ctx* ctx, const char* ppm_path, const char* jpg_path);
+
+/* ---- config-1 microbenchmark: dctArai + quantize + zigzag on stand-alone blocks -------------------- */
+/* dev_in: nblocks*64 fp32 samples (row-major 8x8 per block); dev_out: nblocks*64 int16 zigzag.
+ * Same exactness contract as K1 (FP32 fast path + exact FP64 refinement of boundary cases). */
+int jpgenc_dct_quant_blocks(jpgenc_ctx* ctx, const float* dev_in, int16_t* dev_out, uint64_t nblocks,
+                            const uint8_t q[64], uint64_t* refined_blocks);
+
+/* ---- plain device-memory helpers so a Python/C harness needs no other CUDA binding ---------------- */
+int jpgenc_dev_alloc(jpgenc_ctx* ctx, size_t bytes, void** dev_ptr);
+int jpgenc_dev_free(jpgenc_ctx* ctx, void* dev_ptr);
+int jpgenc_host_alloc_pinned(size_t bytes, void** host_ptr);
+int jpgenc_host_free_pinned(void* host_ptr);
+int jpgenc_memcpy_h2d(jpgenc_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int jpgenc_memcpy_d2h(jpgenc_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+/* device-side synthetic generators so benches need no multi-GB uploads */
+int jpgenc_synth_rgb(jpgenc_ctx* ctx, void* dev_rgb, uint32_t w, uint32_t h, uint32_t seed);
+int jpgenc_synth_blocks(jpgenc_ctx* ctx, float* dev_blocks, uint64_t nblocks);
+/* write `bytes` of a scratch buffer (>= L2 size) to evict L2 between timed iterations */
+int jpgenc_flush_l2(jpgenc_ctx* ctx);
+/* CUDA-event timing on the context's stream: begin/end return elapsed ms of everything enqueued between */
+int jpgenc_timer_begin(jpgenc_ctx* ctx);
+int jpgenc_timer_end(jpgenc_ctx* ctx, float* ms);
+/* number of kernels this library has launched on the context since creation */
+uint64_t jpgenc_launch_count(const jpgenc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

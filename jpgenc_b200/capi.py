@@ -1,0 +1,313 @@
+"""ctypes binding of the C-ABI in include/jpgenc_b200.h (the drop-in boundary of the encode path).
+
+This is the binding a maintainer of the reference would write for a Python harness; the tests and bench.py call
+the CUDA path exclusively through it.  There is no fallback of any kind: if the shared library is missing or no
+B200 is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libjpgenc_b200.so"
+
+OK = 0
+ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_FORMAT, ERR_IO, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
+
+u8p = C.POINTER(C.c_uint8)
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+class HuffTable(C.Structure):
+    _fields_ = [
+        ("code_msb", C.c_uint32 * 256),
+        ("length", C.c_uint8 * 256),
+        ("counts", C.c_uint8 * 16),
+        ("symbols", C.c_uint8 * 256),
+        ("nsymbols", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("real_w", C.c_uint32), ("real_h", C.c_uint32), ("mcu_w", C.c_uint32), ("mcu_h", C.c_uint32),
+        ("n_blocks", C.c_uint64), ("refined_blocks", C.c_uint64), ("scan_bits", C.c_uint64),
+        ("scan_bytes", C.c_uint64), ("stuffed_ff", C.c_uint64),
+        ("ms_forward", C.c_float), ("ms_stats", C.c_float), ("ms_entropy", C.c_float),
+        ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+    ]
+
+
+# every symbol the header declares: name -> (restype, argtypes)
+_SIGNATURES = {
+    "jpgenc_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "jpgenc_destroy": (None, [C.c_void_p]),
+    "jpgenc_last_error": (C.c_char_p, [C.c_void_p]),
+    "jpgenc_stream": (C.c_void_p, [C.c_void_p]),
+    "jpgenc_synchronize": (C.c_int, [C.c_void_p]),
+    "jpgenc_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "jpgenc_set_qtables": (C.c_int, [C.c_void_p, u8p, u8p]),
+    "jpgenc_set_dct_constants": (C.c_int, [C.c_void_p, f64p, f64p]),
+    "jpgenc_upload_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "jpgenc_bind_device_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "jpgenc_color_dct_quant": (C.c_int, [C.c_void_p]),
+    "jpgenc_get_coefficients": (C.c_int, [C.c_void_p, i16p]),
+    "jpgenc_set_coefficients": (C.c_int, [C.c_void_p, i32p, i32p, i32p, C.c_uint32, C.c_uint32]),
+    "jpgenc_set_coefficients_mcu": (C.c_int, [C.c_void_p, i16p, C.c_uint32, C.c_uint32]),
+    "jpgenc_symbol_stats": (C.c_int, [C.c_void_p, u32p, u64p]),
+    "jpgenc_build_huffman": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
+    "jpgenc_entropy_encode": (C.c_int, [C.c_void_p, C.POINTER(HuffTable), u64p]),
+    "jpgenc_download_scan": (C.c_int, [C.c_void_p, u8p, C.c_uint64]),
+    "jpgenc_write_headers": (C.c_size_t, [C.c_uint32, C.c_uint32, u8p, u8p, C.POINTER(HuffTable), u8p]),
+    "jpgenc_encode_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "jpgenc_encode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
+    "jpgenc_encode_ppm_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "jpgenc_dct_quant_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u8p, u64p]),
+    "jpgenc_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "jpgenc_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jpgenc_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "jpgenc_host_free_pinned": (C.c_int, [C.c_void_p]),
+    "jpgenc_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "jpgenc_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "jpgenc_synth_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "jpgenc_synth_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "jpgenc_flush_l2": (C.c_int, [C.c_void_p]),
+    "jpgenc_timer_begin": (C.c_int, [C.c_void_p]),
+    "jpgenc_timer_end": (C.c_int, [C.c_void_p, f32p]),
+    "jpgenc_launch_count": (C.c_uint64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libjpgenc_b200.so and bind every declared symbol; raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); there is no fallback path")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here == the library does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class JpgencError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"jpgenc error {code}: {text}")
+        self.code = code
+
+
+def _np_ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+class Encoder:
+    """One GPU context (= one CUDA stream + its device buffers).  Methods mirror the C-ABI one to one."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.jpgenc_create(device, C.byref(h))
+        if rc != OK:
+            raise JpgencError(rc, (self.lib.jpgenc_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.jpgenc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise JpgencError(rc, (self.lib.jpgenc_last_error(self.h) or b"").decode())
+
+    # ---- parameters -----------------------------------------------------------------------------
+    def set_qtables(self, qy, qc):
+        qy = np.ascontiguousarray(qy, np.uint8).reshape(64)
+        qc = np.ascontiguousarray(qc, np.uint8).reshape(64)
+        self._check(self.lib.jpgenc_set_qtables(self.h, _np_ptr(qy, u8p), _np_ptr(qc, u8p)))
+
+    # ---- input ----------------------------------------------------------------------------------
+    def upload_rgb(self, rgb: np.ndarray, maxval: int = 255):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w, _ = rgb.shape
+        self._check(self.lib.jpgenc_upload_rgb(self.h, rgb.ctypes.data, w, h, maxval))
+
+    def upload_rgb_ptr(self, host_ptr: int, w: int, h: int, maxval: int = 255):
+        self._check(self.lib.jpgenc_upload_rgb(self.h, host_ptr, w, h, maxval))
+
+    def bind_device_rgb(self, dev_ptr: int, w: int, h: int, maxval: int = 255):
+        self._check(self.lib.jpgenc_bind_device_rgb(self.h, dev_ptr, w, h, maxval))
+
+    # ---- stages ---------------------------------------------------------------------------------
+    def color_dct_quant(self):
+        self._check(self.lib.jpgenc_color_dct_quant(self.h))
+
+    def get_coefficients(self) -> np.ndarray:
+        st = self.stats()
+        out = np.empty((st.n_blocks // 6, 6, 64), np.int16)
+        self._check(self.lib.jpgenc_get_coefficients(self.h, _np_ptr(out, i16p)))
+        return out
+
+    def set_coefficients(self, q_y, q_cb, q_cr):
+        q_y, q_cb, q_cr = (np.ascontiguousarray(a, np.int32) for a in (q_y, q_cb, q_cr))
+        mh, mw = q_y.shape[0] // 16, q_y.shape[1] // 16
+        self._check(self.lib.jpgenc_set_coefficients(self.h, _np_ptr(q_y, i32p), _np_ptr(q_cb, i32p), _np_ptr(q_cr, i32p), mw, mh))
+
+    def set_coefficients_mcu(self, coef, mcu_w, mcu_h):
+        coef = np.ascontiguousarray(coef, np.int16)
+        assert coef.size == mcu_w * mcu_h * 6 * 64
+        self._check(self.lib.jpgenc_set_coefficients_mcu(self.h, _np_ptr(coef, i16p), mcu_w, mcu_h))
+
+    def symbol_stats(self):
+        count = np.zeros((4, 256), np.uint32)
+        first = np.zeros((4, 256), np.uint64)
+        self._check(self.lib.jpgenc_symbol_stats(self.h, _np_ptr(count, u32p), _np_ptr(first, u64p)))
+        return count, first
+
+    def build_huffman(self, count, first):
+        tabs = (HuffTable * 4)()
+        for t in range(4):
+            c = np.ascontiguousarray(count[t], np.uint32)
+            f = np.ascontiguousarray(first[t], np.uint64)
+            rc = self.lib.jpgenc_build_huffman(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(tabs[t]))
+            if rc != OK:
+                raise JpgencError(rc, f"jpgenc_build_huffman(table {t})")
+        return tabs
+
+    def entropy_encode(self, tabs) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.jpgenc_entropy_encode(self.h, tabs, C.byref(n)))
+        return n.value
+
+    def download_scan(self) -> np.ndarray:
+        n = self.stats().scan_bytes
+        out = np.empty(n, np.uint8)
+        self._check(self.lib.jpgenc_download_scan(self.h, _np_ptr(out, u8p), n))
+        return out
+
+    def headers(self, tabs, w, h, qy, qc) -> np.ndarray:
+        qy = np.ascontiguousarray(qy, np.uint8).reshape(64)
+        qc = np.ascontiguousarray(qc, np.uint8).reshape(64)
+        n = self.lib.jpgenc_write_headers(w, h, _np_ptr(qy, u8p), _np_ptr(qc, u8p), tabs, None)
+        out = np.empty(n, np.uint8)
+        self.lib.jpgenc_write_headers(w, h, _np_ptr(qy, u8p), _np_ptr(qc, u8p), tabs, _np_ptr(out, u8p))
+        return out
+
+    # ---- whole image ----------------------------------------------------------------------------
+    def encode_bound(self, out: np.ndarray | None = None) -> int:
+        n = C.c_uint64()
+        if out is None:
+            self._check(self.lib.jpgenc_encode_bound(self.h, None, 0, C.byref(n)))
+        else:
+            self._check(self.lib.jpgenc_encode_bound(self.h, out.ctypes.data, out.size, C.byref(n)))
+        return n.value
+
+    def encode_rgb(self, rgb: np.ndarray, maxval: int = 255) -> bytes:
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w, _ = rgb.shape
+        cap = max(4096, rgb.size // 2 + 4096)
+        while True:
+            out = np.empty(cap, np.uint8)
+            n = C.c_uint64()
+            rc = self.lib.jpgenc_encode_rgb(self.h, rgb.ctypes.data, w, h, maxval, out.ctypes.data, cap, C.byref(n))
+            if rc == ERR_CAPACITY:
+                cap = int(n.value) + 16
+                continue
+            self._check(rc)
+            return out[: n.value].tobytes()
+
+    def encode_rgb_into(self, host_ptr: int, w: int, h: int, out_ptr: int, cap: int, maxval: int = 255) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.jpgenc_encode_rgb(self.h, host_ptr, w, h, maxval, out_ptr, cap, C.byref(n)))
+        return n.value
+
+    def encode_ppm_file(self, src: str, dst: str):
+        self._check(self.lib.jpgenc_encode_ppm_file(self.h, src.encode(), dst.encode()))
+
+    # ---- microbench -----------------------------------------------------------------------------
+    def dct_quant_blocks(self, dev_in: int, dev_out: int, nblocks: int, q, want_refined=True) -> int:
+        q = np.ascontiguousarray(q, np.uint8).reshape(64)
+        n = C.c_uint64()
+        self._check(self.lib.jpgenc_dct_quant_blocks(self.h, dev_in, dev_out, nblocks, _np_ptr(q, u8p),
+                                                     C.byref(n) if want_refined else None))
+        return n.value
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.jpgenc_get_stats(self.h, C.byref(s)))
+        return s
+
+    def synchronize(self):
+        self._check(self.lib.jpgenc_synchronize(self.h))
+
+    def stream(self) -> int:
+        return self.lib.jpgenc_stream(self.h)
+
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.jpgenc_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p: int):
+        self._check(self.lib.jpgenc_dev_free(self.h, p))
+
+    def h2d(self, dev: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.lib.jpgenc_memcpy_h2d(self.h, dev, arr.ctypes.data, arr.nbytes))
+
+    def d2h(self, arr: np.ndarray, dev: int):
+        assert arr.flags.c_contiguous
+        self._check(self.lib.jpgenc_memcpy_d2h(self.h, arr.ctypes.data, dev, arr.nbytes))
+
+    def synth_rgb(self, dev: int, w: int, h: int, seed: int = 0):
+        self._check(self.lib.jpgenc_synth_rgb(self.h, dev, w, h, seed))
+
+    def synth_blocks(self, dev: int, nblocks: int):
+        self._check(self.lib.jpgenc_synth_blocks(self.h, dev, nblocks))
+
+    def flush_l2(self):
+        self._check(self.lib.jpgenc_flush_l2(self.h))
+
+    def timer_begin(self):
+        self._check(self.lib.jpgenc_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.jpgenc_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return self.lib.jpgenc_launch_count(self.h)
+
+
+def pinned_empty(nbytes: int):
+    """(numpy view, raw pointer) over freshly allocated page-locked host memory."""
+    lib = load_library()
+    p = C.c_void_p()
+    if lib.jpgenc_host_alloc_pinned(nbytes, C.byref(p)) != OK:
+        raise MemoryError("cudaMallocHost failed")
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    return np.frombuffer(buf, np.uint8), p.value
+
+
+def pinned_free(ptr: int):
+    load_library().jpgenc_host_free_pinned(ptr)

@@ -1,0 +1,128 @@
+// Shared pieces of K2/K3: staging MCU-ordered coefficient tiles in shared memory and walking one block's
+// zigzag sequence as the reference's RLE_AC + encode_category do (include/Coding.hpp:148-183, 197-230, 265-283).
+#pragma once
+#include "common.cuh"
+
+namespace jpgenc {
+
+constexpr int kTileBlocks = 384;                       // 64 MCUs; one thread per block
+constexpr int kTileBytes = kTileBlocks * kBlockBytes;  // 48 KB
+
+// Coalesced copy of `nb` blocks into shared memory.  Slot s keeps its 16-byte chunk c at chunk (c ^ (s & 7)),
+// so that 32 threads reading "their" block's chunk c hit 32 different banks.
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const int16_t* __restrict__ gsrc, int nb, int tid, int nthreads) {
+    const uint4* g = reinterpret_cast<const uint4*>(gsrc);
+    const int chunks = nb * 8;
+    for (int j = tid; j < chunks; j += nthreads) {
+        const int s = j >> 3, c = j & 7;
+        *reinterpret_cast<uint4*>(tile + s * kBlockBytes + ((c ^ (s & 7)) << 4)) = __ldg(g + j);
+    }
+}
+
+__device__ __forceinline__ void load_block(const uint8_t* tile, int slot, uint32_t (&w)[32]) {
+    const uint4* base = reinterpret_cast<const uint4*>(tile + slot * kBlockBytes);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 q = base[c ^ (slot & 7)];
+        w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
+    }
+}
+
+__device__ __forceinline__ int slot_dc(const uint8_t* tile, int slot) {
+    return *reinterpret_cast<const int16_t*>(tile + slot * kBlockBytes + ((slot & 7) << 4));
+}
+
+// DC predictor of block `t` of a tile that starts at global block `first` (a multiple of 6):
+// Y follows MCU order (src/Image.cpp:640-659), Cb and Cr their own raster order (src/Image.cpp:661-677).
+__device__ __forceinline__ int dc_predictor(const uint8_t* tile, const int16_t* __restrict__ coef, uint64_t first, int t) {
+    const int k = t % kBlocksPerMcu, lm = t / kBlocksPerMcu;
+    if (k >= 1 && k <= 3) return slot_dc(tile, t - 1);
+    const int back = (k == 0) ? 3 : 6;          // Y00 <- previous MCU's Y11 ; Cb/Cr <- previous MCU's Cb/Cr
+    if (lm > 0) return slot_dc(tile, t - back);
+    if (first == 0) return 0;
+    return coef[(first + t - back) * kCoefPerBlock];
+}
+
+__device__ __forceinline__ int category_of(int v) { return 32 - __clz(abs(v)); }   // 0 for v == 0
+
+// Calls emit(symbol, value, ordinal) for the DC entry (ordinal -1) and every AC entry in order.
+// `dc_diff` replaces coefficient 0.
+template <class Emit>
+__device__ __forceinline__ void walk_block(const uint32_t (&w)[32], int dc_diff, Emit&& emit) {
+    emit(category_of(dc_diff), dc_diff, -1);
+    int run = 0, ord = 0;
+#pragma unroll
+    for (int i = 1; i < 64; ++i) {
+        const int c = static_cast<int16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu));
+        if (c == 0) {
+            ++run;
+        } else {
+            while (run > 15) { emit(0xF0, 0, ord++); run -= 16; }   // ZRL
+            emit((run << 4) | category_of(c), c, ord++);
+            run = 0;
+        }
+    }
+    if (run > 0) emit(0x00, 0, ord);                                // EOB
+}
+
+// ---- decoupled look-back over 64-bit status words: [63:62] state, [61:0] value ---------------------------
+constexpr unsigned long long kLbAggregate = 1ull << 62;
+constexpr unsigned long long kLbPrefix = 2ull << 62;
+constexpr unsigned long long kLbValueMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE thread of tile `tile`; returns the exclusive prefix of `aggregate` over all earlier tiles.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status, uint32_t tile,
+                                                                 unsigned long long aggregate) {
+    if (tile == 0) {
+        lb_store(status, kLbPrefix | aggregate);
+        return 0;
+    }
+    lb_store(status + tile, kLbAggregate | aggregate);
+    unsigned long long sum = 0;
+    for (int64_t j = static_cast<int64_t>(tile) - 1; j >= 0; --j) {
+        unsigned long long s;
+        do { s = lb_load(status + j); } while ((s >> 62) == 0);
+        sum += s & kLbValueMask;
+        if ((s >> 62) == 2) break;
+    }
+    lb_store(status + tile, kLbPrefix | (sum + aggregate));
+    return sum;
+}
+
+// block-wide exclusive scan of one value per thread (blockDim.x <= 1024); `scratch` holds 33 words
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* scratch, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < nwarps ? scratch[lane] : 0, t = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t += n;
+        }
+        scratch[lane] = t - s;                       // exclusive warp offsets
+        if (lane == 31) scratch[32] = t;             // grand total
+    }
+    __syncthreads();
+    const uint32_t r = scratch[warp] + inc - v;
+    *total = scratch[32];
+    return r;
+}
+
+}  // namespace jpgenc

@@ -1,0 +1,479 @@
+// C-ABI of the encode path (include/jpgenc_b200.h): context, buffers, stage calls, whole-image driver.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "../host/ppm_reader.hpp"
+
+namespace jpgenc {
+int launch_exact_all(jpgenc_ctx* c);
+}
+
+using namespace jpgenc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const uint8_t kAnnexKLuma[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                 14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                 18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};   // src/Image.cpp:850-859
+const uint8_t kAnnexKChroma[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                   24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                   99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                   99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};        // src/Image.cpp:860-869
+
+int fail(jpgenc_ctx* c, int code, const char* what) {
+    c->error = what;
+    return code;
+}
+
+template <class T>
+int ensure(jpgenc_ctx* c, T** ptr, size_t* cap, size_t need_bytes) {
+    if (*ptr && *cap >= need_bytes) return JPGENC_OK;
+    if (*ptr) JPGENC_CUDA(c, cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    void* p = nullptr;
+    const size_t bytes = (need_bytes + 255) & ~static_cast<size_t>(255);
+    JPGENC_CUDA(c, cudaMalloc(&p, bytes));
+    *ptr = static_cast<T*>(p);
+    *cap = bytes;
+    return JPGENC_OK;
+}
+
+int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
+    if (w == 0 || h == 0 || maxval == 0 || maxval > 255) return fail(c, JPGENC_ERR_ARG, "width/height/maxval out of range");
+    c->real_w = w; c->real_h = h; c->maxval = maxval;
+    c->mcu_w = (w + 15) / 16; c->mcu_h = (h + 15) / 16;        // src/Image.cpp:479-489
+    c->have_coef = c->have_scan = false;
+    return JPGENC_OK;
+}
+
+int ensure_coef(jpgenc_ctx* c) {
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
+    if (nblocks * 64 > 0xFFFFFFFFull * 16) return fail(c, JPGENC_ERR_ARG, "image too large");
+    int rc = ensure(c, &c->d_coef, &c->coef_cap, nblocks * kBlockBytes);
+    if (rc) return rc;
+    size_t cap_bytes = c->refine_cap * sizeof(uint32_t);
+    rc = ensure(c, &c->d_refine_list, &cap_bytes, nblocks * sizeof(uint32_t));
+    c->refine_cap = cap_bytes / sizeof(uint32_t);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jpgenc_create(int device, jpgenc_ctx** out) {
+    if (!out) return JPGENC_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return JPGENC_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return JPGENC_ERR_ARG;
+    }
+    jpgenc_ctx* c = new jpgenc_ctx();
+    c->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete c;
+        return JPGENC_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        g_create_error = "device is not sm_100 (Blackwell); the kernels are built for sm_100a only";
+        delete c;
+        return JPGENC_ERR_NO_DEVICE;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_t0, &c->ev_t1, &c->ev_u0, &c->ev_u1})
+        if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    std::memcpy(c->qy, kAnnexKLuma, 64);
+    std::memcpy(c->qc, kAnnexKChroma, 64);
+    default_dct_constants(c->dct_a, c->dct_s);
+    void* p = nullptr;
+    if ((e = cudaMalloc(&p, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    c->d_counters = static_cast<uint32_t*>(p);
+    if ((e = cudaMalloc(&p, 4 * 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    c->d_hist = static_cast<uint32_t*>(p);
+    if ((e = cudaMalloc(&p, 4 * 256 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    c->d_first = static_cast<unsigned long long*>(p);
+    if ((e = cudaMalloc(&p, sizeof(DeviceTables))) != cudaSuccess) return bail("cudaMalloc", e);
+    c->d_tables = static_cast<DeviceTables*>(p);
+    c->pinned_bytes = 64 * 1024;
+    if ((e = cudaMallocHost(&c->h_pinned, c->pinned_bytes)) != cudaSuccess) return bail("cudaMallocHost", e);
+    *out = c;
+    return JPGENC_OK;
+}
+
+void jpgenc_destroy(jpgenc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
+    cudaFree(c->d_hist); cudaFree(c->d_first); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
+    cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1}) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* jpgenc_last_error(const jpgenc_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+void* jpgenc_stream(jpgenc_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+uint64_t jpgenc_launch_count(const jpgenc_ctx* c) { return c ? c->launches : 0; }
+
+int jpgenc_synchronize(jpgenc_ctx* c) {
+    if (!c) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return JPGENC_OK;
+}
+
+int jpgenc_get_stats(jpgenc_ctx* c, jpgenc_stats* out) {
+    if (!c || !out) return JPGENC_ERR_ARG;
+    c->stats.real_w = c->real_w; c->stats.real_h = c->real_h; c->stats.mcu_w = c->mcu_w; c->stats.mcu_h = c->mcu_h;
+    c->stats.n_blocks = static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
+    *out = c->stats;
+    return JPGENC_OK;
+}
+
+int jpgenc_set_qtables(jpgenc_ctx* c, const uint8_t qy[64], const uint8_t qc[64]) {
+    if (!c || !qy || !qc) return JPGENC_ERR_ARG;
+    for (int i = 0; i < 64; ++i)
+        if (qy[i] == 0 || qc[i] == 0) return fail(c, JPGENC_ERR_ARG, "quantiser entries must be >= 1");
+    std::memcpy(c->qy, qy, 64);
+    std::memcpy(c->qc, qc, 64);
+    return JPGENC_OK;
+}
+
+int jpgenc_set_dct_constants(jpgenc_ctx* c, const double a[5], const double s[8]) {
+    if (!c || !a || !s) return JPGENC_ERR_ARG;
+    std::memcpy(c->dct_a, a, sizeof c->dct_a);
+    std::memcpy(c->dct_s, s, sizeof c->dct_s);
+    return JPGENC_OK;
+}
+
+int jpgenc_upload_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
+    if (!c || !host_rgb) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    int rc = set_geometry(c, w, h, maxval);
+    if (rc) return rc;
+    const size_t bytes = static_cast<size_t>(w) * h * 3;
+    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, bytes + 16))) return rc;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned, host_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));            // the caller may reuse host_rgb as soon as we return
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
+    c->d_rgb = c->d_rgb_owned;
+    c->have_pixels = true;
+    return JPGENC_OK;
+}
+
+int jpgenc_bind_device_rgb(jpgenc_ctx* c, const void* dev_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
+    if (!c || !dev_rgb) return JPGENC_ERR_ARG;
+    const int rc = set_geometry(c, w, h, maxval);
+    if (rc) return rc;
+    c->d_rgb = static_cast<const uint8_t*>(dev_rgb);
+    c->have_pixels = true;
+    return JPGENC_OK;
+}
+
+int jpgenc_color_dct_quant(jpgenc_ctx* c) {
+    if (!c) return JPGENC_ERR_ARG;
+    if (!c->have_pixels) return fail(c, JPGENC_ERR_ARG, "no pixels bound: call jpgenc_upload_rgb / jpgenc_bind_device_rgb first");
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_coef(c);
+    if (rc) return rc;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    if ((rc = launch_forward(c))) return rc;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    c->have_coef = true;
+    c->have_scan = false;
+    return JPGENC_OK;
+}
+
+int jpgenc_get_coefficients(jpgenc_ctx* c, int16_t* dst) {
+    if (!c || !dst) return JPGENC_ERR_ARG;
+    if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients yet");
+    const size_t bytes = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu * kBlockBytes;
+    JPGENC_CUDA(c, cudaMemcpyAsync(dst, c->d_coef, bytes, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t refined = 0;
+    JPGENC_CUDA(c, cudaMemcpy(&refined, c->d_counters, sizeof refined, cudaMemcpyDeviceToHost));
+    c->stats.refined_blocks = refined;
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
+    return JPGENC_OK;
+}
+
+int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu_w, uint32_t mcu_h) {
+    if (!c || !coef || !mcu_w || !mcu_h) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    if (c->real_w == 0 || (c->real_w + 15) / 16 != mcu_w || (c->real_h + 15) / 16 != mcu_h) {
+        c->real_w = mcu_w * 16; c->real_h = mcu_h * 16; c->maxval = 255;
+    }
+    c->mcu_w = mcu_w; c->mcu_h = mcu_h;
+    int rc = ensure_coef(c);
+    if (rc) return rc;
+    const size_t bytes = static_cast<size_t>(mcu_w) * mcu_h * kBlocksPerMcu * kBlockBytes;
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_coef, coef, bytes, cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_coef = true;
+    c->have_scan = false;
+    return JPGENC_OK;
+}
+
+int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_cb, const int32_t* q_cr, uint32_t mcu_w,
+                            uint32_t mcu_h) {
+    if (!c || !q_y || !q_cb || !q_cr || !mcu_w || !mcu_h) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    if (c->real_w == 0 || (c->real_w + 15) / 16 != mcu_w || (c->real_h + 15) / 16 != mcu_h) {
+        c->real_w = mcu_w * 16; c->real_h = mcu_h * 16; c->maxval = 255;
+    }
+    c->mcu_w = mcu_w; c->mcu_h = mcu_h;
+    int rc = ensure_coef(c);
+    if (rc) return rc;
+    const size_t ny = static_cast<size_t>(mcu_w) * mcu_h * 256, nc = ny / 4;
+    int32_t* d = nullptr;
+    JPGENC_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&d), (ny + 2 * nc) * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpyAsync(d, q_y, ny * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + ny, q_cb, nc * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + ny + nc, q_cr, nc * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) rc = launch_planes_to_mcu(c, d, d + ny, d + ny + nc);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { c->error = cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
+    if (rc) return rc;
+    c->have_coef = true;
+    c->have_scan = false;
+    return JPGENC_OK;
+}
+
+int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_pos[4][256]) {
+    if (!c || !count || !first_pos) return JPGENC_ERR_ARG;
+    if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    const int rc = launch_symbol_stats(c);
+    if (rc) return rc;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
+    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(h + 4096, c->d_first, 8192, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(count, h, 4096);
+    std::memcpy(first_pos, h + 4096, 8192);
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_stats, c->ev_t0, c->ev_t1));
+    return JPGENC_OK;
+}
+
+int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t* scan_bytes) {
+    if (!c || !tables) return JPGENC_ERR_ARG;
+    if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    // exact size of the scan from the statistics the tables were built from: every symbol costs its code length
+    // plus (symbol & 15) magnitude bits.  The histogram still sits in d_hist from K2; recompute from a fresh copy.
+    uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
+    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint32_t* hist = reinterpret_cast<const uint32_t*>(h);
+    uint64_t total_bits = 0;
+    DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + 8192);
+    for (int t = 0; t < 4; ++t)
+        for (int s = 0; s < 256; ++s) {
+            const uint32_t len = tables[t].length[s];
+            ht->entry[t][s] = len ? (len << 16) | (tables[t].code_msb[s] >> (32 - len)) : 0u;
+            if (hist[t * 256 + s]) {
+                if (!len) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
+                total_bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + (s & 15));
+            }
+        }
+    if (total_bits == 0) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+    const uint64_t nbytes = (total_bits + 7) / 8;
+    const uint64_t nblocks = static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
+    int rc;
+    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, ((nbytes + 15) & ~15ull) + 64))) return rc;
+    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * nbytes + 64))) return rc;
+    const size_t tiles = (nblocks + 383) / 384 + (nbytes + 4095) / 4096 + 8;
+    size_t lb_bytes = c->lookback_cap;
+    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, tiles * sizeof(unsigned long long)))) return rc;
+    c->lookback_cap = lb_bytes;
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, sizeof(DeviceTables), cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    if ((rc = launch_entropy(c, total_bits))) return rc;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    // totals: [0] bits written by K3, [1] number of stuffed FF bytes
+    const size_t tiles3 = (nblocks + 383) / 384, tiles4 = (nbytes + 4095) / 4096;
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(h);
+    JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback + tiles3 + tiles4, 16, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (totals[0] != total_bits) {
+        c->error = "entropy coder wrote " + std::to_string(totals[0]) + " bits, statistics predicted " + std::to_string(total_bits);
+        return JPGENC_ERR_ARG;
+    }
+    c->stats.scan_bits = total_bits;
+    c->stats.stuffed_ff = totals[1];
+    c->stats.scan_bytes = nbytes + totals[1];
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_t0, c->ev_t1));
+    c->have_scan = true;
+    if (scan_bytes) *scan_bytes = c->stats.scan_bytes;
+    return JPGENC_OK;
+}
+
+int jpgenc_download_scan(jpgenc_ctx* c, uint8_t* dst, uint64_t cap) {
+    if (!c || !dst) return JPGENC_ERR_ARG;
+    if (!c->have_scan) return fail(c, JPGENC_ERR_ARG, "no scan yet: run jpgenc_entropy_encode first");
+    if (cap < c->stats.scan_bytes) return fail(c, JPGENC_ERR_CAPACITY, "scan buffer too small");
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(dst, c->d_scan, c->stats.scan_bytes, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_d2h, c->ev_t0, c->ev_t1));
+    return JPGENC_OK;
+}
+
+static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* scan) {
+    int rc;
+    if ((rc = jpgenc_color_dct_quant(c))) return rc;
+    uint32_t count[4][256];
+    uint64_t first_pos[4][256];
+    if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
+    for (int t = 0; t < 4; ++t)
+        if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
+    return jpgenc_entropy_encode(c, tables, scan);
+}
+
+static int assemble(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t scan, uint8_t* dst, uint64_t cap) {
+    const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, nullptr);
+    if (cap < hdr + scan + 2) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
+    jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, dst);
+    const int rc = jpgenc_download_scan(c, dst + hdr, cap - hdr);
+    if (rc) return rc;
+    dst[hdr + scan] = 0xFF;                                      // EOI (JpegSegments.hpp:361-377)
+    dst[hdr + scan + 1] = 0xD9;
+    uint32_t refined = 0;
+    JPGENC_CUDA(c, cudaMemcpy(&refined, c->d_counters, sizeof refined, cudaMemcpyDeviceToHost));
+    c->stats.refined_blocks = refined;
+    return JPGENC_OK;
+}
+
+int jpgenc_encode_bound(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) {
+    if (!c) return JPGENC_ERR_ARG;
+    jpgenc_huff_table tables[4];
+    uint64_t scan = 0;
+    int rc = run_pipeline(c, tables, &scan);
+    if (rc) return rc;
+    const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, nullptr);
+    if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
+    if (!dst) return JPGENC_OK;                                  // device-resident run: the scan stays in HBM
+    return assemble(c, tables, scan, dst, cap);
+}
+
+int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval, uint8_t* dst,
+                      uint64_t cap, uint64_t* jpeg_bytes) {
+    const int rc = jpgenc_upload_rgb(c, host_rgb, w, h, maxval);
+    if (rc) return rc;
+    return jpgenc_encode_bound(c, dst, cap, jpeg_bytes);
+}
+
+int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) {
+    if (!c || !ppm_path || !jpg_path) return JPGENC_ERR_ARG;
+    std::vector<uint8_t> file, p3;
+    int rc = slurp_file(ppm_path, &file);
+    if (rc) return fail(c, rc, "Failed to open input file");
+    PpmHeader h;
+    if ((rc = parse_ppm_header(file.data(), file.size(), &h))) return fail(c, rc, "Only P3 and P6 format is supported!");
+    const uint8_t* samples = nullptr;
+    if ((rc = ppm_samples(file.data(), file.size(), h, &p3, &samples))) return fail(c, rc, "truncated PPM payload");
+    if ((rc = jpgenc_upload_rgb(c, samples, h.width, h.height, h.maxval))) return rc;
+    jpgenc_huff_table tables[4];
+    uint64_t scan = 0;
+    if ((rc = run_pipeline(c, tables, &scan))) return rc;
+    const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, nullptr);
+    std::vector<uint8_t> out(hdr + scan + 2);
+    if ((rc = assemble(c, tables, scan, out.data(), out.size()))) return rc;
+    std::FILE* f = std::fopen(jpg_path, "wb");
+    if (!f) return fail(c, JPGENC_ERR_IO, "Failed to open output file");
+    const size_t wrote = std::fwrite(out.data(), 1, out.size(), f);
+    std::fclose(f);
+    return wrote == out.size() ? JPGENC_OK : fail(c, JPGENC_ERR_IO, "short write");
+}
+
+int jpgenc_dct_quant_blocks(jpgenc_ctx* c, const float* dev_in, int16_t* dev_out, uint64_t nblocks, const uint8_t q[64],
+                            uint64_t* refined_blocks) {
+    if (!c || !dev_in || !dev_out || !q || nblocks == 0 || nblocks > 0xFFFFFFFFull) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    size_t cap_bytes = c->refine_cap * sizeof(uint32_t);
+    int rc = ensure(c, &c->d_refine_list, &cap_bytes, nblocks * sizeof(uint32_t));
+    c->refine_cap = cap_bytes / sizeof(uint32_t);
+    if (rc) return rc;
+    return launch_dct_quant_blocks(c, dev_in, dev_out, nblocks, q, refined_blocks);
+}
+
+int jpgenc_dev_alloc(jpgenc_ctx* c, size_t bytes, void** p) {
+    if (!c || !p) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    JPGENC_CUDA(c, cudaMalloc(p, bytes));
+    return JPGENC_OK;
+}
+int jpgenc_dev_free(jpgenc_ctx* c, void* p) {
+    if (!c) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaFree(p));
+    return JPGENC_OK;
+}
+int jpgenc_host_alloc_pinned(size_t bytes, void** p) { return cudaMallocHost(p, bytes) == cudaSuccess ? JPGENC_OK : JPGENC_ERR_CUDA; }
+int jpgenc_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? JPGENC_OK : JPGENC_ERR_CUDA; }
+int jpgenc_memcpy_h2d(jpgenc_ctx* c, void* d, const void* h, size_t bytes) {
+    if (!c) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return JPGENC_OK;
+}
+int jpgenc_memcpy_d2h(jpgenc_ctx* c, void* h, const void* d, size_t bytes) {
+    if (!c) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return JPGENC_OK;
+}
+int jpgenc_synth_rgb(jpgenc_ctx* c, void* dev_rgb, uint32_t w, uint32_t h, uint32_t seed) {
+    if (!c || !dev_rgb) return JPGENC_ERR_ARG;
+    return launch_synth_rgb(c, static_cast<uint8_t*>(dev_rgb), w, h, seed);
+}
+int jpgenc_synth_blocks(jpgenc_ctx* c, float* dev_blocks, uint64_t nblocks) {
+    if (!c || !dev_blocks) return JPGENC_ERR_ARG;
+    return launch_synth_blocks(c, dev_blocks, nblocks);
+}
+int jpgenc_flush_l2(jpgenc_ctx* c) {
+    if (!c) return JPGENC_ERR_ARG;
+    if (!c->d_flush) {
+        c->flush_bytes = 256ull << 20;                           // 2x the 126 MB L2
+        JPGENC_CUDA(c, cudaMalloc(&c->d_flush, c->flush_bytes));
+    }
+    return launch_flush(c);
+}
+int jpgenc_timer_begin(jpgenc_ctx* c) {
+    if (!c) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_u0, c->stream));
+    return JPGENC_OK;
+}
+int jpgenc_timer_end(jpgenc_ctx* c, float* ms) {
+    if (!c || !ms) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_u1, c->stream));
+    JPGENC_CUDA(c, cudaEventSynchronize(c->ev_u1));
+    JPGENC_CUDA(c, cudaEventElapsedTime(ms, c->ev_u0, c->ev_u1));
+    return JPGENC_OK;
+}
+
+}  // extern "C"

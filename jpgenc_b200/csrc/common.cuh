@@ -1,0 +1,133 @@
+// Shared declarations for the sm_100a JPEG encode path (kernels + C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/jpgenc_b200.h"
+
+namespace jpgenc {
+
+constexpr int kBlocksPerMcu = 6;          // Y00 Y01 Y10 Y11 Cb Cr  (src/Image.cpp:959-967)
+constexpr int kCoefPerBlock = 64;
+constexpr int kBlockBytes = 128;          // 64 x int16
+
+// zigzag scan: natural index (v*8+u) of the i-th coefficient (include/Coding.hpp:57-81)
+#define JPGENC_ZIGZAG_LIST                                                                            \
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, \
+    7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, \
+    31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63
+
+// Per-table constants of the FP32 fast path, natural order.
+//   mul[i] = s_v * s_u / q[i]   (AAN output scales folded with the quantiser; Dct.hpp:36-43, Coding.hpp:92-94)
+//   thr[i] = 0.5 - delta_i      a quotient whose distance to the nearest integer exceeds thr is "on a rounding
+//                               boundary" as far as FP32 can tell; such blocks are redone in exact FP64
+struct QuantConsts {
+    float mul[64];
+    float thr[64];
+};
+
+// Constants of the exact path: the reference's own doubles (Dct.hpp:21-43) and integer quantisers.
+struct ExactConsts {
+    double a1, a2, a3, a4, a5;
+    double s[8];
+    double scale;                         // 255. / maxval  (src/Image.cpp:465)
+    uint8_t qy[64];
+    uint8_t qc[64];
+};
+
+struct ColorConsts {                      // FP32 fast path; sample scale folded in, chroma rows also carry the /4
+    float y[3], cb[3], cr[3];
+};
+
+struct ForwardParams {
+    const uint8_t* rgb;
+    int16_t* coef;
+    uint32_t* refine_list;                // block ids (mcu*6+k) that need the exact path
+    uint32_t* refine_count;
+    uint32_t refine_cap;
+    uint32_t real_w, real_h;
+    uint32_t mcu_w, mcu_h;
+    ColorConsts color;
+    QuantConsts luma;
+    QuantConsts chroma;
+};
+
+__host__ __device__ inline uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// device-side Huffman table entry: (length << 16) | right-aligned code; 0 = absent
+struct DeviceTables {
+    uint32_t entry[4][256];
+};
+
+}  // namespace jpgenc
+
+struct jpgenc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr;
+    std::string error;
+    int sm_count = 148;
+    uint64_t launches = 0;
+
+    // parameters
+    uint8_t qy[64], qc[64];
+    double dct_a[5], dct_s[8];
+
+    // image state
+    const uint8_t* d_rgb = nullptr;       // bound or owned
+    uint8_t* d_rgb_owned = nullptr;
+    size_t rgb_cap = 0;
+    uint32_t real_w = 0, real_h = 0, maxval = 255, mcu_w = 0, mcu_h = 0;
+    bool have_pixels = false, have_coef = false, have_scan = false;
+
+    int16_t* d_coef = nullptr;
+    size_t coef_cap = 0;
+    uint32_t* d_refine_list = nullptr;
+    size_t refine_cap = 0;
+    uint32_t* d_counters = nullptr;       // [0] refine count, [1] lookback ticket, [2..3] spare
+    uint32_t* d_hist = nullptr;           // [4][256]
+    unsigned long long* d_first = nullptr;// [4][256]
+    jpgenc::DeviceTables* d_tables = nullptr;
+    unsigned long long* d_lookback = nullptr;  // one status word per K3 tile
+    size_t lookback_cap = 0;
+    uint32_t* d_raw = nullptr;            // un-stuffed scan, 32-bit words, bytes in stream order
+    size_t raw_cap = 0;
+    uint8_t* d_scan = nullptr;            // stuffed scan
+    size_t scan_cap = 0;
+    unsigned long long* d_stuff_state = nullptr;   // lookback words of K4 + totals
+    size_t stuff_cap = 0;
+    void* d_flush = nullptr;              // L2 eviction scratch
+    size_t flush_bytes = 0;
+    void* h_pinned = nullptr;             // small pinned staging (stats, totals)
+    size_t pinned_bytes = 0;
+
+    jpgenc_stats stats{};
+};
+
+#define JPGENC_CUDA(ctx, expr)                                                                       \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+            return JPGENC_ERR_CUDA;                                                                  \
+        }                                                                                            \
+    } while (0)
+
+// launchers implemented in the kernel translation units
+namespace jpgenc {
+int launch_forward(jpgenc_ctx* c);
+int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
+                            uint64_t* refined);
+int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qcb, const int32_t* d_qcr);
+int launch_symbol_stats(jpgenc_ctx* c);
+int launch_entropy(jpgenc_ctx* c, uint64_t total_bits);
+int launch_synth_rgb(jpgenc_ctx* c, uint8_t* d, uint32_t w, uint32_t h, uint32_t seed);
+int launch_synth_blocks(jpgenc_ctx* c, float* d, uint64_t nblocks);
+int launch_flush(jpgenc_ctx* c);
+void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out);
+void default_dct_constants(double a[5], double s[8]);
+}  // namespace jpgenc

@@ -1,0 +1,227 @@
+// K3 — Huffman encode + MCU interleave + 1-padding;  K4 — FF -> FF 00 byte stuffing.
+//
+// Replaces Image::doHuffmanEncoding, the per-MCU Bitstream concatenation, Bitstream::fill() and the stuffing
+// operator<< (reference src/Image.cpp:737-829, 957-971; include/BitstreamGeneric.hpp:126-146, 182-195, 213-224, 242-248).
+//
+// K3 is one pass over the MCU-ordered coefficients: every thread sizes its block's code (DC code + magnitude bits,
+// AC codes + magnitude bits), the CTA scans the sizes, a decoupled look-back over per-tile status words turns the
+// CTA total into the tile's global bit offset, and the block codes are then assembled MSB-first in a shared-memory
+// bit buffer and written out as whole 32-bit words (only the two words a tile shares with its neighbours use
+// atomicOr).  Tiles take their index from an atomic ticket, so a tile only ever waits for tiles that already run.
+// K4 has the same structure at byte granularity: count FF bytes, scan, look back, compact.
+#include "blockwalk.cuh"
+
+namespace jpgenc {
+
+constexpr int kBitBufWords = 4096;                      // 16 KB of bits per tile before falling back to global atomics
+
+// MSB-first bit writer into 32-bit words ("word bit 31 is the earliest bit"); words are byte-swapped when they go
+// to memory so that memory byte order is stream order.
+template <bool kGlobal>
+struct BitWriter {
+    uint32_t* words;        // shared bit buffer (word 0 = the tile's first, partially foreign, word) or global raw scan
+    uint32_t word;          // current word index
+    uint32_t fill;          // bits already used in the current word
+    uint32_t acc;
+
+    __device__ __forceinline__ void start(uint32_t* base, unsigned long long bitpos) {
+        words = base;
+        word = static_cast<uint32_t>(bitpos >> 5);
+        fill = static_cast<uint32_t>(bitpos & 31);
+        acc = 0;
+    }
+    __device__ __forceinline__ void flush_word() {
+        if (acc) atomicOr(&words[word], kGlobal ? __byte_perm(acc, 0, 0x0123) : acc);
+    }
+    __device__ __forceinline__ void put(uint32_t code, uint32_t n) {      // n <= 31, code < 2^n
+        const unsigned long long v = static_cast<unsigned long long>(code) << (64 - fill - n);
+        acc |= static_cast<uint32_t>(v >> 32);
+        fill += n;
+        if (fill >= 32) {
+            flush_word();
+            ++word;
+            acc = static_cast<uint32_t>(v);
+            fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void finish() { if (fill) flush_word(); }
+};
+
+struct EntropyParams {
+    const int16_t* coef;
+    uint64_t nblocks;
+    const DeviceTables* tables;
+    unsigned long long* status;     // look-back words, zeroed before launch
+    uint32_t* ticket;               // zeroed before launch
+    uint32_t* raw;                  // zeroed before launch, (total_bits+7)/8 bytes rounded up to words (+ slack)
+    unsigned long long* total_out;  // [0] = total bits written (before padding)
+};
+
+template <class Put>
+__device__ __forceinline__ void encode_block(const uint32_t (&w)[32], int diff, const uint32_t* tdc, const uint32_t* tac, Put&& put) {
+    walk_block(w, diff, [&](int sym, int value, int ord) {
+        const uint32_t e = (ord < 0 ? tdc : tac)[sym];
+        const uint32_t cat = sym & 15;                                            // magnitude bit count
+        const uint32_t mag = (value < 0 ? value - 1 : value) & ((1u << cat) - 1); // Coding.hpp:206-212
+        put(((e & 0xFFFFu) << cat) | mag, (e >> 16) + cat);
+    });
+}
+
+__global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tile = smem;
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + kTileBytes);                  // [4][256]
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + kTileBytes + 4096);          // [kBitBufWords]
+    uint32_t* s_scan = s_bits + kBitBufWords;                                          // [33]
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+    for (int i = tid; i < 1024; i += kTileBlocks) s_tab[i] = (&p.tables->entry[0][0])[i];
+    for (int i = tid; i < kBitBufWords; i += kTileBlocks) s_bits[i] = 0;
+    __syncthreads();
+    const uint32_t tile_idx = s_tile;
+    const uint64_t first = static_cast<uint64_t>(tile_idx) * kTileBlocks;
+    const int nb = static_cast<int>(umin64(kTileBlocks, p.nblocks - first));
+    stage_tile(tile, p.coef + first * kCoefPerBlock, nb, tid, kTileBlocks);
+    __syncthreads();
+
+    uint32_t w[32];
+    int diff = 0;
+    uint32_t my_bits = 0;
+    const int k = tid % kBlocksPerMcu;
+    const uint32_t* tdc = s_tab + (k < 4 ? 0 : 512);
+    const uint32_t* tac = tdc + 256;
+    if (tid < nb) {
+        load_block(tile, tid, w);
+        diff = static_cast<int16_t>(w[0] & 0xFFFFu) - dc_predictor(tile, p.coef, first, tid);
+        encode_block(w, diff, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
+    }
+    uint32_t tile_bits;
+    const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
+    if (tid == 0) s_base = lookback_exclusive(p.status, tile_idx, tile_bits);
+    __syncthreads();
+    const unsigned long long base = s_base;
+    const uint32_t lead = static_cast<uint32_t>(base & 31);                 // bits of the first word owned by earlier tiles
+    const bool last_tile = first + nb == p.nblocks;
+    // the last tile also appends the 1-padding of Bitstream::fill() (BitstreamGeneric.hpp:242-248)
+    const uint32_t pad = last_tile ? static_cast<uint32_t>((8 - ((base + tile_bits) & 7)) & 7) : 0;
+    const bool in_smem = lead + tile_bits + pad <= kBitBufWords * 32u;
+
+    if (in_smem) {
+        if (tid < nb) {
+            BitWriter<false> bw;
+            bw.start(s_bits, lead + local);
+            encode_block(w, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            bw.finish();
+        }
+        if (pad && tid == 0) {
+            BitWriter<false> bw;
+            bw.start(s_bits, lead + tile_bits);
+            bw.put((1u << pad) - 1, pad);
+            bw.finish();
+        }
+        __syncthreads();
+        const uint32_t nwords = (lead + tile_bits + pad + 31) >> 5;
+        uint32_t* g = p.raw + (base >> 5);
+        for (uint32_t i = tid; i < nwords; i += kTileBlocks) {
+            const uint32_t v = __byte_perm(s_bits[i], 0, 0x0123);
+            if (i == 0 || i == nwords - 1) { if (v) atomicOr(&g[i], v); }
+            else g[i] = v;
+        }
+    } else {   // very dense tile: write straight to the (zeroed) global words
+        if (tid < nb) {
+            BitWriter<true> bw;
+            bw.start(p.raw, base + local);
+            encode_block(w, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            bw.finish();
+        }
+        if (pad && tid == 0) {
+            BitWriter<true> bw;
+            bw.start(p.raw, base + tile_bits);
+            bw.put((1u << pad) - 1, pad);
+            bw.finish();
+        }
+    }
+    if (last_tile && tid == 0) p.total_out[0] = base + tile_bits;
+}
+
+// ---- K4 ---------------------------------------------------------------------------------------------------
+constexpr int kStuffThreads = 256;
+constexpr int kStuffBytesPerThread = 16;
+constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
+
+__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __restrict__ raw, uint64_t nbytes,
+                                                              uint8_t* __restrict__ out, unsigned long long* status,
+                                                              uint32_t* ticket, unsigned long long* total_ff) {
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t at = static_cast<uint64_t>(tile) * kStuffTile + static_cast<uint64_t>(tid) * kStuffBytesPerThread;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    int n = 0;
+    if (at < nbytes) {
+        n = static_cast<int>(umin64(kStuffBytesPerThread, nbytes - at));
+        q = *reinterpret_cast<const uint4*>(raw + at);         // raw is padded to a multiple of 16 bytes and zero-filled
+    }
+    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+    uint32_t ff = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < n && ((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 0xFFu) ++ff;
+    uint32_t tile_ff;
+    const uint32_t local = block_exclusive_scan(ff, s_scan, &tile_ff);
+    if (tid == 0) s_base = lookback_exclusive(status, tile, tile_ff);
+    __syncthreads();
+    uint8_t* o = out + at + s_base + local;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j < n) {
+            const uint8_t b = static_cast<uint8_t>((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+            *o++ = b;
+            if (b == 0xFF) *o++ = 0;
+        }
+    }
+    if (tid == 0 && static_cast<uint64_t>(tile + 1) * kStuffTile >= nbytes) total_ff[0] = s_base + tile_ff;
+}
+
+int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
+    const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
+    const uint64_t nbytes = (total_bits + 7) / 8;
+    const uint32_t tiles3 = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    const uint32_t tiles4 = static_cast<uint32_t>((nbytes + kStuffTile - 1) / kStuffTile);
+    // status words: [0, tiles3) K3, [tiles3, tiles3+tiles4) K4, then 2 totals
+    unsigned long long* st3 = c->d_lookback;
+    unsigned long long* st4 = c->d_lookback + tiles3;
+    unsigned long long* totals = c->d_lookback + tiles3 + tiles4;
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, (static_cast<size_t>(tiles3) + tiles4 + 2) * sizeof(unsigned long long), c->stream));
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters + 1, 0, 2 * sizeof(uint32_t), c->stream));
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, c->raw_cap, c->stream));
+
+    EntropyParams p{};
+    p.coef = c->d_coef;
+    p.nblocks = nblocks;
+    p.tables = c->d_tables;
+    p.status = st3;
+    p.ticket = c->d_counters + 1;
+    p.raw = c->d_raw;
+    p.total_out = totals;
+    const size_t smem = kTileBytes + 4096 + kBitBufWords * 4 + 33 * 4 + 16;
+    JPGENC_CUDA(c, cudaFuncSetAttribute(huffman_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    huffman_pack_kernel<<<tiles3, kTileBlocks, smem, c->stream>>>(p);
+    JPGENC_CUDA(c, cudaGetLastError());
+    if (tiles4) {
+        stuff_kernel<<<tiles4, kStuffThreads, 0, c->stream>>>(reinterpret_cast<const uint8_t*>(c->d_raw), nbytes, c->d_scan,
+                                                              st4, c->d_counters + 2, totals + 1);
+        JPGENC_CUDA(c, cudaGetLastError());
+    }
+    c->launches += 2;
+    return JPGENC_OK;
+}
+
+}  // namespace jpgenc

@@ -1,0 +1,544 @@
+// K1 — fused colour conversion + 4:2:0 mean subsampling + Arai DCT + quantisation + zigzag.
+//
+// Replaces Image::convertToColorSpace / applySubsampling(S420_m) / applyDCT(Arai) / applyQuantization
+// (reference src/Image.cpp:112-148, 198-235, 540-595, 597-636; include/Dct.hpp:47-215; include/Coding.hpp:57-97).
+//
+// Design (DESIGN.md "K1"):
+//  * one CTA = a strip of kMcus 16x16 MCUs; the RGB strip (16 rows) is staged in shared memory by bulk
+//    (TMA) copies, one per image row, completing on an mbarrier;
+//  * one thread = one 8x8 block, held entirely in registers: no transposes, no shuffles, 30 FP32 instructions
+//    per 8-point AAN pass; the AAN output scales and 1/q are folded into one multiplier per coefficient;
+//  * the reference computes in double.  The FP32 result is only trusted when every quotient is further than
+//    delta from a rounding boundary; otherwise the block id goes to a refine list and refine_kernel redoes
+//    the block in FP64 with the reference's exact operation order (no FMA contraction), so the stored
+//    coefficients are the reference's, bit for bit;
+//  * coefficients leave through a bank-conflict-free swizzled staging buffer as full 512-byte warp stores,
+//    already in the MCU-interleaved order the entropy coder consumes.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jpgenc {
+
+__constant__ uint8_t c_zigzag[64] = {JPGENC_ZIGZAG_LIST};
+
+// ---------------------------------------------------------------------------------------------------
+// FP32 fast path
+// ---------------------------------------------------------------------------------------------------
+// 8-point AAN butterfly, outputs in frequency order and WITHOUT the s_k scales (they are folded into
+// QuantConsts::mul).  Same dataflow as Dct.hpp:52-131, re-associated for FMA: 30 instructions.
+__device__ __forceinline__ void aan8(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
+                                     float& x7) {
+    constexpr float A1 = 0.70710678118654752f;   // cos(4pi/16)
+    constexpr float A2 = 0.54119610014619698f;   // cos(2pi/16) - cos(6pi/16)
+    constexpr float A4 = 1.30656296487637653f;   // cos(6pi/16) + cos(2pi/16)
+    constexpr float A5 = 0.38268343236508977f;   // cos(6pi/16)
+    const float z0 = x0 + x7, z1 = x1 + x6, z2 = x2 + x5, z3 = x3 + x4;
+    const float z4 = x3 - x4, z5 = x2 - x5, z6 = x1 - x6, z7 = x0 - x7;
+    const float r0 = z0 + z3, r1 = z1 + z2, r2 = z1 - z2, r3 = z0 - z3;
+    const float n4 = z4 + z5;                    // -r4
+    const float r5 = z5 + z6, r6 = z6 + z7;
+    const float t2 = r2 + r3;
+    const float tmp = (r6 - n4) * A5;
+    const float u4 = fmaf(n4, A2, -tmp);
+    const float u6 = fmaf(r6, A4, -tmp);
+    const float v5 = fmaf(r5, A1, z7);
+    const float v7 = fmaf(-r5, A1, z7);
+    x0 = r0 + r1;
+    x4 = r0 - r1;
+    x2 = fmaf(t2, A1, r3);
+    x6 = fmaf(-t2, A1, r3);
+    x5 = u4 + v7;
+    x1 = v5 + u6;
+    x7 = v5 - u6;
+    x3 = v7 - u4;
+}
+
+// v[r*8+c] spatial -> v[v*8+u] frequency (unscaled)
+__device__ __forceinline__ void dct8x8(float (&v)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        aan8(v[0 * 8 + c], v[1 * 8 + c], v[2 * 8 + c], v[3 * 8 + c], v[4 * 8 + c], v[5 * 8 + c], v[6 * 8 + c], v[7 * 8 + c]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        aan8(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+}
+
+// scale + quantise + zigzag + pack to 32 words of two int16; returns true when some quotient is too close
+// to a rounding boundary for FP32 to decide.
+__device__ __forceinline__ bool quantize_pack(const float (&v)[64], const QuantConsts& q, uint32_t (&out)[32]) {
+    constexpr float kMagic = 12582912.f;          // 1.5 * 2^23: (x + kMagic) holds rint(x) in its low mantissa bits
+    constexpr int zz[64] = {JPGENC_ZIGZAG_LIST};
+    uint32_t bits[64];
+    bool boundary = false;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const float a = fmaf(v[i], q.mul[i], kMagic);
+        const float k = a - kMagic;
+        const float d = fmaf(v[i], q.mul[i], -k);  // quotient - rint(quotient), exact product inside the FMA
+        boundary |= fabsf(d) > q.thr[i];
+        bits[i] = __float_as_uint(a);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = __byte_perm(bits[zz[2 * j]], bits[zz[2 * j + 1]], 0x5410);
+    return boundary;
+}
+
+// staging slot layout: 128 B per block, 16-byte chunk c of slot s lives at chunk (c ^ (s & 7)) — conflict-free
+// both for the per-thread 16-byte writes and for the linear copy-out
+__device__ __forceinline__ void stage_block(uint8_t* staging, int slot, const uint32_t (&w)[32]) {
+    uint4* base = reinterpret_cast<uint4*>(staging + slot * kBlockBytes);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) base[c ^ (slot & 7)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+
+__device__ __forceinline__ void copy_out(const uint8_t* staging, int16_t* gdst, int nslots, int tid, int nthreads) {
+    uint4* g = reinterpret_cast<uint4*>(gdst);
+    const int chunks = nslots * 8;
+    for (int j = tid; j < chunks; j += nthreads) {
+        const int s = j >> 3, c = j & 7;
+        g[j] = *reinterpret_cast<const uint4*>(staging + s * kBlockBytes + ((c ^ (s & 7)) << 4));
+    }
+}
+
+__device__ __forceinline__ void push_refine(const ForwardParams& p, uint32_t block_id) {
+    const uint32_t at = atomicAdd(p.refine_count, 1u);
+    if (at < p.refine_cap) p.refine_list[at] = block_id;
+}
+
+template <int kMcus>
+struct ForwardSmem {
+    static constexpr int kPitch = kMcus * 48;                 // bytes of RGB per tile row
+    static constexpr int kTileBytes = 16 * kPitch;            // == kMcus*6*128: the staging buffer aliases it
+    static constexpr int kChromaW = kMcus * 8;
+    alignas(128) uint8_t tile[kTileBytes];
+    alignas(16) float chroma[2][8][kChromaW];
+    alignas(8) uint64_t bar;
+};
+
+// kAligned: real_w % 16 == 0 and 16-byte aligned base -> rows are staged with bulk copies; otherwise a clamped
+// byte loader fills the tile (odd sizes; right-edge replication, src/Image.cpp:491-530)
+template <int kMcus, bool kAligned>
+__global__ void __launch_bounds__(kMcus * 4) forward_kernel(const __grid_constant__ ForwardParams p) {
+    using Smem = ForwardSmem<kMcus>;
+    __shared__ Smem sm;
+    constexpr int kThreads = kMcus * 4;
+    const int tid = threadIdx.x;
+    const uint32_t my = blockIdx.y;
+    const uint32_t mcu0 = blockIdx.x * kMcus;
+    const int nm = min(kMcus, static_cast<int>(p.mcu_w - mcu0));
+
+    // ---- stage the 16-row RGB strip ----
+    if constexpr (kAligned) {
+        if (tid == 0) {
+            ptx::mbar_init(&sm.bar, 1);
+            ptx::mbar_init_fence();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t row_bytes = nm * 48;
+            ptx::mbar_expect_tx(&sm.bar, 16 * row_bytes);
+#pragma unroll 1
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t sy = min(my * 16 + r, p.real_h - 1);          // bottom edge replication
+                ptx::bulk_g2s(sm.tile + r * Smem::kPitch, p.rgb + (static_cast<size_t>(sy) * p.real_w + mcu0 * 16) * 3,
+                              row_bytes, &sm.bar);
+            }
+        }
+        ptx::mbar_wait(&sm.bar, 0);
+    } else {
+        const int row_bytes = nm * 48;
+        for (int idx = tid; idx < 16 * row_bytes; idx += kThreads) {
+            const int r = idx / row_bytes, b = idx - r * row_bytes;
+            const uint32_t sx = min(mcu0 * 16 + b / 3, p.real_w - 1);
+            const uint32_t sy = min(my * 16 + r, p.real_h - 1);
+            sm.tile[r * Smem::kPitch + b] = p.rgb[(static_cast<size_t>(sy) * p.real_w + sx) * 3 + (b % 3)];
+        }
+        __syncthreads();
+    }
+
+    // ---- luma thread: block (bx, by) of the strip's 2 x (2*kMcus) block grid ----
+    const int bx = tid % (kMcus * 2), by = tid / (kMcus * 2);
+    const bool active = (bx >> 1) < nm;
+    float v[64];
+    if (active) {
+        const ColorConsts& cc = p.color;
+#pragma unroll
+        for (int rp = 0; rp < 4; ++rp) {
+            float rr[2][8], gg[2][8], bb[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = rp * 2 + h;
+                const uint2* src = reinterpret_cast<const uint2*>(sm.tile + (by * 8 + r) * Smem::kPitch + bx * 24);
+                const uint2 q0 = src[0], q1 = src[1], q2 = src[2];
+                const uint32_t w[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    rr[h][x] = static_cast<float>((w[(3 * x) >> 2] >> (8 * ((3 * x) & 3))) & 0xFFu);
+                    gg[h][x] = static_cast<float>((w[(3 * x + 1) >> 2] >> (8 * ((3 * x + 1) & 3))) & 0xFFu);
+                    bb[h][x] = static_cast<float>((w[(3 * x + 2) >> 2] >> (8 * ((3 * x + 2) & 3))) & 0xFFu);
+                    v[r * 8 + x] = fmaf(cc.y[0], rr[h][x], fmaf(cc.y[1], gg[h][x], fmaf(cc.y[2], bb[h][x], -128.f)));
+                }
+            }
+            float cb[4], cr[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float r4 = (rr[0][2 * x] + rr[0][2 * x + 1]) + (rr[1][2 * x] + rr[1][2 * x + 1]);
+                const float g4 = (gg[0][2 * x] + gg[0][2 * x + 1]) + (gg[1][2 * x] + gg[1][2 * x + 1]);
+                const float b4 = (bb[0][2 * x] + bb[0][2 * x + 1]) + (bb[1][2 * x] + bb[1][2 * x + 1]);
+                cb[x] = fmaf(cc.cb[0], r4, fmaf(cc.cb[1], g4, cc.cb[2] * b4));
+                cr[x] = fmaf(cc.cr[0], r4, fmaf(cc.cr[1], g4, cc.cr[2] * b4));
+            }
+            *reinterpret_cast<float4*>(&sm.chroma[0][by * 4 + rp][bx * 4]) = make_float4(cb[0], cb[1], cb[2], cb[3]);
+            *reinterpret_cast<float4*>(&sm.chroma[1][by * 4 + rp][bx * 4]) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+        }
+    }
+    __syncthreads();   // every RGB byte has been consumed (tile may now be reused as staging); chroma planes complete
+
+    const uint32_t mcu_base = my * p.mcu_w + mcu0;
+    uint32_t packed[32];
+    if (active) {
+        dct8x8(v);
+        const bool boundary = quantize_pack(v, p.luma, packed);
+        const int m = bx >> 1, k = by * 2 + (bx & 1);
+        stage_block(sm.tile, m * kBlocksPerMcu + k, packed);
+        if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + k);
+    }
+    // ---- chroma threads: 2*kMcus blocks (Cb of every MCU, then Cr) ----
+    if (tid < 2 * kMcus) {
+        const int comp = tid / kMcus, m = tid % kMcus;
+        if (m < nm) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 lo = *reinterpret_cast<const float4*>(&sm.chroma[comp][r][m * 8]);
+                const float4 hi = *reinterpret_cast<const float4*>(&sm.chroma[comp][r][m * 8 + 4]);
+                v[r * 8 + 0] = lo.x; v[r * 8 + 1] = lo.y; v[r * 8 + 2] = lo.z; v[r * 8 + 3] = lo.w;
+                v[r * 8 + 4] = hi.x; v[r * 8 + 5] = hi.y; v[r * 8 + 6] = hi.z; v[r * 8 + 7] = hi.w;
+            }
+            dct8x8(v);
+            const bool boundary = quantize_pack(v, p.chroma, packed);
+            stage_block(sm.tile, m * kBlocksPerMcu + 4 + comp, packed);
+            if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + 4 + comp);
+        }
+    }
+    __syncthreads();
+    copy_out(sm.tile, p.coef + static_cast<size_t>(mcu_base) * kBlocksPerMcu * kCoefPerBlock, nm * kBlocksPerMcu, tid, kThreads);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact FP64 path (the reference's arithmetic, operation for operation, no contraction)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+
+// one 8-point pass, Dct.hpp:52-131 / 134-213; o has stride `os`
+__device__ __forceinline__ void aan8_exact(const double* x, int xs, double* o, int os, const ExactConsts& e) {
+    const double x0 = x[0], x1 = x[xs], x2 = x[2 * xs], x3 = x[3 * xs], x4 = x[4 * xs], x5 = x[5 * xs], x6 = x[6 * xs],
+                 x7 = x[7 * xs];
+    const double z0 = dadd(x0, x7), z1 = dadd(x1, x6), z2 = dadd(x2, x5), z3 = dadd(x3, x4);
+    const double z4 = dadd(-x4, x3), z5 = dadd(-x5, x2), z6 = dadd(-x6, x1), z7 = dadd(-x7, x0);
+    const double r0 = dadd(z0, z3), r1 = dadd(z1, z2), r2 = dsub(z1, z2), r3 = dsub(z0, z3);
+    const double r4 = dsub(-z4, z5), r5 = dadd(z5, z6), r6 = dadd(z6, z7), r7 = z7;
+    const double t0 = dadd(r0, r1), t1 = dsub(r0, r1);
+    double t2 = dadd(r2, r3), t4 = r4, t5 = r5, t6 = r6;
+    const double t3 = r3, t7 = r7;
+    const double tmp = dmul(dadd(t4, t6), e.a5);
+    t2 = dmul(t2, e.a1); t4 = dmul(t4, e.a2); t5 = dmul(t5, e.a3); t6 = dmul(t6, e.a4);
+    const double u4 = dsub(-t4, tmp), u6 = dsub(t6, tmp);
+    const double v2 = dadd(t2, t3), v3 = dsub(t3, t2), v5 = dadd(t5, t7), v7 = dsub(t7, t5);
+    const double w4 = dadd(u4, v7), w5 = dadd(v5, u6), w6 = dadd(-u6, v5), w7 = dsub(v7, u4);
+    o[0 * os] = dmul(t0, e.s[0]); o[4 * os] = dmul(t1, e.s[4]); o[2 * os] = dmul(v2, e.s[2]); o[6 * os] = dmul(v3, e.s[6]);
+    o[5 * os] = dmul(w4, e.s[5]); o[1 * os] = dmul(w5, e.s[1]); o[7 * os] = dmul(w6, e.s[7]); o[3 * os] = dmul(w7, e.s[3]);
+}
+
+// blk: spatial samples row-major -> quantised zigzag int16 (Coding.hpp:84-97: int(round(x / q)))
+__device__ void dct_quant_exact(double* blk, const uint8_t* q, const ExactConsts& e, int16_t* out) {
+    double tmp[64];
+    for (int j = 0; j < 8; ++j) aan8_exact(blk + j, 8, tmp + j * 8, 1, e);     // column j -> row j of tmp
+    for (int j = 0; j < 8; ++j) aan8_exact(tmp + j, 8, blk + j * 8, 1, e);     // column j of tmp -> row j of result
+    for (int i = 0; i < 64; ++i) {
+        const int n = c_zigzag[i];
+        out[i] = static_cast<int16_t>(static_cast<int>(round(__ddiv_rn(blk[n], static_cast<double>(q[n])))));
+    }
+}
+
+// colour conversion of one pixel, src/Image.cpp:131-143: float constants widened to double, double arithmetic
+__device__ __forceinline__ double exact_channel(int comp, double r, double g, double b) {
+    if (comp == 0) return dsub(dadd(0.0, dadd(dadd(dmul((double).299f, r), dmul((double).587f, g)), dmul((double).114f, b))), 128.0);
+    if (comp == 1) return dsub(dadd(128.0, dadd(dadd(dmul((double)-.1687f, r), dmul((double)-.3312f, g)), dmul((double).5f, b))), 128.0);
+    return dsub(dadd(128.0, dadd(dadd(dmul((double).5f, r), dmul((double)-.4186f, g)), dmul((double)-.0813f, b))), 128.0);
+}
+
+__device__ __forceinline__ double exact_pixel(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uint32_t x, uint32_t y,
+                                              int comp, double scale) {
+    const uint32_t sx = min(x, real_w - 1), sy = min(y, real_h - 1);            // src/Image.cpp:491-530
+    const uint8_t* px = rgb + (static_cast<size_t>(sy) * real_w + sx) * 3;
+    return exact_channel(comp, dmul(static_cast<double>(px[0]), scale), dmul(static_cast<double>(px[1]), scale),
+                         dmul(static_cast<double>(px[2]), scale));
+}
+
+__global__ void __launch_bounds__(64) refine_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
+                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ count,
+                                                    uint32_t cap, uint32_t real_w, uint32_t real_h, uint32_t mcu_w,
+                                                    const __grid_constant__ ExactConsts e) {
+    const uint32_t n = min(*count, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t id = list[i];
+        const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu;
+        const uint32_t mx = mcu % mcu_w, my = mcu / mcu_w;
+        double blk[64];
+        if (k < 4) {
+            const uint32_t x0 = mx * 16 + (k & 1) * 8, y0 = my * 16 + (k >> 1) * 8;
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c) blk[r * 8 + c] = exact_pixel(rgb, real_w, real_h, x0 + c, y0 + r, 0, e.scale);
+        } else {
+            const int comp = k - 3;
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c) {                                   // S420_m, src/Image.cpp:207-226
+                    const uint32_t x = mx * 16 + 2 * c, y = my * 16 + 2 * r;
+                    const double top = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y, comp, e.scale)),
+                                            exact_pixel(rgb, real_w, real_h, x + 1, y, comp, e.scale));
+                    const double bot = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y + 1, comp, e.scale)),
+                                            exact_pixel(rgb, real_w, real_h, x + 1, y + 1, comp, e.scale));
+                    blk[r * 8 + c] = __ddiv_rn(dadd(top, bot), 4.0);
+                }
+        }
+        dct_quant_exact(blk, k < 4 ? e.qy : e.qc, e, coef + static_cast<size_t>(id) * kCoefPerBlock);
+    }
+}
+
+// every block in FP64 (used when the refine list overflowed, and by tests as a device-side cross-check)
+__global__ void __launch_bounds__(64) exact_all_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
+                                                       uint32_t nblocks, uint32_t real_w, uint32_t real_h, uint32_t mcu_w,
+                                                       const __grid_constant__ ExactConsts e) {
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < nblocks; id += gridDim.x * blockDim.x) {
+        const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu;
+        const uint32_t mx = mcu % mcu_w, my = mcu / mcu_w;
+        double blk[64];
+        if (k < 4) {
+            const uint32_t x0 = mx * 16 + (k & 1) * 8, y0 = my * 16 + (k >> 1) * 8;
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c) blk[r * 8 + c] = exact_pixel(rgb, real_w, real_h, x0 + c, y0 + r, 0, e.scale);
+        } else {
+            const int comp = k - 3;
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t x = mx * 16 + 2 * c, y = my * 16 + 2 * r;
+                    const double top = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y, comp, e.scale)),
+                                            exact_pixel(rgb, real_w, real_h, x + 1, y, comp, e.scale));
+                    const double bot = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y + 1, comp, e.scale)),
+                                            exact_pixel(rgb, real_w, real_h, x + 1, y + 1, comp, e.scale));
+                    blk[r * 8 + c] = __ddiv_rn(dadd(top, bot), 4.0);
+                }
+        }
+        dct_quant_exact(blk, k < 4 ? e.qy : e.qc, e, coef + static_cast<size_t>(id) * kCoefPerBlock);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// config-1 microbenchmark: stand-alone fp32 blocks -> dctArai -> quantize -> zigzag int16
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMbThreads = 128;
+constexpr int kMbPitch = 256 + 16;            // bytes between blocks in shared memory (conflict-free 16-byte reads)
+
+__global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
+                                                                uint64_t nblocks, uint32_t* refine_list,
+                                                                uint32_t* refine_count, uint32_t refine_cap,
+                                                                const __grid_constant__ QuantConsts q) {
+    __shared__ alignas(128) uint8_t tile[kMbThreads * kMbPitch];
+    __shared__ alignas(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const uint64_t first = static_cast<uint64_t>(blockIdx.x) * kMbThreads;
+    const int nb = static_cast<int>(umin64(kMbThreads, nblocks - first));
+    if (tid == 0) {
+        ptx::mbar_init(&bar, 1);
+        ptx::mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0) ptx::mbar_expect_tx(&bar, nb * 256);
+    __syncthreads();                            // the expected byte count is armed before any copy can complete
+    if (tid < nb) ptx::bulk_g2s(tile + tid * kMbPitch, in + (first + tid) * 64, 256, &bar);
+    ptx::mbar_wait(&bar, 0);
+
+    float v[64];
+    if (tid < nb) {
+        const float4* src = reinterpret_cast<const float4*>(tile + tid * kMbPitch);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 f = src[j];
+            v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+        }
+    }
+    __syncthreads();                            // all inputs are in registers: reuse the tile as output staging
+    if (tid < nb) {
+        uint32_t packed[32];
+        dct8x8(v);
+        if (quantize_pack(v, q, packed)) {
+            const uint32_t at = atomicAdd(refine_count, 1u);
+            if (at < refine_cap) refine_list[at] = static_cast<uint32_t>(first + tid);
+        }
+        stage_block(tile, tid, packed);
+    }
+    __syncthreads();
+    copy_out(tile, out + first * 64, nb, tid, kMbThreads);
+}
+
+__global__ void __launch_bounds__(64) refine_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
+                                                           const uint32_t* __restrict__ list,
+                                                           const uint32_t* __restrict__ count, uint32_t cap,
+                                                           uint64_t nblocks, int all, const __grid_constant__ ExactConsts e) {
+    const uint64_t n = all ? nblocks : min(*count, cap);
+    for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t id = all ? i : list[i];
+        double blk[64];
+        for (int j = 0; j < 64; ++j) blk[j] = static_cast<double>(in[id * 64 + j]);
+        dct_quant_exact(blk, e.qy, e, out + id * 64);
+    }
+}
+
+// reference planar natural-order int32 planes -> MCU-ordered zigzag int16 (test hook behind jpgenc_set_coefficients)
+__global__ void planes_to_mcu_kernel(const int32_t* __restrict__ qy, const int32_t* __restrict__ qcb,
+                                     const int32_t* __restrict__ qcr, int16_t* __restrict__ coef, uint32_t mcu_w,
+                                     uint32_t nblocks) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<uint64_t>(nblocks) * 64) return;
+    const uint32_t id = static_cast<uint32_t>(i >> 6), z = i & 63, n = c_zigzag[z];
+    const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu, mx = mcu % mcu_w, my = mcu / mcu_w;
+    int32_t val;
+    if (k < 4) {
+        const size_t W = static_cast<size_t>(mcu_w) * 16;
+        val = qy[(static_cast<size_t>(my) * 16 + (k >> 1) * 8 + (n >> 3)) * W + mx * 16 + (k & 1) * 8 + (n & 7)];
+    } else {
+        const size_t W = static_cast<size_t>(mcu_w) * 8;
+        val = (k == 4 ? qcb : qcr)[(static_cast<size_t>(my) * 8 + (n >> 3)) * W + mx * 8 + (n & 7)];
+    }
+    coef[i] = static_cast<int16_t>(val);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+void default_dct_constants(double a[5], double s[8]) {
+    // the reference's expressions, include/Dct.hpp:21-43 (pi and root_two are Boost's double constants)
+    const double pi = 3.141592653589793238462643383279502884;
+    const double root_two = 1.414213562373095048801688724209698078;
+    double c[8];
+    for (int k = 1; k < 8; ++k) c[k] = std::cos(k * pi / 16);
+    a[0] = c[4];
+    a[1] = c[2] - c[6];
+    a[2] = c[4];
+    a[3] = c[6] + c[2];
+    a[4] = c[6];
+    s[0] = 1 / (2 * root_two);
+    for (int k = 1; k < 8; ++k) s[k] = 1 / (4 * c[k]);
+}
+
+// Bound on |fp32 quotient - reference quotient| used to decide which blocks need the exact path:
+// kErrUnscaled bounds the absolute error of an unscaled 2-D AAN output (|.| <= ~1.4e4) computed in FP32 from
+// 8-bit samples; DESIGN.md "Exactness" derives ~1e-2 worst case, tests/test_forward_gpu.py measures it.
+constexpr double kErrUnscaled = 0.03;
+
+void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out) {
+    for (int v = 0; v < 8; ++v)
+        for (int u = 0; u < 8; ++u) {
+            const double m = s[v] * s[u] / static_cast<double>(q[v * 8 + u]);
+            out->mul[v * 8 + u] = static_cast<float>(m);
+            double delta = kErrUnscaled * m + 1e-6;
+            if (delta > 0.25) delta = 0.25;
+            out->thr[v * 8 + u] = static_cast<float>(0.5 - delta);
+        }
+}
+
+static void fill_exact(const jpgenc_ctx* c, const uint8_t* qy, const uint8_t* qc, double scale, ExactConsts* e) {
+    e->a1 = c->dct_a[0]; e->a2 = c->dct_a[1]; e->a3 = c->dct_a[2]; e->a4 = c->dct_a[3]; e->a5 = c->dct_a[4];
+    for (int i = 0; i < 8; ++i) e->s[i] = c->dct_s[i];
+    e->scale = scale;
+    for (int i = 0; i < 64; ++i) { e->qy[i] = qy[i]; e->qc[i] = qc[i]; }
+}
+
+int launch_forward(jpgenc_ctx* c) {
+    ForwardParams p{};
+    p.rgb = c->d_rgb;
+    p.coef = c->d_coef;
+    p.refine_list = c->d_refine_list;
+    p.refine_count = c->d_counters;
+    p.refine_cap = static_cast<uint32_t>(c->refine_cap);
+    p.real_w = c->real_w; p.real_h = c->real_h; p.mcu_w = c->mcu_w; p.mcu_h = c->mcu_h;
+    const double scale = 255. / c->maxval;
+    const float fy[3] = {.299f, .587f, .114f}, fcb[3] = {-.1687f, -.3312f, .5f}, fcr[3] = {.5f, -.4186f, -.0813f};
+    for (int i = 0; i < 3; ++i) {
+        p.color.y[i] = static_cast<float>(fy[i] * scale);
+        p.color.cb[i] = static_cast<float>(fcb[i] * scale / 4);
+        p.color.cr[i] = static_cast<float>(fcr[i] * scale / 4);
+    }
+    fill_quant_consts(c->qy, c->dct_s, &p.luma);
+    fill_quant_consts(c->qc, c->dct_s, &p.chroma);
+    ExactConsts e;
+    fill_exact(c, c->qy, c->qc, scale, &e);
+
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
+    constexpr int kMcus = 32;
+    const dim3 grid((c->mcu_w + kMcus - 1) / kMcus, c->mcu_h);
+    const bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
+    if (aligned) forward_kernel<kMcus, true><<<grid, kMcus * 4, 0, c->stream>>>(p);
+    else forward_kernel<kMcus, false><<<grid, kMcus * 4, 0, c->stream>>>(p);
+    JPGENC_CUDA(c, cudaGetLastError());
+    refine_kernel<<<c->sm_count * 4, 64, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
+                                                         static_cast<uint32_t>(c->refine_cap), c->real_w, c->real_h,
+                                                         c->mcu_w, e);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return JPGENC_OK;
+}
+
+int launch_exact_all(jpgenc_ctx* c) {
+    ExactConsts e;
+    fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
+    const uint32_t nblocks = c->mcu_w * c->mcu_h * kBlocksPerMcu;
+    exact_all_kernel<<<c->sm_count * 8, 64, 0, c->stream>>>(c->d_rgb, c->d_coef, nblocks, c->real_w, c->real_h, c->mcu_w, e);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return JPGENC_OK;
+}
+
+int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
+                            uint64_t* refined) {
+    QuantConsts qc;
+    fill_quant_consts(q, c->dct_s, &qc);
+    ExactConsts e;
+    fill_exact(c, q, q, 1.0, &e);
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
+    const uint64_t grid = (nblocks + kMbThreads - 1) / kMbThreads;
+    dct_blocks_kernel<<<static_cast<unsigned>(grid), kMbThreads, 0, c->stream>>>(
+        in, out, nblocks, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), qc);
+    JPGENC_CUDA(c, cudaGetLastError());
+    refine_blocks_kernel<<<c->sm_count * 4, 64, 0, c->stream>>>(in, out, c->d_refine_list, c->d_counters,
+                                                                static_cast<uint32_t>(c->refine_cap), nblocks, 0, e);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    if (refined) {
+        uint32_t n = 0;
+        JPGENC_CUDA(c, cudaMemcpyAsync(&n, c->d_counters, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+        JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (n > c->refine_cap) {   // list overflowed: redo everything exactly (correct, slow, never seen on real data)
+            refine_blocks_kernel<<<c->sm_count * 8, 64, 0, c->stream>>>(in, out, c->d_refine_list, c->d_counters,
+                                                                        static_cast<uint32_t>(c->refine_cap), nblocks, 1, e);
+            JPGENC_CUDA(c, cudaGetLastError());
+            c->launches += 1;
+        }
+        *refined = n;
+    }
+    return JPGENC_OK;
+}
+
+int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qcb, const int32_t* d_qcr) {
+    const uint32_t nblocks = c->mcu_w * c->mcu_h * kBlocksPerMcu;
+    const uint64_t n = static_cast<uint64_t>(nblocks) * 64;
+    planes_to_mcu_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(d_qy, d_qcb, d_qcr, c->d_coef,
+                                                                                       c->mcu_w, nblocks);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return JPGENC_OK;
+}
+
+}  // namespace jpgenc
