@@ -56,7 +56,8 @@ typedef struct {
     uint64_t scan_bits;           /* entropy-coded bits before padding */
     uint64_t scan_bytes;          /* after 1-padding and FF00 stuffing */
     uint64_t stuffed_ff;          /* number of 0xFF bytes that received a 0x00 */
-    float    ms_forward;          /* CUDA-event time of the last K1 (+ refine) */
+    float    ms_k1;               /* CUDA-event time of the last K1 fast kernel alone (the roofline kernel) */
+    float    ms_forward;          /* CUDA-event time of the last K1 + exact refinement */
     float    ms_stats;            /* last K2 */
     float    ms_entropy;          /* last K3 + K4 */
     float    ms_h2d, ms_d2h;
@@ -111,6 +112,13 @@ int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256
  *      (src/Image.cpp:737-829, 957-971; BitstreamGeneric.hpp:182-195, 213-224, 242-248) ------------- */
 int jpgenc_entropy_encode(jpgenc_ctx* ctx, const jpgenc_huff_table tables[4], uint64_t* scan_bytes);
 int jpgenc_download_scan(jpgenc_ctx* ctx, uint8_t* dst, uint64_t cap);
+
+/* ---- host: PPM front end with the reference's parsing rules (src/Image.cpp:334-473); no GPU involved ---- */
+/* header of a P3/P6 file held in memory; returns JPGENC_ERR_FORMAT for anything else */
+int jpgenc_ppm_info(const uint8_t* file, size_t n, uint32_t* width, uint32_t* height, uint32_t* maxval, int* magic,
+                    size_t* payload_offset);
+/* raw samples (NOT scaled by 255/maxval) as interleaved u8 RGB; dst holds width*height*3 bytes */
+int jpgenc_ppm_samples(const uint8_t* file, size_t n, uint8_t* dst);
 
 /* ---- whole image: what Image::writeJPEG does after loadPPM ----------------------------------------- */
 /* headers SOI..SOS (src/Image.cpp:933-954, JpegSegments.hpp); returns the length, dst may be NULL */

@@ -40,7 +40,7 @@ class Stats(C.Structure):
         ("real_w", C.c_uint32), ("real_h", C.c_uint32), ("mcu_w", C.c_uint32), ("mcu_h", C.c_uint32),
         ("n_blocks", C.c_uint64), ("refined_blocks", C.c_uint64), ("scan_bits", C.c_uint64),
         ("scan_bytes", C.c_uint64), ("stuffed_ff", C.c_uint64),
-        ("ms_forward", C.c_float), ("ms_stats", C.c_float), ("ms_entropy", C.c_float),
+        ("ms_k1", C.c_float), ("ms_forward", C.c_float), ("ms_stats", C.c_float), ("ms_entropy", C.c_float),
         ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
     ]
 
@@ -65,6 +65,8 @@ _SIGNATURES = {
     "jpgenc_build_huffman": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_entropy_encode": (C.c_int, [C.c_void_p, C.POINTER(HuffTable), u64p]),
     "jpgenc_download_scan": (C.c_int, [C.c_void_p, u8p, C.c_uint64]),
+    "jpgenc_ppm_info": (C.c_int, [C.c_char_p, C.c_size_t, u32p, u32p, u32p, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "jpgenc_ppm_samples": (C.c_int, [C.c_char_p, C.c_size_t, u8p]),
     "jpgenc_write_headers": (C.c_size_t, [C.c_uint32, C.c_uint32, u8p, u8p, C.POINTER(HuffTable), u8p]),
     "jpgenc_encode_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),

@@ -52,6 +52,15 @@ int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
     return JPGENC_OK;
 }
 
+// after the stream has been synchronised past K1: event times and the refine counter
+int refresh_forward_stats(jpgenc_ctx* c) {
+    if (!c->forward_pending) return JPGENC_OK;
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_k1, c->ev_k0, c->ev_k1));
+    c->forward_pending = false;
+    return JPGENC_OK;
+}
+
 int ensure_coef(jpgenc_ctx* c) {
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
     if (nblocks * 64 > 0xFFFFFFFFull * 16) return fail(c, JPGENC_ERR_ARG, "image too large");
@@ -97,7 +106,7 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     }
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_t0, &c->ev_t1, &c->ev_u0, &c->ev_u1})
+    for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_t0, &c->ev_t1, &c->ev_u0, &c->ev_u1, &c->ev_k0, &c->ev_k1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     std::memcpy(c->qy, kAnnexKLuma, 64);
     std::memcpy(c->qc, kAnnexKChroma, 64);
@@ -125,7 +134,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_hist); cudaFree(c->d_first); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -199,6 +208,7 @@ int jpgenc_color_dct_quant(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
     if ((rc = launch_forward(c))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    c->forward_pending = true;
     c->have_coef = true;
     c->have_scan = false;
     return JPGENC_OK;
@@ -213,8 +223,7 @@ int jpgenc_get_coefficients(jpgenc_ctx* c, int16_t* dst) {
     uint32_t refined = 0;
     JPGENC_CUDA(c, cudaMemcpy(&refined, c->d_counters, sizeof refined, cudaMemcpyDeviceToHost));
     c->stats.refined_blocks = refined;
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
-    return JPGENC_OK;
+    return refresh_forward_stats(c);
 }
 
 int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu_w, uint32_t mcu_h) {
@@ -271,9 +280,15 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
     JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096, cudaMemcpyDeviceToHost, c->stream));
     JPGENC_CUDA(c, cudaMemcpyAsync(h + 4096, c->d_first, 8192, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(h + 12288, c->d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     std::memcpy(count, h, 4096);
     std::memcpy(first_pos, h + 4096, 8192);
+    if (c->forward_pending) {
+        c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
+        const int rs = refresh_forward_stats(c);
+        if (rs) return rs;
+    }
     JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_stats, c->ev_t0, c->ev_t1));
     return JPGENC_OK;
 }
@@ -349,7 +364,6 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     uint32_t count[4][256];
     uint64_t first_pos[4][256];
     if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
     for (int t = 0; t < 4; ++t)
         if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
     return jpgenc_entropy_encode(c, tables, scan);
@@ -363,9 +377,6 @@ static int assemble(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t s
     if (rc) return rc;
     dst[hdr + scan] = 0xFF;                                      // EOI (JpegSegments.hpp:361-377)
     dst[hdr + scan + 1] = 0xD9;
-    uint32_t refined = 0;
-    JPGENC_CUDA(c, cudaMemcpy(&refined, c->d_counters, sizeof refined, cudaMemcpyDeviceToHost));
-    c->stats.refined_blocks = refined;
     return JPGENC_OK;
 }
 
@@ -409,6 +420,32 @@ int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_
     const size_t wrote = std::fwrite(out.data(), 1, out.size(), f);
     std::fclose(f);
     return wrote == out.size() ? JPGENC_OK : fail(c, JPGENC_ERR_IO, "short write");
+}
+
+int jpgenc_ppm_info(const uint8_t* file, size_t n, uint32_t* width, uint32_t* height, uint32_t* maxval, int* magic,
+                    size_t* payload_offset) {
+    if (!file) return JPGENC_ERR_ARG;
+    PpmHeader h;
+    const int rc = parse_ppm_header(file, n, &h);
+    if (rc) return rc;
+    if (width) *width = h.width;
+    if (height) *height = h.height;
+    if (maxval) *maxval = h.maxval;
+    if (magic) *magic = h.magic;
+    if (payload_offset) *payload_offset = h.payload;
+    return JPGENC_OK;
+}
+
+int jpgenc_ppm_samples(const uint8_t* file, size_t n, uint8_t* dst) {
+    if (!file || !dst) return JPGENC_ERR_ARG;
+    PpmHeader h;
+    int rc = parse_ppm_header(file, n, &h);
+    if (rc) return rc;
+    std::vector<uint8_t> p3;
+    const uint8_t* view = nullptr;
+    if ((rc = ppm_samples(file, n, h, &p3, &view))) return rc;
+    std::memcpy(dst, view, static_cast<size_t>(h.width) * h.height * 3);
+    return JPGENC_OK;
 }
 
 int jpgenc_dct_quant_blocks(jpgenc_ctx* c, const float* dev_in, int16_t* dev_out, uint64_t nblocks, const uint8_t q[64],

@@ -68,7 +68,7 @@ struct DeviceTables {
 struct jpgenc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     std::string error;
     int sm_count = 148;
     uint64_t launches = 0;
@@ -82,7 +82,7 @@ struct jpgenc_ctx {
     uint8_t* d_rgb_owned = nullptr;
     size_t rgb_cap = 0;
     uint32_t real_w = 0, real_h = 0, maxval = 255, mcu_w = 0, mcu_h = 0;
-    bool have_pixels = false, have_coef = false, have_scan = false;
+    bool have_pixels = false, have_coef = false, have_scan = false, forward_pending = false;
 
     int16_t* d_coef = nullptr;
     size_t coef_cap = 0;

@@ -480,9 +480,11 @@ int launch_forward(jpgenc_ctx* c) {
     constexpr int kMcus = 32;
     const dim3 grid((c->mcu_w + kMcus - 1) / kMcus, c->mcu_h);
     const bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_k0, c->stream));
     if (aligned) forward_kernel<kMcus, true><<<grid, kMcus * 4, 0, c->stream>>>(p);
     else forward_kernel<kMcus, false><<<grid, kMcus * 4, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_k1, c->stream));
     refine_kernel<<<c->sm_count * 4, 64, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
                                                          static_cast<uint32_t>(c->refine_cap), c->real_w, c->real_h,
                                                          c->mcu_w, e);

@@ -1,0 +1,53 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """CPU oracle (test infrastructure only)."""
+    from oracle.pyoracle import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def reference():
+    """The compiled reference (oracle/_ref); tests that need it are skipped where it was never built."""
+    from oracle.pyoracle import REF_SO, Reference, build
+    if not REF_SO.exists():
+        try:
+            build()
+        except Exception:
+            pass
+    if not REF_SO.exists():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return Reference()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "vectors.npz"))
+
+
+@pytest.fixture(scope="session")
+def encoder():
+    """GPU context through the C-ABI.  Raises (does not skip) when the library or the GPU is missing."""
+    from jpgenc_b200.capi import Encoder
+    e = Encoder(0)
+    yield e
+    e.close()
+
+
+def table_fields(t):
+    n = int(sum(t.counts))
+    return (bytes(t.length), bytes(t.code_msb), bytes(t.counts), bytes(t.symbols[:n]))

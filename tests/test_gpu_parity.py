@@ -1,0 +1,234 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI.  Run with `-m gpu` on a B200.
+
+Bar: bit-exact everywhere (integer/byte work; the FP32 DCT fast path is backed by exact FP64 refinement, so the
+quantised coefficients must equal the reference's with ZERO mismatches, not +-1)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import table_fields
+from jpgenc_b200.synth import noise_rgb, synth_rgb
+
+pytestmark = pytest.mark.gpu
+
+
+def _images():
+    flat = np.full((64, 64, 3), 200, np.uint8)
+    stripes = np.zeros((48, 80, 3), np.uint8)
+    stripes[:, ::2] = 255
+    half = np.zeros((32, 32, 3), np.uint8)
+    half[...] = (128, 127, 129)
+    return {
+        "synth_512": (synth_rgb(512, 512, 0), 255),
+        "noise_256": (noise_rgb(256, 256, 1), 255),
+        "odd_203x117": (synth_rgb(203, 117, 3), 255),
+        "odd_noise_100x37": (noise_rgb(100, 37, 2), 255),
+        "one_pixel": (noise_rgb(1, 1, 3), 255),
+        "tiny_5x3": (synth_rgb(5, 3, 1), 255),
+        "w16_h17": (noise_rgb(16, 17, 4), 255),
+        "w33_h16": (noise_rgb(33, 16, 5), 255),
+        "wide_2000x16": (synth_rgb(2000, 16, 6), 255),
+        "tall_16x1000": (synth_rgb(16, 1000, 7), 255),
+        "flat": (flat, 255),
+        "stripes": (stripes, 255),
+        "mid_grey": (half, 255),
+        "black": (np.zeros((40, 40, 3), np.uint8), 255),
+        "white": (np.full((40, 40, 3), 255, np.uint8), 255),
+        "maxval15": (noise_rgb(64, 48, 5) >> 4, 15),
+        "maxval100": (noise_rgb(50, 50, 6) % 101, 100),
+    }
+
+
+IMAGES = _images()
+
+
+@pytest.mark.parametrize("name", list(IMAGES))
+def test_k1_coefficients_bit_exact(encoder, oracle, name):
+    rgb, maxval = IMAGES[name]
+    ref = oracle.forward(rgb, maxval)
+    encoder.upload_rgb(rgb, maxval)
+    encoder.color_dct_quant()
+    got = encoder.get_coefficients()
+    mismatches = int(np.count_nonzero(got != ref))
+    assert mismatches == 0, f"{mismatches} of {ref.size} coefficients differ (max |d| {np.abs(got.astype(int) - ref).max()})"
+
+
+@pytest.mark.parametrize("name", list(IMAGES))
+def test_entropy_stages_bit_exact_on_reference_coefficients(encoder, oracle, name):
+    """K2, host table build, K3, K4 fed with the ORACLE's coefficient array (independent of K1)."""
+    rgb, maxval = IMAGES[name]
+    h, w, _ = rgb.shape
+    _, _, mw, mh = oracle.geometry(w, h)
+    d = oracle.forward_planes(rgb, maxval)
+    encoder.set_coefficients(d["q_y"], d["q_cb"], d["q_cr"])          # the reference's planar int32 arrays
+    ref = oracle.planes_to_mcu(d["q_y"], d["q_cb"], d["q_cr"])
+    assert np.array_equal(encoder.get_coefficients(), ref)
+    count, first = encoder.symbol_stats()
+    ocount, ofirst = oracle.symbol_stats(ref, mw, mh)
+    assert np.array_equal(count, ocount)
+    assert np.array_equal(first, ofirst)
+    tabs = encoder.build_huffman(count, first)
+    otabs, _, onbits, ostuffed = oracle.entropy_encode(ref, mw, mh)
+    for t in range(4):
+        assert table_fields(tabs[t]) == table_fields(otabs[t]), f"table {t}"
+    n = encoder.entropy_encode(tabs)
+    scan = encoder.download_scan()
+    assert n == ostuffed.size and np.array_equal(scan, ostuffed)
+    assert encoder.stats().scan_bits + (-encoder.stats().scan_bits) % 8 == onbits
+
+
+@pytest.mark.parametrize("name", list(IMAGES))
+def test_whole_file_byte_identical(encoder, oracle, name):
+    rgb, maxval = IMAGES[name]
+    mine = encoder.encode_rgb(rgb, maxval)
+    from jpgenc_b200.synth import ppm_p6_bytes
+    theirs = oracle.encode_ppm(ppm_p6_bytes(rgb, maxval))
+    assert mine == theirs
+
+
+def test_golden_files_from_the_reference(encoder, golden, tmp_path):
+    """committed outputs of the compiled reference: PPM file in -> JPEG file out through jpgenc_encode_ppm_file"""
+    for name in [str(n) for n in golden["names"]]:
+        src, dst = tmp_path / f"{name}.ppm", tmp_path / f"{name}.jpg"
+        src.write_bytes(golden[f"{name}/ppm"].tobytes())
+        encoder.encode_ppm_file(str(src), str(dst))
+        assert dst.read_bytes() == golden[f"{name}/jpg"].tobytes(), name
+
+
+def test_pr1_image_pin(encoder):
+    """config 0: the 512x512 synthetic; sha256 pinned by the reference build"""
+    import hashlib
+    jpg = encoder.encode_rgb(synth_rgb(512, 512, 0))
+    assert len(jpg) == 12323
+    assert hashlib.sha256(jpg).hexdigest() == "ceedd1ecae8dbeaf3620f9256abf57c9061167b65f5d574426739cacd82a3c20"
+
+
+def test_error_behaviour(encoder, tmp_path):
+    from jpgenc_b200.capi import ERR_ARG, ERR_FORMAT, ERR_IO, Encoder, JpgencError
+    with pytest.raises(JpgencError) as e:
+        encoder.encode_ppm_file(str(tmp_path / "missing.ppm"), str(tmp_path / "o.jpg"))
+    assert e.value.code == ERR_IO                                   # reference: runtime_error("Failed to open ...")
+    bad = tmp_path / "bad.ppm"
+    bad.write_bytes(b"P5\n2 2\n255\n....")
+    with pytest.raises(JpgencError) as e:
+        encoder.encode_ppm_file(str(bad), str(tmp_path / "o.jpg"))
+    assert e.value.code == ERR_FORMAT and "P3 and P6" in str(e.value)
+    fresh = Encoder(0)
+    with pytest.raises(JpgencError) as e:
+        fresh.color_dct_quant()                                     # stage called out of pipeline order
+    assert e.value.code == ERR_ARG
+    fresh.close()
+
+
+def test_custom_quant_tables(encoder, oracle):
+    rgb = noise_rgb(64, 64, 8)
+    qy = np.clip(oracle.qy.astype(int) // 4, 1, 255).astype(np.uint8)
+    qc = np.ones(64, np.uint8)
+    try:
+        encoder.set_qtables(qy, qc)
+        encoder.upload_rgb(rgb)
+        encoder.color_dct_quant()
+        assert np.array_equal(encoder.get_coefficients(), oracle.forward(rgb, 255, qy, qc))
+    finally:
+        encoder.set_qtables(oracle.qy, oracle.qc)
+
+
+def test_idempotent_and_deterministic(encoder):
+    rgb = noise_rgb(320, 240, 12)
+    a = encoder.encode_rgb(rgb)
+    b = encoder.encode_rgb(synth_rgb(64, 64, 1))
+    c = encoder.encode_rgb(rgb)
+    assert a == c and a != b
+
+
+def test_decoded_image_is_close(encoder):
+    PIL = pytest.importorskip("PIL.Image")
+    rgb = synth_rgb(640, 360, 4)
+    img = np.asarray(PIL.open(io.BytesIO(encoder.encode_rgb(rgb))).convert("RGB")).astype(float)
+    assert img.shape == rgb.shape and np.abs(img - rgb).mean() < 12
+
+
+def test_microbench_blocks_bit_exact(encoder, oracle):
+    """config 1 at a size the oracle finishes in seconds"""
+    nb = 1 << 14
+    d_in, d_out = encoder.dev_alloc(nb * 256), encoder.dev_alloc(nb * 128)
+    try:
+        encoder.synth_blocks(d_in, nb)
+        refined = encoder.dct_quant_blocks(d_in, d_out, nb, oracle.qy)
+        x = np.empty((nb, 64), np.float32)
+        y = np.empty((nb, 64), np.int16)
+        encoder.d2h(x, d_in)
+        encoder.d2h(y, d_out)
+        zz = np.array([oracle.zigzag_index(i) for i in range(64)])
+        i = np.arange(nb * 64, dtype=np.uint64)
+        v = i ^ (i >> np.uint64(16)); v = (v * np.uint64(0x7FEB352D)) & np.uint64(0xFFFFFFFF)
+        v ^= v >> np.uint64(15); v = (v * np.uint64(0x846CA68B)) & np.uint64(0xFFFFFFFF); v ^= v >> np.uint64(16)
+        assert np.array_equal(x.reshape(-1), ((v & np.uint64(255)).astype(np.int64) - 128).astype(np.float32))
+        bad = 0
+        for b in range(0, nb, 7):
+            q = oracle.quantize(oracle.dct(x[b].astype(np.float64).reshape(8, 8)), oracle.qy).reshape(64)[zz]
+            bad += int(np.count_nonzero(q != y[b]))
+        assert bad == 0
+        assert 0 < refined < nb // 4
+    finally:
+        encoder.dev_free(d_in)
+        encoder.dev_free(d_out)
+
+
+def test_device_generator_matches_host_generator(encoder):
+    w, h = 300, 200
+    d = encoder.dev_alloc(w * h * 3)
+    try:
+        encoder.synth_rgb(d, w, h, 5)
+        out = np.empty((h, w, 3), np.uint8)
+        encoder.d2h(out, d)
+        assert np.array_equal(out, synth_rgb(w, h, 5))
+    finally:
+        encoder.dev_free(d)
+
+
+# ---- full BASELINE sizes: size-independent properties -------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(3840, 2160), (16384, 16384)])
+def test_full_size_properties(encoder, oracle, w, h):
+    """configs 2 and 3.  (a) K1 on random MCU rows == oracle; (b) the device scan == the oracle's entropy coder run on
+    the DEVICE's coefficients (table build, Huffman pack, padding, stuffing at full size); (c) JPEG size == the
+    reference pin of SURVEY.md 8(c); (d) FF count consistent with the stuffed length."""
+    pins = {(3840, 2160): 339813, (16384, 16384): 10898928}
+    d = encoder.dev_alloc(w * h * 3)
+    try:
+        encoder.synth_rgb(d, w, h, 0)
+        encoder.bind_device_rgb(d, w, h)
+        out = np.empty(pins[(w, h)] + 1024, np.uint8)
+        n = encoder.encode_bound(out)
+        assert n == pins[(w, h)]
+        st = encoder.stats()
+        coef = encoder.get_coefficients()
+        mw, mh = st.mcu_w, st.mcu_h
+        # (a)
+        rng = np.random.default_rng(0)
+        rows = sorted(set([0, mh - 1] + rng.integers(0, mh, 6).tolist()))
+        for my in rows:
+            band = synth_rgb(w, h, 0, rows=slice(my * 16, min(h, my * 16 + 16)))
+            # the oracle needs the image rows at their true y positions: build a cropped image whose MCU row 0 is ours
+            ref = oracle.forward(band, 255)
+            assert np.array_equal(coef[my * mw:(my + 1) * mw], ref), f"MCU row {my}"
+        # (b)
+        tabs, raw, nbits, stuffed = oracle.entropy_encode(coef, mw, mh)
+        hdr = oracle.headers(w, h, tabs)
+        assert np.array_equal(out[: hdr.size], hdr)
+        assert np.array_equal(out[hdr.size: n - 2], stuffed)
+        assert out[n - 2] == 0xFF and out[n - 1] == 0xD9
+        # (d)
+        assert st.scan_bytes == (st.scan_bits + 7) // 8 + st.stuffed_ff == stuffed.size
+        assert st.stuffed_ff == int(np.count_nonzero(raw == 0xFF))
+    finally:
+        encoder.dev_free(d)
+
+
+def test_batch_frames_independent(encoder, oracle):
+    """config 4 at reduced count: 1920x1080 frames (padded rows 1080 -> 1088), each with its own tables and DC chains"""
+    for k in (0, 1, 2):
+        rgb = synth_rgb(1920, 1080, k)
+        assert encoder.encode_rgb(rgb) == oracle.encode_rgb(rgb)

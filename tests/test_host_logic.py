@@ -1,0 +1,151 @@
+"""CPU-side checks of the product library: it loads, exports every symbol the header declares, its host functions
+(Huffman table build, header writer, PPM front end) agree with the oracle, and it refuses to run without a GPU.
+No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, table_fields
+
+
+def _lib():
+    from jpgenc_b200 import capi
+    return capi, capi.load_library()
+
+
+def test_library_exports_every_declared_symbol():
+    capi, lib = _lib()
+    header = open(os.path.join(ROOT, "include", "jpgenc_b200.h")).read()
+    declared = set(re.findall(r"\b(jpgenc_[a-z0-9_]+)\s*\(", header))
+    declared -= {"jpgenc_ctx"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/jpgenc_b200.h but not exported"
+    assert declared == set(capi._SIGNATURES), declared ^ set(capi._SIGNATURES)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    capi, lib = _lib()
+    h = C.c_void_p()
+    rc = lib.jpgenc_create(0, C.byref(h))
+    assert rc == capi.ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in lib.jpgenc_last_error(None)
+    with pytest.raises(capi.JpgencError):
+        capi.Encoder(0)
+
+
+def test_product_does_not_touch_the_oracle():
+    """the shipped package must not import, link or execute anything under oracle/"""
+    for base, _, files in os.walk(os.path.join(ROOT, "jpgenc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "pyoracle" not in text and "liboracle" not in text and "jo_" not in text, f
+    text = open(os.path.join(ROOT, "Makefile")).read()
+    assert "oracle" not in text
+
+
+def _host_tables(lib, capi, count, first):
+    tabs = (capi.HuffTable * 4)()
+    for t in range(4):
+        c = np.ascontiguousarray(count[t], np.uint32)
+        f = np.ascontiguousarray(first[t], np.uint64)
+        assert lib.jpgenc_build_huffman(c.ctypes.data_as(capi.u32p), f.ctypes.data_as(capi.u64p), C.byref(tabs[t])) == 0
+    return tabs
+
+
+def test_host_huffman_build_matches_oracle(oracle):
+    capi, lib = _lib()
+    rng = np.random.default_rng(21)
+    for trial in range(200):
+        nsym = int(rng.integers(1, 180))
+        alphabet = rng.permutation(256)[:nsym]
+        n = int(rng.integers(nsym, 3000))
+        p = rng.random(nsym) ** (1 + trial % 4)
+        text = rng.choice(alphabet, n, p=p / p.sum())
+        count = np.bincount(text, minlength=256).astype(np.uint32)
+        first = np.full(256, np.iinfo(np.uint64).max, np.uint64)
+        for pos in range(n - 1, -1, -1):
+            first[text[pos]] = pos * 64
+        tab = capi.HuffTable()
+        assert lib.jpgenc_build_huffman(count.ctypes.data_as(capi.u32p), first.ctypes.data_as(capi.u64p), C.byref(tab)) == 0
+        assert table_fields(tab) == table_fields(oracle.huffman_from_text(text)), trial
+
+
+def test_host_huffman_golden(golden):
+    capi, lib = _lib()
+    for name in [str(n) for n in golden["huff_names"]]:
+        text = golden[f"huff/{name}/text"]
+        count = np.bincount(text, minlength=256).astype(np.uint32)
+        first = np.full(256, np.iinfo(np.uint64).max, np.uint64)
+        for pos in range(len(text) - 1, -1, -1):
+            first[text[pos]] = pos
+        tab = capi.HuffTable()
+        assert lib.jpgenc_build_huffman(count.ctypes.data_as(capi.u32p), first.ctypes.data_as(capi.u64p), C.byref(tab)) == 0
+        n = int(sum(tab.counts))
+        assert np.array_equal(np.array(tab.length), golden[f"huff/{name}/length"])
+        assert np.array_equal(np.array(tab.code_msb), golden[f"huff/{name}/code_msb"])
+        assert np.array_equal(np.array(tab.symbols[:n]), golden[f"huff/{name}/symbols"])
+
+
+def test_host_headers_match_oracle(oracle):
+    capi, lib = _lib()
+    from jpgenc_b200.synth import noise_rgb
+    coef = oracle.forward(noise_rgb(48, 32, 2))
+    count, first = oracle.symbol_stats(coef, 3, 2)
+    tabs = _host_tables(lib, capi, count, first)
+    otabs, _, _, _ = oracle.entropy_encode(coef, 3, 2)
+    qy, qc = oracle.qy, oracle.qc
+    n = lib.jpgenc_write_headers(48, 32, qy.ctypes.data_as(capi.u8p), qc.ctypes.data_as(capi.u8p), tabs, None)
+    out = np.empty(n, np.uint8)
+    lib.jpgenc_write_headers(48, 32, qy.ctypes.data_as(capi.u8p), qc.ctypes.data_as(capi.u8p), tabs, out.ctypes.data_as(capi.u8p))
+    assert np.array_equal(out, oracle.headers(48, 32, otabs))
+
+
+def _ppm_info(lib, data):
+    w, h, m, off = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_size_t()
+    magic = C.c_int()
+    rc = lib.jpgenc_ppm_info(data, len(data), C.byref(w), C.byref(h), C.byref(m), C.byref(magic), C.byref(off))
+    return rc, (magic.value, w.value, h.value, m.value, off.value)
+
+
+@pytest.mark.parametrize("data", [
+    b"P6\n4 2\n255\n" + bytes(range(24)),
+    b"P6 4 2 255 " + bytes(range(24)),
+    b"P6\n# a comment\n4 2\n# another\n255\n" + bytes(range(24)),
+    b"P3\n2 2\n15\n1 2 3 4 5 6\n7 8 9 10 11 12\n",
+    b"P3\n# c\n2 2 15 1 2 3 4 5 6 7 8 9 10 11 12",
+    b"\n\n P6\t3\r\n1 63\n" + bytes(range(9)),
+])
+def test_ppm_front_end_matches_oracle(oracle, data):
+    capi, lib = _lib()
+    rc, info = _ppm_info(lib, data)
+    orc, oh = oracle.ppm_parse(data)
+    assert rc == 0 and orc == 0
+    assert info == (oh.magic, oh.width, oh.height, oh.maxval, oh.payload)
+    out = np.empty(info[1] * info[2] * 3, np.uint8)
+    assert lib.jpgenc_ppm_samples(data, len(data), out.ctypes.data_as(capi.u8p)) == 0
+    rgb, _ = oracle.ppm_load(data)
+    assert np.array_equal(out, rgb.reshape(-1))
+
+
+@pytest.mark.parametrize("data", [b"P5\n2 2\n255\n....", b"JFIF", b"P6\n2 2\n65535\n" + bytes(48), b"P6\n0 2\n255\n"])
+def test_ppm_rejects_what_the_reference_rejects(data):
+    capi, lib = _lib()
+    rc, _ = _ppm_info(lib, data)
+    assert rc == capi.ERR_FORMAT          # reference: runtime_error "Only P3 and P6 format is supported!" / assert on maxval
+
+
+def test_golden_ppm_headers(golden, oracle):
+    capi, lib = _lib()
+    for name in [str(n) for n in golden["names"]]:
+        data = golden[f"{name}/ppm"].tobytes()
+        rc, info = _ppm_info(lib, data)
+        orc, oh = oracle.ppm_parse(data)
+        assert rc == 0 and info == (oh.magic, oh.width, oh.height, oh.maxval, oh.payload)
