@@ -45,24 +45,33 @@ __device__ __forceinline__ int dc_predictor(const uint8_t* tile, const int16_t* 
 
 __device__ __forceinline__ int category_of(int v) { return 32 - __clz(abs(v)); }   // 0 for v == 0
 
-// Calls emit(symbol, value, ordinal) for the DC entry (ordinal -1) and every AC entry in order.
-// `dc_diff` replaces coefficient 0.
+// Calls emit(symbol, value, ordinal) for the DC entry (ordinal -1) and every AC entry in zigzag order.
+// `dc_diff` replaces coefficient 0.  The block is read from its (swizzled) shared-memory slot one 16-byte chunk
+// (8 coefficients) at a time; all-zero chunks -- the common case after quantisation -- cost four instructions.
 template <class Emit>
-__device__ __forceinline__ void walk_block(const uint32_t (&w)[32], int dc_diff, Emit&& emit) {
+__device__ __forceinline__ void walk_block(const uint8_t* tile, int slot, int dc_diff, Emit&& emit) {
     emit(category_of(dc_diff), dc_diff, -1);
-    int run = 0, ord = 0;
+    const uint4* base = reinterpret_cast<const uint4*>(tile + slot * kBlockBytes);
+    int run = -1, ord = 0;                           // -1: the DC position is not part of any zero run
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        const uint4 q = base[c ^ (slot & 7)];
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        if (c == 0) w[0] &= 0xFFFF0000u;             // skip the DC coefficient
+        if ((w[0] | w[1] | w[2] | w[3]) == 0) { run += 8; continue; }
 #pragma unroll
-    for (int i = 1; i < 64; ++i) {
-        const int c = static_cast<int16_t>((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu));
-        if (c == 0) {
-            ++run;
-        } else {
-            while (run > 15) { emit(0xF0, 0, ord++); run -= 16; }   // ZRL
-            emit((run << 4) | category_of(c), c, ord++);
-            run = 0;
+        for (int j = 0; j < 8; ++j) {
+            const int v = static_cast<int16_t>((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu));
+            if (v == 0) {
+                ++run;
+            } else {
+                while (run > 15) { emit(0xF0, 0, ord++); run -= 16; }   // ZRL
+                emit((run << 4) | category_of(v), v, ord++);
+                run = 0;
+            }
         }
     }
-    if (run > 0) emit(0x00, 0, ord);                                // EOB
+    if (run > 0) emit(0x00, 0, ord);                 // EOB
 }
 
 // ---- decoupled look-back over 64-bit status words: [63:62] state, [61:0] value ---------------------------
@@ -79,22 +88,34 @@ __device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long lo
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called by ONE thread of tile `tile`; returns the exclusive prefix of `aggregate` over all earlier tiles.
+// Called by ALL 32 lanes of one warp of tile `tile`; returns (to every lane) the exclusive prefix of `aggregate`
+// over all earlier tiles.  Each step inspects 32 predecessors at once.
 __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status, uint32_t tile,
                                                                  unsigned long long aggregate) {
+    const int lane = threadIdx.x & 31;
     if (tile == 0) {
-        lb_store(status, kLbPrefix | aggregate);
+        if (lane == 0) lb_store(status, kLbPrefix | aggregate);
         return 0;
     }
-    lb_store(status + tile, kLbAggregate | aggregate);
+    if (lane == 0) lb_store(status + tile, kLbAggregate | aggregate);
     unsigned long long sum = 0;
-    for (int64_t j = static_cast<int64_t>(tile) - 1; j >= 0; --j) {
-        unsigned long long s;
-        do { s = lb_load(status + j); } while ((s >> 62) == 0);
-        sum += s & kLbValueMask;
-        if ((s >> 62) == 2) break;
+    int64_t hi = static_cast<int64_t>(tile) - 1;     // newest predecessor not yet accounted for
+    while (true) {
+        const int64_t j = hi - lane;
+        unsigned long long s = kLbPrefix;            // lanes past tile 0 behave like an empty prefix
+        if (j >= 0) {
+            do { s = lb_load(status + j); } while ((s >> 62) == 0);
+        }
+        const unsigned prefix_lanes = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const int first = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;       // nearest predecessor with a full prefix
+        unsigned long long v = (lane <= first) ? (s & kLbValueMask) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        sum += v;
+        if (prefix_lanes) break;
+        hi -= 32;
     }
-    lb_store(status + tile, kLbPrefix | (sum + aggregate));
+    if (lane == 0) lb_store(status + tile, kLbPrefix | (sum + aggregate));
     return sum;
 }
 

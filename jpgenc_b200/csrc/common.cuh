@@ -51,6 +51,8 @@ struct ForwardParams {
     uint32_t refine_cap;
     uint32_t real_w, real_h;
     uint32_t mcu_w, mcu_h;
+    uint32_t debug_flags;
+    uint32_t prefetch_ahead;              // CTAs resident at once: each CTA warms L2 for the tile this many ids later
     ColorConsts color;
     QuantConsts luma;
     QuantConsts chroma;

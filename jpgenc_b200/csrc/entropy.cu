@@ -58,8 +58,8 @@ struct EntropyParams {
 };
 
 template <class Put>
-__device__ __forceinline__ void encode_block(const uint32_t (&w)[32], int diff, const uint32_t* tdc, const uint32_t* tac, Put&& put) {
-    walk_block(w, diff, [&](int sym, int value, int ord) {
+__device__ __forceinline__ void encode_block(const uint8_t* tile, int slot, int diff, const uint32_t* tdc, const uint32_t* tac, Put&& put) {
+    walk_block(tile, slot, diff, [&](int sym, int value, int ord) {
         const uint32_t e = (ord < 0 ? tdc : tac)[sym];
         const uint32_t cat = sym & 15;                                            // magnitude bit count
         const uint32_t mag = (value < 0 ? value - 1 : value) & ((1u << cat) - 1); // Coding.hpp:206-212
@@ -87,20 +87,21 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
     stage_tile(tile, p.coef + first * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
 
-    uint32_t w[32];
     int diff = 0;
     uint32_t my_bits = 0;
     const int k = tid % kBlocksPerMcu;
     const uint32_t* tdc = s_tab + (k < 4 ? 0 : 512);
     const uint32_t* tac = tdc + 256;
     if (tid < nb) {
-        load_block(tile, tid, w);
-        diff = static_cast<int16_t>(w[0] & 0xFFFFu) - dc_predictor(tile, p.coef, first, tid);
-        encode_block(w, diff, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
+        diff = slot_dc(tile, tid) - dc_predictor(tile, p.coef, first, tid);
+        encode_block(tile, tid, diff, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
     }
     uint32_t tile_bits;
     const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
-    if (tid == 0) s_base = lookback_exclusive(p.status, tile_idx, tile_bits);
+    if (tid < 32) {
+        const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
+        if (tid == 0) s_base = b;
+    }
     __syncthreads();
     const unsigned long long base = s_base;
     const uint32_t lead = static_cast<uint32_t>(base & 31);                 // bits of the first word owned by earlier tiles
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
         if (tid < nb) {
             BitWriter<false> bw;
             bw.start(s_bits, lead + local);
-            encode_block(w, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            encode_block(tile, tid, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
             bw.finish();
         }
         if (pad && tid == 0) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
         if (tid < nb) {
             BitWriter<true> bw;
             bw.start(p.raw, base + local);
-            encode_block(w, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            encode_block(tile, tid, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
             bw.finish();
         }
         if (pad && tid == 0) {
@@ -176,7 +177,10 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __r
         if (j < n && ((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 0xFFu) ++ff;
     uint32_t tile_ff;
     const uint32_t local = block_exclusive_scan(ff, s_scan, &tile_ff);
-    if (tid == 0) s_base = lookback_exclusive(status, tile, tile_ff);
+    if (tid < 32) {
+        const unsigned long long b = lookback_exclusive(status, tile, tile_ff);
+        if (tid == 0) s_base = b;
+    }
     __syncthreads();
     uint8_t* o = out + at + s_base + local;
 #pragma unroll

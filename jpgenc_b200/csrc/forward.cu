@@ -14,6 +14,8 @@
 //    coefficients are the reference's, bit for bit;
 //  * coefficients leave through a bank-conflict-free swizzled staging buffer as full 512-byte warp stores,
 //    already in the MCU-interleaved order the entropy coder consumes.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -100,6 +102,15 @@ __device__ __forceinline__ void copy_out(const uint8_t* staging, int16_t* gdst, 
     }
 }
 
+// u8 -> f32 of byte `b` of `w` (SASS: I2F.U8 Rd, Rs.Bb).  Inline PTX on purpose: with a plain C cast the compiler
+// proves that sums of converted bytes are exact and rewrites the chroma 2x2 sums as SHF+LOP3 byte extraction +
+// IADD3 + I2FP, tripling their instruction count (ncu, profiles/round1).
+__device__ __forceinline__ float u8f(uint32_t w, int b) {
+    float f;
+    asm("cvt.rn.f32.u8 %0, %1;" : "=f"(f) : "r"(w >> (8 * b)));
+    return f;
+}
+
 __device__ __forceinline__ void push_refine(const ForwardParams& p, uint32_t block_id) {
     const uint32_t at = atomicAdd(p.refine_count, 1u);
     if (at < p.refine_cap) p.refine_list[at] = block_id;
@@ -118,7 +129,7 @@ struct ForwardSmem {
 // kAligned: real_w % 16 == 0 and 16-byte aligned base -> rows are staged with bulk copies; otherwise a clamped
 // byte loader fills the tile (odd sizes; right-edge replication, src/Image.cpp:491-530)
 template <int kMcus, bool kAligned>
-__global__ void __launch_bounds__(kMcus * 4) forward_kernel(const __grid_constant__ ForwardParams p) {
+__global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(const __grid_constant__ ForwardParams p) {
     using Smem = ForwardSmem<kMcus>;
     __shared__ Smem sm;
     constexpr int kThreads = kMcus * 4;
@@ -134,17 +145,29 @@ __global__ void __launch_bounds__(kMcus * 4) forward_kernel(const __grid_constan
             ptx::mbar_init_fence();
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < 16) {
+            // 16 lanes issue one row each (a single thread issuing all 16 serialises ~0.3 us of TMA issue latency)
             const uint32_t row_bytes = nm * 48;
-            ptx::mbar_expect_tx(&sm.bar, 16 * row_bytes);
-#pragma unroll 1
-            for (int r = 0; r < 16; ++r) {
-                const uint32_t sy = min(my * 16 + r, p.real_h - 1);          // bottom edge replication
-                ptx::bulk_g2s(sm.tile + r * Smem::kPitch, p.rgb + (static_cast<size_t>(sy) * p.real_w + mcu0 * 16) * 3,
+            if (tid == 0) ptx::mbar_expect_tx(&sm.bar, 16 * row_bytes);
+            const uint32_t sy = min(my * 16 + tid, p.real_h - 1);              // bottom edge replication
+            if (!(p.debug_flags & 1))
+                ptx::bulk_g2s(sm.tile + tid * Smem::kPitch, p.rgb + (static_cast<size_t>(sy) * p.real_w + mcu0 * 16) * 3,
                               row_bytes, &sm.bar);
+        } else if (tid == 32 && p.prefetch_ahead) {
+            // warm L2 for the strip that the CTA taking this SM slot next will stage (CTAs start in linear-id order)
+            const uint32_t next = blockIdx.y * gridDim.x + blockIdx.x + p.prefetch_ahead;
+            const uint32_t ny = next / gridDim.x, nx = next - ny * gridDim.x;
+            if (ny < gridDim.y) {
+                const uint32_t n0 = nx * kMcus;
+                const uint32_t nbytes = min(kMcus, static_cast<int>(p.mcu_w - n0)) * 48;
+#pragma unroll 1
+                for (int r = 0; r < 16; ++r) {
+                    const uint32_t sy = min(ny * 16 + r, p.real_h - 1);
+                    ptx::bulk_prefetch_l2(p.rgb + (static_cast<size_t>(sy) * p.real_w + n0 * 16) * 3, nbytes);
+                }
             }
         }
-        ptx::mbar_wait(&sm.bar, 0);
+        if (!(p.debug_flags & 1)) ptx::mbar_wait(&sm.bar, 0);
     } else {
         const int row_bytes = nm * 48;
         for (int idx = tid; idx < 16 * row_bytes; idx += kThreads) {
@@ -173,9 +196,9 @@ __global__ void __launch_bounds__(kMcus * 4) forward_kernel(const __grid_constan
                 const uint32_t w[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
 #pragma unroll
                 for (int x = 0; x < 8; ++x) {
-                    rr[h][x] = static_cast<float>((w[(3 * x) >> 2] >> (8 * ((3 * x) & 3))) & 0xFFu);
-                    gg[h][x] = static_cast<float>((w[(3 * x + 1) >> 2] >> (8 * ((3 * x + 1) & 3))) & 0xFFu);
-                    bb[h][x] = static_cast<float>((w[(3 * x + 2) >> 2] >> (8 * ((3 * x + 2) & 3))) & 0xFFu);
+                    rr[h][x] = u8f(w[(3 * x) >> 2], (3 * x) & 3);
+                    gg[h][x] = u8f(w[(3 * x + 1) >> 2], (3 * x + 1) & 3);
+                    bb[h][x] = u8f(w[(3 * x + 2) >> 2], (3 * x + 2) & 3);
                     v[r * 8 + x] = fmaf(cc.y[0], rr[h][x], fmaf(cc.y[1], gg[h][x], fmaf(cc.y[2], bb[h][x], -128.f)));
                 }
             }
@@ -477,12 +500,25 @@ int launch_forward(jpgenc_ctx* c) {
     fill_exact(c, c->qy, c->qc, scale, &e);
 
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
-    constexpr int kMcus = 32;
-    const dim3 grid((c->mcu_w + kMcus - 1) / kMcus, c->mcu_h);
     const bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
+    {
+        const char* env = std::getenv("JPGENC_K1_PREFETCH");
+        p.prefetch_ahead = env ? static_cast<uint32_t>(std::atoi(env)) : 0u;
+        const char* dbg = std::getenv("JPGENC_K1_DEBUG");      // bit 0: skip the tile load (timing experiments only)
+        p.debug_flags = dbg ? static_cast<uint32_t>(std::atoi(dbg)) : 0u;
+    }
+    const char* menv = std::getenv("JPGENC_K1_MCUS");
+    const int mcus = menv ? std::atoi(menv) : 32;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_k0, c->stream));
-    if (aligned) forward_kernel<kMcus, true><<<grid, kMcus * 4, 0, c->stream>>>(p);
-    else forward_kernel<kMcus, false><<<grid, kMcus * 4, 0, c->stream>>>(p);
+    if (mcus == 16) {
+        const dim3 grid((c->mcu_w + 15) / 16, c->mcu_h);
+        if (aligned) forward_kernel<16, true><<<grid, 64, 0, c->stream>>>(p);
+        else forward_kernel<16, false><<<grid, 64, 0, c->stream>>>(p);
+    } else {
+        const dim3 grid((c->mcu_w + 31) / 32, c->mcu_h);
+        if (aligned) forward_kernel<32, true><<<grid, 128, 0, c->stream>>>(p);
+        else forward_kernel<32, false><<<grid, 128, 0, c->stream>>>(p);
+    }
     JPGENC_CUDA(c, cudaGetLastError());
     JPGENC_CUDA(c, cudaEventRecord(c->ev_k1, c->stream));
     refine_kernel<<<c->sm_count * 4, 64, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,

@@ -27,17 +27,14 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const int16_t
     __syncthreads();
 
     if (tid < nb) {
-        uint32_t w[32];
-        load_block(tile, tid, w);
-        const int dc = static_cast<int16_t>(w[0] & 0xFFFFu);
-        const int diff = dc - dc_predictor(tile, coef, first, tid);
+        const int diff = slot_dc(tile, tid) - dc_predictor(tile, coef, first, tid);
         const uint64_t g = first + tid, mcu = g / kBlocksPerMcu;
         const int k = static_cast<int>(g % kBlocksPerMcu);
         const uint64_t mx = mcu % mcu_w, my = mcu / mcu_w;
         const uint64_t text_block = k < 4 ? (my * 2 + (k >> 1)) * (2ull * mcu_w) + mx * 2 + (k & 1)
                                           : static_cast<uint64_t>(k - 4) * n_mcu + mcu;
         const int tdc = k < 4 ? 0 : 2;
-        walk_block(w, diff, [&](int sym, int, int ord) {
+        walk_block(tile, tid, diff, [&](int sym, int, int ord) {
             const int idx = (ord < 0 ? tdc : tdc + 1) * 256 + sym;
             atomicAdd(&s_hist[idx], 1u);
             const unsigned long long key = text_block * 64 + (ord < 0 ? 0 : ord);
