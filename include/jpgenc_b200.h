@@ -102,7 +102,8 @@ int jpgenc_set_coefficients_mcu(jpgenc_ctx* ctx, const int16_t* coef, uint32_t m
 /* ---- K2: applyDCdifferenceCoding + doRLEandCategoryCoding + the symbol texts
  *      (src/Image.cpp:638-735, 888-906; Coding.hpp:148-283) reduced to what the table build needs ----- */
 /* count[t][s] = occurrences of symbol s in table t's text; first_pos[t][s] = an order-preserving key of
- * its first occurrence in that text (UINT64_MAX if absent): (block index in text order)*64 + ordinal */
+ * its first occurrence in that text (UINT64_MAX if absent): (block index in text order)*256 + k with k = 0 for a DC
+ * symbol, 2p for a ZRL emitted before zigzag position p, 2p+1 for the symbol of position p, 129 for EOB */
 int jpgenc_symbol_stats(jpgenc_ctx* ctx, uint32_t count[4][256], uint64_t first_pos[4][256]);
 
 /* ---- host: generateHuffmanCode from the statistics (src/Huffman.cpp:3-66, Huffman.hpp:114-174) ----- */

@@ -45,33 +45,49 @@ __device__ __forceinline__ int dc_predictor(const uint8_t* tile, const int16_t* 
 
 __device__ __forceinline__ int category_of(int v) { return 32 - __clz(abs(v)); }   // 0 for v == 0
 
-// Calls emit(symbol, value, ordinal) for the DC entry (ordinal -1) and every AC entry in zigzag order.
-// `dc_diff` replaces coefficient 0.  The block is read from its (swizzled) shared-memory slot one 16-byte chunk
-// (8 coefficients) at a time; all-zero chunks -- the common case after quantisation -- cost four instructions.
-template <class Emit>
-__device__ __forceinline__ void walk_block(const uint8_t* tile, int slot, int dc_diff, Emit&& emit) {
-    emit(category_of(dc_diff), dc_diff, -1);
+// Bit i of the result = zigzag coefficient i of the block in `slot` is non-zero (i = 1..63; the DC bit is cleared).
+// Branch-free: VIMNMX.U16x2 turns each halfword into a 0/1 flag, 11 instructions per 8 coefficients.
+__device__ __forceinline__ void nonzero_mask(const uint8_t* tile, int slot, uint32_t& lo, uint32_t& hi) {
     const uint4* base = reinterpret_cast<const uint4*>(tile + slot * kBlockBytes);
-    int run = -1, ord = 0;                           // -1: the DC position is not part of any zero run
-#pragma unroll 1
+    lo = hi = 0;
+#pragma unroll
     for (int c = 0; c < 8; ++c) {
         const uint4 q = base[c ^ (slot & 7)];
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        if (c == 0) w[0] &= 0xFFFF0000u;             // skip the DC coefficient
-        if ((w[0] | w[1] | w[2] | w[3]) == 0) { run += 8; continue; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int v = static_cast<int16_t>((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu));
-            if (v == 0) {
-                ++run;
-            } else {
-                while (run > 15) { emit(0xF0, 0, ord++); run -= 16; }   // ZRL
-                emit((run << 4) | category_of(v), v, ord++);
-                run = 0;
-            }
+        const uint32_t f = __vminu2(q.x, 0x00010001u) | (__vminu2(q.y, 0x00010001u) << 2) |
+                           (__vminu2(q.z, 0x00010001u) << 4) | (__vminu2(q.w, 0x00010001u) << 6);
+        const uint32_t byte = (f | (f >> 15)) & 0xFFu;      // even bits: low halfwords, odd bits: high halfwords
+        if (c < 4) lo |= byte << (8 * c);
+        else hi |= byte << (8 * (c - 4));
+    }
+    lo &= ~1u;
+}
+
+__device__ __forceinline__ int slot_coef(const uint8_t* tile, int slot, int pos) {
+    return *reinterpret_cast<const int16_t*>(tile + slot * kBlockBytes + ((((pos >> 3) ^ slot) & 7) << 4) + ((pos & 7) << 1));
+}
+
+// Calls emit(symbol, value, key) for the DC entry (key 0) and every AC entry in zigzag order; `dc_diff` replaces
+// coefficient 0.  key orders the entries inside the block: 2p for a ZRL before position p, 2p+1 for the symbol of
+// position p, 129 for EOB.  Only non-zero coefficients cost loop iterations (the common block has a handful).
+template <class Emit>
+__device__ __forceinline__ void walk_block(const uint8_t* tile, int slot, int dc_diff, uint32_t lo, uint32_t hi, Emit&& emit) {
+    emit(category_of(dc_diff), dc_diff, 0);
+    int prev = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint32_t m = half ? hi : lo;
+#pragma unroll 1
+        while (m) {
+            const int pos = half * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            int run = pos - prev - 1;
+            prev = pos;
+            const int v = slot_coef(tile, slot, pos);
+            while (run > 15) { emit(0xF0, 0, 2 * pos); run -= 16; }      // ZRL
+            emit((run << 4) | category_of(v), v, 2 * pos + 1);
         }
     }
-    if (run > 0) emit(0x00, 0, ord);                 // EOB
+    if (prev != 63) emit(0x00, 0, 129);                                  // EOB
 }
 
 // ---- decoupled look-back over 64-bit status words: [63:62] state, [61:0] value ---------------------------

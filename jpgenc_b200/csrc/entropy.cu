@@ -58,9 +58,10 @@ struct EntropyParams {
 };
 
 template <class Put>
-__device__ __forceinline__ void encode_block(const uint8_t* tile, int slot, int diff, const uint32_t* tdc, const uint32_t* tac, Put&& put) {
-    walk_block(tile, slot, diff, [&](int sym, int value, int ord) {
-        const uint32_t e = (ord < 0 ? tdc : tac)[sym];
+__device__ __forceinline__ void encode_block(const uint8_t* tile, int slot, int diff, uint32_t lo, uint32_t hi,
+                                             const uint32_t* tdc, const uint32_t* tac, Put&& put) {
+    walk_block(tile, slot, diff, lo, hi, [&](int sym, int value, int k) {
+        const uint32_t e = (k == 0 ? tdc : tac)[sym];
         const uint32_t cat = sym & 15;                                            // magnitude bit count
         const uint32_t mag = (value < 0 ? value - 1 : value) & ((1u << cat) - 1); // Coding.hpp:206-212
         put(((e & 0xFFFFu) << cat) | mag, (e >> 16) + cat);
@@ -88,13 +89,14 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
     __syncthreads();
 
     int diff = 0;
-    uint32_t my_bits = 0;
+    uint32_t my_bits = 0, nz_lo = 0, nz_hi = 0;
     const int k = tid % kBlocksPerMcu;
     const uint32_t* tdc = s_tab + (k < 4 ? 0 : 512);
     const uint32_t* tac = tdc + 256;
     if (tid < nb) {
         diff = slot_dc(tile, tid) - dc_predictor(tile, p.coef, first, tid);
-        encode_block(tile, tid, diff, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
+        nonzero_mask(tile, tid, nz_lo, nz_hi);
+        encode_block(tile, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
     }
     uint32_t tile_bits;
     const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
         if (tid < nb) {
             BitWriter<false> bw;
             bw.start(s_bits, lead + local);
-            encode_block(tile, tid, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            encode_block(tile, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
             bw.finish();
         }
         if (pad && tid == 0) {
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
         if (tid < nb) {
             BitWriter<true> bw;
             bw.start(p.raw, base + local);
-            encode_block(tile, tid, diff, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            encode_block(tile, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
             bw.finish();
         }
         if (pad && tid == 0) {

@@ -274,15 +274,9 @@ __device__ __forceinline__ void aan8_exact(const double* x, int xs, double* o, i
     o[5 * os] = dmul(w4, e.s[5]); o[1 * os] = dmul(w5, e.s[1]); o[7 * os] = dmul(w6, e.s[7]); o[3 * os] = dmul(w7, e.s[3]);
 }
 
-// blk: spatial samples row-major -> quantised zigzag int16 (Coding.hpp:84-97: int(round(x / q)))
-__device__ void dct_quant_exact(double* blk, const uint8_t* q, const ExactConsts& e, int16_t* out) {
-    double tmp[64];
-    for (int j = 0; j < 8; ++j) aan8_exact(blk + j, 8, tmp + j * 8, 1, e);     // column j -> row j of tmp
-    for (int j = 0; j < 8; ++j) aan8_exact(tmp + j, 8, blk + j * 8, 1, e);     // column j of tmp -> row j of result
-    for (int i = 0; i < 64; ++i) {
-        const int n = c_zigzag[i];
-        out[i] = static_cast<int16_t>(static_cast<int>(round(__ddiv_rn(blk[n], static_cast<double>(q[n])))));
-    }
+// quantise one coefficient exactly as Coding.hpp:92-94 does: int(std::round(x / q)), division in double
+__device__ __forceinline__ int16_t quantize_exact(double x, uint8_t q) {
+    return static_cast<int16_t>(static_cast<int>(round(__ddiv_rn(x, static_cast<double>(q)))));
 }
 
 // colour conversion of one pixel, src/Image.cpp:131-143: float constants widened to double, double arithmetic
@@ -300,62 +294,60 @@ __device__ __forceinline__ double exact_pixel(const uint8_t* rgb, uint32_t real_
                          dmul(static_cast<double>(px[2]), scale));
 }
 
-__global__ void __launch_bounds__(64) refine_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
-                                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ count,
-                                                    uint32_t cap, uint32_t real_w, uint32_t real_h, uint32_t mcu_w,
-                                                    const __grid_constant__ ExactConsts e) {
-    const uint32_t n = min(*count, cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t id = list[i];
-        const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu;
-        const uint32_t mx = mcu % mcu_w, my = mcu / mcu_w;
-        double blk[64];
-        if (k < 4) {
-            const uint32_t x0 = mx * 16 + (k & 1) * 8, y0 = my * 16 + (k >> 1) * 8;
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c) blk[r * 8 + c] = exact_pixel(rgb, real_w, real_h, x0 + c, y0 + r, 0, e.scale);
-        } else {
-            const int comp = k - 3;
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c) {                                   // S420_m, src/Image.cpp:207-226
-                    const uint32_t x = mx * 16 + 2 * c, y = my * 16 + 2 * r;
-                    const double top = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y, comp, e.scale)),
-                                            exact_pixel(rgb, real_w, real_h, x + 1, y, comp, e.scale));
-                    const double bot = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y + 1, comp, e.scale)),
-                                            exact_pixel(rgb, real_w, real_h, x + 1, y + 1, comp, e.scale));
-                    blk[r * 8 + c] = __ddiv_rn(dadd(top, bot), 4.0);
-                }
+// spatial sample (r, c) of block `id` (mcu*6+k) in the reference's arithmetic
+__device__ __forceinline__ double exact_sample(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uint32_t mcu_w,
+                                               uint32_t id, int r, int c, double scale) {
+    const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu;
+    const uint32_t mx = mcu % mcu_w, my = mcu / mcu_w;
+    if (k < 4) return exact_pixel(rgb, real_w, real_h, mx * 16 + (k & 1) * 8 + c, my * 16 + (k >> 1) * 8 + r, 0, scale);
+    const int comp = k - 3;                                                     // S420_m, src/Image.cpp:207-226
+    const uint32_t x = mx * 16 + 2 * c, y = my * 16 + 2 * r;
+    const double top = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y, comp, scale)),
+                            exact_pixel(rgb, real_w, real_h, x + 1, y, comp, scale));
+    const double bot = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y + 1, comp, scale)),
+                            exact_pixel(rgb, real_w, real_h, x + 1, y + 1, comp, scale));
+    return __ddiv_rn(dadd(top, bot), 4.0);
+}
+
+// Exact 8x8 transform of up to kRefineGroups blocks per CTA, 64 threads per block: thread (r,c) fetches one sample,
+// threads 0..7 of the group run the two 8-point passes through shared memory, then every thread quantises one
+// coefficient.  All groups of a CTA iterate in lockstep (same trip count), so the barriers are uniform.
+constexpr int kRefineGroups = 4;
+
+template <class Sample>
+__device__ __forceinline__ void refine_loop(uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
+                                            const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e, Sample&& sample) {
+    __shared__ double buf[kRefineGroups][2][64];
+    const int g = threadIdx.x >> 6, t = threadIdx.x & 63, r = t >> 3, c = t & 7;
+    const uint32_t stride = gridDim.x * kRefineGroups;
+    for (uint32_t base = blockIdx.x * kRefineGroups; base < n; base += stride) {
+        const uint32_t i = base + g;
+        const bool valid = i < n;
+        const uint32_t id = valid ? (all ? i : list[i]) : 0;
+        if (valid) buf[g][0][t] = sample(id, r, c);
+        __syncthreads();
+        if (valid && t < 8) aan8_exact(&buf[g][0][t], 8, &buf[g][1][t * 8], 1, e);     // column t -> row t of tmp
+        __syncthreads();
+        if (valid && t < 8) aan8_exact(&buf[g][1][t], 8, &buf[g][0][t * 8], 1, e);     // column t of tmp -> row t
+        __syncthreads();
+        if (valid) {
+            const int nat = c_zigzag[t];
+            const uint8_t* q = (id % kBlocksPerMcu) < 4 ? qtab_y : qtab_c;
+            out[static_cast<size_t>(id) * kCoefPerBlock + t] = quantize_exact(buf[g][0][nat], q[nat]);
         }
-        dct_quant_exact(blk, k < 4 ? e.qy : e.qc, e, coef + static_cast<size_t>(id) * kCoefPerBlock);
+        __syncthreads();
     }
 }
 
-// every block in FP64 (used when the refine list overflowed, and by tests as a device-side cross-check)
-__global__ void __launch_bounds__(64) exact_all_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
-                                                       uint32_t nblocks, uint32_t real_w, uint32_t real_h, uint32_t mcu_w,
-                                                       const __grid_constant__ ExactConsts e) {
-    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < nblocks; id += gridDim.x * blockDim.x) {
-        const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu;
-        const uint32_t mx = mcu % mcu_w, my = mcu / mcu_w;
-        double blk[64];
-        if (k < 4) {
-            const uint32_t x0 = mx * 16 + (k & 1) * 8, y0 = my * 16 + (k >> 1) * 8;
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c) blk[r * 8 + c] = exact_pixel(rgb, real_w, real_h, x0 + c, y0 + r, 0, e.scale);
-        } else {
-            const int comp = k - 3;
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t x = mx * 16 + 2 * c, y = my * 16 + 2 * r;
-                    const double top = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y, comp, e.scale)),
-                                            exact_pixel(rgb, real_w, real_h, x + 1, y, comp, e.scale));
-                    const double bot = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y + 1, comp, e.scale)),
-                                            exact_pixel(rgb, real_w, real_h, x + 1, y + 1, comp, e.scale));
-                    blk[r * 8 + c] = __ddiv_rn(dadd(top, bot), 4.0);
-                }
-        }
-        dct_quant_exact(blk, k < 4 ? e.qy : e.qc, e, coef + static_cast<size_t>(id) * kCoefPerBlock);
-    }
+__global__ void __launch_bounds__(64 * kRefineGroups) refine_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
+                                                                    const uint32_t* __restrict__ list,
+                                                                    const uint32_t* __restrict__ count, uint32_t cap, int all,
+                                                                    uint32_t nblocks, uint32_t real_w, uint32_t real_h,
+                                                                    uint32_t mcu_w, const __grid_constant__ ExactConsts e) {
+    const uint32_t n = all ? nblocks : min(*count, cap);
+    refine_loop(n, list, all != 0, coef, e.qy, e.qc, e, [&](uint32_t id, int r, int c) {
+        return exact_sample(rgb, real_w, real_h, mcu_w, id, r, c, e.scale);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -406,17 +398,16 @@ __global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __r
     copy_out(tile, out + first * 64, nb, tid, kMbThreads);
 }
 
-__global__ void __launch_bounds__(64) refine_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
-                                                           const uint32_t* __restrict__ list,
-                                                           const uint32_t* __restrict__ count, uint32_t cap,
-                                                           uint64_t nblocks, int all, const __grid_constant__ ExactConsts e) {
-    const uint64_t n = all ? nblocks : min(*count, cap);
-    for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint64_t id = all ? i : list[i];
-        double blk[64];
-        for (int j = 0; j < 64; ++j) blk[j] = static_cast<double>(in[id * 64 + j]);
-        dct_quant_exact(blk, e.qy, e, out + id * 64);
-    }
+// stand-alone blocks: every block uses table e.qy; ids index blocks directly
+__global__ void __launch_bounds__(64 * kRefineGroups) refine_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
+                                                                           const uint32_t* __restrict__ list,
+                                                                           const uint32_t* __restrict__ count, uint32_t cap,
+                                                                           uint32_t nblocks, int all,
+                                                                           const __grid_constant__ ExactConsts e) {
+    const uint32_t n = all ? nblocks : min(*count, cap);
+    refine_loop(n, list, all != 0, out, e.qy, e.qy, e, [&](uint32_t id, int r, int c) {
+        return static_cast<double>(in[static_cast<size_t>(id) * 64 + r * 8 + c]);
+    });
 }
 
 // reference planar natural-order int32 planes -> MCU-ordered zigzag int16 (test hook behind jpgenc_set_coefficients)
@@ -521,9 +512,9 @@ int launch_forward(jpgenc_ctx* c) {
     }
     JPGENC_CUDA(c, cudaGetLastError());
     JPGENC_CUDA(c, cudaEventRecord(c->ev_k1, c->stream));
-    refine_kernel<<<c->sm_count * 4, 64, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
-                                                         static_cast<uint32_t>(c->refine_cap), c->real_w, c->real_h,
-                                                         c->mcu_w, e);
+    refine_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(
+        c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), 0,
+        c->mcu_w * c->mcu_h * kBlocksPerMcu, c->real_w, c->real_h, c->mcu_w, e);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 2;
     return JPGENC_OK;
@@ -533,7 +524,8 @@ int launch_exact_all(jpgenc_ctx* c) {
     ExactConsts e;
     fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
     const uint32_t nblocks = c->mcu_w * c->mcu_h * kBlocksPerMcu;
-    exact_all_kernel<<<c->sm_count * 8, 64, 0, c->stream>>>(c->d_rgb, c->d_coef, nblocks, c->real_w, c->real_h, c->mcu_w, e);
+    refine_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
+                                                                       0u, 1, nblocks, c->real_w, c->real_h, c->mcu_w, e);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return JPGENC_OK;
@@ -550,8 +542,8 @@ int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64
     dct_blocks_kernel<<<static_cast<unsigned>(grid), kMbThreads, 0, c->stream>>>(
         in, out, nblocks, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), qc);
     JPGENC_CUDA(c, cudaGetLastError());
-    refine_blocks_kernel<<<c->sm_count * 4, 64, 0, c->stream>>>(in, out, c->d_refine_list, c->d_counters,
-                                                                static_cast<uint32_t>(c->refine_cap), nblocks, 0, e);
+    refine_blocks_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(
+        in, out, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), static_cast<uint32_t>(nblocks), 0, e);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 2;
     if (refined) {
@@ -559,8 +551,8 @@ int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64
         JPGENC_CUDA(c, cudaMemcpyAsync(&n, c->d_counters, sizeof n, cudaMemcpyDeviceToHost, c->stream));
         JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
         if (n > c->refine_cap) {   // list overflowed: redo everything exactly (correct, slow, never seen on real data)
-            refine_blocks_kernel<<<c->sm_count * 8, 64, 0, c->stream>>>(in, out, c->d_refine_list, c->d_counters,
-                                                                        static_cast<uint32_t>(c->refine_cap), nblocks, 1, e);
+            refine_blocks_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(
+                in, out, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), static_cast<uint32_t>(nblocks), 1, e);
             JPGENC_CUDA(c, cudaGetLastError());
             c->launches += 1;
         }

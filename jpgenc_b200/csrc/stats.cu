@@ -34,10 +34,12 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const int16_t
         const uint64_t text_block = k < 4 ? (my * 2 + (k >> 1)) * (2ull * mcu_w) + mx * 2 + (k & 1)
                                           : static_cast<uint64_t>(k - 4) * n_mcu + mcu;
         const int tdc = k < 4 ? 0 : 2;
-        walk_block(tile, tid, diff, [&](int sym, int, int ord) {
-            const int idx = (ord < 0 ? tdc : tdc + 1) * 256 + sym;
+        uint32_t lo, hi;
+        nonzero_mask(tile, tid, lo, hi);
+        walk_block(tile, tid, diff, lo, hi, [&](int sym, int, int k) {
+            const int idx = (k == 0 ? tdc : tdc + 1) * 256 + sym;
             atomicAdd(&s_hist[idx], 1u);
-            const unsigned long long key = text_block * 64 + (ord < 0 ? 0 : ord);
+            const unsigned long long key = text_block * 256 + k;
             if (key < s_first[idx]) atomicMin(&s_first[idx], key);
         });
     }

@@ -218,27 +218,31 @@ void jo_category(int value, int* category, uint32_t* bits) {
 }
 
 /* zigzag-ordered block -> symbol list; zz[0] is whatever DC value should be coded */
-static int symbols_from_zigzag(const int32_t zz[64], uint8_t sym[64], uint32_t bits[64], uint8_t nbits[64]) {
+/* okey[] (optional): order key of each entry inside its block, increasing along the text: DC 0, a ZRL 2p, the symbol of
+ * the coefficient at zigzag position p 2p+1, EOB 129 (ZRLs of one run share a key; only their first one can matter) */
+static int symbols_from_zigzag(const int32_t zz[64], uint8_t sym[64], uint32_t bits[64], uint8_t nbits[64], uint8_t* okey) {
     int n = 0, cat;
     uint32_t b;
     jo_category(zz[0], &cat, &b);
+    if (okey) okey[n] = 0;
     sym[n] = (uint8_t)cat; bits[n] = b; nbits[n] = (uint8_t)cat; ++n;
     unsigned zeros = 0;
     for (int i = 1; i < 64; ++i) {
         if (zz[i] == 0) { ++zeros; continue; }
-        while (zeros > 15) { sym[n] = 0xF0; bits[n] = 0; nbits[n] = 0; ++n; zeros -= 16; }
+        while (zeros > 15) { if (okey) okey[n] = (uint8_t)(2 * i); sym[n] = 0xF0; bits[n] = 0; nbits[n] = 0; ++n; zeros -= 16; }
         jo_category(zz[i], &cat, &b);
+        if (okey) okey[n] = (uint8_t)(2 * i + 1);
         sym[n] = (uint8_t)((zeros << 4) | cat); bits[n] = b; nbits[n] = (uint8_t)cat; ++n;
         zeros = 0;
     }
-    if (zeros > 0) { sym[n] = 0; bits[n] = 0; nbits[n] = 0; ++n; }   /* EOB */
+    if (zeros > 0) { if (okey) okey[n] = 129; sym[n] = 0; bits[n] = 0; nbits[n] = 0; ++n; }   /* EOB */
     return n;
 }
 
 int jo_block_symbols(const int32_t natural[64], uint8_t sym[64], uint32_t bits[64], uint8_t nbits[64]) {
     int32_t zz[64];
     for (int i = 0; i < 64; ++i) zz[i] = natural[ZZ[i]];
-    return symbols_from_zigzag(zz, sym, bits, nbits);
+    return symbols_from_zigzag(zz, sym, bits, nbits, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -688,13 +692,13 @@ void jo_planes_to_mcu(const int32_t* q_y, const int32_t* q_cb, const int32_t* q_
 /* per-block symbol list with the DC replaced by its difference.  prev[] = running predictors:
  * [0] Y in MCU order (Image.cpp:640-659), [1] Cb, [2] Cr raster (Image.cpp:661-677) */
 static int mcu_block_symbols(const int16_t* blk, int comp, int32_t prev[3], uint8_t sym[64], uint32_t bits[64],
-                             uint8_t nbits[64]) {
+                             uint8_t nbits[64], uint8_t* okey) {
     int32_t zz[64];
     for (int i = 0; i < 64; ++i) zz[i] = blk[i];
     const int32_t dc = zz[0];
     zz[0] = dc - prev[comp];
     prev[comp] = dc;
-    return symbols_from_zigzag(zz, sym, bits, nbits);
+    return symbols_from_zigzag(zz, sym, bits, nbits, okey);
 }
 
 void jo_symbol_stats(const int16_t* mcu_blocks, uint32_t mcu_w, uint32_t mcu_h, uint32_t count[4][256],
@@ -702,7 +706,7 @@ void jo_symbol_stats(const int16_t* mcu_blocks, uint32_t mcu_w, uint32_t mcu_h, 
     memset(count, 0, sizeof(uint32_t) * 4 * 256);
     memset(first_pos, 0xff, sizeof(uint64_t) * 4 * 256);
     int32_t prev[3] = {0, 0, 0};
-    uint8_t sym[64], nb[64];
+    uint8_t sym[64], nb[64], okey[64];
     uint32_t bits[64];
     const uint64_t ncb = (uint64_t)mcu_w * mcu_h;
     for (uint32_t my = 0; my < mcu_h; ++my)
@@ -710,17 +714,17 @@ void jo_symbol_stats(const int16_t* mcu_blocks, uint32_t mcu_w, uint32_t mcu_h, 
             const int16_t* m = mcu_blocks + ((size_t)my * mcu_w + mx) * 6 * 64;
             for (int k = 0; k < 6; ++k) {
                 const int comp = k < 4 ? 0 : k - 3;
-                const int n = mcu_block_symbols(m + k * 64, comp, prev, sym, bits, nb);
+                const int n = mcu_block_symbols(m + k * 64, comp, prev, sym, bits, nb, okey);
                 /* text order (Image.cpp:892-906): Y blocks raster over the block grid; chroma = all Cb then all Cr */
                 uint64_t blk_index;
                 if (k < 4) blk_index = ((uint64_t)my * 2 + (k >> 1)) * (mcu_w * 2) + mx * 2 + (k & 1);
                 else blk_index = (uint64_t)(k - 4) * ncb + (uint64_t)my * mcu_w + mx;
                 const int tdc = k < 4 ? 0 : 2, tac = tdc + 1;
                 ++count[tdc][sym[0]];
-                if (blk_index * 64 < first_pos[tdc][sym[0]]) first_pos[tdc][sym[0]] = blk_index * 64;
+                if (blk_index * 256 < first_pos[tdc][sym[0]]) first_pos[tdc][sym[0]] = blk_index * 256;
                 for (int i = 1; i < n; ++i) {
                     ++count[tac][sym[i]];
-                    const uint64_t key = blk_index * 64 + (uint64_t)(i - 1);
+                    const uint64_t key = blk_index * 256 + okey[i];
                     if (key < first_pos[tac][sym[i]]) first_pos[tac][sym[i]] = key;
                 }
             }
@@ -754,7 +758,7 @@ void jo_entropy_encode(const int16_t* mcu_blocks, uint32_t mcu_w, uint32_t mcu_h
     for (size_t m = 0; m < nmcu; ++m)             /* Image.cpp:959-967 */
         for (int k = 0; k < 6; ++k) {
             const int comp = k < 4 ? 0 : k - 3;
-            const int n = mcu_block_symbols(mcu_blocks + (m * 6 + k) * 64, comp, prev, sym, bits, nb);
+            const int n = mcu_block_symbols(mcu_blocks + (m * 6 + k) * 64, comp, prev, sym, bits, nb, NULL);
             const jo_huff_table* dc = &tables[k < 4 ? 0 : 2];
             const jo_huff_table* ac = &tables[k < 4 ? 1 : 3];
             jo_bits_push_msb(out, dc->code_msb[sym[0]], dc->length[sym[0]]);   /* Image.cpp:757-759 */

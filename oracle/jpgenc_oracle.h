@@ -102,7 +102,9 @@ void jo_planes_to_mcu(const int32_t* q_y, const int32_t* q_cb, const int32_t* q_
                       uint32_t mcu_w, uint32_t mcu_h, int16_t* out);
 
 /* Entropy statistics in the reference's TEXT order (Image.cpp:888-906): table 0=Y_DC 1=Y_AC 2=C_DC 3=C_AC.
- * first_pos = position of the first occurrence in that table's text, UINT64_MAX if absent. */
+ * first_pos = order-preserving key of the first occurrence in that table's text, UINT64_MAX if absent:
+ * (block index in text order)*256 + k, k = 0 for DC, 2p for a ZRL before zigzag position p, 2p+1 for the symbol of
+ * position p, 129 for EOB. */
 void jo_symbol_stats(const int16_t* mcu_blocks, uint32_t mcu_w, uint32_t mcu_h,
                      uint32_t count[4][256], uint64_t first_pos[4][256]);
 
