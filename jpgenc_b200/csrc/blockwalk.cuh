@@ -8,69 +8,72 @@ namespace jpgenc {
 constexpr int kTileBlocks = 384;                       // 64 MCUs; one thread per block
 constexpr int kTileBytes = kTileBlocks * kBlockBytes;  // 48 KB
 
-// Coalesced copy of `nb` blocks into shared memory.  Slot s keeps its 16-byte chunk c at chunk (c ^ (s & 7)),
-// so that 32 threads reading "their" block's chunk c hit 32 different banks.
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const int16_t* __restrict__ gsrc, int nb, int tid, int nthreads) {
+// 8-bit non-zero flags of one 16-byte chunk (bit j = coefficient j of the chunk != 0).  Branch-free: VIMNMX.U16x2
+// turns every halfword into a 0/1 flag.
+__device__ __forceinline__ uint32_t chunk_flags(const uint4& q) {
+    const uint32_t f = __vminu2(q.x, 0x00010001u) | (__vminu2(q.y, 0x00010001u) << 2) | (__vminu2(q.z, 0x00010001u) << 4) |
+                       (__vminu2(q.w, 0x00010001u) << 6);
+    return (f | (f >> 15)) & 0xFFu;                 // even bits: low halfwords, odd bits: high halfwords
+}
+
+// Shared-memory view of a tile of MCU-ordered blocks:
+//   tile   48 KB  coefficient chunks; slot s keeps chunk c at chunk (c ^ (s & 7)); ALL-ZERO CHUNKS ARE NOT WRITTEN
+//   flags  3 KB   one byte per chunk = chunk_flags(); 8 bytes per slot = the block's 64-bit non-zero mask
+//   dc     768 B  the block's DC coefficient
+struct TileView {
+    uint8_t* tile;
+    uint8_t* flags;
+    int16_t* dc;
+};
+constexpr int kTileSmemBytes = kTileBytes + kTileBlocks * 8 + kTileBlocks * 2;
+
+__device__ __forceinline__ TileView tile_view(uint8_t* smem) {
+    return TileView{smem, smem + kTileBytes, reinterpret_cast<int16_t*>(smem + kTileBytes + kTileBlocks * 8)};
+}
+
+// Coalesced pass over `nb` blocks of global memory: every thread takes 16-byte chunks, derives the chunk's non-zero
+// flags while the data is in registers, and stores only chunks that contain something.
+__device__ __forceinline__ void stage_tile(const TileView& tv, const int16_t* __restrict__ gsrc, int nb, int tid, int nthreads) {
     const uint4* g = reinterpret_cast<const uint4*>(gsrc);
     const int chunks = nb * 8;
     for (int j = tid; j < chunks; j += nthreads) {
         const int s = j >> 3, c = j & 7;
-        *reinterpret_cast<uint4*>(tile + s * kBlockBytes + ((c ^ (s & 7)) << 4)) = __ldg(g + j);
+        const uint4 q = __ldg(g + j);
+        const uint32_t f = chunk_flags(q);
+        tv.flags[j] = static_cast<uint8_t>(c == 0 ? (f & 0xFEu) : f);       // the DC position is not an AC coefficient
+        if (c == 0) tv.dc[s] = static_cast<int16_t>(q.x & 0xFFFFu);
+        if (f) *reinterpret_cast<uint4*>(tv.tile + s * kBlockBytes + ((c ^ (s & 7)) << 4)) = q;
     }
 }
 
-__device__ __forceinline__ void load_block(const uint8_t* tile, int slot, uint32_t (&w)[32]) {
-    const uint4* base = reinterpret_cast<const uint4*>(tile + slot * kBlockBytes);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 q = base[c ^ (slot & 7)];
-        w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
-    }
+__device__ __forceinline__ void load_mask(const TileView& tv, int slot, uint32_t& lo, uint32_t& hi) {
+    const uint2 m = *reinterpret_cast<const uint2*>(tv.flags + slot * 8);
+    lo = m.x;
+    hi = m.y;
 }
 
-__device__ __forceinline__ int slot_dc(const uint8_t* tile, int slot) {
-    return *reinterpret_cast<const int16_t*>(tile + slot * kBlockBytes + ((slot & 7) << 4));
+__device__ __forceinline__ int slot_coef(const TileView& tv, int slot, int pos) {
+    return *reinterpret_cast<const int16_t*>(tv.tile + slot * kBlockBytes + ((((pos >> 3) ^ slot) & 7) << 4) + ((pos & 7) << 1));
 }
 
 // DC predictor of block `t` of a tile that starts at global block `first` (a multiple of 6):
 // Y follows MCU order (src/Image.cpp:640-659), Cb and Cr their own raster order (src/Image.cpp:661-677).
-__device__ __forceinline__ int dc_predictor(const uint8_t* tile, const int16_t* __restrict__ coef, uint64_t first, int t) {
+__device__ __forceinline__ int dc_predictor(const TileView& tv, const int16_t* __restrict__ coef, uint64_t first, int t) {
     const int k = t % kBlocksPerMcu, lm = t / kBlocksPerMcu;
-    if (k >= 1 && k <= 3) return slot_dc(tile, t - 1);
+    if (k >= 1 && k <= 3) return tv.dc[t - 1];
     const int back = (k == 0) ? 3 : 6;          // Y00 <- previous MCU's Y11 ; Cb/Cr <- previous MCU's Cb/Cr
-    if (lm > 0) return slot_dc(tile, t - back);
+    if (lm > 0) return tv.dc[t - back];
     if (first == 0) return 0;
     return coef[(first + t - back) * kCoefPerBlock];
 }
 
 __device__ __forceinline__ int category_of(int v) { return 32 - __clz(abs(v)); }   // 0 for v == 0
 
-// Bit i of the result = zigzag coefficient i of the block in `slot` is non-zero (i = 1..63; the DC bit is cleared).
-// Branch-free: VIMNMX.U16x2 turns each halfword into a 0/1 flag, 11 instructions per 8 coefficients.
-__device__ __forceinline__ void nonzero_mask(const uint8_t* tile, int slot, uint32_t& lo, uint32_t& hi) {
-    const uint4* base = reinterpret_cast<const uint4*>(tile + slot * kBlockBytes);
-    lo = hi = 0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 q = base[c ^ (slot & 7)];
-        const uint32_t f = __vminu2(q.x, 0x00010001u) | (__vminu2(q.y, 0x00010001u) << 2) |
-                           (__vminu2(q.z, 0x00010001u) << 4) | (__vminu2(q.w, 0x00010001u) << 6);
-        const uint32_t byte = (f | (f >> 15)) & 0xFFu;      // even bits: low halfwords, odd bits: high halfwords
-        if (c < 4) lo |= byte << (8 * c);
-        else hi |= byte << (8 * (c - 4));
-    }
-    lo &= ~1u;
-}
-
-__device__ __forceinline__ int slot_coef(const uint8_t* tile, int slot, int pos) {
-    return *reinterpret_cast<const int16_t*>(tile + slot * kBlockBytes + ((((pos >> 3) ^ slot) & 7) << 4) + ((pos & 7) << 1));
-}
-
 // Calls emit(symbol, value, key) for the DC entry (key 0) and every AC entry in zigzag order; `dc_diff` replaces
 // coefficient 0.  key orders the entries inside the block: 2p for a ZRL before position p, 2p+1 for the symbol of
 // position p, 129 for EOB.  Only non-zero coefficients cost loop iterations (the common block has a handful).
 template <class Emit>
-__device__ __forceinline__ void walk_block(const uint8_t* tile, int slot, int dc_diff, uint32_t lo, uint32_t hi, Emit&& emit) {
+__device__ __forceinline__ void walk_block(const TileView& tv, int slot, int dc_diff, uint32_t lo, uint32_t hi, Emit&& emit) {
     emit(category_of(dc_diff), dc_diff, 0);
     int prev = 0;
 #pragma unroll 1
@@ -82,7 +85,7 @@ __device__ __forceinline__ void walk_block(const uint8_t* tile, int slot, int dc
             m &= m - 1;
             int run = pos - prev - 1;
             prev = pos;
-            const int v = slot_coef(tile, slot, pos);
+            const int v = slot_coef(tv, slot, pos);
             while (run > 15) { emit(0xF0, 0, 2 * pos); run -= 16; }      // ZRL
             emit((run << 4) | category_of(v), v, 2 * pos + 1);
         }

@@ -58,9 +58,9 @@ struct EntropyParams {
 };
 
 template <class Put>
-__device__ __forceinline__ void encode_block(const uint8_t* tile, int slot, int diff, uint32_t lo, uint32_t hi,
+__device__ __forceinline__ void encode_block(const TileView& tv, int slot, int diff, uint32_t lo, uint32_t hi,
                                              const uint32_t* tdc, const uint32_t* tac, Put&& put) {
-    walk_block(tile, slot, diff, lo, hi, [&](int sym, int value, int k) {
+    walk_block(tv, slot, diff, lo, hi, [&](int sym, int value, int k) {
         const uint32_t e = (k == 0 ? tdc : tac)[sym];
         const uint32_t cat = sym & 15;                                            // magnitude bit count
         const uint32_t mag = (value < 0 ? value - 1 : value) & ((1u << cat) - 1); // Coding.hpp:206-212
@@ -70,22 +70,22 @@ __device__ __forceinline__ void encode_block(const uint8_t* tile, int slot, int 
 
 __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* tile = smem;
-    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + kTileBytes);                  // [4][256]
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + kTileBytes + 4096);          // [kBitBufWords]
-    uint32_t* s_scan = s_bits + kBitBufWords;                                          // [33]
+    const TileView tv = tile_view(smem);
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + kTileSmemBytes);              // [4][256]
+    uint32_t* s_bits = s_tab + 1024;                                                   // [kBitBufWords + 1]
+    uint32_t* s_scan = s_bits + kBitBufWords + 1;                                      // [33]
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
 
     if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
     for (int i = tid; i < 1024; i += kTileBlocks) s_tab[i] = (&p.tables->entry[0][0])[i];
-    for (int i = tid; i < kBitBufWords; i += kTileBlocks) s_bits[i] = 0;
+    for (int i = tid; i <= kBitBufWords; i += kTileBlocks) s_bits[i] = 0;
     __syncthreads();
     const uint32_t tile_idx = s_tile;
     const uint64_t first = static_cast<uint64_t>(tile_idx) * kTileBlocks;
     const int nb = static_cast<int>(umin64(kTileBlocks, p.nblocks - first));
-    stage_tile(tile, p.coef + first * kCoefPerBlock, nb, tid, kTileBlocks);
+    stage_tile(tv, p.coef + first * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
 
     int diff = 0;
@@ -94,60 +94,64 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
     const uint32_t* tdc = s_tab + (k < 4 ? 0 : 512);
     const uint32_t* tac = tdc + 256;
     if (tid < nb) {
-        diff = slot_dc(tile, tid) - dc_predictor(tile, p.coef, first, tid);
-        nonzero_mask(tile, tid, nz_lo, nz_hi);
-        encode_block(tile, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
+        load_mask(tv, tid, nz_lo, nz_hi);
+        diff = tv.dc[tid] - dc_predictor(tv, p.coef, first, tid);
+        encode_block(tv, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
     }
     uint32_t tile_bits;
     const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
-    if (tid < 32) {
-        const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
-        if (tid == 0) s_base = b;
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    const uint32_t lead = static_cast<uint32_t>(base & 31);                 // bits of the first word owned by earlier tiles
     const bool last_tile = first + nb == p.nblocks;
-    // the last tile also appends the 1-padding of Bitstream::fill() (BitstreamGeneric.hpp:242-248)
-    const uint32_t pad = last_tile ? static_cast<uint32_t>((8 - ((base + tile_bits) & 7)) & 7) : 0;
-    const bool in_smem = lead + tile_bits + pad <= kBitBufWords * 32u;
+    const bool in_smem = tile_bits + 32 <= kBitBufWords * 32u;
 
     if (in_smem) {
+        // The codes are assembled at tile-relative bit positions, so this does not wait for the look-back: the last
+        // warp resolves the tile's global bit offset while the others are still packing.
+        if (tid >= kTileBlocks - 32) {
+            const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
+            if (tid == kTileBlocks - 32) s_base = b;
+        }
         if (tid < nb) {
             BitWriter<false> bw;
-            bw.start(s_bits, lead + local);
-            encode_block(tile, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
-            bw.finish();
-        }
-        if (pad && tid == 0) {
-            BitWriter<false> bw;
-            bw.start(s_bits, lead + tile_bits);
-            bw.put((1u << pad) - 1, pad);
+            bw.start(s_bits, local);
+            encode_block(tv, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
             bw.finish();
         }
         __syncthreads();
-        const uint32_t nwords = (lead + tile_bits + pad + 31) >> 5;
+        const unsigned long long base = s_base;
+        const uint32_t lead = static_cast<uint32_t>(base & 31);             // bits of the first word owned by earlier tiles
+        const uint32_t nwords = (lead + tile_bits + 31) >> 5;
         uint32_t* g = p.raw + (base >> 5);
         for (uint32_t i = tid; i < nwords; i += kTileBlocks) {
-            const uint32_t v = __byte_perm(s_bits[i], 0, 0x0123);
+            // global word i = tile-relative bits [32i - lead, 32i - lead + 32)
+            const uint32_t v = __byte_perm(__funnelshift_r(s_bits[i], i ? s_bits[i - 1] : 0u, lead), 0, 0x0123);
             if (i == 0 || i == nwords - 1) { if (v) atomicOr(&g[i], v); }
             else g[i] = v;
         }
-    } else {   // very dense tile: write straight to the (zeroed) global words
+    } else {   // very dense tile: wait for the offset, then write straight to the (zeroed) global words
+        if (tid < 32) {
+            const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
+            if (tid == 0) s_base = b;
+        }
+        __syncthreads();
         if (tid < nb) {
             BitWriter<true> bw;
-            bw.start(p.raw, base + local);
-            encode_block(tile, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
-            bw.finish();
-        }
-        if (pad && tid == 0) {
-            BitWriter<true> bw;
-            bw.start(p.raw, base + tile_bits);
-            bw.put((1u << pad) - 1, pad);
+            bw.start(p.raw, s_base + local);
+            encode_block(tv, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
             bw.finish();
         }
     }
-    if (last_tile && tid == 0) p.total_out[0] = base + tile_bits;
+    if (last_tile && tid == 0) {
+        // 1-padding of Bitstream::fill() (BitstreamGeneric.hpp:242-248): the open byte is completed with ones
+        const unsigned long long end = s_base + tile_bits;
+        const uint32_t pad = static_cast<uint32_t>((8 - (end & 7)) & 7);
+        if (pad) {
+            BitWriter<true> bw;
+            bw.start(p.raw, end);
+            bw.put((1u << pad) - 1, pad);
+            bw.finish();
+        }
+        p.total_out[0] = end;
+    }
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------------------
@@ -217,7 +221,7 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     p.ticket = c->d_counters + 1;
     p.raw = c->d_raw;
     p.total_out = totals;
-    const size_t smem = kTileBytes + 4096 + kBitBufWords * 4 + 33 * 4 + 16;
+    const size_t smem = kTileSmemBytes + 4096 + (kBitBufWords + 1) * 4 + 33 * 4 + 16;
     JPGENC_CUDA(c, cudaFuncSetAttribute(huffman_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     huffman_pack_kernel<<<tiles3, kTileBlocks, smem, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
