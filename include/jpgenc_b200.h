@@ -127,6 +127,8 @@ size_t jpgenc_write_headers(uint32_t real_w, uint32_t real_h, const uint8_t qy[6
                             const jpgenc_huff_table tables[4], uint8_t* dst);
 /* runs K1..K4 on the pixels bound/uploaded and assembles headers + scan + EOI into dst */
 int jpgenc_encode_bound(jpgenc_ctx* ctx, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);
+/* headers + scan of the LAST jpgenc_encode_bound on this context + EOI into dst, without re-running the pipeline */
+int jpgenc_assemble_last(jpgenc_ctx* ctx, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);
 /* upload + encode (host pixels in, JPEG bytes out) */
 int jpgenc_encode_rgb(jpgenc_ctx* ctx, const uint8_t* host_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval,
                       uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);

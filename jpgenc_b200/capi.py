@@ -69,6 +69,7 @@ _SIGNATURES = {
     "jpgenc_ppm_samples": (C.c_int, [C.c_char_p, C.c_size_t, u8p]),
     "jpgenc_write_headers": (C.c_size_t, [C.c_uint32, C.c_uint32, u8p, u8p, C.POINTER(HuffTable), u8p]),
     "jpgenc_encode_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "jpgenc_assemble_last": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_ppm_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "jpgenc_dct_quant_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u8p, u64p]),

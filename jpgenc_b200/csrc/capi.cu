@@ -366,7 +366,10 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
     for (int t = 0; t < 4; ++t)
         if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
-    return jpgenc_entropy_encode(c, tables, scan);
+    if ((rc = jpgenc_entropy_encode(c, tables, scan))) return rc;
+    std::memcpy(c->last_tables, tables, sizeof c->last_tables);
+    c->have_tables = true;
+    return JPGENC_OK;
 }
 
 static int assemble(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t scan, uint8_t* dst, uint64_t cap) {
@@ -390,6 +393,14 @@ int jpgenc_encode_bound(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpe
     if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
     if (!dst) return JPGENC_OK;                                  // device-resident run: the scan stays in HBM
     return assemble(c, tables, scan, dst, cap);
+}
+
+int jpgenc_assemble_last(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) {
+    if (!c || !dst) return JPGENC_ERR_ARG;
+    if (!c->have_tables || !c->have_scan) return fail(c, JPGENC_ERR_ARG, "no finished encode on this context");
+    const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, c->last_tables, nullptr);
+    if (jpeg_bytes) *jpeg_bytes = hdr + c->stats.scan_bytes + 2;
+    return assemble(c, c->last_tables, c->stats.scan_bytes, dst, cap);
 }
 
 int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval, uint8_t* dst,

@@ -108,6 +108,8 @@ struct jpgenc_ctx {
     size_t pinned_bytes = 0;
 
     jpgenc_stats stats{};
+    jpgenc_huff_table last_tables[4];     // tables of the last whole-image run (for jpgenc_assemble_last)
+    bool have_tables = false;
 };
 
 #define JPGENC_CUDA(ctx, expr)                                                                       \
