@@ -99,29 +99,24 @@ SymbolCodeMap generateCodes(const SymbolsPerLength& symbols) {
 
 std::pair<SymbolCodeMap, SymbolsPerLength> generateHuffmanCode(std::vector<int> text) {
     assert(!text.empty());
-    // histogram + position of first appearance, then the shared builder (the same entry the GPU pipeline uses)
-    uint32_t count[256] = {0};
-    uint64_t first[256];
-    std::memset(first, 0xFF, sizeof first);
-    for (std::size_t i = 0; i < text.size(); ++i) {
-        const int s = text[i] & 255;
-        if (count[s]++ == 0) first[s] = i;
+    // Any int may be a symbol here (the JPEG path only produces 0..255 and goes through jpgenc_build_huffman, which
+    // this function agrees with).  Symbols enter package-merge in the iteration order of a map filled in order of
+    // first appearance -- the library-defined order the reference's tables depend on.
+    std::unordered_map<int, int> frequency;
+    for (int s : text) ++frequency[s];
+    if (frequency.size() == 1) {                      // a lone symbol gets the one-bit code "0"
+        SymbolsPerLength per_length(17);
+        per_length[1].push_back(text[0]);
+        SymbolCodeMap map;
+        map[text[0]] = Code(0, 1);
+        return std::make_pair(map, per_length);
     }
-    jpgenc_huff_table t;
-    jpgenc_build_huffman(count, first, &t);
-    SymbolCodeMap map;
-    SymbolsPerLength per_length(17);
-    int k = 0;
-    for (int len = 1; len <= 16; ++len)
-        for (int i = 0; i < t.counts[len - 1]; ++i) {
-            const int s = t.symbols[k++];
-            per_length[len].push_back(s);
-            Code c;
-            c.code = t.code_msb[s];
-            c.length = t.length[s];
-            map.emplace(s, c);
-        }
-    return std::make_pair(map, per_length);
+    std::vector<Symbol> symbols;
+    symbols.reserve(frequency.size());
+    for (const auto& kv : frequency) symbols.emplace_back(kv.first, kv.second);
+    SymbolsPerLength per_length = package_merge(symbols, 15);
+    preventOnlyOnesCode(per_length);
+    return std::make_pair(generateCodes(per_length), per_length);
 }
 
 Bitstream huffmanEncode(std::vector<int> text, SymbolCodeMap code_map) {

@@ -5,11 +5,17 @@
 // heap orders).  generateHuffmanCode(text) is a thin adaptor over it for callers that still hold a symbol text.
 #pragma once
 #include <cstdint>
+#include <iterator>
 #include <unordered_map>
 #include <utility>
 #include <vector>
 
 #include "BitstreamGeneric.hpp"
+
+// names the reference's header exports into the global namespace (Huffman.hpp:15-18); callers rely on them
+using std::pair;
+using std::unordered_map;
+using std::vector;
 
 struct Code {
     using CodeType = uint32_t;
