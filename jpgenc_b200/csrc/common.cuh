@@ -29,6 +29,12 @@ struct QuantConsts {
     float mul[64];
     float thr[64];
 };
+// the same constants in the pair order of the packed (FP32x2) transform: entry [u*4+q] holds natural indices
+// ((2q)*8+u, (2q+1)*8+u)
+struct QuantConsts2 {
+    float2 mul[32];
+    float2 thr[32];
+};
 
 // Constants of the exact path: the reference's own doubles (Dct.hpp:21-43) and integer quantisers.
 struct ExactConsts {
@@ -54,8 +60,8 @@ struct ForwardParams {
     uint32_t debug_flags;
     uint32_t prefetch_ahead;              // CTAs resident at once: each CTA warms L2 for the tile this many ids later
     ColorConsts color;
-    QuantConsts luma;
-    QuantConsts chroma;
+    QuantConsts2 luma;
+    QuantConsts2 chroma;
 };
 
 __host__ __device__ inline uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }

@@ -85,6 +85,103 @@ __device__ __forceinline__ bool quantize_pack(const float (&v)[64], const QuantC
     return boundary;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// packed FP32x2 fast path (sm_100 FADD2 / FFMA2: two IEEE fp32 operations per issue slot)
+// ---------------------------------------------------------------------------------------------------
+// K1 is bound by instruction issue, not by the FP32 pipes or HBM (ncu, profiles/): two thirds of its instructions
+// are FADD/FFMA.  Blackwell's packed forms halve those.  A block is held as 32 float2: in the first (vertical) pass a
+// pair is two neighbouring columns, so the eight 1-D column transforms run as four packed ones; 2x2 register
+// transposes then turn pairs of columns into pairs of rows for the horizontal pass.  Every lane of a packed operation is
+// an ordinary round-to-nearest fp32 operation, so the results (and the error bound behind the refinement threshold)
+// are those of the scalar code.
+using f2 = float2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 fma2s(f2 a, float k, f2 c) { return __ffma2_rn(a, make_float2(k, k), c); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+
+__device__ __forceinline__ void aan8x2(f2& x0, f2& x1, f2& x2, f2& x3, f2& x4, f2& x5, f2& x6, f2& x7) {
+    constexpr float A1 = 0.70710678118654752f, A2 = 0.54119610014619698f, A4 = 1.30656296487637653f,
+                    A5 = 0.38268343236508977f;
+    const f2 z0 = add2(x0, x7), z1 = add2(x1, x6), z2 = add2(x2, x5), z3 = add2(x3, x4);
+    const f2 z4 = sub2(x3, x4), z5 = sub2(x2, x5), z6 = sub2(x1, x6), z7 = sub2(x0, x7);
+    const f2 r0 = add2(z0, z3), r1 = add2(z1, z2), r2 = sub2(z1, z2), r3 = sub2(z0, z3);
+    const f2 n4 = add2(z4, z5);
+    const f2 r5 = add2(z5, z6), r6 = add2(z6, z7);
+    const f2 t2 = add2(r2, r3);
+    const f2 d = sub2(r6, n4);
+    const f2 tmp = __fmul2_rn(d, make_float2(A5, A5));
+    const f2 u4 = fma2s(n4, A2, neg2(tmp));
+    const f2 u6 = fma2s(r6, A4, neg2(tmp));
+    const f2 v5 = fma2s(r5, A1, z7);
+    const f2 v7 = fma2s(r5, -A1, z7);
+    x0 = add2(r0, r1);
+    x4 = sub2(r0, r1);
+    x2 = fma2s(t2, A1, r3);
+    x6 = fma2s(t2, -A1, r3);
+    x5 = add2(u4, v7);
+    x1 = add2(v5, u6);
+    x7 = sub2(v5, u6);
+    x3 = sub2(v7, u4);
+}
+
+// in : v[r*4+p] = (s[r][2p], s[r][2p+1])   spatial samples, pairs of neighbouring columns
+// out: v[u*4+q] = (F[2q][u], F[2q+1][u])   unscaled frequencies F[v][u], pairs of neighbouring vertical frequencies
+__device__ __forceinline__ void dct8x8_packed(f2 (&v)[32]) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        aan8x2(v[0 * 4 + p], v[1 * 4 + p], v[2 * 4 + p], v[3 * 4 + p], v[4 * 4 + p], v[5 * 4 + p], v[6 * 4 + p], v[7 * 4 + p]);
+    f2 t[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const f2 a = v[(2 * q) * 4 + p], b = v[(2 * q + 1) * 4 + p];
+            t[(2 * p) * 4 + q] = make_float2(a.x, b.x);
+            t[(2 * p + 1) * 4 + q] = make_float2(a.y, b.y);
+        }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        aan8x2(t[0 * 4 + q], t[1 * 4 + q], t[2 * 4 + q], t[3 * 4 + q], t[4 * 4 + q], t[5 * 4 + q], t[6 * 4 + q], t[7 * 4 + q]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = t[i];
+}
+
+// QuantConsts2: the same multipliers/thresholds as QuantConsts, stored in the pair order dct8x8_packed leaves:
+// entry [u*4+q] = (natural index (2q)*8+u, natural index (2q+1)*8+u)
+__device__ __forceinline__ bool quantize_pack_packed(const f2 (&v)[32], const QuantConsts2& q, uint32_t (&out)[32]) {
+    constexpr float kMagic = 12582912.f;
+    constexpr int zz[64] = {JPGENC_ZIGZAG_LIST};
+    uint32_t bits[64];
+    bool boundary = false;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const int j = u * 4 + qq;
+            const f2 a = fma2(v[j], q.mul[j], make_float2(kMagic, kMagic));
+            const f2 k = add2(a, make_float2(-kMagic, -kMagic));
+            const f2 d = fma2(v[j], q.mul[j], neg2(k));
+            boundary |= fabsf(d.x) > q.thr[j].x;
+            boundary |= fabsf(d.y) > q.thr[j].y;
+            bits[(2 * qq) * 8 + u] = __float_as_uint(a.x);
+            bits[(2 * qq + 1) * 8 + u] = __float_as_uint(a.y);
+        }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = __byte_perm(bits[zz[2 * j]], bits[zz[2 * j + 1]], 0x5410);
+    return boundary;
+}
+
+// bytes `lo` and `hi` of the 24-byte row segment w[] as floats: PRMT splices each byte under the exponent of 2^23
+// (0x4B0000bb == 8388608 + b exactly), one packed subtraction removes the 2^23.  Runs on the ALU + FMA pipes; the
+// plain I2F.U8 conversion is a quarter-rate XU instruction and would become the bottleneck once the arithmetic is packed.
+__device__ __forceinline__ f2 bytes_to_f2(const uint32_t (&w)[6], int lo, int hi) {
+    const uint32_t a = __byte_perm(w[lo >> 2], 0x4B000000u, 0x7650 | (lo & 3));
+    const uint32_t b = __byte_perm(w[hi >> 2], 0x4B000000u, 0x7650 | (hi & 3));
+    return add2(make_float2(__uint_as_float(a), __uint_as_float(b)), make_float2(-8388608.f, -8388608.f));
+}
+
 // staging slot layout: 128 B per block, 16-byte chunk c of slot s lives at chunk (c ^ (s & 7)) — conflict-free
 // both for the per-thread 16-byte writes and for the linear copy-out
 __device__ __forceinline__ void stage_block(uint8_t* staging, int slot, const uint32_t (&w)[32]) {
@@ -182,12 +279,12 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
     // ---- luma thread: block (bx, by) of the strip's 2 x (2*kMcus) block grid ----
     const int bx = tid % (kMcus * 2), by = tid / (kMcus * 2);
     const bool active = (bx >> 1) < nm;
-    float v[64];
+    f2 v[32];                                     // v[r*4+p] = samples (r, 2p) and (r, 2p+1)
     if (active) {
         const ColorConsts& cc = p.color;
 #pragma unroll
         for (int rp = 0; rp < 4; ++rp) {
-            float rr[2][8], gg[2][8], bb[2][8];
+            f2 rr[2][4], gg[2][4], bb[2][4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = rp * 2 + h;
@@ -195,24 +292,32 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
                 const uint2 q0 = src[0], q1 = src[1], q2 = src[2];
                 const uint32_t w[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
 #pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                    rr[h][x] = u8f(w[(3 * x) >> 2], (3 * x) & 3);
-                    gg[h][x] = u8f(w[(3 * x + 1) >> 2], (3 * x + 1) & 3);
-                    bb[h][x] = u8f(w[(3 * x + 2) >> 2], (3 * x + 2) & 3);
-                    v[r * 8 + x] = fmaf(cc.y[0], rr[h][x], fmaf(cc.y[1], gg[h][x], fmaf(cc.y[2], bb[h][x], -128.f)));
+                for (int pp = 0; pp < 4; ++pp) {                  // pixels 2pp, 2pp+1 = bytes 6pp .. 6pp+5
+                    rr[h][pp] = bytes_to_f2(w, 6 * pp, 6 * pp + 3);
+                    gg[h][pp] = bytes_to_f2(w, 6 * pp + 1, 6 * pp + 4);
+                    bb[h][pp] = bytes_to_f2(w, 6 * pp + 2, 6 * pp + 5);
+                    v[r * 4 + pp] = fma2s(rr[h][pp], cc.y[0], fma2s(gg[h][pp], cc.y[1], fma2s(bb[h][pp], cc.y[2], make_float2(-128.f, -128.f))));
                 }
             }
-            float cb[4], cr[4];
+            // 2x2 sums are sums of small integers: exact in any order (reference order: (a+b)+(c+d), src/Image.cpp:209-224)
+            float r4[4], g4[4], b4[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const float r4 = (rr[0][2 * x] + rr[0][2 * x + 1]) + (rr[1][2 * x] + rr[1][2 * x + 1]);
-                const float g4 = (gg[0][2 * x] + gg[0][2 * x + 1]) + (gg[1][2 * x] + gg[1][2 * x + 1]);
-                const float b4 = (bb[0][2 * x] + bb[0][2 * x + 1]) + (bb[1][2 * x] + bb[1][2 * x + 1]);
-                cb[x] = fmaf(cc.cb[0], r4, fmaf(cc.cb[1], g4, cc.cb[2] * b4));
-                cr[x] = fmaf(cc.cr[0], r4, fmaf(cc.cr[1], g4, cc.cr[2] * b4));
+            for (int pp = 0; pp < 4; ++pp) {
+                const f2 sr = add2(rr[0][pp], rr[1][pp]), sg = add2(gg[0][pp], gg[1][pp]), sb = add2(bb[0][pp], bb[1][pp]);
+                r4[pp] = sr.x + sr.y;
+                g4[pp] = sg.x + sg.y;
+                b4[pp] = sb.x + sb.y;
             }
-            *reinterpret_cast<float4*>(&sm.chroma[0][by * 4 + rp][bx * 4]) = make_float4(cb[0], cb[1], cb[2], cb[3]);
-            *reinterpret_cast<float4*>(&sm.chroma[1][by * 4 + rp][bx * 4]) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+            f2 cb[2], cr[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const f2 r2 = make_float2(r4[2 * j], r4[2 * j + 1]), g2 = make_float2(g4[2 * j], g4[2 * j + 1]),
+                         b2 = make_float2(b4[2 * j], b4[2 * j + 1]);
+                cb[j] = fma2s(r2, cc.cb[0], fma2s(g2, cc.cb[1], __fmul2_rn(b2, make_float2(cc.cb[2], cc.cb[2]))));
+                cr[j] = fma2s(r2, cc.cr[0], fma2s(g2, cc.cr[1], __fmul2_rn(b2, make_float2(cc.cr[2], cc.cr[2]))));
+            }
+            *reinterpret_cast<float4*>(&sm.chroma[0][by * 4 + rp][bx * 4]) = make_float4(cb[0].x, cb[0].y, cb[1].x, cb[1].y);
+            *reinterpret_cast<float4*>(&sm.chroma[1][by * 4 + rp][bx * 4]) = make_float4(cr[0].x, cr[0].y, cr[1].x, cr[1].y);
         }
     }
     __syncthreads();   // every RGB byte has been consumed (tile may now be reused as staging); chroma planes complete
@@ -220,8 +325,8 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
     const uint32_t mcu_base = my * p.mcu_w + mcu0;
     uint32_t packed[32];
     if (active) {
-        dct8x8(v);
-        const bool boundary = quantize_pack(v, p.luma, packed);
+        dct8x8_packed(v);
+        const bool boundary = quantize_pack_packed(v, p.luma, packed);
         const int m = bx >> 1, k = by * 2 + (bx & 1);
         stage_block(sm.tile, m * kBlocksPerMcu + k, packed);
         if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + k);
@@ -234,11 +339,11 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
             for (int r = 0; r < 8; ++r) {
                 const float4 lo = *reinterpret_cast<const float4*>(&sm.chroma[comp][r][m * 8]);
                 const float4 hi = *reinterpret_cast<const float4*>(&sm.chroma[comp][r][m * 8 + 4]);
-                v[r * 8 + 0] = lo.x; v[r * 8 + 1] = lo.y; v[r * 8 + 2] = lo.z; v[r * 8 + 3] = lo.w;
-                v[r * 8 + 4] = hi.x; v[r * 8 + 5] = hi.y; v[r * 8 + 6] = hi.z; v[r * 8 + 7] = hi.w;
+                v[r * 4 + 0] = make_float2(lo.x, lo.y); v[r * 4 + 1] = make_float2(lo.z, lo.w);
+                v[r * 4 + 2] = make_float2(hi.x, hi.y); v[r * 4 + 3] = make_float2(hi.z, hi.w);
             }
-            dct8x8(v);
-            const bool boundary = quantize_pack(v, p.chroma, packed);
+            dct8x8_packed(v);
+            const bool boundary = quantize_pack_packed(v, p.chroma, packed);
             stage_block(sm.tile, m * kBlocksPerMcu + 4 + comp, packed);
             if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + 4 + comp);
         }
@@ -463,6 +568,17 @@ void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out)
         }
 }
 
+static void fill_quant_consts2(const uint8_t q[64], const double s[8], QuantConsts2* out) {
+    QuantConsts c;
+    fill_quant_consts(q, s, &c);
+    for (int u = 0; u < 8; ++u)
+        for (int qq = 0; qq < 4; ++qq) {
+            const int lo = (2 * qq) * 8 + u, hi = (2 * qq + 1) * 8 + u;
+            out->mul[u * 4 + qq] = make_float2(c.mul[lo], c.mul[hi]);
+            out->thr[u * 4 + qq] = make_float2(c.thr[lo], c.thr[hi]);
+        }
+}
+
 static void fill_exact(const jpgenc_ctx* c, const uint8_t* qy, const uint8_t* qc, double scale, ExactConsts* e) {
     e->a1 = c->dct_a[0]; e->a2 = c->dct_a[1]; e->a3 = c->dct_a[2]; e->a4 = c->dct_a[3]; e->a5 = c->dct_a[4];
     for (int i = 0; i < 8; ++i) e->s[i] = c->dct_s[i];
@@ -485,8 +601,8 @@ int launch_forward(jpgenc_ctx* c) {
         p.color.cb[i] = static_cast<float>(fcb[i] * scale / 4);
         p.color.cr[i] = static_cast<float>(fcr[i] * scale / 4);
     }
-    fill_quant_consts(c->qy, c->dct_s, &p.luma);
-    fill_quant_consts(c->qc, c->dct_s, &p.chroma);
+    fill_quant_consts2(c->qy, c->dct_s, &p.luma);
+    fill_quant_consts2(c->qc, c->dct_s, &p.chroma);
     ExactConsts e;
     fill_exact(c, c->qy, c->qc, scale, &e);
 
