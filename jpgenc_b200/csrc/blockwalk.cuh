@@ -1,5 +1,5 @@
-// Shared pieces of K2/K3: staging MCU-ordered coefficient tiles in shared memory and walking one block's
-// zigzag sequence as the reference's RLE_AC + encode_category do (include/Coding.hpp:148-183, 197-230, 265-283).
+// Shared pieces of K2/K3/K4: staging MCU-ordered coefficient tiles in shared memory, the symbol-item format, CTA scan
+// and decoupled look-back.
 #pragma once
 #include "common.cuh"
 
@@ -26,6 +26,7 @@ struct TileView {
     int16_t* dc;
 };
 constexpr int kTileSmemBytes = kTileBytes + kTileBlocks * 8 + kTileBlocks * 2;
+constexpr int kItemsPerBlockMax = 65;                  // DC + 63 AC + EOB can never coexist, 65 is a safe bound
 
 __device__ __forceinline__ TileView tile_view(uint8_t* smem) {
     return TileView{smem, smem + kTileBytes, reinterpret_cast<int16_t*>(smem + kTileBytes + kTileBlocks * 8)};
@@ -69,28 +70,19 @@ __device__ __forceinline__ int dc_predictor(const TileView& tv, const int16_t* _
 
 __device__ __forceinline__ int category_of(int v) { return 32 - __clz(abs(v)); }   // 0 for v == 0
 
-// Calls emit(symbol, value, key) for the DC entry (key 0) and every AC entry in zigzag order; `dc_diff` replaces
-// coefficient 0.  key orders the entries inside the block: 2p for a ZRL before position p, 2p+1 for the symbol of
-// position p, 129 for EOB.  Only non-zero coefficients cost loop iterations (the common block has a handful).
-template <class Emit>
-__device__ __forceinline__ void walk_block(const TileView& tv, int slot, int dc_diff, uint32_t lo, uint32_t hi, Emit&& emit) {
-    emit(category_of(dc_diff), dc_diff, 0);
-    int prev = 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        uint32_t m = half ? hi : lo;
-#pragma unroll 1
-        while (m) {
-            const int pos = half * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            int run = pos - prev - 1;
-            prev = pos;
-            const int v = slot_coef(tv, slot, pos);
-            while (run > 15) { emit(0xF0, 0, 2 * pos); run -= 16; }      // ZRL
-            emit((run << 4) | category_of(v), v, 2 * pos + 1);
-        }
-    }
-    if (prev != 63) emit(0x00, 0, 129);                                  // EOB
+// ---- symbol items ------------------------------------------------------------------------------------------
+// K2 turns every block into the reference's symbol sequence (include/Coding.hpp:148-183, 265-283) exactly once and
+// leaves it in HBM as a flat stream of 32-bit items in scan order (MCU order, zigzag order inside a block); K3 only
+// maps items to codes.  One item = one Huffman symbol with its magnitude bits, plus the ZRL symbols (0xF0) that
+// precede it:
+//   [7:0]   symbol: DC category, or (run << 4) | category, or 0x00 = EOB
+//   [9:8]   table id (0 Y_DC, 1 Y_AC, 2 C_DC, 3 C_AC)
+//   [11:10] number of ZRL symbols emitted before this symbol (0..3)
+//   [27:12] magnitude bits (category = symbol & 15 of them; value for v > 0, v - 1 truncated for v < 0, Coding.hpp:206-212)
+__device__ __forceinline__ uint32_t make_item(int table, int symbol, int nzrl, int value) {
+    const uint32_t cat = symbol & 15;
+    const uint32_t mag = static_cast<uint32_t>(value < 0 ? value - 1 : value) & ((1u << cat) - 1u);
+    return static_cast<uint32_t>(symbol) | (static_cast<uint32_t>(table) << 8) | (static_cast<uint32_t>(nzrl) << 10) | (mag << 12);
 }
 
 // ---- decoupled look-back over 64-bit status words: [63:62] state, [61:0] value ---------------------------

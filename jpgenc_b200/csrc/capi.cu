@@ -48,7 +48,7 @@ int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
     if (w == 0 || h == 0 || maxval == 0 || maxval > 255) return fail(c, JPGENC_ERR_ARG, "width/height/maxval out of range");
     c->real_w = w; c->real_h = h; c->maxval = maxval;
     c->mcu_w = (w + 15) / 16; c->mcu_h = (h + 15) / 16;        // src/Image.cpp:479-489
-    c->have_coef = c->have_scan = false;
+    c->have_coef = c->have_scan = c->have_items = false;
     return JPGENC_OK;
 }
 
@@ -120,6 +120,8 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     c->d_first = static_cast<unsigned long long*>(p);
     if ((e = cudaMalloc(&p, sizeof(DeviceTables))) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_tables = static_cast<DeviceTables*>(p);
+    if ((e = cudaMalloc(&p, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    c->d_item_cursor = static_cast<unsigned long long*>(p);
     c->pinned_bytes = 64 * 1024;
     if ((e = cudaMallocHost(&c->h_pinned, c->pinned_bytes)) != cudaSuccess) return bail("cudaMallocHost", e);
     *out = c;
@@ -133,6 +135,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_hist); cudaFree(c->d_first); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
+    cudaFree(c->d_items); cudaFree(c->d_tile_off); cudaFree(c->d_tile_cnt); cudaFree(c->d_item_cursor);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -210,7 +213,7 @@ int jpgenc_color_dct_quant(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     c->forward_pending = true;
     c->have_coef = true;
-    c->have_scan = false;
+    c->have_scan = c->have_items = false;
     return JPGENC_OK;
 }
 
@@ -239,7 +242,7 @@ int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_coef, coef, bytes, cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_coef = true;
-    c->have_scan = false;
+    c->have_scan = c->have_items = false;
     return JPGENC_OK;
 }
 
@@ -265,7 +268,7 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
     if (e != cudaSuccess) { c->error = cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
     if (rc) return rc;
     c->have_coef = true;
-    c->have_scan = false;
+    c->have_scan = c->have_items = false;
     return JPGENC_OK;
 }
 
@@ -273,9 +276,15 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     if (!c || !count || !first_pos) return JPGENC_ERR_ARG;
     if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
+    int rc;
+    // worst case one item per coefficient position plus DC/EOB; typical images use a few percent of it
+    if ((rc = ensure(c, &c->d_items, &c->items_cap, nblocks * 65 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_tile_off, &c->tile_off_cap, tiles * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, tiles * sizeof(uint32_t)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-    const int rc = launch_symbol_stats(c);
-    if (rc) return rc;
+    if ((rc = launch_symbol_stats(c))) return rc;
+    c->have_items = true;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
     JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096, cudaMemcpyDeviceToHost, c->stream));
@@ -296,6 +305,7 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
 int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t* scan_bytes) {
     if (!c || !tables) return JPGENC_ERR_ARG;
     if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
+    if (!c->have_items) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     // exact size of the scan from the statistics the tables were built from: every symbol costs its code length
     // plus (symbol & 15) magnitude bits.  The histogram still sits in d_hist from K2; recompute from a fresh copy.

@@ -99,6 +99,14 @@ struct jpgenc_ctx {
     uint32_t* d_counters = nullptr;       // [0] refine count, [1] lookback ticket, [2..3] spare
     uint32_t* d_hist = nullptr;           // [4][256]
     unsigned long long* d_first = nullptr;// [4][256]
+    uint32_t* d_items = nullptr;          // K2's symbol stream (blockwalk.cuh), consumed by K3
+    size_t items_cap = 0;
+    unsigned long long* d_tile_off = nullptr;   // per K2 tile: first item / number of items; [tiles] is followed by the cursor
+    size_t tile_off_cap = 0;
+    uint32_t* d_tile_cnt = nullptr;
+    size_t tile_cnt_cap = 0;
+    unsigned long long* d_item_cursor = nullptr;
+    bool have_items = false;
     jpgenc::DeviceTables* d_tables = nullptr;
     unsigned long long* d_lookback = nullptr;  // one status word per K3 tile
     size_t lookback_cap = 0;

@@ -3,11 +3,13 @@
 // Replaces Image::doHuffmanEncoding, the per-MCU Bitstream concatenation, Bitstream::fill() and the stuffing
 // operator<< (reference src/Image.cpp:737-829, 957-971; include/BitstreamGeneric.hpp:126-146, 182-195, 213-224, 242-248).
 //
-// K3 is one pass over the MCU-ordered coefficients: every thread sizes its block's code (DC code + magnitude bits,
-// AC codes + magnitude bits), the CTA scans the sizes, a decoupled look-back over per-tile status words turns the
-// CTA total into the tile's global bit offset, and the block codes are then assembled MSB-first in a shared-memory
-// bit buffer and written out as whole 32-bit words (only the two words a tile shares with its neighbours use
-// atomicOr).  Tiles take their index from an atomic ticket, so a tile only ever waits for tiles that already run.
+// K3 reads the symbol items K2 left in HBM (blockwalk.cuh), never the coefficients.  A tile is the item range of one
+// K2 tile (384 blocks, 64 MCUs).  Its items are dealt to the threads in equal consecutive shares, so every thread does
+// the same amount of work whatever the blocks look like: each thread sizes its share (code length + magnitude bits per
+// item), the CTA scans the sizes, a decoupled look-back over per-tile status words turns the CTA total into the
+// tile's global bit offset, and the codes are assembled MSB-first in a shared-memory bit buffer and written out as
+// whole 32-bit words (only the two words a tile shares with its neighbours use atomicOr).  Tiles take their index from
+// an atomic ticket, so a tile only ever waits for tiles that already run.
 // K4 has the same structure at byte granularity: count FF bytes, scan, look back, compact.
 #include "blockwalk.cuh"
 
@@ -48,8 +50,10 @@ struct BitWriter {
 };
 
 struct EntropyParams {
-    const int16_t* coef;
-    uint64_t nblocks;
+    const uint32_t* items;              // K2's symbol stream
+    const unsigned long long* tile_off; // [tiles] first item of tile
+    const uint32_t* tile_cnt;           // [tiles] items of tile
+    uint32_t ntiles;
     const DeviceTables* tables;
     unsigned long long* status;     // look-back words, zeroed before launch
     uint32_t* ticket;               // zeroed before launch
@@ -57,63 +61,67 @@ struct EntropyParams {
     unsigned long long* total_out;  // [0] = total bits written (before padding)
 };
 
+// code bits of one item: `nz` ZRL codes first, then the symbol's code with the magnitude bits appended
+// (src/Image.cpp:757-766: table[symbol] top `length` bits, then the category's bits)
 template <class Put>
-__device__ __forceinline__ void encode_block(const TileView& tv, int slot, int diff, uint32_t lo, uint32_t hi,
-                                             const uint32_t* tdc, const uint32_t* tac, Put&& put) {
-    walk_block(tv, slot, diff, lo, hi, [&](int sym, int value, int k) {
-        const uint32_t e = (k == 0 ? tdc : tac)[sym];
-        const uint32_t cat = sym & 15;                                            // magnitude bit count
-        const uint32_t mag = (value < 0 ? value - 1 : value) & ((1u << cat) - 1); // Coding.hpp:206-212
-        put(((e & 0xFFFFu) << cat) | mag, (e >> 16) + cat);
-    });
+__device__ __forceinline__ void item_codes(uint32_t item, const uint32_t* s_tab, Put&& put) {
+    const uint32_t* tab = s_tab + ((item >> 8) & 3u) * 256u;
+    const uint32_t nz = (item >> 10) & 3u;
+    if (nz) {
+        const uint32_t z = tab[0xF0];
+        for (uint32_t i = 0; i < nz; ++i) put(z & 0xFFFFu, z >> 16);
+    }
+    const uint32_t e = tab[item & 0xFFu], cat = item & 15u;
+    put(((e & 0xFFFFu) << cat) | (item >> 12), (e >> 16) + cat);
 }
 
-__global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const TileView tv = tile_view(smem);
-    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + kTileSmemBytes);              // [4][256]
-    uint32_t* s_bits = s_tab + 1024;                                                   // [kBitBufWords + 1]
-    uint32_t* s_scan = s_bits + kBitBufWords + 1;                                      // [33]
+__device__ __forceinline__ uint32_t item_bits(uint32_t item, const uint32_t* s_tab) {
+    const uint32_t* tab = s_tab + ((item >> 8) & 3u) * 256u;
+    return (tab[item & 0xFFu] >> 16) + (item & 15u) + ((item >> 10) & 3u) * (tab[0xF0] >> 16);
+}
+
+constexpr int kPackThreads = 256;
+
+__global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
+    __shared__ uint32_t s_tab[1024];                  // [4][256] (length << 16) | code
+    __shared__ uint32_t s_bits[kBitBufWords + 1];
+    __shared__ uint32_t s_scan[36];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
 
     if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
-    for (int i = tid; i < 1024; i += kTileBlocks) s_tab[i] = (&p.tables->entry[0][0])[i];
-    for (int i = tid; i <= kBitBufWords; i += kTileBlocks) s_bits[i] = 0;
+    for (int i = tid; i < 1024; i += kPackThreads) s_tab[i] = (&p.tables->entry[0][0])[i];
     __syncthreads();
     const uint32_t tile_idx = s_tile;
-    const uint64_t first = static_cast<uint64_t>(tile_idx) * kTileBlocks;
-    const int nb = static_cast<int>(umin64(kTileBlocks, p.nblocks - first));
-    stage_tile(tv, p.coef + first * kCoefPerBlock, nb, tid, kTileBlocks);
-    __syncthreads();
+    const uint32_t n = p.tile_cnt[tile_idx];
+    const uint32_t* __restrict__ items = p.items + p.tile_off[tile_idx];
+    // blocked arrangement: thread t owns items [t*per, t*per + per) so that it can merge their bits in registers
+    const uint32_t per = (n + kPackThreads - 1) / kPackThreads;
+    const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
 
-    int diff = 0;
-    uint32_t my_bits = 0, nz_lo = 0, nz_hi = 0;
-    const int k = tid % kBlocksPerMcu;
-    const uint32_t* tdc = s_tab + (k < 4 ? 0 : 512);
-    const uint32_t* tac = tdc + 256;
-    if (tid < nb) {
-        load_mask(tv, tid, nz_lo, nz_hi);
-        diff = tv.dc[tid] - dc_predictor(tv, p.coef, first, tid);
-        encode_block(tv, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t, uint32_t n) { my_bits += n; });
-    }
+    uint32_t my_bits = 0;
+    for (uint32_t i = i0; i < i1; ++i) my_bits += item_bits(__ldg(items + i), s_tab);
     uint32_t tile_bits;
     const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
-    const bool last_tile = first + nb == p.nblocks;
+    const bool last_tile = tile_idx + 1 == p.ntiles;
     const bool in_smem = tile_bits + 32 <= kBitBufWords * 32u;
 
     if (in_smem) {
+        const uint32_t zero_words = ((tile_bits + 31) >> 5) + 1;
+        for (uint32_t i = tid; i < zero_words; i += kPackThreads) s_bits[i] = 0;
+        __syncthreads();
         // The codes are assembled at tile-relative bit positions, so this does not wait for the look-back: the last
         // warp resolves the tile's global bit offset while the others are still packing.
-        if (tid >= kTileBlocks - 32) {
+        if (tid >= kPackThreads - 32) {
             const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
-            if (tid == kTileBlocks - 32) s_base = b;
+            if (tid == kPackThreads - 32) s_base = b;
         }
-        if (tid < nb) {
+        if (i0 < i1) {
             BitWriter<false> bw;
             bw.start(s_bits, local);
-            encode_block(tv, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            for (uint32_t i = i0; i < i1; ++i)
+                item_codes(__ldg(items + i), s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
             bw.finish();
         }
         __syncthreads();
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
         const uint32_t lead = static_cast<uint32_t>(base & 31);             // bits of the first word owned by earlier tiles
         const uint32_t nwords = (lead + tile_bits + 31) >> 5;
         uint32_t* g = p.raw + (base >> 5);
-        for (uint32_t i = tid; i < nwords; i += kTileBlocks) {
+        for (uint32_t i = tid; i < nwords; i += kPackThreads) {
             // global word i = tile-relative bits [32i - lead, 32i - lead + 32)
             const uint32_t v = __byte_perm(__funnelshift_r(s_bits[i], i ? s_bits[i - 1] : 0u, lead), 0, 0x0123);
             if (i == 0 || i == nwords - 1) { if (v) atomicOr(&g[i], v); }
@@ -133,10 +141,11 @@ __global__ void __launch_bounds__(kTileBlocks) huffman_pack_kernel(const __grid_
             if (tid == 0) s_base = b;
         }
         __syncthreads();
-        if (tid < nb) {
+        if (i0 < i1) {
             BitWriter<true> bw;
             bw.start(p.raw, s_base + local);
-            encode_block(tv, tid, diff, nz_lo, nz_hi, tdc, tac, [&](uint32_t code, uint32_t n) { bw.put(code, n); });
+            for (uint32_t i = i0; i < i1; ++i)
+                item_codes(__ldg(items + i), s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
             bw.finish();
         }
     }
@@ -214,16 +223,16 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, c->raw_cap, c->stream));
 
     EntropyParams p{};
-    p.coef = c->d_coef;
-    p.nblocks = nblocks;
+    p.items = c->d_items;
+    p.tile_off = c->d_tile_off;
+    p.tile_cnt = c->d_tile_cnt;
+    p.ntiles = tiles3;
     p.tables = c->d_tables;
     p.status = st3;
     p.ticket = c->d_counters + 1;
     p.raw = c->d_raw;
     p.total_out = totals;
-    const size_t smem = kTileSmemBytes + 4096 + (kBitBufWords + 1) * 4 + 33 * 4 + 16;
-    JPGENC_CUDA(c, cudaFuncSetAttribute(huffman_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    huffman_pack_kernel<<<tiles3, kTileBlocks, smem, c->stream>>>(p);
+    huffman_pack_kernel<<<tiles3, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     if (tiles4) {
         stuff_kernel<<<tiles4, kStuffThreads, 0, c->stream>>>(reinterpret_cast<const uint8_t*>(c->d_raw), nbytes, c->d_scan,
