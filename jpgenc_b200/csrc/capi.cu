@@ -330,7 +330,7 @@ int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint
     int rc;
     if ((rc = ensure(c, &c->d_raw, &c->raw_cap, ((nbytes + 15) & ~15ull) + 64))) return rc;
     if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * nbytes + 64))) return rc;
-    const size_t tiles = (nblocks + 383) / 384 + (nbytes + 4095) / 4096 + 8;
+    const size_t tiles = (nblocks + 383) / 384 + (nbytes + 4095) / 4096 + 16;      // upper bound on K3 + K4 tiles + totals
     size_t lb_bytes = c->lookback_cap;
     if ((rc = ensure(c, &c->d_lookback, &lb_bytes, tiles * sizeof(unsigned long long)))) return rc;
     c->lookback_cap = lb_bytes;
@@ -339,9 +339,8 @@ int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint
     if ((rc = launch_entropy(c, total_bits))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     // totals: [0] bits written by K3, [1] number of stuffed FF bytes
-    const size_t tiles3 = (nblocks + 383) / 384, tiles4 = (nbytes + 4095) / 4096;
     unsigned long long* totals = reinterpret_cast<unsigned long long*>(h);
-    JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback + tiles3 + tiles4, 16, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback, 16, cudaMemcpyDeviceToHost, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     if (totals[0] != total_bits) {
         c->error = "entropy coder wrote " + std::to_string(totals[0]) + " bits, statistics predicted " + std::to_string(total_bits);

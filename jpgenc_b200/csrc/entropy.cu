@@ -15,7 +15,7 @@
 
 namespace jpgenc {
 
-constexpr int kBitBufWords = 4096;                      // 16 KB of bits per tile before falling back to global atomics
+constexpr int kBitBufWords = 8192;                      // 32 KB of bits per tile before falling back to global atomics
 
 // MSB-first bit writer into 32-bit words ("word bit 31 is the earliest bit"); words are byte-swapped when they go
 // to memory so that memory byte order is stream order.
@@ -53,7 +53,8 @@ struct EntropyParams {
     const uint32_t* items;              // K2's symbol stream
     const unsigned long long* tile_off; // [tiles] first item of tile
     const uint32_t* tile_cnt;           // [tiles] items of tile
-    uint32_t ntiles;
+    uint32_t nranges;                   // number of K2 tiles
+    uint32_t ntiles;                    // number of K3 tiles = ceil(nranges / kPackGroup)
     const DeviceTables* tables;
     unsigned long long* status;     // look-back words, zeroed before launch
     uint32_t* ticket;               // zeroed before launch
@@ -81,6 +82,28 @@ __device__ __forceinline__ uint32_t item_bits(uint32_t item, const uint32_t* s_t
 }
 
 constexpr int kPackThreads = 256;
+constexpr int kPackGroup = 4;                          // K2 tiles (item ranges) per K3 tile
+
+// The items of a K3 tile are kPackGroup separate ranges of the item stream (K2 tiles claim their ranges in completion
+// order).  for_items walks the slice [i0, i1) of their concatenation.
+template <class F>
+__device__ __forceinline__ void for_items(const uint32_t* __restrict__ items, const unsigned long long* s_off, const uint32_t* s_cum,
+                                          uint32_t i0, uint32_t i1, F&& f) {
+    int g = 0;
+    while (g + 1 < kPackGroup && s_cum[g + 1] <= i0) ++g;
+    for (uint32_t i = i0; i < i1; ++g) {
+        const uint32_t end = min(i1, s_cum[g + 1]);
+        const uint32_t* __restrict__ ptr = items + s_off[g] + (i - s_cum[g]);
+        const uint32_t n = end - i;
+        uint32_t j = 0;
+        for (; j + 4 <= n; j += 4) {                    // four independent loads in flight
+            const uint32_t a = __ldg(ptr + j), b = __ldg(ptr + j + 1), c = __ldg(ptr + j + 2), d = __ldg(ptr + j + 3);
+            f(a); f(b); f(c); f(d);
+        }
+        for (; j < n; ++j) f(__ldg(ptr + j));
+        i = end;
+    }
+}
 
 __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
     __shared__ uint32_t s_tab[1024];                  // [4][256] (length << 16) | code
@@ -88,20 +111,33 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     __shared__ uint32_t s_scan[36];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_off[kPackGroup];
+    __shared__ uint32_t s_cum[kPackGroup + 1];
     const int tid = threadIdx.x;
 
-    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+    if (tid == 0) {
+        const uint32_t t = atomicAdd(p.ticket, 1u);
+        s_tile = t;
+        uint32_t cum = 0;
+        for (int g = 0; g < kPackGroup; ++g) {
+            const uint32_t k2 = t * kPackGroup + g;
+            s_cum[g] = cum;
+            s_off[g] = k2 < p.nranges ? p.tile_off[k2] : 0ull;
+            cum += k2 < p.nranges ? p.tile_cnt[k2] : 0u;
+        }
+        s_cum[kPackGroup] = cum;
+    }
     for (int i = tid; i < 1024; i += kPackThreads) s_tab[i] = (&p.tables->entry[0][0])[i];
     __syncthreads();
     const uint32_t tile_idx = s_tile;
-    const uint32_t n = p.tile_cnt[tile_idx];
-    const uint32_t* __restrict__ items = p.items + p.tile_off[tile_idx];
+    const uint32_t n = s_cum[kPackGroup];
+    const uint32_t* __restrict__ items = p.items;
     // blocked arrangement: thread t owns items [t*per, t*per + per) so that it can merge their bits in registers
     const uint32_t per = (n + kPackThreads - 1) / kPackThreads;
     const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
 
     uint32_t my_bits = 0;
-    for (uint32_t i = i0; i < i1; ++i) my_bits += item_bits(__ldg(items + i), s_tab);
+    for_items(items, s_off, s_cum, i0, i1, [&](uint32_t item) { my_bits += item_bits(item, s_tab); });
     uint32_t tile_bits;
     const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
     const bool last_tile = tile_idx + 1 == p.ntiles;
@@ -120,8 +156,9 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
         if (i0 < i1) {
             BitWriter<false> bw;
             bw.start(s_bits, local);
-            for (uint32_t i = i0; i < i1; ++i)
-                item_codes(__ldg(items + i), s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+            for_items(items, s_off, s_cum, i0, i1, [&](uint32_t item) {
+                item_codes(item, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+            });
             bw.finish();
         }
         __syncthreads();
@@ -144,8 +181,9 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
         if (i0 < i1) {
             BitWriter<true> bw;
             bw.start(p.raw, s_base + local);
-            for (uint32_t i = i0; i < i1; ++i)
-                item_codes(__ldg(items + i), s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+            for_items(items, s_off, s_cum, i0, i1, [&](uint32_t item) {
+                item_codes(item, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+            });
             bw.finish();
         }
     }
@@ -164,7 +202,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------------------
-constexpr int kStuffThreads = 256;
+constexpr int kStuffThreads = 1024;
 constexpr int kStuffBytesPerThread = 16;
 constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
 
@@ -212,12 +250,13 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __r
 int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
     const uint64_t nbytes = (total_bits + 7) / 8;
-    const uint32_t tiles3 = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    const uint32_t ranges = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    const uint32_t tiles3 = (ranges + kPackGroup - 1) / kPackGroup;
     const uint32_t tiles4 = static_cast<uint32_t>((nbytes + kStuffTile - 1) / kStuffTile);
-    // status words: [0, tiles3) K3, [tiles3, tiles3+tiles4) K4, then 2 totals
-    unsigned long long* st3 = c->d_lookback;
-    unsigned long long* st4 = c->d_lookback + tiles3;
-    unsigned long long* totals = c->d_lookback + tiles3 + tiles4;
+    // status words: [0,1] totals (bits written by K3, FF bytes stuffed by K4), then K3's tiles, then K4's
+    unsigned long long* totals = c->d_lookback;
+    unsigned long long* st3 = c->d_lookback + 2;
+    unsigned long long* st4 = st3 + tiles3;
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, (static_cast<size_t>(tiles3) + tiles4 + 2) * sizeof(unsigned long long), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters + 1, 0, 2 * sizeof(uint32_t), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, c->raw_cap, c->stream));
@@ -226,6 +265,7 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     p.items = c->d_items;
     p.tile_off = c->d_tile_off;
     p.tile_cnt = c->d_tile_cnt;
+    p.nranges = ranges;
     p.ntiles = tiles3;
     p.tables = c->d_tables;
     p.status = st3;

@@ -12,9 +12,10 @@
 // Work distribution.  Blocks hold very different numbers of non-zero coefficients, so "one thread walks one block"
 // diverges badly.  Instead a tile of 384 blocks is flattened: every thread sizes its block with a popcount of the
 // block's 64-bit non-zero mask, a CTA scan gives each block its first item index, the threads expand their masks into
-// 16-bit (block, position) descriptors, and then consecutive lanes process consecutive ITEMS: the run length of an
-// item comes from the mask with one CLZ (distance to the previous set bit), so no lane ever loops over zeros and the
-// item stores are coalesced.
+// 16-bit (block, position) descriptors, and then consecutive lanes process consecutive non-zero COEFFICIENTS: the run
+// length comes from the mask with one CLZ (distance to the previous set bit), so no lane ever loops over zeros, the
+// work per lane is equal whatever the blocks look like, and the item stores are coalesced.  The DC and EOB symbols
+// exist exactly once (at most once) per block and stay with the block's own thread.
 #include "blockwalk.cuh"
 
 namespace jpgenc {
@@ -37,22 +38,18 @@ struct StatsParams {
 // One histogram update for the whole warp: lanes with the same bin are counted by their lowest lane, so the hot
 // symbols (EOB, +-1 coefficients, the common DC category) cost one shared-memory atomic instead of up to 32.
 __device__ __forceinline__ void warp_count(uint32_t* s_hist, unsigned long long* s_first, bool has, int idx,
-                                           unsigned long long key, uint32_t weight = 1) {
+                                           unsigned long long key) {
     const int lane = threadIdx.x & 31;
     const unsigned grp = __match_any_sync(0xffffffffu, has ? idx : (0x10000 | lane));
     if (has) {
-        if (weight == 1) {
-            if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[idx], static_cast<uint32_t>(__popc(grp)));
-        } else {
-            atomicAdd(&s_hist[idx], weight);
-        }
+        if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[idx], static_cast<uint32_t>(__popc(grp)));
         if (key < s_first[idx]) atomicMin(&s_first[idx], key);
     }
 }
 
 constexpr int kStatsSmem = kTileSmemBytes                // tile + masks + dc
-                           + kTileBlocks * 2             // dc difference
                            + kTileBlocks * 8             // text key of the block
+                           + kTileBlocks * 4             // first item / first AC descriptor of the block
                            + kDescCap * 2                // descriptors
                            + 4096 + 8192                 // histogram, first-occurrence keys
                            + 36 * 4;                     // scan scratch
@@ -61,15 +58,15 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_
     extern __shared__ __align__(128) uint8_t smem[];
     const TileView tv = tile_view(smem);
     uint8_t* at = smem + kTileSmemBytes;
-    int16_t* s_diff = reinterpret_cast<int16_t*>(at);                         at += kTileBlocks * 2;
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(at);    at += kTileBlocks * 8;
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(at);                       at += kTileBlocks * 4;
     uint16_t* s_desc = reinterpret_cast<uint16_t*>(at);                       at += kDescCap * 2;
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(at);                       at += 4096;
     unsigned long long* s_first = reinterpret_cast<unsigned long long*>(at);  at += 8192;
     uint32_t* s_scan = reinterpret_cast<uint32_t*>(at);
     __shared__ unsigned long long s_off;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t first = blockIdx.x * kTileBlocks;
     const int nb = static_cast<int>(min(static_cast<uint32_t>(kTileBlocks), p.nblocks - first));
 
@@ -79,19 +76,30 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_
     stage_tile(tv, p.coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
 
-    // ---- per block: item count, DC difference, text key ----
-    uint32_t lo = 0, hi = 0, count = 0;
-    if (tid < nb) {
+    // ---- per block: mask, DC difference, text key, item counts ----
+    const bool live = tid < nb;
+    const int k = tid % kBlocksPerMcu;                                    // tiles start on an MCU boundary
+    const int tdc = k < 4 ? 0 : 2;
+    uint32_t lo = 0, hi = 0, nac = 0, eob = 0;
+    int diff = 0;
+    unsigned long long key = 0;
+    if (live) {
         load_mask(tv, tid, lo, hi);
-        s_diff[tid] = static_cast<int16_t>(tv.dc[tid] - dc_predictor(tv, p.coef, first, tid));
-        count = 1u + __popc(lo) + __popc(hi) + ((hi >> 31) ? 0u : 1u);        // DC + non-zero ACs + EOB unless coefficient 63 != 0
-        const uint32_t g = first + tid, mcu = g / kBlocksPerMcu, k = g - mcu * kBlocksPerMcu;
+        diff = tv.dc[tid] - dc_predictor(tv, p.coef, first, tid);
+        nac = __popc(lo) + __popc(hi);
+        eob = (hi >> 31) ? 0u : 1u;                                       // no EOB when coefficient 63 is non-zero
+        const uint32_t mcu = (first + tid) / kBlocksPerMcu;
         const uint32_t my = mcu / p.mcu_w, mx = mcu - my * p.mcu_w;
-        s_key[tid] = 256ull * (k < 4 ? static_cast<unsigned long long>(my * 2 + (k >> 1)) * (2ull * p.mcu_w) + mx * 2 + (k & 1)
-                                     : static_cast<unsigned long long>(k - 4) * p.n_mcu + mcu);
+        key = 256ull * (k < 4 ? static_cast<unsigned long long>(my * 2 + (k >> 1)) * (2ull * p.mcu_w) + mx * 2 + (k & 1)
+                              : static_cast<unsigned long long>(k - 4) * p.n_mcu + mcu);
+        s_key[tid] = key;
     }
-    uint32_t total;
-    const uint32_t base = block_exclusive_scan(count, s_scan, &total);
+    // one scan for both prefix sums: items (DC + ACs + EOB) in the low half, AC descriptors in the high half
+    const uint32_t count = live ? 1u + nac + eob : 0u;
+    uint32_t totals;
+    const uint32_t base2 = block_exclusive_scan(count | (nac << 16), s_scan, &totals);
+    const uint32_t base = base2 & 0xFFFFu, total = totals & 0xFFFFu, total_ac = totals >> 16;
+    s_base[tid] = base2;
     if (tid == 0) {
         s_off = atomicAdd(p.cursor, static_cast<unsigned long long>(total));
         p.tile_cnt[blockIdx.x] = total;
@@ -101,12 +109,29 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_
     if (tid == 0) p.tile_off[blockIdx.x] = off;
     uint32_t* __restrict__ out = p.items + off;
 
-    for (uint32_t win = 0; win < total; win += kDescCap) {
-        // ---- expand: descriptors (block << 7 | position) of the items in [win, win + kDescCap); position 0 = DC, 64 = EOB
-        if (tid < nb && base < win + kDescCap && base + count > win) {
-            uint32_t g = base;
-            if (g >= win) s_desc[g - win] = static_cast<uint16_t>(tid << 7);
-            ++g;
+    // ---- DC and EOB: exactly one (at most one) per block, so the block's own thread handles them ----
+    const int dcat = category_of(diff);
+    if (live) {
+        out[base] = make_item(tdc, dcat, 0, diff);
+        if (eob) out[base + count - 1] = make_item(tdc + 1, 0, 0, 0);
+    }
+    warp_count(s_hist, s_first, live, tdc * 256 + dcat, key);
+    {
+        const unsigned by = __ballot_sync(0xffffffffu, eob && k < 4), bc = __ballot_sync(0xffffffffu, eob && k >= 4);
+        if (lane == 0) {
+            if (by) atomicAdd(&s_hist[256], static_cast<uint32_t>(__popc(by)));
+            if (bc) atomicAdd(&s_hist[768], static_cast<uint32_t>(__popc(bc)));
+        }
+        const int ti = (tdc + 1) * 256;
+        if (eob && key + 129 < s_first[ti]) atomicMin(&s_first[ti], key + 129);
+    }
+
+    // ---- AC coefficients, flattened ----
+    const uint32_t base_ac = base2 >> 16;
+    for (uint32_t win = 0; win < total_ac; win += kDescCap) {
+        // expand: descriptor (block << 6 | position) of every non-zero AC coefficient in [win, win + kDescCap)
+        if (live && base_ac < win + kDescCap && base_ac + nac > win) {
+            uint32_t g = base_ac - win;                                   // wraps to a huge value while g is before the window
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 uint32_t m = half ? hi : lo;
@@ -114,61 +139,50 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_
                 while (m) {
                     const int pos = half * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    if (g - win < kDescCap) s_desc[g - win] = static_cast<uint16_t>((tid << 7) | pos);     // g < win wraps to a huge value
+                    if (g < kDescCap) s_desc[g] = static_cast<uint16_t>((tid << 6) | pos);
                     ++g;
                 }
             }
-            if (!(hi >> 31) && g - win < kDescCap) s_desc[g - win] = static_cast<uint16_t>((tid << 7) | 64);
         }
         __syncthreads();
-        // ---- flat: consecutive lanes take consecutive items ----
-        const uint32_t n = min(static_cast<uint32_t>(kDescCap), total - win);
+        // consecutive lanes take consecutive coefficients; the run length is the distance to the previous set mask bit
+        const uint32_t n = min(static_cast<uint32_t>(kDescCap), total_ac - win);
         for (uint32_t j0 = 0; j0 < n; j0 += kTileBlocks) {              // uniform trip count: warp_count is a warp-wide operation
             const uint32_t j = j0 + tid;
-            const bool live = j < n;
-            int idx = 0, value = 0, nzrl = 0, table = 0, symbol = 0;
-            unsigned long long key = 0;
-            if (live) {
-                const uint32_t d = s_desc[j], b = d >> 7, pos = d & 127;
-                const int k = static_cast<int>(b % kBlocksPerMcu);          // tiles start on an MCU boundary
-                const int tdc = k < 4 ? 0 : 2;
-                key = s_key[b];
-                if (pos == 0) {
-                    value = s_diff[b];
-                    symbol = category_of(value);
-                    table = tdc;
-                } else if (pos == 64) {
-                    table = tdc + 1;
-                    key += 129;
-                } else {
-                    uint32_t mlo, mhi;
-                    load_mask(tv, b, mlo, mhi);
-                    const unsigned long long below = ((static_cast<unsigned long long>(mhi) << 32) | mlo) & ((1ull << pos) - 1ull);
-                    const int prev = below ? 63 - __clzll(static_cast<long long>(below)) : 0;
-                    int run = static_cast<int>(pos) - prev - 1;
-                    nzrl = run >> 4;
-                    run &= 15;
-                    value = slot_coef(tv, b, pos);
-                    symbol = (run << 4) | category_of(value);
-                    table = tdc + 1;
-                    key += 2 * pos + 1;
-                }
+            const bool has = j < n;
+            int idx = 0, nzrl = 0, table = 0;
+            unsigned long long ikey = 0;
+            if (has) {
+                const uint32_t d = s_desc[j], b = d >> 6, pos = d & 63;
+                uint32_t mlo, mhi;
+                load_mask(tv, b, mlo, mhi);
+                const unsigned long long below = ((static_cast<unsigned long long>(mhi) << 32) | mlo) & ((1ull << pos) - 1ull);
+                const int prev = 63 - __clzll(static_cast<long long>(below | 1ull));        // bit 0 stands for the DC position
+                int run = static_cast<int>(pos) - prev - 1;
+                nzrl = run >> 4;
+                run &= 15;
+                const int value = slot_coef(tv, b, pos);
+                const int symbol = (run << 4) | category_of(value);
+                table = ((b % kBlocksPerMcu) < 4 ? 0 : 2) + 1;
                 idx = table * 256 + symbol;
-                out[win + j] = make_item(table, symbol, nzrl, value);
+                ikey = s_key[b] + 2 * pos + 1;
+                const uint32_t sb = s_base[b];
+                out[(sb & 0xFFFFu) + 1u + (win + j - (sb >> 16))] = make_item(table, symbol, nzrl, value);
             }
-            warp_count(s_hist, s_first, live, idx, key);
+            warp_count(s_hist, s_first, has, idx, ikey);
             if (__any_sync(0xffffffffu, nzrl != 0)) {                   // ZRLs (runs of 16 zeros) are rare
                 if (nzrl) {
                     const int zi = table * 256 + 0xF0;
                     atomicAdd(&s_hist[zi], static_cast<uint32_t>(nzrl));
-                    const unsigned long long kz = key - 1;               // 2*pos: just before the symbol of position pos
+                    const unsigned long long kz = ikey - 1;              // 2*pos: just before the symbol of position pos
                     if (kz < s_first[zi]) atomicMin(&s_first[zi], kz);
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();                                                // s_desc is reused by the next window
     }
 
+    __syncthreads();                                                    // all shared-memory histogram updates are in
     for (int i = tid; i < 1024; i += kTileBlocks) {
         const uint32_t n = s_hist[i];
         if (n) {
