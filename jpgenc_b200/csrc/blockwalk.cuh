@@ -6,7 +6,6 @@
 namespace jpgenc {
 
 constexpr int kTileBlocks = 384;                       // 64 MCUs; one thread per block
-constexpr int kTileBytes = kTileBlocks * kBlockBytes;  // 48 KB
 
 // 8-bit non-zero flags of one 16-byte chunk (bit j = coefficient j of the chunk != 0).  Branch-free: VIMNMX.U16x2
 // turns every halfword into a 0/1 flag.
@@ -16,34 +15,45 @@ __device__ __forceinline__ uint32_t chunk_flags(const uint4& q) {
     return (f | (f >> 15)) & 0xFFu;                 // even bits: low halfwords, odd bits: high halfwords
 }
 
-// Shared-memory view of a tile of MCU-ordered blocks:
-//   tile   48 KB  coefficient chunks; slot s keeps chunk c at chunk (c ^ (s & 7)); ALL-ZERO CHUNKS ARE NOT WRITTEN
-//   flags  3 KB   one byte per chunk = chunk_flags(); 8 bytes per slot = the block's 64-bit non-zero mask
-//   dc     768 B  the block's DC coefficient
+// Per-tile summary of the coefficient blocks a CTA works on, in shared memory:
+//   flags  one byte per 16-byte chunk = chunk_flags(); 8 bytes per block = the block's 64-bit non-zero mask over the
+//          zigzag positions (bit 0, the DC position, is cleared: it is not an AC coefficient)
+//   dc     the block's DC coefficient
+// The coefficients themselves are not kept: the few non-zero ones are re-read through L1/L2 when their items are built.
 struct TileView {
-    uint8_t* tile;
     uint8_t* flags;
     int16_t* dc;
 };
-constexpr int kTileSmemBytes = kTileBytes + kTileBlocks * 8 + kTileBlocks * 2;
+constexpr int kTileSmemBytes = kTileBlocks * 8 + kTileBlocks * 2;
 constexpr int kItemsPerBlockMax = 65;                  // DC + 63 AC + EOB can never coexist, 65 is a safe bound
 
 __device__ __forceinline__ TileView tile_view(uint8_t* smem) {
-    return TileView{smem, smem + kTileBytes, reinterpret_cast<int16_t*>(smem + kTileBytes + kTileBlocks * 8)};
+    return TileView{smem, reinterpret_cast<int16_t*>(smem + kTileBlocks * 8)};
 }
 
-// Coalesced pass over `nb` blocks of global memory: every thread takes 16-byte chunks, derives the chunk's non-zero
-// flags while the data is in registers, and stores only chunks that contain something.
-__device__ __forceinline__ void stage_tile(const TileView& tv, const int16_t* __restrict__ gsrc, int nb, int tid, int nthreads) {
+// Coalesced pass over `nb` blocks of global memory: every thread takes 16-byte chunks (four loads in flight) and
+// reduces each to its non-zero flags while the data is in registers.
+__device__ __forceinline__ void scan_tile(const TileView& tv, const int16_t* __restrict__ gsrc, int nb, int tid, int nthreads) {
     const uint4* g = reinterpret_cast<const uint4*>(gsrc);
     const int chunks = nb * 8;
-    for (int j = tid; j < chunks; j += nthreads) {
-        const int s = j >> 3, c = j & 7;
-        const uint4 q = __ldg(g + j);
-        const uint32_t f = chunk_flags(q);
-        tv.flags[j] = static_cast<uint8_t>(c == 0 ? (f & 0xFEu) : f);       // the DC position is not an AC coefficient
-        if (c == 0) tv.dc[s] = static_cast<int16_t>(q.x & 0xFFFFu);
-        if (f) *reinterpret_cast<uint4*>(tv.tile + s * kBlockBytes + ((c ^ (s & 7)) << 4)) = q;
+    constexpr int kInFlight = 4;
+    for (int j0 = 0; j0 < chunks; j0 += kInFlight * nthreads) {
+        uint4 q[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int j = j0 + u * nthreads + tid;
+            q[u] = j < chunks ? __ldg(g + j) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int j = j0 + u * nthreads + tid;
+            if (j < chunks) {
+                const uint32_t f = chunk_flags(q[u]);
+                const bool head = (j & 7) == 0;
+                tv.flags[j] = static_cast<uint8_t>(head ? (f & 0xFEu) : f);
+                if (head) tv.dc[j >> 3] = static_cast<int16_t>(q[u].x & 0xFFFFu);
+            }
+        }
     }
 }
 
@@ -51,10 +61,6 @@ __device__ __forceinline__ void load_mask(const TileView& tv, int slot, uint32_t
     const uint2 m = *reinterpret_cast<const uint2*>(tv.flags + slot * 8);
     lo = m.x;
     hi = m.y;
-}
-
-__device__ __forceinline__ int slot_coef(const TileView& tv, int slot, int pos) {
-    return *reinterpret_cast<const int16_t*>(tv.tile + slot * kBlockBytes + ((((pos >> 3) ^ slot) & 7) << 4) + ((pos & 7) << 1));
 }
 
 // DC predictor of block `t` of a tile that starts at global block `first` (a multiple of 6):

@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------------------
+// FF -> FF 00 (BitstreamGeneric.hpp:213-224).  A tile is 16 KB of the raw scan.  Every thread counts the FF bytes of its
+// 16 input bytes (SIMD byte compare), a CTA scan + look-back give the output position, the tile's output is assembled
+// in shared memory (word stores; byte stores only at a thread's unaligned ends or where an FF actually occurs) and
+// leaves as coalesced 32-bit stores, funnel-shifted to the alignment of the global position.
 constexpr int kStuffThreads = 1024;
 constexpr int kStuffBytesPerThread = 16;
 constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
@@ -209,6 +213,7 @@ constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
 __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __restrict__ raw, uint64_t nbytes,
                                                               uint8_t* __restrict__ out, unsigned long long* status,
                                                               uint32_t* ticket, unsigned long long* total_ff) {
+    __shared__ alignas(16) uint8_t s_out[2 * kStuffTile + 16];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
@@ -216,35 +221,72 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __r
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t at = static_cast<uint64_t>(tile) * kStuffTile + static_cast<uint64_t>(tid) * kStuffBytesPerThread;
+    const uint64_t tile_at = static_cast<uint64_t>(tile) * kStuffTile;
+    const uint64_t at = tile_at + static_cast<uint64_t>(tid) * kStuffBytesPerThread;
     uint4 q = make_uint4(0, 0, 0, 0);
     int n = 0;
     if (at < nbytes) {
         n = static_cast<int>(umin64(kStuffBytesPerThread, nbytes - at));
         q = *reinterpret_cast<const uint4*>(raw + at);         // raw is padded to a multiple of 16 bytes and zero-filled
     }
-    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-    uint32_t ff = 0;
+    uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+    if (n < 16) {                                              // bytes past the end of the scan are not FF candidates
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-        if (j < n && ((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 0xFFu) ++ff;
+        for (int j = 0; j < 16; ++j)
+            if (j >= n) wv[j >> 2] &= ~(0xFFu << (8 * (j & 3)));
+    }
+    const uint32_t ff = (__popc(__vcmpeq4(wv[0], 0xFFFFFFFFu)) + __popc(__vcmpeq4(wv[1], 0xFFFFFFFFu)) +
+                         __popc(__vcmpeq4(wv[2], 0xFFFFFFFFu)) + __popc(__vcmpeq4(wv[3], 0xFFFFFFFFu))) >> 3;
     uint32_t tile_ff;
     const uint32_t local = block_exclusive_scan(ff, s_scan, &tile_ff);
-    if (tid < 32) {
+    if (tid >= kStuffThreads - 32) {                           // the last warp resolves the global position meanwhile
         const unsigned long long b = lookback_exclusive(status, tile, tile_ff);
-        if (tid == 0) s_base = b;
+        if (tid == kStuffThreads - 32) s_base = b;
     }
-    __syncthreads();
-    uint8_t* o = out + at + s_base + local;
+    // ---- assemble the tile's output at tile-relative positions ----
+    uint32_t o = tid * kStuffBytesPerThread + local;
+    if (ff == 0 && n == 16) {
+        const uint32_t lead = (4u - (o & 3u)) & 3u;            // bytes up to the next word boundary
+        if (lead == 0) {
+            *reinterpret_cast<uint32_t*>(s_out + o) = wv[0];
+            *reinterpret_cast<uint32_t*>(s_out + o + 4) = wv[1];
+            *reinterpret_cast<uint32_t*>(s_out + o + 8) = wv[2];
+            *reinterpret_cast<uint32_t*>(s_out + o + 12) = wv[3];
+        } else {
+            for (uint32_t j = 0; j < lead; ++j) s_out[o + j] = static_cast<uint8_t>(wv[0] >> (8 * j));
+            const uint32_t sh = 8 * lead;
+            uint32_t* w = reinterpret_cast<uint32_t*>(s_out + o + lead);
+            w[0] = __funnelshift_r(wv[0], wv[1], sh);
+            w[1] = __funnelshift_r(wv[1], wv[2], sh);
+            w[2] = __funnelshift_r(wv[2], wv[3], sh);
+            for (uint32_t j = 0; j < 4u - lead; ++j) s_out[o + lead + 12 + j] = static_cast<uint8_t>(wv[3] >> (sh + 8 * j));
+        }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        if (j < n) {
-            const uint8_t b = static_cast<uint8_t>((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu);
-            *o++ = b;
-            if (b == 0xFF) *o++ = 0;
+        for (int j = 0; j < 16; ++j) {
+            if (j < n) {
+                const uint8_t b = static_cast<uint8_t>((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                s_out[o++] = b;
+                if (b == 0xFF) s_out[o++] = 0;
+            }
         }
     }
-    if (tid == 0 && static_cast<uint64_t>(tile + 1) * kStuffTile >= nbytes) total_ff[0] = s_base + tile_ff;
+    __syncthreads();
+    // ---- copy out: global word w holds tile-relative bytes [4w - sh, 4w - sh + 4) ----
+    const uint32_t in_tile = static_cast<uint32_t>(umin64(kStuffTile, nbytes - tile_at));
+    const uint32_t len = in_tile + tile_ff;
+    uint8_t* g = out + tile_at + s_base;
+    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 3u);
+    const uint32_t head = min(len, (4u - sh) & 3u);            // bytes before the first aligned global word
+    const uint32_t nwords = (len - head) >> 2;
+    if (tid < head) g[tid] = s_out[tid];
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_out);
+    uint32_t* gw = reinterpret_cast<uint32_t*>(g + head);
+    for (uint32_t w = tid; w < nwords; w += kStuffThreads)
+        gw[w] = head ? __funnelshift_r(sw[w], sw[w + 1], 8 * head) : sw[w];
+    const uint32_t tail0 = head + 4 * nwords;
+    if (tid < len - tail0) g[tail0 + tid] = s_out[tail0 + tid];
+    if (tid == 0 && tile_at + kStuffTile >= nbytes) total_ff[0] = s_base + tile_ff;
 }
 
 int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {

@@ -47,14 +47,14 @@ __device__ __forceinline__ void warp_count(uint32_t* s_hist, unsigned long long*
     }
 }
 
-constexpr int kStatsSmem = kTileSmemBytes                // tile + masks + dc
+constexpr int kStatsSmem = kTileSmemBytes                // masks + dc
                            + kTileBlocks * 8             // text key of the block
                            + kTileBlocks * 4             // first item / first AC descriptor of the block
                            + kDescCap * 2                // descriptors
                            + 4096 + 8192                 // histogram, first-occurrence keys
                            + 36 * 4;                     // scan scratch
 
-__global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_constant__ StatsParams p) {
+__global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __grid_constant__ StatsParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const TileView tv = tile_view(smem);
     uint8_t* at = smem + kTileSmemBytes;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_
     // the global minima seen so far bound what this tile can still contribute: after the first tiles almost no
     // key is smaller, so the shared-memory atomicMin below is rarely executed
     for (int i = tid; i < 1024; i += kTileBlocks) { s_hist[i] = 0; s_first[i] = __ldcg(&p.g_first[i]); }
-    stage_tile(tv, p.coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
+    scan_tile(tv, p.coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
 
     // ---- per block: mask, DC difference, text key, item counts ----
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kTileBlocks) symbol_stats_kernel(const __grid_
                 int run = static_cast<int>(pos) - prev - 1;
                 nzrl = run >> 4;
                 run &= 15;
-                const int value = slot_coef(tv, b, pos);
+                const int value = p.coef[static_cast<size_t>(first + b) * kCoefPerBlock + pos];     // L1/L2 hit: the tile was just read
                 const int symbol = (run << 4) | category_of(value);
                 table = ((b % kBlocksPerMcu) < 4 ? 0 : 2) + 1;
                 idx = table * 256 + symbol;
