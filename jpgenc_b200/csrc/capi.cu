@@ -293,6 +293,7 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     std::memcpy(count, h, 4096);
     std::memcpy(first_pos, h + 4096, 8192);
+    std::memcpy(c->host_hist, h, 4096);                          // the scan size is computed from it in jpgenc_entropy_encode
     if (c->forward_pending) {
         c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
         const int rs = refresh_forward_stats(c);
@@ -308,11 +309,9 @@ int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint
     if (!c->have_items) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     // exact size of the scan from the statistics the tables were built from: every symbol costs its code length
-    // plus (symbol & 15) magnitude bits.  The histogram still sits in d_hist from K2; recompute from a fresh copy.
+    // plus (symbol & 15) magnitude bits.
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096, cudaMemcpyDeviceToHost, c->stream));
-    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    const uint32_t* hist = reinterpret_cast<const uint32_t*>(h);
+    const uint32_t* hist = c->host_hist;
     uint64_t total_bits = 0;
     DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + 8192);
     for (int t = 0; t < 4; ++t)

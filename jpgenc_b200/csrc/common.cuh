@@ -107,6 +107,7 @@ struct jpgenc_ctx {
     size_t tile_cnt_cap = 0;
     unsigned long long* d_item_cursor = nullptr;
     bool have_items = false;
+    uint32_t host_hist[4 * 256];          // K2's histogram as last read back
     jpgenc::DeviceTables* d_tables = nullptr;
     unsigned long long* d_lookback = nullptr;  // one status word per K3 tile
     size_t lookback_cap = 0;

@@ -301,7 +301,7 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     unsigned long long* st4 = st3 + tiles3;
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, (static_cast<size_t>(tiles3) + tiles4 + 2) * sizeof(unsigned long long), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters + 1, 0, 2 * sizeof(uint32_t), c->stream));
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, c->raw_cap, c->stream));
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, ((nbytes + 15) & ~15ull) + 64, c->stream));
 
     EntropyParams p{};
     p.items = c->d_items;

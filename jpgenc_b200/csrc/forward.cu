@@ -6,8 +6,9 @@
 // Design (DESIGN.md "K1"):
 //  * one CTA = a strip of kMcus 16x16 MCUs; the RGB strip (16 rows) is staged in shared memory by bulk
 //    (TMA) copies, one per image row, completing on an mbarrier;
-//  * one thread = one 8x8 block, held entirely in registers: no transposes, no shuffles, 30 FP32 instructions
-//    per 8-point AAN pass; the AAN output scales and 1/q are folded into one multiplier per coefficient;
+//  * one thread = one 8x8 block, held entirely in registers as 32 packed float pairs: no shuffles, 30 packed FP32x2
+//    instructions per PAIR of 8-point AAN passes; the AAN output scales and 1/q are folded into one multiplier per
+//    coefficient;
 //  * the reference computes in double.  The FP32 result is only trusted when every quotient is further than
 //    delta from a rounding boundary; otherwise the block id goes to a refine list and refine_kernel redoes
 //    the block in FP64 with the reference's exact operation order (no FMA contraction), so the stored
@@ -24,72 +25,12 @@ namespace jpgenc {
 __constant__ uint8_t c_zigzag[64] = {JPGENC_ZIGZAG_LIST};
 
 // ---------------------------------------------------------------------------------------------------
-// FP32 fast path
+// FP32 fast path, packed FP32x2 (sm_100 FADD2 / FFMA2: two IEEE fp32 operations per issue slot)
 // ---------------------------------------------------------------------------------------------------
-// 8-point AAN butterfly, outputs in frequency order and WITHOUT the s_k scales (they are folded into
-// QuantConsts::mul).  Same dataflow as Dct.hpp:52-131, re-associated for FMA: 30 instructions.
-__device__ __forceinline__ void aan8(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
-                                     float& x7) {
-    constexpr float A1 = 0.70710678118654752f;   // cos(4pi/16)
-    constexpr float A2 = 0.54119610014619698f;   // cos(2pi/16) - cos(6pi/16)
-    constexpr float A4 = 1.30656296487637653f;   // cos(6pi/16) + cos(2pi/16)
-    constexpr float A5 = 0.38268343236508977f;   // cos(6pi/16)
-    const float z0 = x0 + x7, z1 = x1 + x6, z2 = x2 + x5, z3 = x3 + x4;
-    const float z4 = x3 - x4, z5 = x2 - x5, z6 = x1 - x6, z7 = x0 - x7;
-    const float r0 = z0 + z3, r1 = z1 + z2, r2 = z1 - z2, r3 = z0 - z3;
-    const float n4 = z4 + z5;                    // -r4
-    const float r5 = z5 + z6, r6 = z6 + z7;
-    const float t2 = r2 + r3;
-    const float tmp = (r6 - n4) * A5;
-    const float u4 = fmaf(n4, A2, -tmp);
-    const float u6 = fmaf(r6, A4, -tmp);
-    const float v5 = fmaf(r5, A1, z7);
-    const float v7 = fmaf(-r5, A1, z7);
-    x0 = r0 + r1;
-    x4 = r0 - r1;
-    x2 = fmaf(t2, A1, r3);
-    x6 = fmaf(-t2, A1, r3);
-    x5 = u4 + v7;
-    x1 = v5 + u6;
-    x7 = v5 - u6;
-    x3 = v7 - u4;
-}
-
-// v[r*8+c] spatial -> v[v*8+u] frequency (unscaled)
-__device__ __forceinline__ void dct8x8(float (&v)[64]) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        aan8(v[0 * 8 + c], v[1 * 8 + c], v[2 * 8 + c], v[3 * 8 + c], v[4 * 8 + c], v[5 * 8 + c], v[6 * 8 + c], v[7 * 8 + c]);
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-        aan8(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
-}
-
-// scale + quantise + zigzag + pack to 32 words of two int16; returns true when some quotient is too close
-// to a rounding boundary for FP32 to decide.
-__device__ __forceinline__ bool quantize_pack(const float (&v)[64], const QuantConsts& q, uint32_t (&out)[32]) {
-    constexpr float kMagic = 12582912.f;          // 1.5 * 2^23: (x + kMagic) holds rint(x) in its low mantissa bits
-    constexpr int zz[64] = {JPGENC_ZIGZAG_LIST};
-    uint32_t bits[64];
-    bool boundary = false;
-#pragma unroll
-    for (int i = 0; i < 64; ++i) {
-        const float a = fmaf(v[i], q.mul[i], kMagic);
-        const float k = a - kMagic;
-        const float d = fmaf(v[i], q.mul[i], -k);  // quotient - rint(quotient), exact product inside the FMA
-        boundary |= fabsf(d) > q.thr[i];
-        bits[i] = __float_as_uint(a);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) out[j] = __byte_perm(bits[zz[2 * j]], bits[zz[2 * j + 1]], 0x5410);
-    return boundary;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// packed FP32x2 fast path (sm_100 FADD2 / FFMA2: two IEEE fp32 operations per issue slot)
-// ---------------------------------------------------------------------------------------------------
-// K1 is bound by instruction issue, not by the FP32 pipes or HBM (ncu, profiles/): two thirds of its instructions
-// are FADD/FFMA.  Blackwell's packed forms halve those.  A block is held as 32 float2: in the first (vertical) pass a
+// K1 is bound by instruction issue, not by the FP32 pipes or HBM (ncu, profiles/): as scalar code two thirds of its
+// instructions were FADD/FFMA.  Blackwell's packed forms halve those.  The 8-point AAN butterfly has the dataflow of
+// Dct.hpp:52-131 re-associated for FMA (30 operations) and leaves out the s_k output scales: they are folded, together
+// with 1/q, into one multiplier per coefficient (QuantConsts2::mul).  A block is held as 32 float2: in the first (vertical) pass a
 // pair is two neighbouring columns, so the eight 1-D column transforms run as four packed ones; 2x2 register
 // transposes then turn pairs of columns into pairs of rows for the horizontal pass.  Every lane of a packed operation is
 // an ordinary round-to-nearest fp32 operation, so the results (and the error bound behind the refinement threshold)
@@ -198,15 +139,6 @@ __device__ __forceinline__ void copy_out(const uint8_t* staging, int16_t* gdst, 
         const int s = j >> 3, c = j & 7;
         g[j] = *reinterpret_cast<const uint4*>(staging + s * kBlockBytes + ((c ^ (s & 7)) << 4));
     }
-}
-
-// u8 -> f32 of byte `b` of `w` (SASS: I2F.U8 Rd, Rs.Bb).  Inline PTX on purpose: with a plain C cast the compiler
-// proves that sums of converted bytes are exact and rewrites the chroma 2x2 sums as SHF+LOP3 byte extraction +
-// IADD3 + I2FP, tripling their instruction count (ncu, profiles/round1).
-__device__ __forceinline__ float u8f(uint32_t w, int b) {
-    float f;
-    asm("cvt.rn.f32.u8 %0, %1;" : "=f"(f) : "r"(w >> (8 * b)));
-    return f;
 }
 
 __device__ __forceinline__ void push_refine(const ForwardParams& p, uint32_t block_id) {
@@ -415,37 +347,80 @@ __device__ __forceinline__ double exact_sample(const uint8_t* rgb, uint32_t real
     return __ddiv_rn(dadd(top, bot), 4.0);
 }
 
-// Exact 8x8 transform of up to kRefineGroups blocks per CTA, 64 threads per block: thread (r,c) fetches one sample,
-// threads 0..7 of the group run the two 8-point passes through shared memory, then every thread quantises one
-// coefficient.  All groups of a CTA iterate in lockstep (same trip count), so the barriers are uniform.
-constexpr int kRefineGroups = 4;
+// Exact 8x8 transform, 8 threads per block (4 blocks per warp), everything in registers: thread c fetches column c
+// of the block and runs the vertical pass on it (the reference's pass 1 turns column j into row j of its temporary,
+// Dct.hpp:52-132), an 8x8 register transpose over the 8 lanes (three butterfly exchanges) hands every thread one column
+// of the temporary, the second pass turns that into row j of the result (Dct.hpp:134-214), and the thread quantises
+// and stores its 8 coefficients.  No shared memory, no barriers.
+constexpr int kRefineThreads = 256;
+
+// x[i] <-> partner's x[i ^ m] for the lanes whose bit `m` differs: one butterfly stage of the 8x8 transpose
+template <int kM>
+__device__ __forceinline__ void transpose_stage(double (&x)[8], int lane8) {
+    const bool upper = (lane8 & kM) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i & kM) continue;
+        // lower lanes send x[i | kM] and receive into it; upper lanes send x[i] and receive into it
+        const double send = upper ? x[i] : x[i | kM];
+        const double got = __shfl_xor_sync(0xffffffffu, send, kM);
+        if (upper) x[i] = got; else x[i | kM] = got;
+    }
+}
+
+// one 8-point pass on registers, Dct.hpp:52-131 / 134-213
+__device__ __forceinline__ void aan8_exact_regs(const double (&x)[8], double (&o)[8], const ExactConsts& e) {
+    const double z0 = dadd(x[0], x[7]), z1 = dadd(x[1], x[6]), z2 = dadd(x[2], x[5]), z3 = dadd(x[3], x[4]);
+    const double z4 = dadd(-x[4], x[3]), z5 = dadd(-x[5], x[2]), z6 = dadd(-x[6], x[1]), z7 = dadd(-x[7], x[0]);
+    const double r0 = dadd(z0, z3), r1 = dadd(z1, z2), r2 = dsub(z1, z2), r3 = dsub(z0, z3);
+    const double r4 = dsub(-z4, z5), r5 = dadd(z5, z6), r6 = dadd(z6, z7), r7 = z7;
+    const double t0 = dadd(r0, r1), t1 = dsub(r0, r1);
+    double t2 = dadd(r2, r3), t4 = r4, t5 = r5, t6 = r6;
+    const double t3 = r3, t7 = r7;
+    const double tmp = dmul(dadd(t4, t6), e.a5);
+    t2 = dmul(t2, e.a1); t4 = dmul(t4, e.a2); t5 = dmul(t5, e.a3); t6 = dmul(t6, e.a4);
+    const double u4 = dsub(-t4, tmp), u6 = dsub(t6, tmp);
+    const double v2 = dadd(t2, t3), v3 = dsub(t3, t2), v5 = dadd(t5, t7), v7 = dsub(t7, t5);
+    const double w4 = dadd(u4, v7), w5 = dadd(v5, u6), w6 = dadd(-u6, v5), w7 = dsub(v7, u4);
+    o[0] = dmul(t0, e.s[0]); o[4] = dmul(t1, e.s[4]); o[2] = dmul(v2, e.s[2]); o[6] = dmul(v3, e.s[6]);
+    o[5] = dmul(w4, e.s[5]); o[1] = dmul(w5, e.s[1]); o[7] = dmul(w6, e.s[7]); o[3] = dmul(w7, e.s[3]);
+}
+
+__constant__ uint8_t c_inv_zigzag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                         41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                         46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 
 template <class Sample>
 __device__ __forceinline__ void refine_loop(uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
                                             const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e, Sample&& sample) {
-    __shared__ double buf[kRefineGroups][2][64];
-    const int g = threadIdx.x >> 6, t = threadIdx.x & 63, r = t >> 3, c = t & 7;
-    const uint32_t stride = gridDim.x * kRefineGroups;
-    for (uint32_t base = blockIdx.x * kRefineGroups; base < n; base += stride) {
-        const uint32_t i = base + g;
+    const int lane8 = threadIdx.x & 7;
+    const uint32_t group = (blockIdx.x * kRefineThreads + threadIdx.x) >> 3, ngroups = (gridDim.x * kRefineThreads) >> 3;
+    const uint32_t rounds = (n + ngroups - 1) / ngroups;             // same trip count for every lane of a warp (shuffles inside)
+    for (uint32_t it = 0; it < rounds; ++it) {
+        const uint32_t i = it * ngroups + group;
         const bool valid = i < n;
         const uint32_t id = valid ? (all ? i : list[i]) : 0;
-        if (valid) buf[g][0][t] = sample(id, r, c);
-        __syncthreads();
-        if (valid && t < 8) aan8_exact(&buf[g][0][t], 8, &buf[g][1][t * 8], 1, e);     // column t -> row t of tmp
-        __syncthreads();
-        if (valid && t < 8) aan8_exact(&buf[g][1][t], 8, &buf[g][0][t * 8], 1, e);     // column t of tmp -> row t
-        __syncthreads();
+        double x[8], t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = valid ? sample(id, r, lane8) : 0.0;
+        aan8_exact_regs(x, t, e);                                     // t[k] = temporary(row lane8, column k)
+        transpose_stage<1>(t, lane8);
+        transpose_stage<2>(t, lane8);
+        transpose_stage<4>(t, lane8);                                 // t[k] = temporary(row k, column lane8)
+        aan8_exact_regs(t, x, e);                                     // x[k] = result(row lane8, column k)
         if (valid) {
-            const int nat = c_zigzag[t];
             const uint8_t* q = (id % kBlocksPerMcu) < 4 ? qtab_y : qtab_c;
-            out[static_cast<size_t>(id) * kCoefPerBlock + t] = quantize_exact(buf[g][0][nat], q[nat]);
+            int16_t* dst = out + static_cast<size_t>(id) * kCoefPerBlock;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int nat = lane8 * 8 + k;
+                dst[c_inv_zigzag[nat]] = quantize_exact(x[k], q[nat]);
+            }
         }
-        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(64 * kRefineGroups) refine_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
+__global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
                                                                     const uint32_t* __restrict__ list,
                                                                     const uint32_t* __restrict__ count, uint32_t cap, int all,
                                                                     uint32_t nblocks, uint32_t real_w, uint32_t real_h,
@@ -465,7 +440,7 @@ constexpr int kMbPitch = 256 + 16;            // bytes between blocks in shared 
 __global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
                                                                 uint64_t nblocks, uint32_t* refine_list,
                                                                 uint32_t* refine_count, uint32_t refine_cap,
-                                                                const __grid_constant__ QuantConsts q) {
+                                                                const __grid_constant__ QuantConsts2 q) {
     __shared__ alignas(128) uint8_t tile[kMbThreads * kMbPitch];
     __shared__ alignas(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -481,20 +456,21 @@ __global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __r
     if (tid < nb) ptx::bulk_g2s(tile + tid * kMbPitch, in + (first + tid) * 64, 256, &bar);
     ptx::mbar_wait(&bar, 0);
 
-    float v[64];
+    f2 v[32];                                   // v[r*4+p] = samples (r, 2p), (r, 2p+1)
     if (tid < nb) {
         const float4* src = reinterpret_cast<const float4*>(tile + tid * kMbPitch);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float4 f = src[j];
-            v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+            v[2 * j] = make_float2(f.x, f.y);
+            v[2 * j + 1] = make_float2(f.z, f.w);
         }
     }
     __syncthreads();                            // all inputs are in registers: reuse the tile as output staging
     if (tid < nb) {
         uint32_t packed[32];
-        dct8x8(v);
-        if (quantize_pack(v, q, packed)) {
+        dct8x8_packed(v);
+        if (quantize_pack_packed(v, q, packed)) {
             const uint32_t at = atomicAdd(refine_count, 1u);
             if (at < refine_cap) refine_list[at] = static_cast<uint32_t>(first + tid);
         }
@@ -505,7 +481,7 @@ __global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __r
 }
 
 // stand-alone blocks: every block uses table e.qy; ids index blocks directly
-__global__ void __launch_bounds__(64 * kRefineGroups) refine_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
+__global__ void __launch_bounds__(kRefineThreads) refine_blocks_kernel(const float* __restrict__ in, int16_t* __restrict__ out,
                                                                            const uint32_t* __restrict__ list,
                                                                            const uint32_t* __restrict__ count, uint32_t cap,
                                                                            uint32_t nblocks, int all,
@@ -629,7 +605,7 @@ int launch_forward(jpgenc_ctx* c) {
     }
     JPGENC_CUDA(c, cudaGetLastError());
     JPGENC_CUDA(c, cudaEventRecord(c->ev_k1, c->stream));
-    refine_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(
+    refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
         c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), 0,
         c->mcu_w * c->mcu_h * kBlocksPerMcu, c->real_w, c->real_h, c->mcu_w, e);
     JPGENC_CUDA(c, cudaGetLastError());
@@ -641,7 +617,7 @@ int launch_exact_all(jpgenc_ctx* c) {
     ExactConsts e;
     fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
     const uint32_t nblocks = c->mcu_w * c->mcu_h * kBlocksPerMcu;
-    refine_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
+    refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
                                                                        0u, 1, nblocks, c->real_w, c->real_h, c->mcu_w, e);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -650,8 +626,8 @@ int launch_exact_all(jpgenc_ctx* c) {
 
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
                             uint64_t* refined) {
-    QuantConsts qc;
-    fill_quant_consts(q, c->dct_s, &qc);
+    QuantConsts2 qc;
+    fill_quant_consts2(q, c->dct_s, &qc);
     ExactConsts e;
     fill_exact(c, q, q, 1.0, &e);
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
@@ -659,7 +635,7 @@ int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64
     dct_blocks_kernel<<<static_cast<unsigned>(grid), kMbThreads, 0, c->stream>>>(
         in, out, nblocks, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), qc);
     JPGENC_CUDA(c, cudaGetLastError());
-    refine_blocks_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(
+    refine_blocks_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
         in, out, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), static_cast<uint32_t>(nblocks), 0, e);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 2;
@@ -668,7 +644,7 @@ int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64
         JPGENC_CUDA(c, cudaMemcpyAsync(&n, c->d_counters, sizeof n, cudaMemcpyDeviceToHost, c->stream));
         JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
         if (n > c->refine_cap) {   // list overflowed: redo everything exactly (correct, slow, never seen on real data)
-            refine_blocks_kernel<<<c->sm_count * 8, 64 * kRefineGroups, 0, c->stream>>>(
+            refine_blocks_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
                 in, out, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), static_cast<uint32_t>(nblocks), 1, e);
             JPGENC_CUDA(c, cudaGetLastError());
             c->launches += 1;
