@@ -25,7 +25,8 @@ struct TileView {
     int16_t* dc;
 };
 constexpr int kTileSmemBytes = kTileBlocks * 8 + kTileBlocks * 2;
-constexpr int kItemsPerBlockMax = 65;                  // DC + 63 AC + EOB can never coexist, 65 is a safe bound
+constexpr int kItemsPerBlockMax = 64;                  // DC + 63 AC, or DC + at most 62 AC + EOB
+constexpr int kSlabItems = kTileBlocks * kItemsPerBlockMax;   // item slots reserved per tile (worst case; typical use: a few %)
 
 __device__ __forceinline__ TileView tile_view(uint8_t* smem) {
     return TileView{smem, reinterpret_cast<int16_t*>(smem + kTileBlocks * 8)};
@@ -78,13 +79,15 @@ __device__ __forceinline__ int category_of(int v) { return 32 - __clz(abs(v)); }
 
 // ---- symbol items ------------------------------------------------------------------------------------------
 // K2 turns every block into the reference's symbol sequence (include/Coding.hpp:148-183, 265-283) exactly once and
-// leaves it in HBM as a flat stream of 32-bit items in scan order (MCU order, zigzag order inside a block); K3 only
-// maps items to codes.  One item = one Huffman symbol with its magnitude bits, plus the ZRL symbols (0xF0) that
+// leaves it in HBM as 32-bit items in scan order (MCU order, zigzag order inside a block): tile t (384 blocks) fills the
+// first tile_cnt[t] slots of its own fixed slab of kSlabItems slots, so no tile waits for another.  K3 only maps items
+// to codes.  One item = one Huffman symbol with its magnitude bits, plus the ZRL symbols (0xF0) that
 // precede it:
 //   [7:0]   symbol: DC category, or (run << 4) | category, or 0x00 = EOB
 //   [9:8]   table id (0 Y_DC, 1 Y_AC, 2 C_DC, 3 C_AC)
 //   [11:10] number of ZRL symbols emitted before this symbol (0..3)
-//   [27:12] magnitude bits (category = symbol & 15 of them; value for v > 0, v - 1 truncated for v < 0, Coding.hpp:206-212)
+//   [26:12] magnitude bits (category = symbol & 15 of them; value for v > 0, v - 1 truncated for v < 0, Coding.hpp:206-212)
+//   [31:27] zero (K3 overwrites items in shared memory with (bit count << 27) | bits, which never has these bits zero)
 __device__ __forceinline__ uint32_t make_item(int table, int symbol, int nzrl, int value) {
     const uint32_t cat = symbol & 15;
     const uint32_t mag = static_cast<uint32_t>(value < 0 ? value - 1 : value) & ((1u << cat) - 1u);

@@ -120,8 +120,6 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     c->d_first = static_cast<unsigned long long*>(p);
     if ((e = cudaMalloc(&p, sizeof(DeviceTables))) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_tables = static_cast<DeviceTables*>(p);
-    if ((e = cudaMalloc(&p, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
-    c->d_item_cursor = static_cast<unsigned long long*>(p);
     c->pinned_bytes = 64 * 1024;
     if ((e = cudaMallocHost(&c->h_pinned, c->pinned_bytes)) != cudaSuccess) return bail("cudaMallocHost", e);
     *out = c;
@@ -135,7 +133,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_hist); cudaFree(c->d_first); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
-    cudaFree(c->d_items); cudaFree(c->d_tile_off); cudaFree(c->d_tile_cnt); cudaFree(c->d_item_cursor);
+    cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -278,10 +276,12 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     int rc;
-    // worst case one item per coefficient position plus DC/EOB; typical images use a few percent of it
-    if ((rc = ensure(c, &c->d_items, &c->items_cap, nblocks * 65 * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_tile_off, &c->tile_off_cap, tiles * sizeof(unsigned long long)))) return rc;
+    // one fixed slab of item slots per tile, sized for the worst case (every coefficient non-zero); typical images
+    // touch a few percent of it
+    if ((rc = ensure(c, &c->d_items, &c->items_cap, tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, tiles * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, tiles * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, tiles * sizeof(unsigned long long)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
     if ((rc = launch_symbol_stats(c))) return rc;
     c->have_items = true;
@@ -317,7 +317,9 @@ int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint
     for (int t = 0; t < 4; ++t)
         for (int s = 0; s < 256; ++s) {
             const uint32_t len = tables[t].length[s];
-            ht->entry[t][s] = len ? (len << 16) | (tables[t].code_msb[s] >> (32 - len)) : 0u;
+            const uint32_t code = len ? tables[t].code_msb[s] >> (32 - len) : 0u, cat = s & 15;
+            ht->entry[t][s] = len ? (len << 16) | code : 0u;
+            ht->fast[t][s] = (len && len + cat <= 27) ? ((len + cat) << 27) | (code << cat) : 0u;
             if (hist[t * 256 + s]) {
                 if (!len) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
                 total_bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + (s & 15));

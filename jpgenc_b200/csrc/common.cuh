@@ -66,9 +66,13 @@ struct ForwardParams {
 
 __host__ __device__ inline uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
-// device-side Huffman table entry: (length << 16) | right-aligned code; 0 = absent
+// device-side Huffman tables, indexed [table][symbol]:
+//   entry  (length << 16) | right-aligned code; 0 = absent
+//   fast   ((length + cat) << 27) | (code << cat) with cat = symbol & 15: OR the magnitude bits in and the word is the
+//          complete (bit count, bits) pair of the symbol; 0 where that does not fit in 27 bits (or the symbol is absent)
 struct DeviceTables {
     uint32_t entry[4][256];
+    uint32_t fast[4][256];
 };
 
 }  // namespace jpgenc
@@ -101,11 +105,12 @@ struct jpgenc_ctx {
     unsigned long long* d_first = nullptr;// [4][256]
     uint32_t* d_items = nullptr;          // K2's symbol stream (blockwalk.cuh), consumed by K3
     size_t items_cap = 0;
-    unsigned long long* d_tile_off = nullptr;   // per K2 tile: first item / number of items; [tiles] is followed by the cursor
-    size_t tile_off_cap = 0;
-    uint32_t* d_tile_cnt = nullptr;
+    uint32_t* d_tile_cnt = nullptr;             // per K2 tile: number of items in its slab
     size_t tile_cnt_cap = 0;
-    unsigned long long* d_item_cursor = nullptr;
+    uint32_t* d_range_bits = nullptr;           // per K2 tile: bits its items encode to (K3a)
+    size_t range_bits_cap = 0;
+    unsigned long long* d_range_base = nullptr; // per K2 tile: bit offset in the scan (K3s)
+    size_t range_base_cap = 0;
     bool have_items = false;
     uint32_t host_hist[4 * 256];          // K2's histogram as last read back
     jpgenc::DeviceTables* d_tables = nullptr;

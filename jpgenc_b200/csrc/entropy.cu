@@ -3,19 +3,19 @@
 // Replaces Image::doHuffmanEncoding, the per-MCU Bitstream concatenation, Bitstream::fill() and the stuffing
 // operator<< (reference src/Image.cpp:737-829, 957-971; include/BitstreamGeneric.hpp:126-146, 182-195, 213-224, 242-248).
 //
-// K3 reads the symbol items K2 left in HBM (blockwalk.cuh), never the coefficients.  A tile is the item range of one
-// K2 tile (384 blocks, 64 MCUs).  Its items are dealt to the threads in equal consecutive shares, so every thread does
-// the same amount of work whatever the blocks look like: each thread sizes its share (code length + magnitude bits per
-// item), the CTA scans the sizes, a decoupled look-back over per-tile status words turns the CTA total into the
-// tile's global bit offset, and the codes are assembled MSB-first in a shared-memory bit buffer and written out as
-// whole 32-bit words (only the two words a tile shares with its neighbours use atomicOr).  Tiles take their index from
-// an atomic ticket, so a tile only ever waits for tiles that already run.
-// K4 has the same structure at byte granularity: count FF bytes, scan, look back, compact.
+// K3 reads the symbol items K2 left in HBM (blockwalk.cuh), never the coefficients, in three launches:
+//   K3a  one warp per item range (= one K2 tile, 384 blocks): coalesced pass, bits the range encodes to;
+//   K3s  exclusive scan of those sizes -> bit offset of every range (and the total, checked against the histogram);
+//   K3b  one warp per range: codes assembled MSB-first in a per-warp shared-memory bit buffer and written out as whole
+//        32-bit words (only the two words a chunk shares with its neighbours use atomicOr).
+// With the offsets known up front no warp ever waits for another one: no tickets, no look-back, no block barriers.
+// K4: count FF bytes, CTA scan, decoupled look-back over per-tile status words, compact.
+#include <cstdlib>
+
 #include "blockwalk.cuh"
 
 namespace jpgenc {
 
-constexpr int kBitBufWords = 8192;                      // 32 KB of bits per tile before falling back to global atomics
 
 // MSB-first bit writer into 32-bit words ("word bit 31 is the earliest bit"); words are byte-swapped when they go
 // to memory so that memory byte order is stream order.
@@ -50,16 +50,14 @@ struct BitWriter {
 };
 
 struct EntropyParams {
-    const uint32_t* items;              // K2's symbol stream
-    const unsigned long long* tile_off; // [tiles] first item of tile
-    const uint32_t* tile_cnt;           // [tiles] items of tile
+    const uint32_t* items;              // K2's symbol items: range t = the first range_cnt[t] slots of slab t
+    const uint32_t* range_cnt;          // [nranges]
     uint32_t nranges;                   // number of K2 tiles
-    uint32_t ntiles;                    // number of K3 tiles = ceil(nranges / kPackGroup)
     const DeviceTables* tables;
-    unsigned long long* status;     // look-back words, zeroed before launch
-    uint32_t* ticket;               // zeroed before launch
-    uint32_t* raw;                  // zeroed before launch, (total_bits+7)/8 bytes rounded up to words (+ slack)
-    unsigned long long* total_out;  // [0] = total bits written (before padding)
+    uint32_t* range_bits;               // [nranges] bits the range encodes to            (K3a writes, K3s reads)
+    unsigned long long* range_base;     // [nranges] bit offset of the range in the scan  (K3s writes, K3b reads)
+    uint32_t* raw;                      // zeroed before launch, (total_bits+7)/8 bytes rounded up to words (+ slack)
+    unsigned long long* total_out;      // [0] = total bits written (before padding)
 };
 
 // code bits of one item: `nz` ZRL codes first, then the symbol's code with the magnitude bits appended
@@ -81,123 +79,183 @@ __device__ __forceinline__ uint32_t item_bits(uint32_t item, const uint32_t* s_t
     return (tab[item & 0xFFu] >> 16) + (item & 15u) + ((item >> 10) & 3u) * (tab[0xF0] >> 16);
 }
 
-constexpr int kPackThreads = 256;
-constexpr int kPackGroup = 4;                          // K2 tiles (item ranges) per K3 tile
-
-// The items of a K3 tile are kPackGroup separate ranges of the item stream (K2 tiles claim their ranges in completion
-// order).  for_items walks the slice [i0, i1) of their concatenation.
-template <class F>
-__device__ __forceinline__ void for_items(const uint32_t* __restrict__ items, const unsigned long long* s_off, const uint32_t* s_cum,
-                                          uint32_t i0, uint32_t i1, F&& f) {
-    int g = 0;
-    while (g + 1 < kPackGroup && s_cum[g + 1] <= i0) ++g;
-    for (uint32_t i = i0; i < i1; ++g) {
-        const uint32_t end = min(i1, s_cum[g + 1]);
-        const uint32_t* __restrict__ ptr = items + s_off[g] + (i - s_cum[g]);
-        const uint32_t n = end - i;
-        uint32_t j = 0;
-        for (; j + 4 <= n; j += 4) {                    // four independent loads in flight
-            const uint32_t a = __ldg(ptr + j), b = __ldg(ptr + j + 1), c = __ldg(ptr + j + 2), d = __ldg(ptr + j + 3);
-            f(a); f(b); f(c); f(d);
-        }
-        for (; j < n; ++j) f(__ldg(ptr + j));
-        i = end;
-    }
+// the common case in one lookup: returns (bit count << 27) | bits, or 0 when the item needs the general path
+// (ZRLs in front of it, or a code + magnitude longer than 27 bits)
+__device__ __forceinline__ uint32_t item_fast(uint32_t item, const uint32_t* s_fast) {
+    const uint32_t e = s_fast[item & 0x3FFu];
+    return ((item >> 10) & 3u) || !e ? 0u : e | (item >> 12);
 }
 
-__global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
-    __shared__ uint32_t s_tab[1024];                  // [4][256] (length << 16) | code
-    __shared__ uint32_t s_bits[kBitBufWords + 1];
-    __shared__ uint32_t s_scan[36];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_base;
-    __shared__ unsigned long long s_off[kPackGroup];
-    __shared__ uint32_t s_cum[kPackGroup + 1];
-    const int tid = threadIdx.x;
+constexpr int kPackThreads = 256;                       // 8 warps, one item range each
+constexpr int kPackWarps = kPackThreads / 32;
 
-    if (tid == 0) {
-        const uint32_t t = atomicAdd(p.ticket, 1u);
-        s_tile = t;
-        uint32_t cum = 0;
-        for (int g = 0; g < kPackGroup; ++g) {
-            const uint32_t k2 = t * kPackGroup + g;
-            s_cum[g] = cum;
-            s_off[g] = k2 < p.nranges ? p.tile_off[k2] : 0ull;
-            cum += k2 < p.nranges ? p.tile_cnt[k2] : 0u;
-        }
-        s_cum[kPackGroup] = cum;
+// ---- K3a: bits per range (coalesced pass over the items) -----------------------------------------------------
+__global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_constant__ EntropyParams p) {
+    __shared__ uint32_t s_tab[1024], s_fast[1024];
+    for (int i = threadIdx.x; i < 1024; i += kPackThreads) {
+        s_tab[i] = (&p.tables->entry[0][0])[i];
+        s_fast[i] = (&p.tables->fast[0][0])[i];
     }
-    for (int i = tid; i < 1024; i += kPackThreads) s_tab[i] = (&p.tables->entry[0][0])[i];
     __syncthreads();
-    const uint32_t tile_idx = s_tile;
-    const uint32_t n = s_cum[kPackGroup];
-    const uint32_t* __restrict__ items = p.items;
-    // blocked arrangement: thread t owns items [t*per, t*per + per) so that it can merge their bits in registers
-    const uint32_t per = (n + kPackThreads - 1) / kPackThreads;
-    const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
-
-    uint32_t my_bits = 0;
-    for_items(items, s_off, s_cum, i0, i1, [&](uint32_t item) { my_bits += item_bits(item, s_tab); });
-    uint32_t tile_bits;
-    const uint32_t local = block_exclusive_scan(my_bits, s_scan, &tile_bits);
-    const bool last_tile = tile_idx + 1 == p.ntiles;
-    const bool in_smem = tile_bits + 32 <= kBitBufWords * 32u;
-
-    if (in_smem) {
-        const uint32_t zero_words = ((tile_bits + 31) >> 5) + 1;
-        for (uint32_t i = tid; i < zero_words; i += kPackThreads) s_bits[i] = 0;
-        __syncthreads();
-        // The codes are assembled at tile-relative bit positions, so this does not wait for the look-back: the last
-        // warp resolves the tile's global bit offset while the others are still packing.
-        if (tid >= kPackThreads - 32) {
-            const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
-            if (tid == kPackThreads - 32) s_base = b;
-        }
-        if (i0 < i1) {
-            BitWriter<false> bw;
-            bw.start(s_bits, local);
-            for_items(items, s_off, s_cum, i0, i1, [&](uint32_t item) {
-                item_codes(item, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
-            });
-            bw.finish();
-        }
-        __syncthreads();
-        const unsigned long long base = s_base;
-        const uint32_t lead = static_cast<uint32_t>(base & 31);             // bits of the first word owned by earlier tiles
-        const uint32_t nwords = (lead + tile_bits + 31) >> 5;
-        uint32_t* g = p.raw + (base >> 5);
-        for (uint32_t i = tid; i < nwords; i += kPackThreads) {
-            // global word i = tile-relative bits [32i - lead, 32i - lead + 32)
-            const uint32_t v = __byte_perm(__funnelshift_r(s_bits[i], i ? s_bits[i - 1] : 0u, lead), 0, 0x0123);
-            if (i == 0 || i == nwords - 1) { if (v) atomicOr(&g[i], v); }
-            else g[i] = v;
-        }
-    } else {   // very dense tile: wait for the offset, then write straight to the (zeroed) global words
-        if (tid < 32) {
-            const unsigned long long b = lookback_exclusive(p.status, tile_idx, tile_bits);
-            if (tid == 0) s_base = b;
-        }
-        __syncthreads();
-        if (i0 < i1) {
-            BitWriter<true> bw;
-            bw.start(p.raw, s_base + local);
-            for_items(items, s_off, s_cum, i0, i1, [&](uint32_t item) {
-                item_codes(item, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
-            });
-            bw.finish();
-        }
+    const uint32_t range = blockIdx.x * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (range >= p.nranges) return;
+    const uint32_t n = p.range_cnt[range];
+    const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
+    uint32_t bits = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t item = __ldg(items + i), w = item_fast(item, s_fast);
+        bits += w ? w >> 27 : item_bits(item, s_tab);
     }
-    if (last_tile && tid == 0) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+    if (lane == 0) p.range_bits[range] = bits;
+}
+
+// ---- K3s: exclusive scan of the range sizes (one CTA; a few thousand to a few ten-thousand values) -------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanPer = 16;                            // consecutive ranges per thread and round (independent loads)
+__global__ void __launch_bounds__(kScanThreads) range_scan_kernel(const __grid_constant__ EntropyParams p) {
+    __shared__ unsigned long long s_warp[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long carry = 0;
+    for (uint32_t round0 = 0; round0 < p.nranges; round0 += kScanThreads * kScanPer) {
+        const uint32_t i0 = round0 + tid * kScanPer;
+        uint32_t v[kScanPer];
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) v[k] = i0 + k < p.nranges ? p.range_bits[i0 + k] : 0u;
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) sum += v[k];
+        unsigned long long inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += up;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = s_warp[lane];
+            unsigned long long t = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, t, d);
+                if (lane >= d) t += up;
+            }
+            s_warp[lane] = t - w;
+            if (lane == 31) s_warp[32] = t;
+        }
+        __syncthreads();
+        unsigned long long at = carry + s_warp[warp] + inc - sum;
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            if (i0 + k < p.nranges) p.range_base[i0 + k] = at;
+            at += v[k];
+        }
+        carry += s_warp[32];
+        __syncthreads();
+    }
+    if (tid == 0) p.total_out[0] = carry;
+}
+
+// ---- K3b: pack ---------------------------------------------------------------------------------------------------
+// One warp per range, no block-wide synchronisation.  The range is taken in chunks of 512 items: 16 coalesced row
+// loads put the chunk into a padded shared-memory array, from which every lane reads ITS 16 consecutive items
+// (blocked arrangement, bank-conflict-free thanks to the padding), sizes them, a warp scan places the lanes, each lane
+// assembles its bits MSB-first in registers and ORs whole words into the warp's bit buffer.  The buffer is laid out
+// with the same word alignment as the global scan, so flushing is a plain coalesced copy (atomicOr only for the two
+// words shared with neighbours).
+constexpr int kChunkRows = 16;
+constexpr int kChunkItems = kChunkRows * 32;
+constexpr int kWarpBitWords = 512;                      // 16 Kbit per chunk (32 bits per item on average) before falling back
+
+__global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid_constant__ EntropyParams p) {
+    __shared__ uint32_t s_tab[1024], s_fast[1024];                      // DeviceTables::entry / ::fast
+    __shared__ uint32_t s_items[kPackWarps][kChunkItems + kChunkRows];  // item j of the chunk at j + (j >> 5)
+    __shared__ uint32_t s_bits[kPackWarps][kWarpBitWords + 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 1024; i += kPackThreads) {
+        s_tab[i] = (&p.tables->entry[0][0])[i];
+        s_fast[i] = (&p.tables->fast[0][0])[i];
+    }
+    for (int i = lane; i < kWarpBitWords + 2; i += 32) s_bits[warp][i] = 0;
+    __syncthreads();
+    const uint32_t range = blockIdx.x * kPackWarps + warp;
+    if (range >= p.nranges) return;
+    const uint32_t n = p.range_cnt[range];
+    const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
+    uint32_t* it = s_items[warp];
+    uint32_t* bitbuf = s_bits[warp];
+    unsigned long long cur = p.range_base[range];                       // global bit position of the next chunk
+
+    for (uint32_t c0 = 0; c0 < n; c0 += kChunkItems) {
+        const uint32_t m = min(static_cast<uint32_t>(kChunkItems), n - c0);
+        const uint32_t rows = (m + 31) >> 5;
+#pragma unroll 4
+        for (uint32_t r = 0; r < rows; ++r) {
+            const uint32_t j = r * 32 + lane;
+            if (j < m) it[j + r] = __ldg(items + c0 + j);
+        }
+        __syncwarp();
+        const uint32_t j0 = min(m, lane * rows), j1 = min(m, j0 + rows);   // this lane's consecutive items
+        // sizing pass; an item that resolves with one lookup is replaced in place by its (bit count << 27) | bits word,
+        // so the packing pass below does not touch the tables again
+        uint32_t my_bits = 0;
+        for (uint32_t j = j0; j < j1; ++j) {
+            const uint32_t at = j + (j >> 5), item = it[at], w = item_fast(item, s_fast);
+            if (w) { it[at] = w; my_bits += w >> 27; }
+            else my_bits += item_bits(item, s_tab);
+        }
+        uint32_t inc = my_bits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t lead = static_cast<uint32_t>(cur & 31);          // bits of the first word that belong to whoever came before
+        if (lead + total <= kWarpBitWords * 32u) {
+            if (j0 < j1) {
+                BitWriter<false> bw;
+                bw.start(bitbuf, lead + inc - my_bits);
+                for (uint32_t j = j0; j < j1; ++j) {
+                    const uint32_t w = it[j + (j >> 5)];
+                    if (w >> 27) bw.put(w & 0x07FFFFFFu, w >> 27);
+                    else item_codes(w, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+                }
+                bw.finish();
+            }
+            __syncwarp();
+            const uint32_t nwords = (lead + total + 31) >> 5;
+            uint32_t* g = p.raw + (cur >> 5);
+            for (uint32_t i = lane; i < nwords; i += 32) {
+                const uint32_t v = __byte_perm(bitbuf[i], 0, 0x0123);
+                bitbuf[i] = 0;
+                if (i == 0 || i == nwords - 1) { if (v) atomicOr(&g[i], v); }
+                else g[i] = v;
+            }
+        } else if (j0 < j1) {   // very dense chunk: straight to the (zeroed) global words
+            BitWriter<true> bw;
+            bw.start(p.raw, cur + inc - my_bits);
+            for (uint32_t j = j0; j < j1; ++j) {
+                const uint32_t w = it[j + (j >> 5)];
+                if (w >> 27) bw.put(w & 0x07FFFFFFu, w >> 27);
+                else item_codes(w, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+            }
+            bw.finish();
+        }
+        __syncwarp();
+        cur += total;
+    }
+    if (range + 1 == p.nranges && lane == 0) {
         // 1-padding of Bitstream::fill() (BitstreamGeneric.hpp:242-248): the open byte is completed with ones
-        const unsigned long long end = s_base + tile_bits;
-        const uint32_t pad = static_cast<uint32_t>((8 - (end & 7)) & 7);
+        const uint32_t pad = static_cast<uint32_t>((8 - (cur & 7)) & 7);
         if (pad) {
             BitWriter<true> bw;
-            bw.start(p.raw, end);
+            bw.start(p.raw, cur);
             bw.put((1u << pad) - 1, pad);
             bw.finish();
         }
-        p.total_out[0] = end;
     }
 }
 
@@ -293,35 +351,36 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
     const uint64_t nbytes = (total_bits + 7) / 8;
     const uint32_t ranges = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
-    const uint32_t tiles3 = (ranges + kPackGroup - 1) / kPackGroup;
     const uint32_t tiles4 = static_cast<uint32_t>((nbytes + kStuffTile - 1) / kStuffTile);
-    // status words: [0,1] totals (bits written by K3, FF bytes stuffed by K4), then K3's tiles, then K4's
+    // status words: [0,1] totals (bits written by K3, FF bytes stuffed by K4), then K4's look-back words
     unsigned long long* totals = c->d_lookback;
-    unsigned long long* st3 = c->d_lookback + 2;
-    unsigned long long* st4 = st3 + tiles3;
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, (static_cast<size_t>(tiles3) + tiles4 + 2) * sizeof(unsigned long long), c->stream));
+    unsigned long long* st4 = c->d_lookback + 2;
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, (static_cast<size_t>(tiles4) + 2) * sizeof(unsigned long long), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters + 1, 0, 2 * sizeof(uint32_t), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, ((nbytes + 15) & ~15ull) + 64, c->stream));
 
     EntropyParams p{};
     p.items = c->d_items;
-    p.tile_off = c->d_tile_off;
-    p.tile_cnt = c->d_tile_cnt;
+    p.range_cnt = c->d_tile_cnt;
     p.nranges = ranges;
-    p.ntiles = tiles3;
     p.tables = c->d_tables;
-    p.status = st3;
-    p.ticket = c->d_counters + 1;
+    p.range_bits = c->d_range_bits;
+    p.range_base = c->d_range_base;
     p.raw = c->d_raw;
     p.total_out = totals;
-    huffman_pack_kernel<<<tiles3, kPackThreads, 0, c->stream>>>(p);
+    const unsigned grid = (ranges + kPackWarps - 1) / kPackWarps;
+    range_bits_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
+    JPGENC_CUDA(c, cudaGetLastError());
+    range_scan_kernel<<<1, kScanThreads, 0, c->stream>>>(p);
+    JPGENC_CUDA(c, cudaGetLastError());
+    huffman_pack_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     if (tiles4) {
         stuff_kernel<<<tiles4, kStuffThreads, 0, c->stream>>>(reinterpret_cast<const uint8_t*>(c->d_raw), nbytes, c->d_scan,
                                                               st4, c->d_counters + 2, totals + 1);
         JPGENC_CUDA(c, cudaGetLastError());
     }
-    c->launches += 2;
+    c->launches += 4;
     return JPGENC_OK;
 }
 

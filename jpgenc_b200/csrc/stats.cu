@@ -29,9 +29,7 @@ struct StatsParams {
     uint32_t n_mcu;
     uint32_t* g_hist;                 // [4][256]
     unsigned long long* g_first;      // [4][256]
-    uint32_t* items;                  // flat item stream
-    unsigned long long* cursor;       // next free item slot (tiles claim ranges in completion order)
-    unsigned long long* tile_off;     // [tiles] first item of the tile
+    uint32_t* items;                  // item stream: tile t owns the slab [t * kSlabItems, (t + 1) * kSlabItems)
     uint32_t* tile_cnt;               // [tiles] items of the tile
 };
 
@@ -64,7 +62,6 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(at);                       at += 4096;
     unsigned long long* s_first = reinterpret_cast<unsigned long long*>(at);  at += 8192;
     uint32_t* s_scan = reinterpret_cast<uint32_t*>(at);
-    __shared__ unsigned long long s_off;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t first = blockIdx.x * kTileBlocks;
@@ -100,14 +97,8 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     const uint32_t base2 = block_exclusive_scan(count | (nac << 16), s_scan, &totals);
     const uint32_t base = base2 & 0xFFFFu, total = totals & 0xFFFFu, total_ac = totals >> 16;
     s_base[tid] = base2;
-    if (tid == 0) {
-        s_off = atomicAdd(p.cursor, static_cast<unsigned long long>(total));
-        p.tile_cnt[blockIdx.x] = total;
-    }
-    __syncthreads();
-    const unsigned long long off = s_off;
-    if (tid == 0) p.tile_off[blockIdx.x] = off;
-    uint32_t* __restrict__ out = p.items + off;
+    if (tid == 0) p.tile_cnt[blockIdx.x] = total;
+    uint32_t* __restrict__ out = p.items + static_cast<size_t>(blockIdx.x) * kSlabItems;
 
     // ---- DC and EOB: exactly one (at most one) per block, so the block's own thread handles them ----
     const int dcat = category_of(diff);
@@ -198,7 +189,6 @@ int launch_symbol_stats(jpgenc_ctx* c) {
     const unsigned grid = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_hist, 0, 4 * 256 * sizeof(uint32_t), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_first, 0xFF, 4 * 256 * sizeof(unsigned long long), c->stream));
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_item_cursor, 0, sizeof(unsigned long long), c->stream));
     StatsParams p{};
     p.coef = c->d_coef;
     p.nblocks = static_cast<uint32_t>(nblocks);
@@ -207,8 +197,6 @@ int launch_symbol_stats(jpgenc_ctx* c) {
     p.g_hist = c->d_hist;
     p.g_first = c->d_first;
     p.items = c->d_items;
-    p.cursor = c->d_item_cursor;
-    p.tile_off = c->d_tile_off;
     p.tile_cnt = c->d_tile_cnt;
     JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
     symbol_stats_kernel<<<grid, kTileBlocks, kStatsSmem, c->stream>>>(p);
