@@ -1,4 +1,5 @@
 // C-ABI of the encode path (include/jpgenc_b200.h): context, buffers, stage calls, whole-image driver.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -106,6 +107,9 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     }
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (cudaEvent_t& ev : c->ev_band)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_t0, &c->ev_t1, &c->ev_u0, &c->ev_u1, &c->ev_k0, &c->ev_k1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     std::memcpy(c->qy, kAnnexKLuma, 64);
@@ -136,6 +140,8 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -294,6 +300,11 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     std::memcpy(count, h, 4096);
     std::memcpy(first_pos, h + 4096, 8192);
     std::memcpy(c->host_hist, h, 4096);                          // the scan size is computed from it in jpgenc_entropy_encode
+    if (c->upload_pending) {          // banded upload of jpgenc_encode_rgb: the compute stream waited for every band
+        c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
+        JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
+        c->upload_pending = false;
+    }
     if (c->forward_pending) {
         c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
         const int rs = refresh_forward_stats(c);
@@ -368,9 +379,9 @@ int jpgenc_download_scan(jpgenc_ctx* c, uint8_t* dst, uint64_t cap) {
     return JPGENC_OK;
 }
 
-static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* scan) {
+// K2 .. K4 on the coefficients K1 left on the device
+static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* scan) {
     int rc;
-    if ((rc = jpgenc_color_dct_quant(c))) return rc;
     uint32_t count[4][256];
     uint64_t first_pos[4][256];
     if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
@@ -379,6 +390,46 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     if ((rc = jpgenc_entropy_encode(c, tables, scan))) return rc;
     std::memcpy(c->last_tables, tables, sizeof c->last_tables);
     c->have_tables = true;
+    return JPGENC_OK;
+}
+
+static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* scan) {
+    const int rc = jpgenc_color_dct_quant(c);
+    return rc ? rc : run_entropy_stages(c, tables, scan);
+}
+
+// Host pixels -> coefficients with the upload hidden behind K1: the image is cut into bands of MCU rows, every band
+// is copied on the copy stream and transformed on the compute stream as soon as its copy has landed, so after the last
+// byte has crossed PCIe only one band of K1 work (plus the refinement) is left.
+static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    int rc = set_geometry(c, w, h, maxval);
+    if (rc) return rc;
+    const size_t row_bytes = static_cast<size_t>(w) * 3, bytes = row_bytes * h;
+    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, bytes + 16))) return rc;
+    c->d_rgb = c->d_rgb_owned;
+    c->have_pixels = true;
+    if ((rc = ensure_coef(c))) return rc;
+    constexpr uint32_t kMaxBands = sizeof(c->ev_band) / sizeof(c->ev_band[0]);
+    // bands of at least ~8 MB (a copy that size already runs at full PCIe rate), at most kMaxBands of them
+    uint32_t rows_per_band = static_cast<uint32_t>(std::max<size_t>(1, (8u << 20) / (row_bytes * 16)));
+    rows_per_band = std::max(rows_per_band, (c->mcu_h + kMaxBands - 1) / kMaxBands);
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->copy_stream));
+    uint32_t band = 0;
+    for (uint32_t y0 = 0; y0 < c->mcu_h; y0 += rows_per_band, ++band) {
+        const uint32_t rows = std::min(rows_per_band, c->mcu_h - y0);
+        const size_t px0 = static_cast<size_t>(y0) * 16, px1 = std::min<size_t>(h, static_cast<size_t>(y0 + rows) * 16);
+        if (px1 > px0)
+            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + px0 * row_bytes, host_rgb + px0 * row_bytes, (px1 - px0) * row_bytes,
+                                           cudaMemcpyHostToDevice, c->copy_stream));
+        JPGENC_CUDA(c, cudaEventRecord(c->ev_band[band], c->copy_stream));
+        JPGENC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_band[band], 0));
+        if ((rc = launch_forward_rows(c, y0, rows, y0 == 0, y0 + rows >= c->mcu_h))) return rc;
+    }
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->copy_stream));
+    c->upload_pending = true;
+    c->have_coef = true;
+    c->have_scan = c->have_items = false;
     return JPGENC_OK;
 }
 
@@ -415,9 +466,16 @@ int jpgenc_assemble_last(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jp
 
 int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval, uint8_t* dst,
                       uint64_t cap, uint64_t* jpeg_bytes) {
-    const int rc = jpgenc_upload_rgb(c, host_rgb, w, h, maxval);
+    if (!c || !host_rgb) return JPGENC_ERR_ARG;
+    int rc = upload_and_forward(c, host_rgb, w, h, maxval);
     if (rc) return rc;
-    return jpgenc_encode_bound(c, dst, cap, jpeg_bytes);
+    jpgenc_huff_table tables[4];
+    uint64_t scan = 0;
+    if ((rc = run_entropy_stages(c, tables, &scan))) return rc;       // its first synchronisation also covers the copies
+    const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, nullptr);
+    if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
+    if (!dst) return JPGENC_OK;
+    return assemble(c, tables, scan, dst, cap);
 }
 
 int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) {

@@ -57,8 +57,7 @@ struct ForwardParams {
     uint32_t refine_cap;
     uint32_t real_w, real_h;
     uint32_t mcu_w, mcu_h;
-    uint32_t debug_flags;
-    uint32_t prefetch_ahead;              // CTAs resident at once: each CTA warms L2 for the tile this many ids later
+    uint32_t mcu_y0;                      // first MCU row of this launch (band-wise launches behind the H2D copies)
     ColorConsts color;
     QuantConsts2 luma;
     QuantConsts2 chroma;
@@ -80,6 +79,8 @@ struct DeviceTables {
 struct jpgenc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-to-device copies of jpgenc_encode_rgb, overlapped with K1 band by band
+    cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     std::string error;
     int sm_count = 148;
@@ -94,7 +95,7 @@ struct jpgenc_ctx {
     uint8_t* d_rgb_owned = nullptr;
     size_t rgb_cap = 0;
     uint32_t real_w = 0, real_h = 0, maxval = 255, mcu_w = 0, mcu_h = 0;
-    bool have_pixels = false, have_coef = false, have_scan = false, forward_pending = false;
+    bool have_pixels = false, have_coef = false, have_scan = false, forward_pending = false, upload_pending = false;
 
     int16_t* d_coef = nullptr;
     size_t coef_cap = 0;
@@ -144,6 +145,7 @@ struct jpgenc_ctx {
 // launchers implemented in the kernel translation units
 namespace jpgenc {
 int launch_forward(jpgenc_ctx* c);
+int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, bool last);
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
                             uint64_t* refined);
 int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qcb, const int32_t* d_qcr);
