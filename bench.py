@@ -35,7 +35,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "image16k": (16384, 16384, "single 16384x16384 synthetic image (268 Mpx), whole encode"),
     "frame4k": (3840, 2160, "single 3840x2160 synthetic frame, whole encode"),
+    "batch1080p": (1920, 1080, "batch of 1024 synthetic 1920x1080 frames sharded by image across the ranks"),
 }
+BATCH_FRAMES = 1024
 CPU_SAMPLE = (2048, 2048)          # bounded sample of the same generator for the CPU arms (~0.7 s per encode)
 METRIC, UNIT = "encode_throughput", "Mpx/s"
 
@@ -296,6 +298,95 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
+def batch_frames_per_s(local, frames_ptrs, w, h, workers, device_frames, out_ptrs=None, caps=None, reps=1):
+    """frames/s of jpgenc_batch_encode(_device) on this rank, host wall clock around the (synchronous) call"""
+    from jpgenc_b200.capi import Batch
+    b = Batch(local, workers=workers)
+    try:
+        warm = frames_ptrs[: min(len(frames_ptrs), 4 * workers)]
+        b.encode_ptrs(warm, w, h, out_ptrs[: len(warm)] if out_ptrs else None, caps[: len(warm)] if caps else None,
+                      device_frames=device_frames)
+        t = time.perf_counter()
+        for _ in range(reps):
+            sizes = b.encode_ptrs(frames_ptrs, w, h, out_ptrs, caps, device_frames=device_frames)
+        dt = (time.perf_counter() - t) / reps
+    finally:
+        b.close()
+    return len(frames_ptrs) / dt, dt, sizes
+
+
+def run_batch(args):
+    """BASELINE config 4: 1024 frames of 1920x1080, frame k (seed k) encoded by rank owner_of(k); no collective on the
+    data path.  value = frames resident in HBM; e2e = frames in pinned host memory, files back in pinned host memory."""
+    import torch
+    from jpgenc_b200.capi import Encoder, pinned_empty, pinned_free
+    from jpgenc_b200.sharding import frames_for_rank
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w, h, desc = WORKLOADS["batch1080p"]
+    mine = frames_for_rank(BATCH_FRAMES, rank, world)
+    nf, fbytes = len(mine), w * h * 3
+    enc = Encoder(local)
+    d_all = enc.dev_alloc(nf * fbytes)
+    for i, k in enumerate(mine):
+        enc.synth_rgb(d_all + i * fbytes, w, h, k)
+    enc.synchronize()
+    dev_ptrs = [d_all + i * fbytes for i in range(nf)]
+    workers = 8
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    fps_dev, dt_dev, sizes = batch_frames_per_s(local, dev_ptrs, w, h, workers, True, reps=max(1, args.steps // 50))
+    barrier()
+    clocks = sampler.summary()
+    dt_dev = max_over_ranks(dt_dev)
+    # end to end: the same frames in pinned host memory, complete files written to pinned host memory
+    host, host_ptr = pinned_empty(nf * fbytes)
+    enc.d2h(host, d_all)
+    cap = max(sizes) + 4096
+    out, out_ptr = pinned_empty(nf * cap)
+    barrier()
+    fps_e2e, dt_e2e, sizes2 = batch_frames_per_s(local, [host_ptr + i * fbytes for i in range(nf)], w, h, workers, False,
+                                                 [out_ptr + i * cap for i in range(nf)], [cap] * nf)
+    barrier()
+    dt_e2e = max_over_ranks(dt_e2e)
+    assert sizes2 == sizes and out[0] == 0xFF and out[1] == 0xD8
+    mpx = BATCH_FRAMES * w * h / 1e6
+    line = {"metric": METRIC, "value": round(mpx / dt_dev, 1), "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
+            "ms_per_step": round(dt_dev * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": desc, "frames": BATCH_FRAMES, "frames_per_gpu": nf, "width": w, "height": h,
+                       "contexts_per_gpu": workers, "timing": "host wall clock around the synchronous batch call (several streams per GPU), max over ranks",
+                       "l2": "inputs larger than L2 (%.1f GB of frames per GPU)" % (nf * fbytes / 1e9)},
+            "e2e": {"value": round(mpx / dt_e2e, 1), "unit": UNIT, "h2d_bytes_per_step": nf * fbytes, "d2h_bytes_per_step": int(sum(sizes)),
+                    "ms_per_step": round(dt_e2e * 1e3, 3), "frames_per_s": round(BATCH_FRAMES / dt_e2e, 1)},
+            "frames_per_s": round(BATCH_FRAMES / dt_dev, 1), "gpu_launches": 7 * nf, "clocks": clocks,
+            "jpeg_bytes_per_frame": int(sum(sizes) / max(nf, 1))}
+    pinned_free(host_ptr); pinned_free(out_ptr); enc.dev_free(d_all); enc.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def extra_workloads(enc, args, peak):
     """the other single-GPU configurations of BASELINE.json, measured the same way (reported, not the headline)"""
     import numpy as np
@@ -341,6 +432,29 @@ def extra_workloads(enc, args, peak):
         out["frame4k"] = {"ms_per_frame": round(tot / reps, 4), "mpx_per_s": round(w * h / 1e6 / (tot / reps / 1e3), 1),
                           "k1_ms": round(s.ms_k1, 4), "l2": "flushed between iterations (256 MB write)"}
         enc.dev_free(d)
+    # configs[4] in small: 256 frames of 1920x1080 through the batch API (8 contexts on this GPU)
+    try:
+        from jpgenc_b200.capi import pinned_empty, pinned_free
+        w, h, nf = 1920, 1080, 256
+        fbytes = w * h * 3
+        d_all = enc.dev_alloc(nf * fbytes)
+        for k in range(nf):
+            enc.synth_rgb(d_all + k * fbytes, w, h, k)
+        enc.synchronize()
+        fps_dev, _, sizes = batch_frames_per_s(enc.device, [d_all + k * fbytes for k in range(nf)], w, h, 8, True, reps=2)
+        host, host_ptr = pinned_empty(nf * fbytes)
+        enc.d2h(host, d_all)
+        cap = max(sizes) + 4096
+        outb, out_ptr = pinned_empty(nf * cap)
+        fps_e2e, _, _ = batch_frames_per_s(enc.device, [host_ptr + k * fbytes for k in range(nf)], w, h, 8, False,
+                                           [out_ptr + k * cap for k in range(nf)], [cap] * nf, reps=2)
+        pinned_free(host_ptr); pinned_free(out_ptr); enc.dev_free(d_all)
+        out["batch1080p_256"] = {"frames": nf, "contexts": 8, "device_resident_frames_per_s": round(fps_dev, 1),
+                                 "device_resident_mpx_per_s": round(fps_dev * w * h / 1e6, 1),
+                                 "e2e_frames_per_s": round(fps_e2e, 1), "e2e_mpx_per_s": round(fps_e2e * w * h / 1e6, 1),
+                                 "timing": "host wall clock around the synchronous batch call"}
+    except Exception as ex:
+        out["batch1080p_256"] = {"error": repr(ex)}
     return out
 
 
@@ -355,6 +469,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "batch1080p":
+        run_batch(args)
     else:
         run_ours(args)
 

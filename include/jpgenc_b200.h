@@ -135,6 +135,22 @@ int jpgenc_encode_rgb(jpgenc_ctx* ctx, const uint8_t* host_rgb, uint32_t real_w,
 /* main.cpp:8-32 — PPM file in, JPEG file out */
 int jpgenc_encode_ppm_file(jpgenc_ctx* ctx, const char* ppm_path, const char* jpg_path);
 
+/* ---- batches: independent images on one GPU (what a caller looping over Image::writeJPEG gets) ------ */
+/* `workers` contexts on `device`, driven by as many host threads; frames are handed out dynamically.  Outputs are
+ * byte-identical to encoding the frames one by one. */
+typedef struct jpgenc_batch jpgenc_batch;
+int  jpgenc_batch_create(int device, int workers, jpgenc_batch** out);
+void jpgenc_batch_destroy(jpgenc_batch* batch);
+const char* jpgenc_batch_last_error(const jpgenc_batch* batch);
+int  jpgenc_batch_set_qtables(jpgenc_batch* batch, const uint8_t qy[64], const uint8_t qc[64]);
+/* n frames of w x h interleaved RGB in host memory (pinned for full PCIe speed); out[i] (capacity caps[i]) receives
+ * the complete JFIF file of frame i, sizes[i] its length.  Returns the first error (text in jpgenc_batch_last_error). */
+int jpgenc_batch_encode(jpgenc_batch* batch, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h,
+                        uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
+/* same for frames that already live in device memory; out may be NULL (scans stay on the device, sizes are reported) */
+int jpgenc_batch_encode_device(jpgenc_batch* batch, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h,
+                               uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
+
 /* ---- config-1 microbenchmark: dctArai + quantize + zigzag on stand-alone blocks -------------------- */
 /* dev_in: nblocks*64 fp32 samples (row-major 8x8 per block); dev_out: nblocks*64 int16 zigzag.
  * Same exactness contract as K1 (FP32 fast path + exact FP64 refinement of boundary cases). */

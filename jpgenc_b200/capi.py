@@ -85,6 +85,14 @@ _SIGNATURES = {
     "jpgenc_timer_begin": (C.c_int, [C.c_void_p]),
     "jpgenc_timer_end": (C.c_int, [C.c_void_p, f32p]),
     "jpgenc_launch_count": (C.c_uint64, [C.c_void_p]),
+    "jpgenc_batch_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "jpgenc_batch_destroy": (None, [C.c_void_p]),
+    "jpgenc_batch_last_error": (C.c_char_p, [C.c_void_p]),
+    "jpgenc_batch_set_qtables": (C.c_int, [C.c_void_p, u8p, u8p]),
+    "jpgenc_batch_encode": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.POINTER(C.c_void_p), u64p, u64p]),
+    "jpgenc_batch_encode_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32,
+                                             C.POINTER(C.c_void_p), u64p, u64p]),
 }
 
 _lib = None
@@ -300,6 +308,53 @@ class Encoder:
 
     def launch_count(self) -> int:
         return self.lib.jpgenc_launch_count(self.h)
+
+
+class Batch:
+    """Several contexts on one GPU driven by host threads inside the library: independent frames in, JPEG files out."""
+
+    def __init__(self, device: int = 0, workers: int = 4):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.jpgenc_batch_create(device, workers, C.byref(h))
+        if rc != OK:
+            raise JpgencError(rc, (self.lib.jpgenc_last_error(None) or b"").decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.jpgenc_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise JpgencError(rc, (self.lib.jpgenc_batch_last_error(self.h) or b"").decode())
+
+    def encode_ptrs(self, frame_ptrs, w: int, h: int, out_ptrs, caps, maxval: int = 255, device_frames: bool = False):
+        """raw-pointer form (pinned host or device frames); out_ptrs may be None for device frames -> sizes only"""
+        n = len(frame_ptrs)
+        frames = (C.c_void_p * n)(*frame_ptrs)
+        sizes = (C.c_uint64 * n)()
+        outs = (C.c_void_p * n)(*out_ptrs) if out_ptrs is not None else None
+        capv = (C.c_uint64 * n)(*caps) if caps is not None else None
+        fn = self.lib.jpgenc_batch_encode_device if device_frames else self.lib.jpgenc_batch_encode
+        self._check(fn(self.h, n, frames, w, h, maxval, outs, capv, sizes))
+        return [int(x) for x in sizes]
+
+    def encode(self, frames, maxval: int = 255):
+        """list of HxWx3 uint8 arrays of one size -> list of JPEG byte strings"""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        h, w, _ = frames[0].shape
+        cap = max(4096, frames[0].size + 4096)
+        outs = [np.empty(cap, np.uint8) for _ in frames]
+        sizes = self.encode_ptrs([f.ctypes.data for f in frames], w, h, [o.ctypes.data for o in outs], [cap] * len(frames), maxval)
+        return [o[:n].tobytes() for o, n in zip(outs, sizes)]
 
 
 def pinned_empty(nbytes: int):

@@ -1,5 +1,9 @@
 // C-ABI of the encode path (include/jpgenc_b200.h): context, buffers, stage calls, whole-image driver.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -10,6 +14,79 @@
 
 namespace jpgenc {
 int launch_exact_all(jpgenc_ctx* c);
+
+// The four Huffman tables of an image are independent and the build is sequential host work (tens of microseconds
+// for a dozen symbols, half a millisecond for a full AC alphabet) during which the GPU has nothing to do.  Three
+// worker threads plus the calling thread build them side by side.  Waking a sleeping thread costs about as much as a
+// small table, so the workers are ARMED (woken, then spinning) when the statistics kernel is launched and find the
+// histogram as soon as it arrives; they go back to sleep after every image.
+class TablePool {
+public:
+    TablePool() {
+        for (int i = 0; i < 3; ++i) workers_[i] = std::thread([this, i] { run(i); });
+    }
+    ~TablePool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread& t : workers_) t.join();
+    }
+    void arm() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            ++armed_;
+        }
+        cv_.notify_all();
+    }
+    // after arm(): builds tables[t] from count[t] / first[t] for t = 0..3 (with null pointers: just releases the workers)
+    int build(const uint32_t (*count)[256], const uint64_t (*first)[256], jpgenc_huff_table* tables) {
+        count_ = count; first_ = first; tables_ = tables;
+        for (int& r : rc_) r = JPGENC_OK;
+        done_.store(0, std::memory_order_relaxed);
+        published_.store(armed_, std::memory_order_release);
+        static const int kMine = 1;                                   // Y_AC: normally the largest alphabet
+        if (count) rc_[kMine] = jpgenc_build_huffman(count[kMine], first[kMine], &tables[kMine]);
+        while (done_.load(std::memory_order_acquire) != 3) cpu_relax();
+        for (int r : rc_) if (r) return r;
+        return JPGENC_OK;
+    }
+
+private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void run(int idx) {
+        static const int kTable[3] = {0, 2, 3};
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return quit_ || armed_ != seen; });
+                if (quit_) return;
+                seen = armed_;
+            }
+            while (published_.load(std::memory_order_acquire) != seen) cpu_relax();
+            const int t = kTable[idx];
+            if (count_) rc_[t] = jpgenc_build_huffman(count_[t], first_[t], &tables_[t]);
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    std::thread workers_[3];
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool quit_ = false;
+    uint64_t armed_ = 0;
+    std::atomic<uint64_t> published_{0};
+    std::atomic<int> done_{0};
+    const uint32_t (*count_)[256] = nullptr;
+    const uint64_t (*first_)[256] = nullptr;
+    jpgenc_huff_table* tables_ = nullptr;
+    int rc_[4] = {0, 0, 0, 0};
+};
 }
 
 using namespace jpgenc;
@@ -134,6 +211,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    delete c->pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_hist); cudaFree(c->d_first); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
@@ -302,6 +380,7 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     std::memcpy(c->host_hist, h, 4096);                          // the scan size is computed from it in jpgenc_entropy_encode
     if (c->upload_pending) {          // banded upload of jpgenc_encode_rgb: the compute stream waited for every band
         c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
+        JPGENC_CUDA(c, cudaEventSynchronize(c->ev_b));           // recorded on the copy stream right after the last band
         JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
         c->upload_pending = false;
     }
@@ -384,9 +463,19 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
     int rc;
     uint32_t count[4][256];
     uint64_t first_pos[4][256];
-    if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
-    for (int t = 0; t < 4; ++t)
-        if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
+    if (!c->parallel_tables) {
+        if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
+        for (int t = 0; t < 4; ++t)
+            if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
+    } else {
+        if (!c->pool) c->pool = new TablePool();
+        c->pool->arm();                                             // the workers wake up while K2 runs
+        if ((rc = jpgenc_symbol_stats(c, count, first_pos))) {
+            c->pool->build(nullptr, nullptr, nullptr);              // release them again
+            return rc;
+        }
+        if ((rc = c->pool->build(count, first_pos, tables))) return fail(c, rc, "Huffman table build failed");
+    }
     if ((rc = jpgenc_entropy_encode(c, tables, scan))) return rc;
     std::memcpy(c->last_tables, tables, sizeof c->last_tables);
     c->have_tables = true;

@@ -232,3 +232,18 @@ def test_batch_frames_independent(encoder, oracle):
     for k in (0, 1, 2):
         rgb = synth_rgb(1920, 1080, k)
         assert encoder.encode_rgb(rgb) == oracle.encode_rgb(rgb)
+
+
+@pytest.mark.gpu
+def test_batch_api_matches_single_encodes(encoder, oracle):
+    """jpgenc_batch_encode: frames handed to several contexts/threads come back byte-identical, in order"""
+    from jpgenc_b200.capi import Batch
+    frames = [synth_rgb(208, 120, s) for s in range(12)] + [noise_rgb(208, 120, 99)]
+    want = [oracle.encode_rgb(f) for f in frames]
+    b = Batch(0, workers=4)
+    try:
+        assert b.encode(frames) == want
+        assert b.encode(frames[:1]) == want[:1]                  # fewer frames than workers
+        assert b.encode(frames[::-1]) == want[::-1]              # contexts are reusable
+    finally:
+        b.close()
