@@ -67,21 +67,51 @@ __device__ __forceinline__ void aan8x2(f2& x0, f2& x1, f2& x2, f2& x3, f2& x4, f
     x3 = sub2(v7, u4);
 }
 
+// Same butterfly, but the last stage is done with scalar operations so that the 16 results can land in ANY registers:
+// o[k] receives frequency k of the first lane (.x of the inputs), o[8 + k] that of the second lane.  Used for the
+// vertical pass, whose results have to be re-paired (two rows instead of two columns) for the horizontal pass; letting
+// the final additions write straight into the new pairs costs 8 extra instructions per call and saves the
+// register-to-register moves of an explicit 2x2 transpose.
+__device__ __forceinline__ void aan8x2_split(const f2& x0, const f2& x1, const f2& x2, const f2& x3, const f2& x4, const f2& x5,
+                                             const f2& x6, const f2& x7, float (&o)[16]) {
+    constexpr float A1 = 0.70710678118654752f, A2 = 0.54119610014619698f, A4 = 1.30656296487637653f,
+                    A5 = 0.38268343236508977f;
+    const f2 z0 = add2(x0, x7), z1 = add2(x1, x6), z2 = add2(x2, x5), z3 = add2(x3, x4);
+    const f2 z4 = sub2(x3, x4), z5 = sub2(x2, x5), z6 = sub2(x1, x6), z7 = sub2(x0, x7);
+    const f2 r0 = add2(z0, z3), r1 = add2(z1, z2), r2 = sub2(z1, z2), r3 = sub2(z0, z3);
+    const f2 n4 = add2(z4, z5);
+    const f2 r5 = add2(z5, z6), r6 = add2(z6, z7);
+    const f2 t2 = add2(r2, r3);
+    const f2 d = sub2(r6, n4);
+    const f2 tmp = __fmul2_rn(d, make_float2(A5, A5));
+    const f2 u4 = fma2s(n4, A2, neg2(tmp));
+    const f2 u6 = fma2s(r6, A4, neg2(tmp));
+    const f2 v5 = fma2s(r5, A1, z7);
+    const f2 v7 = fma2s(r5, -A1, z7);
+    o[0] = r0.x + r1.x;            o[8 + 0] = r0.y + r1.y;
+    o[4] = r0.x - r1.x;            o[8 + 4] = r0.y - r1.y;
+    o[2] = fmaf(t2.x, A1, r3.x);   o[8 + 2] = fmaf(t2.y, A1, r3.y);
+    o[6] = fmaf(t2.x, -A1, r3.x);  o[8 + 6] = fmaf(t2.y, -A1, r3.y);
+    o[5] = u4.x + v7.x;            o[8 + 5] = u4.y + v7.y;
+    o[1] = v5.x + u6.x;            o[8 + 1] = v5.y + u6.y;
+    o[7] = v5.x - u6.x;            o[8 + 7] = v5.y - u6.y;
+    o[3] = v7.x - u4.x;            o[8 + 3] = v7.y - u4.y;
+}
+
 // in : v[r*4+p] = (s[r][2p], s[r][2p+1])   spatial samples, pairs of neighbouring columns
 // out: v[u*4+q] = (F[2q][u], F[2q+1][u])   unscaled frequencies F[v][u], pairs of neighbouring vertical frequencies
 __device__ __forceinline__ void dct8x8_packed(f2 (&v)[32]) {
+    f2 t[32];                                     // t[c*4+q] = (T[2q][c], T[2q+1][c]): column c after the vertical pass
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-        aan8x2(v[0 * 4 + p], v[1 * 4 + p], v[2 * 4 + p], v[3 * 4 + p], v[4 * 4 + p], v[5 * 4 + p], v[6 * 4 + p], v[7 * 4 + p]);
-    f2 t[32];
+    for (int p = 0; p < 4; ++p) {
+        float o[16];
+        aan8x2_split(v[0 * 4 + p], v[1 * 4 + p], v[2 * 4 + p], v[3 * 4 + p], v[4 * 4 + p], v[5 * 4 + p], v[6 * 4 + p], v[7 * 4 + p], o);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const f2 a = v[(2 * q) * 4 + p], b = v[(2 * q + 1) * 4 + p];
-            t[(2 * p) * 4 + q] = make_float2(a.x, b.x);
-            t[(2 * p + 1) * 4 + q] = make_float2(a.y, b.y);
+        for (int q = 0; q < 4; ++q) {
+            t[(2 * p) * 4 + q] = make_float2(o[2 * q], o[2 * q + 1]);
+            t[(2 * p + 1) * 4 + q] = make_float2(o[8 + 2 * q], o[8 + 2 * q + 1]);
         }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         aan8x2(t[0 * 4 + q], t[1 * 4 + q], t[2 * 4 + q], t[3 * 4 + q], t[4 * 4 + q], t[5 * 4 + q], t[6 * 4 + q], t[7 * 4 + q]);
