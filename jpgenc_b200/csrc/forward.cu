@@ -100,17 +100,35 @@ __device__ __forceinline__ void aan8x2_split(const f2& x0, const f2& x1, const f
 
 // in : v[r*4+p] = (s[r][2p], s[r][2p+1])   spatial samples, pairs of neighbouring columns
 // out: v[u*4+q] = (F[2q][u], F[2q+1][u])   unscaled frequencies F[v][u], pairs of neighbouring vertical frequencies
+// kSplit picks how the pairs are re-formed between the passes: scalar last butterfly stage (fewer instructions: K1,
+// which is bound by instruction issue) or packed butterflies + explicit 2x2 register transposes (fewer FP32 operations
+// in flight: the stand-alone block kernel, which is bound by HBM and was 20 % slower with the scalar stage).
+template <bool kSplit>
 __device__ __forceinline__ void dct8x8_packed(f2 (&v)[32]) {
     f2 t[32];                                     // t[c*4+q] = (T[2q][c], T[2q+1][c]): column c after the vertical pass
+    if constexpr (kSplit) {
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        float o[16];
-        aan8x2_split(v[0 * 4 + p], v[1 * 4 + p], v[2 * 4 + p], v[3 * 4 + p], v[4 * 4 + p], v[5 * 4 + p], v[6 * 4 + p], v[7 * 4 + p], o);
+        for (int p = 0; p < 4; ++p) {
+            float o[16];
+            aan8x2_split(v[0 * 4 + p], v[1 * 4 + p], v[2 * 4 + p], v[3 * 4 + p], v[4 * 4 + p], v[5 * 4 + p], v[6 * 4 + p], v[7 * 4 + p], o);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            t[(2 * p) * 4 + q] = make_float2(o[2 * q], o[2 * q + 1]);
-            t[(2 * p + 1) * 4 + q] = make_float2(o[8 + 2 * q], o[8 + 2 * q + 1]);
+            for (int q = 0; q < 4; ++q) {
+                t[(2 * p) * 4 + q] = make_float2(o[2 * q], o[2 * q + 1]);
+                t[(2 * p + 1) * 4 + q] = make_float2(o[8 + 2 * q], o[8 + 2 * q + 1]);
+            }
         }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            aan8x2(v[0 * 4 + p], v[1 * 4 + p], v[2 * 4 + p], v[3 * 4 + p], v[4 * 4 + p], v[5 * 4 + p], v[6 * 4 + p], v[7 * 4 + p]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const f2 a = v[(2 * q) * 4 + p], b = v[(2 * q + 1) * 4 + p];
+                t[(2 * p) * 4 + q] = make_float2(a.x, b.x);
+                t[(2 * p + 1) * 4 + q] = make_float2(a.y, b.y);
+            }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
     const uint32_t mcu_base = my * p.mcu_w + mcu0;
     uint32_t packed[32];
     if (active) {
-        dct8x8_packed(v);
+        dct8x8_packed<true>(v);
         const bool boundary = quantize_pack_packed(v, p.luma, packed);
         const int m = bx >> 1, k = by * 2 + (bx & 1);
         stage_block(sm.tile, m * kBlocksPerMcu + k, packed);
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
                 v[r * 4 + 0] = make_float2(lo.x, lo.y); v[r * 4 + 1] = make_float2(lo.z, lo.w);
                 v[r * 4 + 2] = make_float2(hi.x, hi.y); v[r * 4 + 3] = make_float2(hi.z, hi.w);
             }
-            dct8x8_packed(v);
+            dct8x8_packed<true>(v);
             const bool boundary = quantize_pack_packed(v, p.chroma, packed);
             stage_block(sm.tile, m * kBlocksPerMcu + 4 + comp, packed);
             if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + 4 + comp);
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __r
     __syncthreads();                            // all inputs are in registers: reuse the tile as output staging
     if (tid < nb) {
         uint32_t packed[32];
-        dct8x8_packed(v);
+        dct8x8_packed<false>(v);
         if (quantize_pack_packed(v, q, packed)) {
             const uint32_t at = atomicAdd(refine_count, 1u);
             if (at < refine_cap) refine_list[at] = static_cast<uint32_t>(first + tid);
