@@ -247,3 +247,16 @@ def test_batch_api_matches_single_encodes(encoder, oracle):
         assert b.encode(frames[::-1]) == want[::-1]              # contexts are reusable
     finally:
         b.close()
+
+
+@pytest.mark.parametrize("w,h", [(4096, 1536), (3001, 1203)])
+def test_banded_upload_matches_resident_encode(encoder, oracle, w, h):
+    """jpgenc_encode_rgb uploads in bands with K1 per band (several bands here, also with an odd width where K1 takes
+    the clamped loader): same bytes as the one-shot upload + encode, and as the oracle"""
+    rgb = synth_rgb(w, h, 5)
+    banded = encoder.encode_rgb(rgb)
+    encoder.upload_rgb(rgb)
+    out = np.empty(len(banded) + 64, np.uint8)
+    n = encoder.encode_bound(out)
+    assert out[:n].tobytes() == banded
+    assert banded == oracle.encode_rgb(rgb)
