@@ -195,10 +195,11 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     void* p = nullptr;
     if ((e = cudaMalloc(&p, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_counters = static_cast<uint32_t*>(p);
-    if ((e = cudaMalloc(&p, 4 * 256 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMemset(p, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+    // histogram, first-occurrence keys and a copy of the refinement counter live side by side: one read-back per image
+    if ((e = cudaMalloc(&p, 4096 + 8192 + 16)) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_hist = static_cast<uint32_t*>(p);
-    if ((e = cudaMalloc(&p, 4 * 256 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
-    c->d_first = static_cast<unsigned long long*>(p);
+    c->d_first = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(p) + 4096);
     if ((e = cudaMalloc(&p, sizeof(DeviceTables))) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_tables = static_cast<DeviceTables*>(p);
     c->pinned_bytes = 64 * 1024;
@@ -213,7 +214,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     delete c->pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
-    cudaFree(c->d_hist); cudaFree(c->d_first); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
+    cudaFree(c->d_hist); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -365,15 +366,13 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     if ((rc = ensure(c, &c->d_items, &c->items_cap, tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, tiles * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, tiles * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, tiles * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, (tiles / 8 + tiles / 2048 + 8) * sizeof(unsigned long long)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
     if ((rc = launch_symbol_stats(c))) return rc;
     c->have_items = true;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096, cudaMemcpyDeviceToHost, c->stream));
-    JPGENC_CUDA(c, cudaMemcpyAsync(h + 4096, c->d_first, 8192, cudaMemcpyDeviceToHost, c->stream));
-    JPGENC_CUDA(c, cudaMemcpyAsync(h + 12288, c->d_counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096 + 8192 + 16, cudaMemcpyDeviceToHost, c->stream));   // + K2's copy of the refine counter
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     std::memcpy(count, h, 4096);
     std::memcpy(first_pos, h + 4096, 8192);

@@ -114,7 +114,7 @@ struct jpgenc_ctx {
     size_t tile_cnt_cap = 0;
     uint32_t* d_range_bits = nullptr;           // per K2 tile: bits its items encode to (K3a)
     size_t range_bits_cap = 0;
-    unsigned long long* d_range_base = nullptr; // per K2 tile: bit offset in the scan (K3s)
+    unsigned long long* d_range_base = nullptr; // bits per group of 8 tiles, then per 256 groups (K3a); K3b derives offsets from them
     size_t range_base_cap = 0;
     bool have_items = false;
     uint32_t host_hist[4 * 256];          // K2's histogram as last read back

@@ -3,9 +3,10 @@
 // Replaces Image::doHuffmanEncoding, the per-MCU Bitstream concatenation, Bitstream::fill() and the stuffing
 // operator<< (reference src/Image.cpp:737-829, 957-971; include/BitstreamGeneric.hpp:126-146, 182-195, 213-224, 242-248).
 //
-// K3 reads the symbol items K2 left in HBM (blockwalk.cuh), never the coefficients, in three launches:
+// K3 reads the symbol items K2 left in HBM (blockwalk.cuh), never the coefficients, in two launches:
 //   K3a  one warp per item range (= one K2 tile, 384 blocks): coalesced pass, bits the range encodes to;
-//   K3s  exclusive scan of those sizes -> bit offset of every range (and the total, checked against the histogram);
+//        sizes are also accumulated per group of 8 ranges and per 256 groups, from which
+//        K3b derives every range's bit offset with a few hundred additions (no serial scan);
 //   K3b  one warp per range: codes assembled MSB-first in a per-warp shared-memory bit buffer and written out as whole
 //        32-bit words (only the two words a chunk shares with its neighbours use atomicOr).
 // With the offsets known up front no warp ever waits for another one: no tickets, no look-back, no block barriers.
@@ -54,10 +55,15 @@ struct EntropyParams {
     const uint32_t* range_cnt;          // [nranges]
     uint32_t nranges;                   // number of K2 tiles
     const DeviceTables* tables;
-    uint32_t* range_bits;               // [nranges] bits the range encodes to            (K3a writes, K3s reads)
-    unsigned long long* range_base;     // [nranges] bit offset of the range in the scan  (K3s writes, K3b reads)
-    uint32_t* raw;                      // zeroed before launch, (total_bits+7)/8 bytes rounded up to words (+ slack)
-    unsigned long long* total_out;      // [0] = total bits written (before padding)
+    uint32_t* range_bits;               // [nranges] bits the range encodes to (K3a)
+    unsigned long long* group_bits;     // [ceil(nranges/8)] bits of the 8 ranges one CTA handles (K3a)
+    unsigned long long* super_bits;     // [ceil(groups/256)] bits of 256 consecutive groups (K3a, atomics; zeroed before K2)
+    uint32_t* raw;                      // (total_bits+7)/8 bytes rounded up to 16 (+ slack); K3a zeroes it, K3b fills it
+    unsigned long long raw_words16;     // size of raw in 16-byte units
+    unsigned long long* total_out;      // [0] = total bits of the scan (before padding), [1] = K4's FF count
+    unsigned long long* k4_status;      // K4's look-back words ...
+    uint32_t k4_tiles;                  // ... and how many
+    uint32_t* counters;                 // [1] K4's tile ticket
 };
 
 // code bits of one item: `nz` ZRL codes first, then the symbol's code with the magnitude bits appended
@@ -89,73 +95,48 @@ __device__ __forceinline__ uint32_t item_fast(uint32_t item, const uint32_t* s_f
 constexpr int kPackThreads = 256;                       // 8 warps, one item range each
 constexpr int kPackWarps = kPackThreads / 32;
 
-// ---- K3a: bits per range (coalesced pass over the items) -----------------------------------------------------
+// ---- K3a: bits per range (coalesced pass over the items) + housekeeping ---------------------------------------
+// Besides sizing the ranges this launch zeroes what the later kernels expect zeroed (the raw scan, K4's look-back words
+// and ticket), so that no memset sits between the host's table build and the first kernel.  Sizes are kept at three
+// levels -- range, group (the 8 ranges of a CTA), super-group (256 groups, accumulated with atomics) -- so that K3b can
+// derive any range's bit offset from a few hundred values instead of waiting for a serial scan.
 __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_constant__ EntropyParams p) {
     __shared__ uint32_t s_tab[1024], s_fast[1024];
+    __shared__ uint32_t s_wbits[kPackWarps];
     for (int i = threadIdx.x; i < 1024; i += kPackThreads) {
         s_tab[i] = (&p.tables->entry[0][0])[i];
         s_fast[i] = (&p.tables->fast[0][0])[i];
     }
+    {   // housekeeping, spread over the grid
+        const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * kPackThreads + threadIdx.x;
+        const unsigned long long gsize = static_cast<unsigned long long>(gridDim.x) * kPackThreads;
+        uint4* raw16 = reinterpret_cast<uint4*>(p.raw);
+        for (unsigned long long i = gtid; i < p.raw_words16; i += gsize) raw16[i] = make_uint4(0, 0, 0, 0);
+        for (unsigned long long i = gtid; i < p.k4_tiles; i += gsize) p.k4_status[i] = 0ull;
+        if (gtid == 0) { p.counters[1] = 0u; p.total_out[1] = 0ull; }
+    }
     __syncthreads();
     const uint32_t range = blockIdx.x * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (range >= p.nranges) return;
-    const uint32_t n = p.range_cnt[range];
-    const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
     uint32_t bits = 0;
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t item = __ldg(items + i), w = item_fast(item, s_fast);
-        bits += w ? w >> 27 : item_bits(item, s_tab);
+    if (range < p.nranges) {
+        const uint32_t n = p.range_cnt[range];
+        const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t item = __ldg(items + i), w = item_fast(item, s_fast);
+            bits += w ? w >> 27 : item_bits(item, s_tab);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+        if (lane == 0) p.range_bits[range] = bits;
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
-    if (lane == 0) p.range_bits[range] = bits;
-}
-
-// ---- K3s: exclusive scan of the range sizes (one CTA; a few thousand to a few ten-thousand values) -------------
-constexpr int kScanThreads = 1024;
-constexpr int kScanPer = 16;                            // consecutive ranges per thread and round (independent loads)
-__global__ void __launch_bounds__(kScanThreads) range_scan_kernel(const __grid_constant__ EntropyParams p) {
-    __shared__ unsigned long long s_warp[33];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long carry = 0;
-    for (uint32_t round0 = 0; round0 < p.nranges; round0 += kScanThreads * kScanPer) {
-        const uint32_t i0 = round0 + tid * kScanPer;
-        uint32_t v[kScanPer];
-#pragma unroll
-        for (int k = 0; k < kScanPer; ++k) v[k] = i0 + k < p.nranges ? p.range_bits[i0 + k] : 0u;
+    if (lane == 0) s_wbits[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
         unsigned long long sum = 0;
-#pragma unroll
-        for (int k = 0; k < kScanPer; ++k) sum += v[k];
-        unsigned long long inc = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += up;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const unsigned long long w = s_warp[lane];
-            unsigned long long t = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long up = __shfl_up_sync(0xffffffffu, t, d);
-                if (lane >= d) t += up;
-            }
-            s_warp[lane] = t - w;
-            if (lane == 31) s_warp[32] = t;
-        }
-        __syncthreads();
-        unsigned long long at = carry + s_warp[warp] + inc - sum;
-#pragma unroll
-        for (int k = 0; k < kScanPer; ++k) {
-            if (i0 + k < p.nranges) p.range_base[i0 + k] = at;
-            at += v[k];
-        }
-        carry += s_warp[32];
-        __syncthreads();
+        for (int w = 0; w < kPackWarps; ++w) sum += s_wbits[w];
+        p.group_bits[blockIdx.x] = sum;
+        atomicAdd(&p.super_bits[blockIdx.x >> 8], sum);
     }
-    if (tid == 0) p.total_out[0] = carry;
 }
 
 // ---- K3b: pack ---------------------------------------------------------------------------------------------------
@@ -173,6 +154,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     __shared__ uint32_t s_tab[1024], s_fast[1024];                      // DeviceTables::entry / ::fast
     __shared__ uint32_t s_items[kPackWarps][kChunkItems + kChunkRows];  // item j of the chunk at j + (j >> 5)
     __shared__ uint32_t s_bits[kPackWarps][kWarpBitWords + 2];
+    __shared__ unsigned long long s_part[kPackWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += kPackThreads) {
         s_tab[i] = (&p.tables->entry[0][0])[i];
@@ -180,13 +162,28 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     }
     for (int i = lane; i < kWarpBitWords + 2; i += 32) s_bits[warp][i] = 0;
     __syncthreads();
+    // bit offset of this CTA's first range: whole super-groups before it + the groups before it in its own super-group
+    // (at most 255 + 255 values for images up to 500 Mpx; summed cooperatively), then the ranges before this warp's
+    unsigned long long part = 0;
+    {
+        const uint32_t sup = blockIdx.x >> 8;
+        for (uint32_t i = tid; i < sup; i += kPackThreads) part += __ldcg(p.super_bits + i);
+        for (uint32_t i = (sup << 8) + tid; i < blockIdx.x; i += kPackThreads) part += __ldcg(p.group_bits + i);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
     const uint32_t range = blockIdx.x * kPackWarps + warp;
+    unsigned long long cur = 0;                                         // global bit position of the next chunk
+    for (int w = 0; w < kPackWarps; ++w) cur += s_part[w];
+    for (int w = 0; w < warp; ++w)
+        if (blockIdx.x * kPackWarps + w < p.nranges) cur += __ldcg(p.range_bits + blockIdx.x * kPackWarps + w);
     if (range >= p.nranges) return;
     const uint32_t n = p.range_cnt[range];
     const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
     uint32_t* it = s_items[warp];
     uint32_t* bitbuf = s_bits[warp];
-    unsigned long long cur = p.range_base[range];                       // global bit position of the next chunk
 
     for (uint32_t c0 = 0; c0 < n; c0 += kChunkItems) {
         const uint32_t m = min(static_cast<uint32_t>(kChunkItems), n - c0);
@@ -256,6 +253,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
             bw.put((1u << pad) - 1, pad);
             bw.finish();
         }
+        p.total_out[0] = cur;                                           // bits of the scan; the host checks it against the histogram
     }
 }
 
@@ -352,12 +350,10 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     const uint64_t nbytes = (total_bits + 7) / 8;
     const uint32_t ranges = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
     const uint32_t tiles4 = static_cast<uint32_t>((nbytes + kStuffTile - 1) / kStuffTile);
-    // status words: [0,1] totals (bits written by K3, FF bytes stuffed by K4), then K4's look-back words
+    // status words: [0,1] totals (bits of the scan from K3s, FF bytes stuffed by K4), then K4's look-back words; K3a zeroes
+    // them together with the raw scan
     unsigned long long* totals = c->d_lookback;
     unsigned long long* st4 = c->d_lookback + 2;
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, (static_cast<size_t>(tiles4) + 2) * sizeof(unsigned long long), c->stream));
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters + 1, 0, 2 * sizeof(uint32_t), c->stream));
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_raw, 0, ((nbytes + 15) & ~15ull) + 64, c->stream));
 
     EntropyParams p{};
     p.items = c->d_items;
@@ -365,13 +361,16 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
     p.nranges = ranges;
     p.tables = c->d_tables;
     p.range_bits = c->d_range_bits;
-    p.range_base = c->d_range_base;
+    p.group_bits = c->d_range_base;                                  // [groups] then [supers]
+    p.super_bits = c->d_range_base + (ranges + kPackWarps - 1) / kPackWarps;
     p.raw = c->d_raw;
+    p.raw_words16 = (((nbytes + 15) & ~15ull) + 64) / 16;
     p.total_out = totals;
+    p.k4_status = st4;
+    p.k4_tiles = tiles4;
+    p.counters = c->d_counters + 1;                                  // d_counters[2] is K4's ticket
     const unsigned grid = (ranges + kPackWarps - 1) / kPackWarps;
     range_bits_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
-    JPGENC_CUDA(c, cudaGetLastError());
-    range_scan_kernel<<<1, kScanThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     huffman_pack_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
@@ -380,7 +379,7 @@ int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
                                                               st4, c->d_counters + 2, totals + 1);
         JPGENC_CUDA(c, cudaGetLastError());
     }
-    c->launches += 4;
+    c->launches += 3;
     return JPGENC_OK;
 }
 

@@ -31,6 +31,8 @@ struct StatsParams {
     unsigned long long* g_first;      // [4][256]
     uint32_t* items;                  // item stream: tile t owns the slab [t * kSlabItems, (t + 1) * kSlabItems)
     uint32_t* tile_cnt;               // [tiles] items of the tile
+    const uint32_t* refine_count;     // K1's refinement counter ...
+    uint32_t* refine_copy;            // ... copied next to the statistics so that one read-back fetches everything
 };
 
 // One histogram update for the whole warp: lanes with the same bin are counted by their lowest lane, so the hot
@@ -97,7 +99,10 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     const uint32_t base2 = block_exclusive_scan(count | (nac << 16), s_scan, &totals);
     const uint32_t base = base2 & 0xFFFFu, total = totals & 0xFFFFu, total_ac = totals >> 16;
     s_base[tid] = base2;
-    if (tid == 0) p.tile_cnt[blockIdx.x] = total;
+    if (tid == 0) {
+        p.tile_cnt[blockIdx.x] = total;
+        if (blockIdx.x == 0) *p.refine_copy = *p.refine_count;
+    }
     uint32_t* __restrict__ out = p.items + static_cast<size_t>(blockIdx.x) * kSlabItems;
 
     // ---- DC and EOB: exactly one (at most one) per block, so the block's own thread handles them ----
@@ -189,6 +194,8 @@ int launch_symbol_stats(jpgenc_ctx* c) {
     const unsigned grid = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_hist, 0, 4 * 256 * sizeof(uint32_t), c->stream));
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_first, 0xFF, 4 * 256 * sizeof(unsigned long long), c->stream));
+    // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base; clear it off the critical path
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, (grid / 8 + grid / 2048 + 4) * sizeof(unsigned long long), c->stream));
     StatsParams p{};
     p.coef = c->d_coef;
     p.nblocks = static_cast<uint32_t>(nblocks);
@@ -198,6 +205,8 @@ int launch_symbol_stats(jpgenc_ctx* c) {
     p.g_first = c->d_first;
     p.items = c->d_items;
     p.tile_cnt = c->d_tile_cnt;
+    p.refine_count = c->d_counters;
+    p.refine_copy = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->d_hist) + 4096 + 8192);
     JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
     symbol_stats_kernel<<<grid, kTileBlocks, kStatsSmem, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
