@@ -34,10 +34,28 @@ __device__ __forceinline__ TileView tile_view(uint8_t* smem) {
 
 // Coalesced pass over `nb` blocks of global memory: every thread takes 16-byte chunks (four loads in flight) and
 // reduces each to its non-zero flags while the data is in registers.
+__device__ __forceinline__ void scan_chunk(const TileView& tv, int j, const uint4& q) {
+    const uint32_t f = chunk_flags(q);
+    const bool head = (j & 7) == 0;
+    tv.flags[j] = static_cast<uint8_t>(head ? (f & 0xFEu) : f);
+    if (head) tv.dc[j >> 3] = static_cast<int16_t>(q.x & 0xFFFFu);
+}
+
 __device__ __forceinline__ void scan_tile(const TileView& tv, const int16_t* __restrict__ gsrc, int nb, int tid, int nthreads) {
     const uint4* g = reinterpret_cast<const uint4*>(gsrc);
     const int chunks = nb * 8;
     constexpr int kInFlight = 4;
+    if (nb == kTileBlocks) {                        // full tile: no bounds checks
+#pragma unroll
+        for (int j0 = 0; j0 < kTileBlocks * 8; j0 += kInFlight * kTileBlocks) {
+            uint4 q[kInFlight];
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u) q[u] = __ldg(g + j0 + u * kTileBlocks + tid);
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u) scan_chunk(tv, j0 + u * kTileBlocks + tid, q[u]);
+        }
+        return;
+    }
     for (int j0 = 0; j0 < chunks; j0 += kInFlight * nthreads) {
         uint4 q[kInFlight];
 #pragma unroll
@@ -48,12 +66,7 @@ __device__ __forceinline__ void scan_tile(const TileView& tv, const int16_t* __r
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
             const int j = j0 + u * nthreads + tid;
-            if (j < chunks) {
-                const uint32_t f = chunk_flags(q[u]);
-                const bool head = (j & 7) == 0;
-                tv.flags[j] = static_cast<uint8_t>(head ? (f & 0xFEu) : f);
-                if (head) tv.dc[j >> 3] = static_cast<int16_t>(q[u].x & 0xFFFFu);
-            }
+            if (j < chunks) scan_chunk(tv, j, q[u]);
         }
     }
 }

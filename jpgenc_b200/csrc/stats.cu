@@ -12,9 +12,9 @@
 // Work distribution.  Blocks hold very different numbers of non-zero coefficients, so "one thread walks one block"
 // diverges badly.  Instead a tile of 384 blocks is flattened: every thread sizes its block with a popcount of the
 // block's 64-bit non-zero mask, a CTA scan gives each block its first item index, the threads expand their masks into
-// 16-bit (block, position) descriptors, and then consecutive lanes process consecutive non-zero COEFFICIENTS: the run
-// length comes from the mask with one CLZ (distance to the previous set bit), so no lane ever loops over zeros, the
-// work per lane is equal whatever the blocks look like, and the item stores are coalesced.  The DC and EOB symbols
+// (block, position, run) descriptors -- a loop of a few instructions per set bit -- and then consecutive lanes process
+// consecutive non-zero COEFFICIENTS: no lane ever loops over zeros, the work per lane is equal whatever the blocks look
+// like, the loop body is branch-free and the item stores are coalesced.  The DC and EOB symbols
 // exist exactly once (at most once) per block and stay with the block's own thread.
 #include "blockwalk.cuh"
 
@@ -50,7 +50,7 @@ __device__ __forceinline__ void warp_count(uint32_t* s_hist, unsigned long long*
 constexpr int kStatsSmem = kTileSmemBytes                // masks + dc
                            + kTileBlocks * 8             // text key of the block
                            + kTileBlocks * 4             // first item / first AC descriptor of the block
-                           + kDescCap * 2                // descriptors
+                           + kDescCap * 4                // descriptors
                            + 4096 + 8192                 // histogram, first-occurrence keys
                            + 36 * 4;                     // scan scratch
 
@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     uint8_t* at = smem + kTileSmemBytes;
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(at);    at += kTileBlocks * 8;
     uint32_t* s_base = reinterpret_cast<uint32_t*>(at);                       at += kTileBlocks * 4;
-    uint16_t* s_desc = reinterpret_cast<uint16_t*>(at);                       at += kDescCap * 2;
+    uint32_t* s_desc = reinterpret_cast<uint32_t*>(at);                       at += kDescCap * 4;
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(at);                       at += 4096;
     unsigned long long* s_first = reinterpret_cast<unsigned long long*>(at);  at += 8192;
     uint32_t* s_scan = reinterpret_cast<uint32_t*>(at);
+    __shared__ uint32_t s_origin[2];                                      // MCU column / row of the tile's first MCU
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t first = blockIdx.x * kTileBlocks;
@@ -72,6 +73,11 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     // the global minima seen so far bound what this tile can still contribute: after the first tiles almost no
     // key is smaller, so the shared-memory atomicMin below is rarely executed
     for (int i = tid; i < 1024; i += kTileBlocks) { s_hist[i] = 0; s_first[i] = __ldcg(&p.g_first[i]); }
+    if (tid == 0) {                                                       // the tile's only division
+        const uint32_t m0 = first / kBlocksPerMcu, y0 = m0 / p.mcu_w;
+        s_origin[0] = m0 - y0 * p.mcu_w;
+        s_origin[1] = y0;
+    }
     scan_tile(tv, p.coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
 
@@ -87,8 +93,9 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
         diff = tv.dc[tid] - dc_predictor(tv, p.coef, first, tid);
         nac = __popc(lo) + __popc(hi);
         eob = (hi >> 31) ? 0u : 1u;                                       // no EOB when coefficient 63 is non-zero
-        const uint32_t mcu = (first + tid) / kBlocksPerMcu;
-        const uint32_t my = mcu / p.mcu_w, mx = mcu - my * p.mcu_w;
+        const uint32_t lm = tid / kBlocksPerMcu, mcu = first / kBlocksPerMcu + lm;
+        uint32_t mx = s_origin[0] + lm, my = s_origin[1];
+        while (mx >= p.mcu_w) { mx -= p.mcu_w; ++my; }                    // a 64-MCU tile wraps rarely
         key = 256ull * (k < 4 ? static_cast<unsigned long long>(my * 2 + (k >> 1)) * (2ull * p.mcu_w) + mx * 2 + (k & 1)
                               : static_cast<unsigned long long>(k - 4) * p.n_mcu + mcu);
         s_key[tid] = key;
@@ -125,9 +132,12 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     // ---- AC coefficients, flattened ----
     const uint32_t base_ac = base2 >> 16;
     for (uint32_t win = 0; win < total_ac; win += kDescCap) {
-        // expand: descriptor (block << 6 | position) of every non-zero AC coefficient in [win, win + kDescCap)
+        // expand: one descriptor per non-zero AC coefficient in [win, win + kDescCap):
+        //   [5:0] zigzag position, [11:6] zeros since the previous non-zero coefficient (or the DC), [20:12] block, [21] chroma
         if (live && base_ac < win + kDescCap && base_ac + nac > win) {
             uint32_t g = base_ac - win;                                   // wraps to a huge value while g is before the window
+            const uint32_t tag = (static_cast<uint32_t>(tid) << 12) | (k < 4 ? 0u : 1u << 21);
+            int prev = 0;
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 uint32_t m = half ? hi : lo;
@@ -135,13 +145,14 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
                 while (m) {
                     const int pos = half * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    if (g < kDescCap) s_desc[g] = static_cast<uint16_t>((tid << 6) | pos);
+                    if (g < kDescCap) s_desc[g] = tag | static_cast<uint32_t>((pos - prev - 1) << 6) | static_cast<uint32_t>(pos);
+                    prev = pos;
                     ++g;
                 }
             }
         }
         __syncthreads();
-        // consecutive lanes take consecutive coefficients; the run length is the distance to the previous set mask bit
+        // consecutive lanes take consecutive coefficients
         const uint32_t n = min(static_cast<uint32_t>(kDescCap), total_ac - win);
         for (uint32_t j0 = 0; j0 < n; j0 += kTileBlocks) {              // uniform trip count: warp_count is a warp-wide operation
             const uint32_t j = j0 + tid;
@@ -149,17 +160,11 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
             int idx = 0, nzrl = 0, table = 0;
             unsigned long long ikey = 0;
             if (has) {
-                const uint32_t d = s_desc[j], b = d >> 6, pos = d & 63;
-                uint32_t mlo, mhi;
-                load_mask(tv, b, mlo, mhi);
-                const unsigned long long below = ((static_cast<unsigned long long>(mhi) << 32) | mlo) & ((1ull << pos) - 1ull);
-                const int prev = 63 - __clzll(static_cast<long long>(below | 1ull));        // bit 0 stands for the DC position
-                int run = static_cast<int>(pos) - prev - 1;
-                nzrl = run >> 4;
-                run &= 15;
+                const uint32_t d = s_desc[j], pos = d & 63u, run = (d >> 6) & 63u, b = (d >> 12) & 511u;
+                nzrl = static_cast<int>(run >> 4);
                 const int value = p.coef[static_cast<size_t>(first + b) * kCoefPerBlock + pos];     // L1/L2 hit: the tile was just read
-                const int symbol = (run << 4) | category_of(value);
-                table = ((b % kBlocksPerMcu) < 4 ? 0 : 2) + 1;
+                const int symbol = static_cast<int>((run & 15u) << 4) | category_of(value);
+                table = static_cast<int>(d >> 21) * 2 + 1;
                 idx = table * 256 + symbol;
                 ikey = s_key[b] + 2 * pos + 1;
                 const uint32_t sb = s_base[b];
