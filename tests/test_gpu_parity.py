@@ -260,3 +260,13 @@ def test_banded_upload_matches_resident_encode(encoder, oracle, w, h):
     n = encoder.encode_bound(out)
     assert out[:n].tobytes() == banded
     assert banded == oracle.encode_rgb(rgb)
+
+
+def test_high_entropy_image_byte_identical(encoder, oracle):
+    """2048x2048 uniform noise: ~40 AC symbols per block, so K2 needs several descriptor windows per tile, item
+    ranges are ~25x longer than on smooth images and the scan has many FF bytes to stuff"""
+    rgb = noise_rgb(2048, 2048, 7)
+    mine = encoder.encode_rgb(rgb)
+    st = encoder.stats()
+    assert st.stuffed_ff > 1000 and st.scan_bits > 8 * 2048 * 2048 // 4
+    assert mine == oracle.encode_rgb(rgb)
