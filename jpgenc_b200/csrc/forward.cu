@@ -15,6 +15,7 @@
 //    coefficients are the reference's, bit for bit;
 //  * coefficients leave through a bank-conflict-free swizzled staging buffer as full 512-byte warp stores,
 //    already in the MCU-interleaved order the entropy coder consumes.
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -563,19 +564,68 @@ void default_dct_constants(double a[5], double s[8]) {
     for (int k = 1; k < 8; ++k) s[k] = 1 / (4 * c[k]);
 }
 
-// Bound on |fp32 quotient - reference quotient| used to decide which blocks need the exact path:
-// kErrUnscaled bounds the absolute error of an unscaled 2-D AAN output (|.| <= ~1.4e4) computed in FP32 from
-// 8-bit samples; DESIGN.md "Exactness" derives ~1e-2 worst case, tests/test_forward_gpu.py measures it.
-constexpr double kErrUnscaled = 0.03;
+// ---- how far the FP32 fast path can be from the reference: a computed, rigorous bound per coefficient ------------
+// Every intermediate of the two packed AAN passes (aan8x2 / aan8x2_split, identical operation sequences) is tracked as
+// (mag, err): mag bounds the magnitude of the ideal (real-arithmetic = reference, whose double rounding is ~1e-13)
+// value, err bounds |fp32 value - ideal value|.  With u = 2^-24: an addition adds u*(|x|+|y|) to the incoming errors, a
+// multiplication by a constant c (itself rounded to fp32) scales them by |c| and adds 2u|c||x|; an FMA does both.
+// Magnitudes are propagated as sums, i.e. for the worst 8-bit input pattern.  The result (0.009 for the DC term up to
+// 0.030 for the (1,1)/(7,7)-type terms) replaces a single hand-derived constant: low frequencies, where almost all
+// rounding-boundary hits occur, get a 2-3 times tighter threshold, which cuts the number of blocks sent to the FP64 path.
+namespace {
+struct Bound { double mag, err; };
+constexpr double kU = 5.9604644775390625e-8;                      // 2^-24
+Bound b_add(Bound x, Bound y) { return {x.mag + y.mag, x.err + y.err + kU * (x.mag + y.mag + x.err + y.err)}; }
+Bound b_mul(Bound x, double c) {
+    c = std::fabs(c);
+    return {c * x.mag, c * (1 + kU) * x.err + kU * c * x.mag + kU * c * (1 + kU) * (x.mag + x.err)};
+}
+Bound b_fma(Bound x, double c, Bound y) {                            // x * c + y
+    c = std::fabs(c);
+    const double prod = c * (1 + kU) * (x.mag + x.err);
+    return {c * x.mag + y.mag, c * (1 + kU) * x.err + kU * c * x.mag + y.err + kU * (prod + y.mag + y.err)};
+}
+void b_aan8(const Bound (&x)[8], Bound (&o)[8]) {                    // same dataflow as aan8x2
+    constexpr double A1 = 0.70710678118654752, A2 = 0.54119610014619698, A4 = 1.30656296487637653, A5 = 0.38268343236508977;
+    const Bound z0 = b_add(x[0], x[7]), z1 = b_add(x[1], x[6]), z2 = b_add(x[2], x[5]), z3 = b_add(x[3], x[4]);
+    const Bound z4 = b_add(x[3], x[4]), z5 = b_add(x[2], x[5]), z6 = b_add(x[1], x[6]), z7 = b_add(x[0], x[7]);
+    const Bound r0 = b_add(z0, z3), r1 = b_add(z1, z2), r2 = b_add(z1, z2), r3 = b_add(z0, z3);
+    const Bound n4 = b_add(z4, z5), r5 = b_add(z5, z6), r6 = b_add(z6, z7);
+    const Bound t2 = b_add(r2, r3);
+    const Bound tmp = b_mul(b_add(r6, n4), A5);
+    const Bound u4 = b_fma(n4, A2, tmp), u6 = b_fma(r6, A4, tmp), v5 = b_fma(r5, A1, z7), v7 = b_fma(r5, A1, z7);
+    o[0] = b_add(r0, r1); o[4] = b_add(r0, r1); o[2] = b_fma(t2, A1, r3); o[6] = b_fma(t2, A1, r3);
+    o[5] = b_add(u4, v7); o[1] = b_add(v5, u6); o[7] = b_add(v5, u6); o[3] = b_add(v7, u4);
+}
+// bounds of the unscaled 2-D output F[v][u] for samples in [-128, 128] that carry an input error of at most err_in
+void aan2d_bounds(double err_in, Bound (&out)[64]) {
+    Bound in[8], pass1[8];
+    for (Bound& b : in) b = {128.0, err_in};
+    b_aan8(in, pass1);
+    for (int v = 0; v < 8; ++v) {
+        Bound row[8], res[8];
+        for (Bound& b : row) b = pass1[v];
+        b_aan8(row, res);
+        for (int u = 0; u < 8; ++u) out[v * 8 + u] = res[u];
+    }
+}
+// error of the colour conversion feeding the transform: three FMAs on magnitudes <= 383 plus the fp32 rounding of the
+// three folded constants (<= 1404 u for Y, less for Cb/Cr); the stand-alone block kernel has exact inputs
+constexpr double kColourErr = 1.0e-4;
+}  // namespace
 
 void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out) {
+    Bound bound[64];
+    aan2d_bounds(kColourErr, bound);
     for (int v = 0; v < 8; ++v)
         for (int u = 0; u < 8; ++u) {
-            const double m = s[v] * s[u] / static_cast<double>(q[v * 8 + u]);
-            out->mul[v * 8 + u] = static_cast<float>(m);
-            double delta = kErrUnscaled * m + 1e-6;
+            const int i = v * 8 + u;
+            const double m = s[v] * s[u] / static_cast<double>(q[i]);
+            out->mul[i] = static_cast<float>(m);
+            // |fp32 quotient - reference quotient| <= m * (err + u * mag)  [transform error, rounding of m]  + the final FMA
+            double delta = 1.0001 * m * (bound[i].err + kU * bound[i].mag) + 1e-7;
             if (delta > 0.25) delta = 0.25;
-            out->thr[v * 8 + u] = static_cast<float>(0.5 - delta);
+            out->thr[i] = static_cast<float>(0.5 - delta);
         }
 }
 
