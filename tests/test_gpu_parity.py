@@ -270,3 +270,47 @@ def test_high_entropy_image_byte_identical(encoder, oracle):
     st = encoder.stats()
     assert st.stuffed_ff > 1000 and st.scan_bits > 8 * 2048 * 2048 // 4
     assert mine == oracle.encode_rgb(rgb)
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 16])
+def test_adversarial_blocks_bit_exact(encoder, oracle, q):
+    """The FP32 fast path is only trusted outside a computed error bound around rounding boundaries.  Stress it with
+    inputs built to maximise FP32 error and boundary hits: +-128 patterns (largest magnitudes in every butterfly),
+    sparse impulses, and flat quantisers q (a flat q=1 table makes every quotient a full-magnitude coefficient, so
+    the threshold is at its loosest); blocks with ties (exact x.5 quotients) must round half away like the reference."""
+    rng = np.random.default_rng(100 + q)
+    blocks = []
+    for r in range(8):                                   # separable +-128 sign patterns: extreme magnitudes
+        for c in range(8):
+            sr = np.where(np.cos((2 * np.arange(8) + 1) * r * np.pi / 16) >= 0, 1.0, -1.0)
+            sc = np.where(np.cos((2 * np.arange(8) + 1) * c * np.pi / 16) >= 0, 1.0, -1.0)
+            blocks.append(128.0 * np.outer(sr, sc))
+            blocks.append(-128.0 * np.outer(sr, sc))
+    blocks += [np.full((8, 8), v, np.float64) for v in (-128, -127, -1, 0, 1, 4, 12, 127, 128)]   # DC only: exact ties for q | 8v
+    for _ in range(400):                                 # +-128 random signs
+        blocks.append(128.0 * rng.choice([-1.0, 1.0], (8, 8)))
+    for _ in range(400):                                 # saturated / near-saturated integers
+        blocks.append(rng.choice([-128.0, -127.0, 126.0, 127.0], (8, 8)))
+    for _ in range(400):                                 # impulses
+        b = np.zeros((8, 8)); b[rng.integers(8), rng.integers(8)] = rng.integers(-128, 128); blocks.append(b)
+    for _ in range(800):                                 # plain 8-bit noise
+        blocks.append(rng.integers(-128, 128, (8, 8)).astype(np.float64))
+    x = np.ascontiguousarray(np.stack(blocks).reshape(-1, 64), np.float32)
+    nb = x.shape[0]
+    table = np.full(64, q, np.uint8)
+    d_in, d_out = encoder.dev_alloc(nb * 256), encoder.dev_alloc(nb * 128)
+    try:
+        encoder.h2d(d_in, x)
+        refined = encoder.dct_quant_blocks(d_in, d_out, nb, table)
+        y = np.empty((nb, 64), np.int16)
+        encoder.d2h(y, d_out)
+        zz = np.array([oracle.zigzag_index(i) for i in range(64)])
+        qt = table.reshape(8, 8)
+        bad = 0
+        for b in range(nb):
+            want = oracle.quantize(oracle.dct(x[b].astype(np.float64).reshape(8, 8)), qt).reshape(64)[zz]
+            bad += int(np.count_nonzero(want != y[b]))
+        assert bad == 0, f"{bad} coefficients differ (q={q}, {refined} of {nb} blocks refined)"
+    finally:
+        encoder.dev_free(d_in)
+        encoder.dev_free(d_out)
