@@ -148,9 +148,9 @@ std::vector<Byte> Image::encodeJPEG() {
             }
     }
     jpgenc_ctx* c = g_gpu.get();
-    check(c, jpgenc_upload_rgb(c, samples_.data(), real_width, real_height, maxval_));
     uint64_t need = 0;
-    check(c, jpgenc_encode_bound(c, nullptr, 0, &need));           // scan stays on the device, size comes back
+    // upload (in bands, overlapped with the first kernel) + encode; the scan stays on the device, its size comes back
+    check(c, jpgenc_encode_rgb(c, samples_.data(), real_width, real_height, maxval_, nullptr, 0, &need));
     std::vector<Byte> out(need);
     check(c, jpgenc_assemble_last(c, out.data(), out.size(), &need));   // headers + D2H of the scan + EOI
     return out;
