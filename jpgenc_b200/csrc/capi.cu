@@ -126,7 +126,20 @@ int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
     if (w == 0 || h == 0 || maxval == 0 || maxval > 255) return fail(c, JPGENC_ERR_ARG, "width/height/maxval out of range");
     c->real_w = w; c->real_h = h; c->maxval = maxval;
     c->mcu_w = (w + 15) / 16; c->mcu_h = (h + 15) / 16;        // src/Image.cpp:479-489
+    c->nframes = 1;
     c->have_coef = c->have_scan = c->have_items = false;
+    return JPGENC_OK;
+}
+
+constexpr size_t kStatsBytes = 4096 + 8192;                    // per frame: histogram + first-occurrence keys (stats.cu)
+
+// pinned host staging, grown on demand
+int ensure_pinned(jpgenc_ctx* c, size_t bytes) {
+    if (c->pinned_bytes >= bytes) return JPGENC_OK;
+    if (c->h_pinned) JPGENC_CUDA(c, cudaFreeHost(c->h_pinned));
+    c->h_pinned = nullptr; c->pinned_bytes = 0;
+    JPGENC_CUDA(c, cudaMallocHost(&c->h_pinned, bytes));
+    c->pinned_bytes = bytes;
     return JPGENC_OK;
 }
 
@@ -140,8 +153,8 @@ int refresh_forward_stats(jpgenc_ctx* c) {
 }
 
 int ensure_coef(jpgenc_ctx* c) {
-    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
-    if (nblocks * 64 > 0xFFFFFFFFull * 16) return fail(c, JPGENC_ERR_ARG, "image too large");
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu * c->nframes;
+    if (nblocks * 64 > 0xFFFFFFFFull * 16) return fail(c, JPGENC_ERR_ARG, "image (or batch) too large");
     int rc = ensure(c, &c->d_coef, &c->coef_cap, nblocks * kBlockBytes);
     if (rc) return rc;
     size_t cap_bytes = c->refine_cap * sizeof(uint32_t);
@@ -196,12 +209,6 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     if ((e = cudaMalloc(&p, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_counters = static_cast<uint32_t*>(p);
     if ((e = cudaMemset(p, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
-    // histogram, first-occurrence keys and a copy of the refinement counter live side by side: one read-back per image
-    if ((e = cudaMalloc(&p, 4096 + 8192 + 16)) != cudaSuccess) return bail("cudaMalloc", e);
-    c->d_hist = static_cast<uint32_t*>(p);
-    c->d_first = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(p) + 4096);
-    if ((e = cudaMalloc(&p, sizeof(DeviceTables))) != cudaSuccess) return bail("cudaMalloc", e);
-    c->d_tables = static_cast<DeviceTables*>(p);
     c->pinned_bytes = 64 * 1024;
     if ((e = cudaMallocHost(&c->h_pinned, c->pinned_bytes)) != cudaSuccess) return bail("cudaMallocHost", e);
     *out = c;
@@ -214,7 +221,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     delete c->pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
-    cudaFree(c->d_hist); cudaFree(c->d_tables); cudaFree(c->d_lookback); cudaFree(c->d_raw);
+    cudaFree(c->d_stats); cudaFree(c->d_meta); cudaFree(c->d_tables); cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -355,36 +362,45 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
     return JPGENC_OK;
 }
 
-int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_pos[4][256]) {
-    if (!c || !count || !first_pos) return JPGENC_ERR_ARG;
-    if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
+// ---- K2 and K3/K4 for all frames bound to the context (one image = one frame) ------------------------------------
+// pinned staging: [statistics F * kStatsBytes + 16][device tables F * 8 KB][meta][totals F * 16]
+static size_t stage_tables_off(uint32_t F) { return ((F * kStatsBytes + 16 + 255) / 256) * 256; }
+static size_t stage_meta_off(uint32_t F) { return stage_tables_off(F) + F * sizeof(DeviceTables); }
+static size_t meta_bytes(uint32_t F) { return ((F * 16 + (F + 1) * 4 + 15) / 16) * 16; }
+static size_t stage_totals_off(uint32_t F) { return stage_meta_off(F) + meta_bytes(F); }
+static size_t stage_bytes(uint32_t F) { return stage_totals_off(F) + F * 16 + 64; }
+
+static int stats_frames(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t F = c->nframes;
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     int rc;
     // one fixed slab of item slots per tile, sized for the worst case (every coefficient non-zero); typical images
     // touch a few percent of it
-    if ((rc = ensure(c, &c->d_items, &c->items_cap, tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, tiles * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, tiles * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, (tiles / 8 + tiles / 2048 + 8) * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, &c->d_items, &c->items_cap, F * tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, F * tiles * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, F * tiles * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, F * (tiles / 8 + tiles / 2048 + 4) * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, &c->d_stats, &c->stats_cap, F * kStatsBytes + 16))) return rc;
+    if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
     if ((rc = launch_symbol_stats(c))) return rc;
     c->have_items = true;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_hist, 4096 + 8192 + 16, cudaMemcpyDeviceToHost, c->stream));   // + K2's copy of the refine counter
+    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_stats, F * kStatsBytes + 16, cudaMemcpyDeviceToHost, c->stream));   // + K2's copy of the refine counter
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::memcpy(count, h, 4096);
-    std::memcpy(first_pos, h + 4096, 8192);
-    std::memcpy(c->host_hist, h, 4096);                          // the scan size is computed from it in jpgenc_entropy_encode
+    c->host_hist.resize(static_cast<size_t>(F) * 1024);
+    for (uint32_t f = 0; f < F; ++f) std::memcpy(&c->host_hist[f * 1024], h + f * kStatsBytes, 4096);
+    const uint32_t refined = *reinterpret_cast<const uint32_t*>(h + F * kStatsBytes);
     if (c->upload_pending) {          // banded upload of jpgenc_encode_rgb: the compute stream waited for every band
-        c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
+        c->stats.refined_blocks = refined;
         JPGENC_CUDA(c, cudaEventSynchronize(c->ev_b));           // recorded on the copy stream right after the last band
         JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
         c->upload_pending = false;
     }
     if (c->forward_pending) {
-        c->stats.refined_blocks = *reinterpret_cast<const uint32_t*>(h + 12288);
+        c->stats.refined_blocks = refined;
         const int rs = refresh_forward_stats(c);
         if (rs) return rs;
     }
@@ -392,55 +408,102 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     return JPGENC_OK;
 }
 
+// tables: [F][4].  Afterwards c->frame_bits / frame_raw_off / frame_ff describe every frame's scan in d_scan
+// (frame f's stuffed scan starts at byte 2 * frame_raw_off[f]).
+static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t F = c->nframes;
+    if (c->host_hist.size() != static_cast<size_t>(F) * 1024) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+    int rc;
+    if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
+    uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
+    DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + stage_tables_off(F));
+    unsigned long long* m_off = reinterpret_cast<unsigned long long*>(h + stage_meta_off(F));
+    unsigned long long* m_bytes = m_off + F;
+    uint32_t* m_tile0 = reinterpret_cast<uint32_t*>(m_bytes + F);
+    c->frame_bits.assign(F, 0); c->frame_raw_off.assign(F, 0); c->frame_ff.assign(F, 0);
+    // exact size of every scan from the statistics the tables were built from: a symbol costs its code length plus
+    // (symbol & 15) magnitude bits
+    uint64_t raw_total = 0, k4_tiles = 0;
+    for (uint32_t f = 0; f < F; ++f) {
+        const uint32_t* hist = &c->host_hist[static_cast<size_t>(f) * 1024];
+        uint64_t bits = 0;
+        for (int t = 0; t < 4; ++t) {
+            const jpgenc_huff_table& tab = tables[f * 4 + t];
+            for (int s = 0; s < 256; ++s) {
+                const uint32_t len = tab.length[s];
+                const uint32_t code = len ? tab.code_msb[s] >> (32 - len) : 0u, cat = s & 15;
+                ht[f].entry[t][s] = len ? (len << 16) | code : 0u;
+                ht[f].fast[t][s] = (len && len + cat <= 27) ? ((len + cat) << 27) | (code << cat) : 0u;
+                if (hist[t * 256 + s]) {
+                    if (!len) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
+                    bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + cat);
+                }
+            }
+        }
+        if (bits == 0) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+        const uint64_t nbytes = (bits + 7) / 8;
+        c->frame_bits[f] = bits;
+        c->frame_raw_off[f] = raw_total;
+        m_off[f] = raw_total;
+        m_bytes[f] = nbytes;
+        m_tile0[f] = static_cast<uint32_t>(k4_tiles);
+        raw_total += ((nbytes + 15) & ~15ull) + 64;              // 16-byte aligned, with slack for the last words
+        k4_tiles += (nbytes + kK4TileBytes - 1) / kK4TileBytes;
+    }
+    m_tile0[F] = static_cast<uint32_t>(k4_tiles);
+    if (k4_tiles > 0xFFFFFFFFull) return fail(c, JPGENC_ERR_ARG, "scan too large");
+    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, raw_total))) return rc;
+    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * raw_total + 64))) return rc;
+    if ((rc = ensure(c, &c->d_tables, &c->tables_cap, F * sizeof(DeviceTables)))) return rc;
+    if ((rc = ensure(c, &c->d_meta, &c->meta_cap, meta_bytes(F)))) return rc;
+    size_t lb_bytes = c->lookback_cap;
+    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (2 * static_cast<size_t>(F) + k4_tiles + 8) * sizeof(unsigned long long)))) return rc;
+    c->lookback_cap = lb_bytes;
+    // tables and meta sit next to each other in the staging buffer: two copies
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables), cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_meta, m_off, meta_bytes(F), cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    if ((rc = launch_entropy(c, raw_total, static_cast<uint32_t>(k4_tiles)))) return rc;
+    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    // totals: bits written by K3 [F], stuffed FF bytes [F]
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(h + stage_totals_off(F));
+    JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback, F * 16, cudaMemcpyDeviceToHost, c->stream));
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t f = 0; f < F; ++f) {
+        if (totals[f] != c->frame_bits[f]) {
+            c->error = "entropy coder wrote " + std::to_string(totals[f]) + " bits, statistics predicted " + std::to_string(c->frame_bits[f]);
+            return JPGENC_ERR_ARG;
+        }
+        c->frame_ff[f] = totals[F + f];
+    }
+    c->stats.scan_bits = c->frame_bits[0];
+    c->stats.stuffed_ff = c->frame_ff[0];
+    c->stats.scan_bytes = (c->frame_bits[0] + 7) / 8 + c->frame_ff[0];
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_t0, c->ev_t1));
+    c->have_scan = true;
+    return JPGENC_OK;
+}
+
+int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_pos[4][256]) {
+    if (!c || !count || !first_pos) return JPGENC_ERR_ARG;
+    if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
+    if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
+    const int rc = stats_frames(c);
+    if (rc) return rc;
+    const uint8_t* h = static_cast<const uint8_t*>(c->h_pinned);
+    std::memcpy(count, h, 4096);
+    std::memcpy(first_pos, h + 4096, 8192);
+    return JPGENC_OK;
+}
+
 int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t* scan_bytes) {
     if (!c || !tables) return JPGENC_ERR_ARG;
     if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
     if (!c->have_items) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
-    JPGENC_CUDA(c, cudaSetDevice(c->device));
-    // exact size of the scan from the statistics the tables were built from: every symbol costs its code length
-    // plus (symbol & 15) magnitude bits.
-    uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    const uint32_t* hist = c->host_hist;
-    uint64_t total_bits = 0;
-    DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + 8192);
-    for (int t = 0; t < 4; ++t)
-        for (int s = 0; s < 256; ++s) {
-            const uint32_t len = tables[t].length[s];
-            const uint32_t code = len ? tables[t].code_msb[s] >> (32 - len) : 0u, cat = s & 15;
-            ht->entry[t][s] = len ? (len << 16) | code : 0u;
-            ht->fast[t][s] = (len && len + cat <= 27) ? ((len + cat) << 27) | (code << cat) : 0u;
-            if (hist[t * 256 + s]) {
-                if (!len) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
-                total_bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + (s & 15));
-            }
-        }
-    if (total_bits == 0) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
-    const uint64_t nbytes = (total_bits + 7) / 8;
-    const uint64_t nblocks = static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
-    int rc;
-    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, ((nbytes + 15) & ~15ull) + 64))) return rc;
-    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * nbytes + 64))) return rc;
-    const size_t tiles = (nblocks + 383) / 384 + (nbytes + 4095) / 4096 + 16;      // upper bound on K3 + K4 tiles + totals
-    size_t lb_bytes = c->lookback_cap;
-    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, tiles * sizeof(unsigned long long)))) return rc;
-    c->lookback_cap = lb_bytes;
-    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, sizeof(DeviceTables), cudaMemcpyHostToDevice, c->stream));
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-    if ((rc = launch_entropy(c, total_bits))) return rc;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
-    // totals: [0] bits written by K3, [1] number of stuffed FF bytes
-    unsigned long long* totals = reinterpret_cast<unsigned long long*>(h);
-    JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback, 16, cudaMemcpyDeviceToHost, c->stream));
-    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (totals[0] != total_bits) {
-        c->error = "entropy coder wrote " + std::to_string(totals[0]) + " bits, statistics predicted " + std::to_string(total_bits);
-        return JPGENC_ERR_ARG;
-    }
-    c->stats.scan_bits = total_bits;
-    c->stats.stuffed_ff = totals[1];
-    c->stats.scan_bytes = nbytes + totals[1];
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_t0, c->ev_t1));
-    c->have_scan = true;
+    if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
+    const int rc = entropy_frames(c, tables);
+    if (rc) return rc;
     if (scan_bytes) *scan_bytes = c->stats.scan_bytes;
     return JPGENC_OK;
 }

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/jpgenc_b200.h"
 
@@ -50,7 +51,9 @@ struct ColorConsts {                      // FP32 fast path; sample scale folded
 };
 
 struct ForwardParams {
-    const uint8_t* rgb;
+    const uint8_t* rgb;                   // one image ...
+    const uint8_t* const* frames;         // ... or (non-null) one device pointer per frame of a batch of equally sized frames
+    uint32_t blocks_per_frame;            // frame f owns coefficient blocks [f * blocks_per_frame, (f + 1) * blocks_per_frame)
     int16_t* coef;
     uint32_t* refine_list;                // block ids (mcu*6+k) that need the exact path
     uint32_t* refine_count;
@@ -95,6 +98,10 @@ struct jpgenc_ctx {
     double dct_a[5], dct_s[8];
 
     // image state
+    uint32_t nframes = 1;                 // > 1: a batch of equally sized frames goes through every kernel at once
+    const uint8_t** d_frame_ptrs = nullptr;   // [nframes] device pointers of the frames (batches only)
+    size_t frame_ptrs_cap = 0;
+    bool frames_aligned = false;          // every frame pointer is 16-byte aligned (bulk-copy path of K1)
     const uint8_t* d_rgb = nullptr;       // bound or owned
     uint8_t* d_rgb_owned = nullptr;
     size_t rgb_cap = 0;
@@ -106,8 +113,10 @@ struct jpgenc_ctx {
     uint32_t* d_refine_list = nullptr;
     size_t refine_cap = 0;
     uint32_t* d_counters = nullptr;       // [0] refine count, [1] lookback ticket, [2..3] spare
-    uint32_t* d_hist = nullptr;           // [4][256]
-    unsigned long long* d_first = nullptr;// [4][256]
+    uint8_t* d_stats = nullptr;           // per frame: hist u32[4][256] + first-occurrence keys u64[4][256]; then a copy of the refine counter
+    size_t stats_cap = 0;
+    uint8_t* d_meta = nullptr;            // per-frame entropy geometry: raw_off u64[F] | raw_bytes u64[F] | k4_tile0 u32[F+1]
+    size_t meta_cap = 0;
     uint32_t* d_items = nullptr;          // K2's symbol stream (blockwalk.cuh), consumed by K3
     size_t items_cap = 0;
     uint32_t* d_tile_cnt = nullptr;             // per K2 tile: number of items in its slab
@@ -117,9 +126,12 @@ struct jpgenc_ctx {
     unsigned long long* d_range_base = nullptr; // bits per group of 8 tiles, then per 256 groups (K3a); K3b derives offsets from them
     size_t range_base_cap = 0;
     bool have_items = false;
-    uint32_t host_hist[4 * 256];          // K2's histogram as last read back
-    jpgenc::DeviceTables* d_tables = nullptr;
-    unsigned long long* d_lookback = nullptr;  // one status word per K3 tile
+    std::vector<uint32_t> host_hist;      // K2's histograms as last read back, [nframes][4][256]
+    std::vector<uint64_t> frame_bits, frame_raw_off, frame_ff;   // per frame after K3/K4: scan bits, byte offset of its raw scan, stuffed FFs
+    bool k2_configured = false;
+    jpgenc::DeviceTables* d_tables = nullptr;   // [nframes]
+    size_t tables_cap = 0;
+    unsigned long long* d_lookback = nullptr;  // total_bits u64[F] | total_ff u64[F] | one look-back word per K4 tile
     size_t lookback_cap = 0;
     uint32_t* d_raw = nullptr;            // un-stuffed scan, 32-bit words, bytes in stream order
     size_t raw_cap = 0;
@@ -154,7 +166,8 @@ int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64
                             uint64_t* refined);
 int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qcb, const int32_t* d_qcr);
 int launch_symbol_stats(jpgenc_ctx* c);
-int launch_entropy(jpgenc_ctx* c, uint64_t total_bits);
+int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles);
+constexpr uint32_t kK4TileBytes = 16384;   // input bytes per K4 tile (entropy.cu static_asserts it)
 int launch_synth_rgb(jpgenc_ctx* c, uint8_t* d, uint32_t w, uint32_t h, uint32_t seed);
 int launch_synth_blocks(jpgenc_ctx* c, float* d, uint64_t nblocks);
 int launch_flush(jpgenc_ctx* c);

@@ -50,19 +50,28 @@ struct BitWriter {
     __device__ __forceinline__ void finish() { if (fill) flush_word(); }
 };
 
+// Per-frame geometry of the entropy stage.  One image is the batch of one frame; in a batch every frame has its own
+// tables, its own stretch of the raw and of the stuffed scan, and its own totals.
 struct EntropyParams {
-    const uint32_t* items;              // K2's symbol items: range t = the first range_cnt[t] slots of slab t
-    const uint32_t* range_cnt;          // [nranges]
-    uint32_t nranges;                   // number of K2 tiles
-    const DeviceTables* tables;
-    uint32_t* range_bits;               // [nranges] bits the range encodes to (K3a)
-    unsigned long long* group_bits;     // [ceil(nranges/8)] bits of the 8 ranges one CTA handles (K3a)
-    unsigned long long* super_bits;     // [ceil(groups/256)] bits of 256 consecutive groups (K3a, atomics; zeroed before K2)
-    uint32_t* raw;                      // (total_bits+7)/8 bytes rounded up to 16 (+ slack); K3a zeroes it, K3b fills it
+    const uint32_t* items;              // K2's symbol items: range R = the first range_cnt[R] slots of slab R
+    const uint32_t* range_cnt;          // [nframes * ranges_per_frame]
+    uint32_t nframes;
+    uint32_t ranges_per_frame;          // K2 tiles per frame
+    uint32_t groups_per_frame;          // ceil(ranges_per_frame / 8): one CTA of K3a/K3b each
+    uint32_t supers_per_frame;          // ceil(groups_per_frame / 256)
+    const DeviceTables* tables;         // [nframes]
+    uint32_t* range_bits;               // [nframes * ranges_per_frame] bits the range encodes to (K3a)
+    unsigned long long* group_bits;     // [nframes * groups_per_frame] bits of the 8 ranges one CTA handles (K3a)
+    unsigned long long* super_bits;     // [nframes * supers_per_frame] bits of 256 consecutive groups (K3a, atomics; zeroed before K2)
+    uint32_t* raw;                      // all frames' un-stuffed scans; K3a zeroes it, K3b fills it
     unsigned long long raw_words16;     // size of raw in 16-byte units
-    unsigned long long* total_out;      // [0] = total bits of the scan (before padding), [1] = K4's FF count
-    unsigned long long* k4_status;      // K4's look-back words ...
-    uint32_t k4_tiles;                  // ... and how many
+    const unsigned long long* raw_off;  // [nframes] byte offset of the frame's raw scan (multiple of 16); its stuffed scan starts at twice that
+    const unsigned long long* raw_bytes;// [nframes] bytes of the frame's raw scan = ceil(bits / 8), known from the histogram
+    const uint32_t* k4_tile0;           // [nframes + 1] first K4 tile of the frame
+    unsigned long long* total_bits;     // [nframes] out: bits of the scan (before padding)
+    unsigned long long* total_ff;       // [nframes] out: FF bytes K4 stuffed
+    unsigned long long* k4_status;      // K4's look-back words, one per tile
+    uint32_t k4_tiles;
     uint32_t* counters;                 // [1] K4's tile ticket
 };
 
@@ -103,9 +112,11 @@ constexpr int kPackWarps = kPackThreads / 32;
 __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_constant__ EntropyParams p) {
     __shared__ uint32_t s_tab[1024], s_fast[1024];
     __shared__ uint32_t s_wbits[kPackWarps];
+    const uint32_t frame = blockIdx.x / p.groups_per_frame, group = blockIdx.x - frame * p.groups_per_frame;
+    const DeviceTables* tables = p.tables + frame;
     for (int i = threadIdx.x; i < 1024; i += kPackThreads) {
-        s_tab[i] = (&p.tables->entry[0][0])[i];
-        s_fast[i] = (&p.tables->fast[0][0])[i];
+        s_tab[i] = (&tables->entry[0][0])[i];
+        s_fast[i] = (&tables->fast[0][0])[i];
     }
     {   // housekeeping, spread over the grid
         const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * kPackThreads + threadIdx.x;
@@ -113,21 +124,22 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
         uint4* raw16 = reinterpret_cast<uint4*>(p.raw);
         for (unsigned long long i = gtid; i < p.raw_words16; i += gsize) raw16[i] = make_uint4(0, 0, 0, 0);
         for (unsigned long long i = gtid; i < p.k4_tiles; i += gsize) p.k4_status[i] = 0ull;
-        if (gtid == 0) { p.counters[1] = 0u; p.total_out[1] = 0ull; }
+        if (gtid == 0) p.counters[1] = 0u;
     }
     __syncthreads();
-    const uint32_t range = blockIdx.x * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t range = group * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     uint32_t bits = 0;
-    if (range < p.nranges) {
-        const uint32_t n = p.range_cnt[range];
-        const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
+    if (range < p.ranges_per_frame) {
+        const size_t slab = static_cast<size_t>(frame) * p.ranges_per_frame + range;
+        const uint32_t n = p.range_cnt[slab];
+        const uint32_t* __restrict__ items = p.items + slab * kSlabItems;
         for (uint32_t i = lane; i < n; i += 32) {
             const uint32_t item = __ldg(items + i), w = item_fast(item, s_fast);
             bits += w ? w >> 27 : item_bits(item, s_tab);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
-        if (lane == 0) p.range_bits[range] = bits;
+        if (lane == 0) p.range_bits[slab] = bits;
     }
     if (lane == 0) s_wbits[threadIdx.x >> 5] = bits;
     __syncthreads();
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
         unsigned long long sum = 0;
         for (int w = 0; w < kPackWarps; ++w) sum += s_wbits[w];
         p.group_bits[blockIdx.x] = sum;
-        atomicAdd(&p.super_bits[blockIdx.x >> 8], sum);
+        atomicAdd(&p.super_bits[frame * p.supers_per_frame + (group >> 8)], sum);
     }
 }
 
@@ -156,32 +168,39 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     __shared__ uint32_t s_bits[kPackWarps][kWarpBitWords + 2];
     __shared__ unsigned long long s_part[kPackWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t frame = blockIdx.x / p.groups_per_frame, group = blockIdx.x - frame * p.groups_per_frame;
+    const DeviceTables* tables = p.tables + frame;
     for (int i = tid; i < 1024; i += kPackThreads) {
-        s_tab[i] = (&p.tables->entry[0][0])[i];
-        s_fast[i] = (&p.tables->fast[0][0])[i];
+        s_tab[i] = (&tables->entry[0][0])[i];
+        s_fast[i] = (&tables->fast[0][0])[i];
     }
     for (int i = lane; i < kWarpBitWords + 2; i += 32) s_bits[warp][i] = 0;
     __syncthreads();
-    // bit offset of this CTA's first range: whole super-groups before it + the groups before it in its own super-group
-    // (at most 255 + 255 values for images up to 500 Mpx; summed cooperatively), then the ranges before this warp's
+    // bit offset of this CTA's first range inside its frame: whole super-groups before it + the groups before it in its
+    // own super-group (at most 255 + 255 values for images up to 500 Mpx; summed cooperatively), then the ranges before
+    // this warp's
     unsigned long long part = 0;
     {
-        const uint32_t sup = blockIdx.x >> 8;
-        for (uint32_t i = tid; i < sup; i += kPackThreads) part += __ldcg(p.super_bits + i);
-        for (uint32_t i = (sup << 8) + tid; i < blockIdx.x; i += kPackThreads) part += __ldcg(p.group_bits + i);
+        const uint32_t sup = group >> 8;
+        const unsigned long long* supers = p.super_bits + static_cast<size_t>(frame) * p.supers_per_frame;
+        const unsigned long long* groups = p.group_bits + static_cast<size_t>(frame) * p.groups_per_frame;
+        for (uint32_t i = tid; i < sup; i += kPackThreads) part += __ldcg(supers + i);
+        for (uint32_t i = (sup << 8) + tid; i < group; i += kPackThreads) part += __ldcg(groups + i);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (lane == 0) s_part[warp] = part;
     __syncthreads();
-    const uint32_t range = blockIdx.x * kPackWarps + warp;
-    unsigned long long cur = 0;                                         // global bit position of the next chunk
+    const uint32_t range = group * kPackWarps + warp;
+    const size_t slab0 = static_cast<size_t>(frame) * p.ranges_per_frame + group * kPackWarps;
+    const unsigned long long frame_bit0 = p.raw_off[frame] * 8ull;      // where the frame's scan starts in `raw`
+    unsigned long long cur = frame_bit0;                                // global bit position of the next chunk
     for (int w = 0; w < kPackWarps; ++w) cur += s_part[w];
     for (int w = 0; w < warp; ++w)
-        if (blockIdx.x * kPackWarps + w < p.nranges) cur += __ldcg(p.range_bits + blockIdx.x * kPackWarps + w);
-    if (range >= p.nranges) return;
-    const uint32_t n = p.range_cnt[range];
-    const uint32_t* __restrict__ items = p.items + static_cast<size_t>(range) * kSlabItems;
+        if (group * kPackWarps + w < p.ranges_per_frame) cur += __ldcg(p.range_bits + slab0 + w);
+    if (range >= p.ranges_per_frame) return;
+    const uint32_t n = p.range_cnt[slab0 + warp];
+    const uint32_t* __restrict__ items = p.items + (slab0 + warp) * kSlabItems;
     uint32_t* it = s_items[warp];
     uint32_t* bitbuf = s_bits[warp];
 
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
         __syncwarp();
         cur += total;
     }
-    if (range + 1 == p.nranges && lane == 0) {
+    if (range + 1 == p.ranges_per_frame && lane == 0) {
         // 1-padding of Bitstream::fill() (BitstreamGeneric.hpp:242-248): the open byte is completed with ones
         const uint32_t pad = static_cast<uint32_t>((8 - (cur & 7)) & 7);
         if (pad) {
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
             bw.put((1u << pad) - 1, pad);
             bw.finish();
         }
-        p.total_out[0] = cur;                                           // bits of the scan; the host checks it against the histogram
+        p.total_bits[frame] = cur - frame_bit0;                         // bits of the scan; the host checks it against the histogram
     }
 }
 
@@ -265,18 +284,32 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
 constexpr int kStuffThreads = 1024;
 constexpr int kStuffBytesPerThread = 16;
 constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
+static_assert(kStuffTile == kK4TileBytes, "capi.cu numbers K4 tiles with kK4TileBytes");
 
-__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __restrict__ raw, uint64_t nbytes,
-                                                              uint8_t* __restrict__ out, unsigned long long* status,
-                                                              uint32_t* ticket, unsigned long long* total_ff) {
+__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_constant__ EntropyParams p, uint8_t* __restrict__ scan) {
     __shared__ alignas(16) uint8_t s_out[2 * kStuffTile + 16];
     __shared__ uint32_t s_scan[33];
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_frame;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (tid == 0) {
+        // tiles are numbered frame by frame; tickets are handed out in start order, so every tile a look-back waits for
+        // is already running
+        const uint32_t t = atomicAdd(&p.counters[1], 1u);
+        uint32_t lo = 0, hi = p.nframes;                       // frame f owns tiles [k4_tile0[f], k4_tile0[f + 1])
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.k4_tile0[mid] <= t) lo = mid; else hi = mid;
+        }
+        s_tile = t;
+        s_frame = lo;
+    }
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t frame = s_frame, tile0 = p.k4_tile0[frame], tile = s_tile - tile0;
+    const uint64_t nbytes = p.raw_bytes[frame];
+    const uint8_t* __restrict__ raw = reinterpret_cast<const uint8_t*>(p.raw) + p.raw_off[frame];
+    uint8_t* __restrict__ out = scan + 2 * p.raw_off[frame];
+    unsigned long long* status = p.k4_status + tile0;
     const uint64_t tile_at = static_cast<uint64_t>(tile) * kStuffTile;
     const uint64_t at = tile_at + static_cast<uint64_t>(tid) * kStuffBytesPerThread;
     uint4 q = make_uint4(0, 0, 0, 0);
@@ -342,41 +375,44 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const uint8_t* __r
         gw[w] = head ? __funnelshift_r(sw[w], sw[w + 1], 8 * head) : sw[w];
     const uint32_t tail0 = head + 4 * nwords;
     if (tid < len - tail0) g[tail0 + tid] = s_out[tail0 + tid];
-    if (tid == 0 && tile_at + kStuffTile >= nbytes) total_ff[0] = s_base + tile_ff;
+    if (tid == 0 && tile_at + kStuffTile >= nbytes) p.total_ff[frame] = s_base + tile_ff;
 }
 
-int launch_entropy(jpgenc_ctx* c, uint64_t total_bits) {
+// Frame geometry (raw offsets, sizes, K4 tile numbering) comes from the caller: it is computed on the host from the
+// histograms and code lengths and already sits in device memory (c->d_meta, layout below).
+int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
-    const uint64_t nbytes = (total_bits + 7) / 8;
-    const uint32_t ranges = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
-    const uint32_t tiles4 = static_cast<uint32_t>((nbytes + kStuffTile - 1) / kStuffTile);
-    // status words: [0,1] totals (bits of the scan from K3s, FF bytes stuffed by K4), then K4's look-back words; K3a zeroes
-    // them together with the raw scan
-    unsigned long long* totals = c->d_lookback;
-    unsigned long long* st4 = c->d_lookback + 2;
-
+    const uint32_t F = c->nframes;
     EntropyParams p{};
     p.items = c->d_items;
     p.range_cnt = c->d_tile_cnt;
-    p.nranges = ranges;
+    p.nframes = F;
+    p.ranges_per_frame = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    p.groups_per_frame = (p.ranges_per_frame + kPackWarps - 1) / kPackWarps;
+    p.supers_per_frame = (p.groups_per_frame + 255) / 256;
     p.tables = c->d_tables;
     p.range_bits = c->d_range_bits;
-    p.group_bits = c->d_range_base;                                  // [groups] then [supers]
-    p.super_bits = c->d_range_base + (ranges + kPackWarps - 1) / kPackWarps;
+    p.group_bits = c->d_range_base;                                  // [F * groups] then [F * supers]
+    p.super_bits = c->d_range_base + static_cast<size_t>(F) * p.groups_per_frame;
     p.raw = c->d_raw;
-    p.raw_words16 = (((nbytes + 15) & ~15ull) + 64) / 16;
-    p.total_out = totals;
-    p.k4_status = st4;
-    p.k4_tiles = tiles4;
+    p.raw_words16 = raw_bytes_total / 16;
+    // d_meta: raw_off u64[F] | raw_bytes u64[F] | k4_tile0 u32[F + 1]
+    p.raw_off = reinterpret_cast<const unsigned long long*>(c->d_meta);
+    p.raw_bytes = p.raw_off + F;
+    p.k4_tile0 = reinterpret_cast<const uint32_t*>(p.raw_bytes + F);
+    // d_lookback: total_bits u64[F] | total_ff u64[F] | K4 status words
+    p.total_bits = c->d_lookback;
+    p.total_ff = c->d_lookback + F;
+    p.k4_status = c->d_lookback + 2 * static_cast<size_t>(F);
+    p.k4_tiles = k4_tiles;
     p.counters = c->d_counters + 1;                                  // d_counters[2] is K4's ticket
-    const unsigned grid = (ranges + kPackWarps - 1) / kPackWarps;
+    const unsigned grid = p.groups_per_frame * F;
     range_bits_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     huffman_pack_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
-    if (tiles4) {
-        stuff_kernel<<<tiles4, kStuffThreads, 0, c->stream>>>(reinterpret_cast<const uint8_t*>(c->d_raw), nbytes, c->d_scan,
-                                                              st4, c->d_counters + 2, totals + 1);
+    if (k4_tiles) {
+        stuff_kernel<<<k4_tiles, kStuffThreads, 0, c->stream>>>(p, c->d_scan);
         JPGENC_CUDA(c, cudaGetLastError());
     }
     c->launches += 3;

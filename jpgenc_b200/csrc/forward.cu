@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
     const uint32_t my = p.mcu_y0 + blockIdx.y;
     const uint32_t mcu0 = blockIdx.x * kMcus;
     const int nm = min(kMcus, static_cast<int>(p.mcu_w - mcu0));
+    const uint8_t* __restrict__ rgb = p.frames ? p.frames[blockIdx.z] : p.rgb;      // batch: grid.z walks over the frames
+    const uint32_t frame_block0 = blockIdx.z * p.blocks_per_frame;
 
     // ---- stage the 16-row RGB strip ----
     if constexpr (kAligned) {
@@ -229,8 +231,7 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
             const uint32_t row_bytes = nm * 48;
             if (tid == 0) ptx::mbar_expect_tx(&sm.bar, 16 * row_bytes);
             const uint32_t sy = min(my * 16 + tid, p.real_h - 1);              // bottom edge replication
-            ptx::bulk_g2s(sm.tile + tid * Smem::kPitch, p.rgb + (static_cast<size_t>(sy) * p.real_w + mcu0 * 16) * 3,
-                              row_bytes, &sm.bar);
+            ptx::bulk_g2s(sm.tile + tid * Smem::kPitch, rgb + (static_cast<size_t>(sy) * p.real_w + mcu0 * 16) * 3, row_bytes, &sm.bar);
         }
         ptx::mbar_wait(&sm.bar, 0);
     } else {
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
             const int r = idx / row_bytes, b = idx - r * row_bytes;
             const uint32_t sx = min(mcu0 * 16 + b / 3, p.real_w - 1);
             const uint32_t sy = min(my * 16 + r, p.real_h - 1);
-            sm.tile[r * Smem::kPitch + b] = p.rgb[(static_cast<size_t>(sy) * p.real_w + sx) * 3 + (b % 3)];
+            sm.tile[r * Smem::kPitch + b] = rgb[(static_cast<size_t>(sy) * p.real_w + sx) * 3 + (b % 3)];
         }
         __syncthreads();
     }
@@ -291,13 +292,14 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
     __syncthreads();   // every RGB byte has been consumed (tile may now be reused as staging); chroma planes complete
 
     const uint32_t mcu_base = my * p.mcu_w + mcu0;
+    const uint32_t block_base = frame_block0 + mcu_base * kBlocksPerMcu;     // first coefficient block of this strip
     uint32_t packed[32];
     if (active) {
         dct8x8_packed<true>(v);
         const bool boundary = quantize_pack_packed(v, p.luma, packed);
         const int m = bx >> 1, k = by * 2 + (bx & 1);
         stage_block(sm.tile, m * kBlocksPerMcu + k, packed);
-        if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + k);
+        if (boundary) push_refine(p, block_base + m * kBlocksPerMcu + k);
     }
     // ---- chroma threads: 2*kMcus blocks (Cb of every MCU, then Cr) ----
     if (tid < 2 * kMcus) {
@@ -313,11 +315,11 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
             dct8x8_packed<true>(v);
             const bool boundary = quantize_pack_packed(v, p.chroma, packed);
             stage_block(sm.tile, m * kBlocksPerMcu + 4 + comp, packed);
-            if (boundary) push_refine(p, (mcu_base + m) * kBlocksPerMcu + 4 + comp);
+            if (boundary) push_refine(p, block_base + m * kBlocksPerMcu + 4 + comp);
         }
     }
     __syncthreads();
-    copy_out(sm.tile, p.coef + static_cast<size_t>(mcu_base) * kBlocksPerMcu * kCoefPerBlock, nm * kBlocksPerMcu, tid, kThreads);
+    copy_out(sm.tile, p.coef + static_cast<size_t>(block_base) * kCoefPerBlock, nm * kBlocksPerMcu, tid, kThreads);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -427,7 +429,8 @@ __constant__ uint8_t c_inv_zigzag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4, 
 
 template <class Sample>
 __device__ __forceinline__ void refine_loop(uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
-                                            const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e, Sample&& sample) {
+                                            uint32_t blocks_per_frame, const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e,
+                                            Sample&& sample) {
     const int lane8 = threadIdx.x & 7;
     const uint32_t group = (blockIdx.x * kRefineThreads + threadIdx.x) >> 3, ngroups = (gridDim.x * kRefineThreads) >> 3;
     const uint32_t rounds = (n + ngroups - 1) / ngroups;             // same trip count for every lane of a warp (shuffles inside)
@@ -444,7 +447,7 @@ __device__ __forceinline__ void refine_loop(uint32_t n, const uint32_t* __restri
         transpose_stage<4>(t, lane8);                                 // t[k] = temporary(row k, column lane8)
         aan8_exact_regs(t, x, e);                                     // x[k] = result(row lane8, column k)
         if (valid) {
-            const uint8_t* q = (id % kBlocksPerMcu) < 4 ? qtab_y : qtab_c;
+            const uint8_t* q = ((id % blocks_per_frame) % kBlocksPerMcu) < 4 ? qtab_y : qtab_c;
             int16_t* dst = out + static_cast<size_t>(id) * kCoefPerBlock;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -455,14 +458,17 @@ __device__ __forceinline__ void refine_loop(uint32_t n, const uint32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* __restrict__ rgb, int16_t* __restrict__ coef,
+// ids are global block indices; with `frames` (a batch) block id belongs to frame id / blocks_per_frame
+__global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* __restrict__ rgb, const uint8_t* const* __restrict__ frames,
+                                                                    uint32_t blocks_per_frame, int16_t* __restrict__ coef,
                                                                     const uint32_t* __restrict__ list,
                                                                     const uint32_t* __restrict__ count, uint32_t cap, int all,
                                                                     uint32_t nblocks, uint32_t real_w, uint32_t real_h,
                                                                     uint32_t mcu_w, const __grid_constant__ ExactConsts e) {
     const uint32_t n = all ? nblocks : min(*count, cap);
-    refine_loop(n, list, all != 0, coef, e.qy, e.qc, e, [&](uint32_t id, int r, int c) {
-        return exact_sample(rgb, real_w, real_h, mcu_w, id, r, c, e.scale);
+    refine_loop(n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e, [&](uint32_t id, int r, int c) {
+        const uint32_t f = id / blocks_per_frame;
+        return exact_sample(frames ? frames[f] : rgb, real_w, real_h, mcu_w, id - f * blocks_per_frame, r, c, e.scale);
     });
 }
 
@@ -522,7 +528,7 @@ __global__ void __launch_bounds__(kRefineThreads) refine_blocks_kernel(const flo
                                                                            uint32_t nblocks, int all,
                                                                            const __grid_constant__ ExactConsts e) {
     const uint32_t n = all ? nblocks : min(*count, cap);
-    refine_loop(n, list, all != 0, out, e.qy, e.qy, e, [&](uint32_t id, int r, int c) {
+    refine_loop(n, list, all != 0, out, 0xFFFFFFFFu, e.qy, e.qy, e, [&](uint32_t id, int r, int c) {
         return static_cast<double>(in[static_cast<size_t>(id) * 64 + r * 8 + c]);
     });
 }
@@ -647,73 +653,68 @@ static void fill_exact(const jpgenc_ctx* c, const uint8_t* qy, const uint8_t* qc
     for (int i = 0; i < 64; ++i) { e->qy[i] = qy[i]; e->qc[i] = qc[i]; }
 }
 
-// K1 over the MCU rows [y0, y0 + rows).  The whole image is the common case; jpgenc_encode_rgb launches it band by
-// band behind the matching host-to-device copies.  `first` clears the refinement list, `last` appends the exact
-// refinement pass over everything the bands flagged.
-int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, bool last) {
-    ForwardParams p{};
-    p.rgb = c->d_rgb;
-    p.coef = c->d_coef;
-    p.refine_list = c->d_refine_list;
-    p.refine_count = c->d_counters;
-    p.refine_cap = static_cast<uint32_t>(c->refine_cap);
-    p.real_w = c->real_w; p.real_h = c->real_h; p.mcu_w = c->mcu_w; p.mcu_h = c->mcu_h;
-    p.mcu_y0 = y0;
+// Everything K1 needs to know about the image(s) bound to the context
+static void fill_forward_params(const jpgenc_ctx* c, ForwardParams* p) {
+    p->rgb = c->d_rgb;
+    p->frames = c->nframes > 1 ? c->d_frame_ptrs : nullptr;
+    p->blocks_per_frame = c->mcu_w * c->mcu_h * kBlocksPerMcu;
+    p->coef = c->d_coef;
+    p->refine_list = c->d_refine_list;
+    p->refine_count = c->d_counters;
+    p->refine_cap = static_cast<uint32_t>(c->refine_cap);
+    p->real_w = c->real_w; p->real_h = c->real_h; p->mcu_w = c->mcu_w; p->mcu_h = c->mcu_h;
     const double scale = 255. / c->maxval;
     const float fy[3] = {.299f, .587f, .114f}, fcb[3] = {-.1687f, -.3312f, .5f}, fcr[3] = {.5f, -.4186f, -.0813f};
     for (int i = 0; i < 3; ++i) {
-        p.color.y[i] = static_cast<float>(fy[i] * scale);
-        p.color.cb[i] = static_cast<float>(fcb[i] * scale / 4);
-        p.color.cr[i] = static_cast<float>(fcr[i] * scale / 4);
+        p->color.y[i] = static_cast<float>(fy[i] * scale);
+        p->color.cb[i] = static_cast<float>(fcb[i] * scale / 4);
+        p->color.cr[i] = static_cast<float>(fcr[i] * scale / 4);
     }
-    fill_quant_consts2(c->qy, c->dct_s, &p.luma);
-    fill_quant_consts2(c->qc, c->dct_s, &p.chroma);
+    fill_quant_consts2(c->qy, c->dct_s, &p->luma);
+    fill_quant_consts2(c->qc, c->dct_s, &p->chroma);
+}
 
+// exact FP64 pass over the blocks K1 flagged (all == false) or over every block (all == true)
+static int launch_refine(jpgenc_ctx* c, bool all) {
+    ExactConsts e;
+    fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
+    const uint32_t bpf = c->mcu_w * c->mcu_h * kBlocksPerMcu;
+    refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
+        c->d_rgb, c->nframes > 1 ? c->d_frame_ptrs : nullptr, bpf, c->d_coef, c->d_refine_list, c->d_counters,
+        all ? 0u : static_cast<uint32_t>(c->refine_cap), all ? 1 : 0, bpf * c->nframes, c->real_w, c->real_h, c->mcu_w, e);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return JPGENC_OK;
+}
+
+// K1 over the MCU rows [y0, y0 + rows) of every frame.  The whole image is the common case; jpgenc_encode_rgb launches
+// it band by band behind the matching host-to-device copies.  `first` clears the refinement list, `last` appends the
+// exact refinement pass over everything the bands flagged.
+int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, bool last) {
+    ForwardParams p{};
+    fill_forward_params(c, &p);
+    p.mcu_y0 = y0;
     if (first) JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
-    const bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
-    const dim3 grid((c->mcu_w + 31) / 32, rows);
+    bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
+    if (c->nframes > 1) aligned = (c->real_w % 16 == 0) && c->frames_aligned;
+    const dim3 grid((c->mcu_w + 31) / 32, rows, c->nframes);
     if (aligned) forward_kernel<32, true><<<grid, 128, 0, c->stream>>>(p);
     else forward_kernel<32, false><<<grid, 128, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
-    if (last) {
-        ExactConsts e;
-        fill_exact(c, c->qy, c->qc, scale, &e);
-        refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
-            c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), 0,
-            c->mcu_w * c->mcu_h * kBlocksPerMcu, c->real_w, c->real_h, c->mcu_w, e);
-        JPGENC_CUDA(c, cudaGetLastError());
-        c->launches += 1;
-    }
-    return JPGENC_OK;
+    return last ? launch_refine(c, false) : JPGENC_OK;
 }
 
 int launch_forward(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaEventRecord(c->ev_k0, c->stream));
     // the fast kernel alone is timed (ev_k0..ev_k1): it is the roofline kernel; the refinement follows
-    int rc = launch_forward_rows(c, 0, c->mcu_h, true, false);
+    const int rc = launch_forward_rows(c, 0, c->mcu_h, true, false);
     if (rc) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_k1, c->stream));
-    ExactConsts e;
-    fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
-    refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
-        c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters, static_cast<uint32_t>(c->refine_cap), 0,
-        c->mcu_w * c->mcu_h * kBlocksPerMcu, c->real_w, c->real_h, c->mcu_w, e);
-    JPGENC_CUDA(c, cudaGetLastError());
-    c->launches += 1;
-    return JPGENC_OK;
+    return launch_refine(c, false);
 }
 
-int launch_exact_all(jpgenc_ctx* c) {
-    ExactConsts e;
-    fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
-    const uint32_t nblocks = c->mcu_w * c->mcu_h * kBlocksPerMcu;
-    refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(c->d_rgb, c->d_coef, c->d_refine_list, c->d_counters,
-                                                                       0u, 1, nblocks, c->real_w, c->real_h, c->mcu_w, e);
-    JPGENC_CUDA(c, cudaGetLastError());
-    c->launches += 1;
-    return JPGENC_OK;
-}
+int launch_exact_all(jpgenc_ctx* c) { return launch_refine(c, true); }
 
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
                             uint64_t* refined) {

@@ -24,11 +24,11 @@ constexpr int kDescCap = 2048;                           // descriptors per roun
 
 struct StatsParams {
     const int16_t* coef;
-    uint32_t nblocks;
+    uint32_t nblocks;                 // blocks per frame
+    uint32_t tiles_per_frame;         // CTA blockIdx.x handles tile blockIdx.x % tiles_per_frame of frame blockIdx.x / tiles_per_frame
     uint32_t mcu_w;
     uint32_t n_mcu;
-    uint32_t* g_hist;                 // [4][256]
-    unsigned long long* g_first;      // [4][256]
+    uint8_t* g_stats;                 // per frame kStatsBytes: hist u32[4][256], then first-occurrence keys u64[4][256]
     uint32_t* items;                  // item stream: tile t owns the slab [t * kSlabItems, (t + 1) * kSlabItems)
     uint32_t* tile_cnt;               // [tiles] items of the tile
     const uint32_t* refine_count;     // K1's refinement counter ...
@@ -46,6 +46,8 @@ __device__ __forceinline__ void warp_count(uint32_t* s_hist, unsigned long long*
         if (key < s_first[idx]) atomicMin(&s_first[idx], key);
     }
 }
+
+constexpr size_t kStatsBytes = 4096 + 8192;
 
 constexpr int kStatsSmem = kTileSmemBytes                // masks + dc
                            + kTileBlocks * 8             // text key of the block
@@ -67,18 +69,22 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     __shared__ uint32_t s_origin[2];                                      // MCU column / row of the tile's first MCU
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t first = blockIdx.x * kTileBlocks;
+    const uint32_t frame = blockIdx.x / p.tiles_per_frame;
+    const uint32_t first = (blockIdx.x - frame * p.tiles_per_frame) * kTileBlocks;      // first block of the tile, within its frame
     const int nb = static_cast<int>(min(static_cast<uint32_t>(kTileBlocks), p.nblocks - first));
+    const int16_t* __restrict__ coef = p.coef + static_cast<size_t>(frame) * p.nblocks * kCoefPerBlock;
+    uint32_t* __restrict__ g_hist = reinterpret_cast<uint32_t*>(p.g_stats + frame * kStatsBytes);
+    unsigned long long* __restrict__ g_first = reinterpret_cast<unsigned long long*>(p.g_stats + frame * kStatsBytes + 4096);
 
     // the global minima seen so far bound what this tile can still contribute: after the first tiles almost no
     // key is smaller, so the shared-memory atomicMin below is rarely executed
-    for (int i = tid; i < 1024; i += kTileBlocks) { s_hist[i] = 0; s_first[i] = __ldcg(&p.g_first[i]); }
+    for (int i = tid; i < 1024; i += kTileBlocks) { s_hist[i] = 0; s_first[i] = __ldcg(&g_first[i]); }
     if (tid == 0) {                                                       // the tile's only division
         const uint32_t m0 = first / kBlocksPerMcu, y0 = m0 / p.mcu_w;
         s_origin[0] = m0 - y0 * p.mcu_w;
         s_origin[1] = y0;
     }
-    scan_tile(tv, p.coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
+    scan_tile(tv, coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
 
     // ---- per block: mask, DC difference, text key, item counts ----
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     unsigned long long key = 0;
     if (live) {
         load_mask(tv, tid, lo, hi);
-        diff = tv.dc[tid] - dc_predictor(tv, p.coef, first, tid);
+        diff = tv.dc[tid] - dc_predictor(tv, coef, first, tid);
         nac = __popc(lo) + __popc(hi);
         eob = (hi >> 31) ? 0u : 1u;                                       // no EOB when coefficient 63 is non-zero
         const uint32_t lm = tid / kBlocksPerMcu, mcu = first / kBlocksPerMcu + lm;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
             if (has) {
                 const uint32_t d = s_desc[j], pos = d & 63u, run = (d >> 6) & 63u, b = (d >> 12) & 511u;
                 nzrl = static_cast<int>(run >> 4);
-                const int value = p.coef[static_cast<size_t>(first + b) * kCoefPerBlock + pos];     // L1/L2 hit: the tile was just read
+                const int value = coef[static_cast<size_t>(first + b) * kCoefPerBlock + pos];     // L1/L2 hit: the tile was just read
                 const int symbol = static_cast<int>((run & 15u) << 4) | category_of(value);
                 table = static_cast<int>(d >> 21) * 2 + 1;
                 idx = table * 256 + symbol;
@@ -187,32 +193,36 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     for (int i = tid; i < 1024; i += kTileBlocks) {
         const uint32_t n = s_hist[i];
         if (n) {
-            atomicAdd(&p.g_hist[i], n);
+            atomicAdd(&g_hist[i], n);
             const unsigned long long k = s_first[i];
-            if (k < __ldcg(&p.g_first[i])) atomicMin(&p.g_first[i], k);
+            if (k < __ldcg(&g_first[i])) atomicMin(&g_first[i], k);
         }
     }
 }
 
 int launch_symbol_stats(jpgenc_ctx* c) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
-    const unsigned grid = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_hist, 0, 4 * 256 * sizeof(uint32_t), c->stream));
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_first, 0xFF, 4 * 256 * sizeof(unsigned long long), c->stream));
+    const unsigned tiles = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks), grid = tiles * c->nframes;
+    // per frame: histogram = 0, first-occurrence keys = all ones
+    JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats, kStatsBytes, 0, 4096, c->nframes, c->stream));
+    JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats + 4096, kStatsBytes, 0xFF, 8192, c->nframes, c->stream));
     // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base; clear it off the critical path
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, (grid / 8 + grid / 2048 + 4) * sizeof(unsigned long long), c->stream));
+    JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, c->range_base_cap, c->stream));
     StatsParams p{};
     p.coef = c->d_coef;
     p.nblocks = static_cast<uint32_t>(nblocks);
+    p.tiles_per_frame = tiles;
     p.mcu_w = c->mcu_w;
     p.n_mcu = static_cast<uint32_t>(n_mcu);
-    p.g_hist = c->d_hist;
-    p.g_first = c->d_first;
+    p.g_stats = c->d_stats;
     p.items = c->d_items;
     p.tile_cnt = c->d_tile_cnt;
     p.refine_count = c->d_counters;
-    p.refine_copy = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->d_hist) + 4096 + 8192);
-    JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
+    p.refine_copy = reinterpret_cast<uint32_t*>(c->d_stats + c->nframes * kStatsBytes);
+    if (!c->k2_configured) {
+        JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
+        c->k2_configured = true;
+    }
     symbol_stats_kernel<<<grid, kTileBlocks, kStatsSmem, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
