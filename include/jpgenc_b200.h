@@ -151,6 +151,12 @@ int jpgenc_batch_encode(jpgenc_batch* batch, uint32_t n, const uint8_t* const* f
 int jpgenc_batch_encode_device(jpgenc_batch* batch, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h,
                                uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
 
+/* all frames TOGETHER through every kernel on one context (one launch of each kernel per pass instead of per frame; the
+ * 4*n Huffman tables are built in parallel on host threads).  Frames must have one size and live in device memory;
+ * out may be NULL (sizes only).  Results are byte-identical to encoding the frames one by one. */
+int jpgenc_encode_frames_device(jpgenc_ctx* ctx, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h,
+                                uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
+
 /* ---- config-1 microbenchmark: dctArai + quantize + zigzag on stand-alone blocks -------------------- */
 /* dev_in: nblocks*64 fp32 samples (row-major 8x8 per block); dev_out: nblocks*64 int16 zigzag.
  * Same exactness contract as K1 (FP32 fast path + exact FP64 refinement of boundary cases). */

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <cmath>
@@ -20,6 +21,70 @@ int launch_exact_all(jpgenc_ctx* c);
 // worker threads plus the calling thread build them side by side.  Waking a sleeping thread costs about as much as a
 // small table, so the workers are ARMED (woken, then spinning) when the statistics kernel is launched and find the
 // histogram as soon as it arrives; they go back to sleep after every image.
+// parallel_for over n jobs on persistent host threads (the 4 * F table builds of a batch of F frames)
+class HostPool {
+public:
+    explicit HostPool(unsigned workers) {
+        for (unsigned i = 0; i < workers; ++i) threads_.emplace_back([this] { run(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread& t : threads_) t.join();
+    }
+    template <class F>
+    void parallel_for(uint32_t n, F&& fn) {
+        std::function<void(uint32_t)> job = fn;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &job; n_ = n; next_.store(0); pending_ = static_cast<uint32_t>(threads_.size()); ++generation_;
+        }
+        cv_.notify_all();
+        drain(job);
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void drain(const std::function<void(uint32_t)>& job) {
+        for (;;) {
+            const uint32_t i = next_.fetch_add(1);
+            if (i >= n_) return;
+            job(i);
+        }
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(uint32_t)>* job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return quit_ || generation_ != seen; });
+                if (quit_) return;
+                seen = generation_;
+                job = job_;
+            }
+            drain(*job);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    bool quit_ = false;
+    uint64_t generation_ = 0;
+    const std::function<void(uint32_t)>* job_ = nullptr;
+    uint32_t n_ = 0, pending_ = 0;
+    std::atomic<uint32_t> next_{0};
+};
+
 class TablePool {
 public:
     TablePool() {
@@ -220,6 +285,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     delete c->pool;
+    delete c->host_pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_stats); cudaFree(c->d_meta); cudaFree(c->d_tables); cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
@@ -627,6 +693,77 @@ int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
     if (!dst) return JPGENC_OK;
     return assemble(c, tables, scan, dst, cap);
+}
+
+// A batch of equally sized frames that already live in device memory, taken through every kernel together: one K1
+// launch over all frames, one K2, the 4 * F tables built in parallel on the host, one K3a/K3b/K4.  Launch count and host
+// synchronisations are per PASS (a slice of the batch sized to a few GB of scratch), not per frame.
+int jpgenc_encode_frames_device(jpgenc_ctx* c, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h, uint32_t maxval,
+                                uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
+    if (!c || !dev_frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    int rc = set_geometry(c, w, h, maxval);
+    if (rc) return rc;
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
+    // frames per pass: item slabs (worst-case reservation, 96 KB per tile) within ~4 GB, coefficients within 2^32 blocks
+    uint32_t per_pass = static_cast<uint32_t>(std::max<size_t>(1, (4ull << 30) / (tiles * 384 * 64 * 4)));
+    per_pass = static_cast<uint32_t>(std::min<size_t>(per_pass, 0x7FFFFFFFull / nblocks));
+    per_pass = std::min(per_pass, 1024u);
+    if (!c->host_pool) c->host_pool = new HostPool(std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
+    std::vector<jpgenc_huff_table> tables;
+    for (uint32_t f0 = 0; f0 < n; f0 += per_pass) {
+        const uint32_t F = std::min(per_pass, n - f0);
+        c->nframes = F;
+        c->have_coef = c->have_scan = c->have_items = false;
+        bool aligned = true;
+        for (uint32_t f = 0; f < F; ++f) aligned = aligned && (reinterpret_cast<uintptr_t>(dev_frames[f0 + f]) % 16 == 0);
+        c->frames_aligned = aligned;
+        c->d_rgb = static_cast<const uint8_t*>(dev_frames[f0]);
+        c->have_pixels = true;
+        {
+            size_t cap = c->frame_ptrs_cap;
+            void* p = c->d_frame_ptrs;
+            if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&p), &cap, F * sizeof(void*)))) return rc;
+            c->d_frame_ptrs = static_cast<const uint8_t**>(p);
+            c->frame_ptrs_cap = cap;
+        }
+        JPGENC_CUDA(c, cudaMemcpyAsync(c->d_frame_ptrs, dev_frames + f0, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = ensure_coef(c))) return rc;
+        if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
+        c->have_coef = true;
+        if ((rc = stats_frames(c))) return rc;
+        // 4 * F independent table builds
+        tables.resize(static_cast<size_t>(F) * 4);
+        const uint8_t* hs = static_cast<const uint8_t*>(c->h_pinned);
+        std::atomic<int> build_rc{JPGENC_OK};
+        c->host_pool->parallel_for(F * 4, [&](uint32_t j) {
+            const uint32_t f = j >> 2, t = j & 3;
+            const uint32_t* count = reinterpret_cast<const uint32_t*>(hs + f * kStatsBytes) + t * 256;
+            const uint64_t* first = reinterpret_cast<const uint64_t*>(hs + f * kStatsBytes + 4096) + t * 256;
+            const int r = jpgenc_build_huffman(count, first, &tables[j]);
+            if (r) build_rc.store(r);
+        });
+        if (build_rc.load()) return fail(c, build_rc.load(), "Huffman table build failed");
+        if ((rc = entropy_frames(c, tables.data()))) return rc;
+        // files: header + scan + EOI per frame; the scans come back with one copy each, one synchronisation per pass
+        for (uint32_t f = 0; f < F; ++f) {
+            const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
+            const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], nullptr);
+            sizes[f0 + f] = hdr + scan + 2;
+            if (!out) continue;
+            uint8_t* dst = out[f0 + f];
+            if (caps[f0 + f] < hdr + scan + 2) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
+            jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], dst);
+            JPGENC_CUDA(c, cudaMemcpyAsync(dst + hdr, c->d_scan + 2 * c->frame_raw_off[f], scan, cudaMemcpyDeviceToHost, c->stream));
+            dst[hdr + scan] = 0xFF;                                  // EOI
+            dst[hdr + scan + 1] = 0xD9;
+        }
+        if (out) JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->nframes = 1;                                                  // the context goes back to single-image state
+    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false;
+    c->host_hist.clear();
+    return JPGENC_OK;
 }
 
 int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) {

@@ -79,11 +79,12 @@ struct DeviceTables {
 
 }  // namespace jpgenc
 
-namespace jpgenc { class TablePool; }
+namespace jpgenc { class TablePool; class HostPool; }
 
 struct jpgenc_ctx {
     int device = 0;
     jpgenc::TablePool* pool = nullptr;    // host worker threads that build the four Huffman tables side by side
+    jpgenc::HostPool* host_pool = nullptr;   // parallel table builds of a batch of frames
     bool parallel_tables = true;          // false inside a batch: there the frames run in parallel instead
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-to-device copies of jpgenc_encode_rgb, overlapped with K1 band by band

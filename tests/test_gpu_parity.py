@@ -314,3 +314,27 @@ def test_adversarial_blocks_bit_exact(encoder, oracle, q):
     finally:
         encoder.dev_free(d_in)
         encoder.dev_free(d_out)
+
+
+@pytest.mark.parametrize("w,h,n", [(208, 120, 13), (512, 384, 5), (101, 67, 9), (16, 16, 40)])
+def test_frames_through_the_kernels_together(encoder, oracle, w, h, n):
+    """jpgenc_encode_frames_device: a batch of frames in ONE pass through every kernel (grid dimension = frame) must give
+    the files of n separate encodes: own DC chains, own first-occurrence orders, own tables, own padding and stuffing"""
+    frames = [synth_rgb(w, h, s) if s % 3 else noise_rgb(w, h, s) for s in range(n)]
+    want = [oracle.encode_rgb(f) for f in frames]
+    fb = w * h * 3
+    d = encoder.dev_alloc(n * fb + 64)
+    try:
+        for i, f in enumerate(frames):
+            encoder.h2d(d + i * fb, np.ascontiguousarray(f))
+        cap = max(len(x) for x in want) + 64
+        outs = [np.zeros(cap, np.uint8) for _ in range(n)]
+        sizes = encoder.encode_frames_device([d + i * fb for i in range(n)], w, h, [o.ctypes.data for o in outs], [cap] * n)
+        assert sizes == [len(x) for x in want]
+        for i in range(n):
+            assert outs[i][: sizes[i]].tobytes() == want[i], f"frame {i}"
+        assert encoder.encode_frames_device([d + i * fb for i in range(n)], w, h) == sizes      # sizes only
+        # the context is usable for single images afterwards
+        assert encoder.encode_rgb(frames[0]) == want[0]
+    finally:
+        encoder.dev_free(d)
