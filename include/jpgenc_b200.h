@@ -156,6 +156,10 @@ int jpgenc_batch_encode_device(jpgenc_batch* batch, uint32_t n, const void* cons
  * out may be NULL (sizes only).  Results are byte-identical to encoding the frames one by one. */
 int jpgenc_encode_frames_device(jpgenc_ctx* ctx, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h,
                                 uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
+/* the same for frames in host memory (pinned for full PCIe speed): uploads of the next slice of the batch overlap the
+ * kernels of the current one */
+int jpgenc_encode_frames(jpgenc_ctx* ctx, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h,
+                         uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
 
 /* ---- config-1 microbenchmark: dctArai + quantize + zigzag on stand-alone blocks -------------------- */
 /* dev_in: nblocks*64 fp32 samples (row-major 8x8 per block); dev_out: nblocks*64 int16 zigzag.

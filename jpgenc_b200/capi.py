@@ -87,6 +87,8 @@ _SIGNATURES = {
     "jpgenc_launch_count": (C.c_uint64, [C.c_void_p]),
     "jpgenc_encode_frames_device": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32,
                                               C.POINTER(C.c_void_p), u64p, u64p]),
+    "jpgenc_encode_frames": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.POINTER(C.c_void_p), u64p, u64p]),
     "jpgenc_batch_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "jpgenc_batch_destroy": (None, [C.c_void_p]),
     "jpgenc_batch_last_error": (C.c_char_p, [C.c_void_p]),
@@ -252,14 +254,16 @@ class Encoder:
         self._check(self.lib.jpgenc_encode_rgb(self.h, host_ptr, w, h, maxval, out_ptr, cap, C.byref(n)))
         return n.value
 
-    def encode_frames_device(self, frame_ptrs, w: int, h: int, out_ptrs=None, caps=None, maxval: int = 255):
-        """equally sized frames in device memory through every kernel together; returns the JPEG sizes"""
+    def encode_frames_device(self, frame_ptrs, w: int, h: int, out_ptrs=None, caps=None, maxval: int = 255, host_frames=False):
+        """equally sized frames (device memory, or host memory with host_frames=True) through every kernel together;
+        returns the JPEG sizes"""
         n = len(frame_ptrs)
         frames = (C.c_void_p * n)(*frame_ptrs)
         sizes = (C.c_uint64 * n)()
         outs = (C.c_void_p * n)(*out_ptrs) if out_ptrs is not None else None
         capv = (C.c_uint64 * n)(*caps) if caps is not None else None
-        self._check(self.lib.jpgenc_encode_frames_device(self.h, n, frames, w, h, maxval, outs, capv, sizes))
+        fn = self.lib.jpgenc_encode_frames if host_frames else self.lib.jpgenc_encode_frames_device
+        self._check(fn(self.h, n, frames, w, h, maxval, outs, capv, sizes))
         return [int(x) for x in sizes]
 
     def encode_ppm_file(self, src: str, dst: str):

@@ -695,75 +695,132 @@ int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     return assemble(c, tables, scan, dst, cap);
 }
 
-// A batch of equally sized frames that already live in device memory, taken through every kernel together: one K1
-// launch over all frames, one K2, the 4 * F tables built in parallel on the host, one K3a/K3b/K4.  Launch count and host
-// synchronisations are per PASS (a slice of the batch sized to a few GB of scratch), not per frame.
+// ---- batches of equally sized frames, taken through every kernel together ---------------------------------------
+// One K1 launch over all frames of a pass, one K2, the 4 * F tables built in parallel on the host, one K3a/K3b/K4: launch
+// count and host synchronisations are per PASS (a slice of the batch sized to a few GB of scratch), not per frame.
+static uint32_t frames_per_pass(const jpgenc_ctx* c) {
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
+    // item slabs (worst-case reservation, 96 KB per tile) within ~4 GB, block ids within 31 bits
+    size_t per_pass = std::max<size_t>(1, (4ull << 30) / (tiles * 384 * 64 * 4));
+    per_pass = std::min<size_t>(per_pass, 0x7FFFFFFFull / nblocks);
+    return static_cast<uint32_t>(std::min<size_t>(per_pass, 1024));
+}
+
+// F frames at the device pointers `dev_frames` (host array); geometry is already set.  `ready` (optional): event on
+// another stream after which the pixels are valid.
+static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_frames, cudaEvent_t ready, uint8_t* const* out,
+                              const uint64_t* caps, uint64_t* sizes, std::vector<jpgenc_huff_table>& tables) {
+    int rc;
+    c->nframes = F;
+    c->have_coef = c->have_scan = c->have_items = false;
+    bool aligned = true;
+    for (uint32_t f = 0; f < F; ++f) aligned = aligned && (reinterpret_cast<uintptr_t>(dev_frames[f]) % 16 == 0);
+    c->frames_aligned = aligned;
+    c->d_rgb = static_cast<const uint8_t*>(dev_frames[0]);
+    c->have_pixels = true;
+    {
+        size_t cap = c->frame_ptrs_cap;
+        void* p = c->d_frame_ptrs;
+        if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&p), &cap, F * sizeof(void*)))) return rc;
+        c->d_frame_ptrs = static_cast<const uint8_t**>(p);
+        c->frame_ptrs_cap = cap;
+    }
+    // the pointer array is staged through pinned memory so that the copy is truly asynchronous
+    if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_frame_ptrs, dev_frames, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = ensure_coef(c))) return rc;
+    if (ready) JPGENC_CUDA(c, cudaStreamWaitEvent(c->stream, ready, 0));
+    if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
+    c->have_coef = true;
+    if ((rc = stats_frames(c))) return rc;
+    // 4 * F independent table builds
+    tables.resize(static_cast<size_t>(F) * 4);
+    const uint8_t* hs = static_cast<const uint8_t*>(c->h_pinned);
+    std::atomic<int> build_rc{JPGENC_OK};
+    c->host_pool->parallel_for(F * 4, [&](uint32_t j) {
+        const uint32_t f = j >> 2, t = j & 3;
+        const uint32_t* count = reinterpret_cast<const uint32_t*>(hs + f * kStatsBytes) + t * 256;
+        const uint64_t* first = reinterpret_cast<const uint64_t*>(hs + f * kStatsBytes + 4096) + t * 256;
+        const int r = jpgenc_build_huffman(count, first, &tables[j]);
+        if (r) build_rc.store(r);
+    });
+    if (build_rc.load()) return fail(c, build_rc.load(), "Huffman table build failed");
+    if ((rc = entropy_frames(c, tables.data()))) return rc;
+    // files: header + scan + EOI per frame; the scans come back with one copy each, one synchronisation per pass
+    for (uint32_t f = 0; f < F; ++f) {
+        const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
+        const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], nullptr);
+        sizes[f] = hdr + scan + 2;
+        if (!out) continue;
+        uint8_t* dst = out[f];
+        if (caps[f] < hdr + scan + 2) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
+        jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], dst);
+        JPGENC_CUDA(c, cudaMemcpyAsync(dst + hdr, c->d_scan + 2 * c->frame_raw_off[f], scan, cudaMemcpyDeviceToHost, c->stream));
+        dst[hdr + scan] = 0xFF;                                  // EOI
+        dst[hdr + scan + 1] = 0xD9;
+    }
+    if (out) JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return JPGENC_OK;
+}
+
+static void leave_batch_state(jpgenc_ctx* c) {
+    c->nframes = 1;                                                  // the context goes back to single-image state
+    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false;
+    c->host_hist.clear();
+}
+
 int jpgenc_encode_frames_device(jpgenc_ctx* c, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h, uint32_t maxval,
                                 uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
     if (!c || !dev_frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
-    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
-    // frames per pass: item slabs (worst-case reservation, 96 KB per tile) within ~4 GB, coefficients within 2^32 blocks
-    uint32_t per_pass = static_cast<uint32_t>(std::max<size_t>(1, (4ull << 30) / (tiles * 384 * 64 * 4)));
-    per_pass = static_cast<uint32_t>(std::min<size_t>(per_pass, 0x7FFFFFFFull / nblocks));
-    per_pass = std::min(per_pass, 1024u);
     if (!c->host_pool) c->host_pool = new HostPool(std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
+    const uint32_t per_pass = frames_per_pass(c);
     std::vector<jpgenc_huff_table> tables;
-    for (uint32_t f0 = 0; f0 < n; f0 += per_pass) {
+    for (uint32_t f0 = 0; f0 < n && !rc; f0 += per_pass)
+        rc = encode_frames_pass(c, std::min(per_pass, n - f0), dev_frames + f0, nullptr, out ? out + f0 : nullptr,
+                                caps ? caps + f0 : nullptr, sizes + f0, tables);
+    leave_batch_state(c);
+    return rc;
+}
+
+// The same for frames in host memory (pinned for full PCIe speed): the frames of pass p+1 are uploaded on the copy
+// stream into the other half of a double-buffered staging area while pass p goes through the kernels.
+int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h, uint32_t maxval,
+                         uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
+    if (!c || !frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    int rc = set_geometry(c, w, h, maxval);
+    if (rc) return rc;
+    if (!c->host_pool) c->host_pool = new HostPool(std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
+    const size_t fbytes = static_cast<size_t>(w) * h * 3, fstride = (fbytes + 255) & ~static_cast<size_t>(255);
+    // passes small enough that the first one starts soon and copies overlap compute finely, large enough to amortise
+    const uint32_t per_pass = std::max(1u, std::min<uint32_t>(frames_per_pass(c), static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / fstride))));
+    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, 2 * per_pass * fstride + 16))) return rc;
+    std::vector<jpgenc_huff_table> tables;
+    std::vector<const void*> ptrs(per_pass);
+    auto upload = [&](uint32_t f0, int half) -> int {
         const uint32_t F = std::min(per_pass, n - f0);
-        c->nframes = F;
-        c->have_coef = c->have_scan = c->have_items = false;
-        bool aligned = true;
-        for (uint32_t f = 0; f < F; ++f) aligned = aligned && (reinterpret_cast<uintptr_t>(dev_frames[f0 + f]) % 16 == 0);
-        c->frames_aligned = aligned;
-        c->d_rgb = static_cast<const uint8_t*>(dev_frames[f0]);
-        c->have_pixels = true;
-        {
-            size_t cap = c->frame_ptrs_cap;
-            void* p = c->d_frame_ptrs;
-            if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&p), &cap, F * sizeof(void*)))) return rc;
-            c->d_frame_ptrs = static_cast<const uint8_t**>(p);
-            c->frame_ptrs_cap = cap;
-        }
-        JPGENC_CUDA(c, cudaMemcpyAsync(c->d_frame_ptrs, dev_frames + f0, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
-        if ((rc = ensure_coef(c))) return rc;
-        if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
-        c->have_coef = true;
-        if ((rc = stats_frames(c))) return rc;
-        // 4 * F independent table builds
-        tables.resize(static_cast<size_t>(F) * 4);
-        const uint8_t* hs = static_cast<const uint8_t*>(c->h_pinned);
-        std::atomic<int> build_rc{JPGENC_OK};
-        c->host_pool->parallel_for(F * 4, [&](uint32_t j) {
-            const uint32_t f = j >> 2, t = j & 3;
-            const uint32_t* count = reinterpret_cast<const uint32_t*>(hs + f * kStatsBytes) + t * 256;
-            const uint64_t* first = reinterpret_cast<const uint64_t*>(hs + f * kStatsBytes + 4096) + t * 256;
-            const int r = jpgenc_build_huffman(count, first, &tables[j]);
-            if (r) build_rc.store(r);
-        });
-        if (build_rc.load()) return fail(c, build_rc.load(), "Huffman table build failed");
-        if ((rc = entropy_frames(c, tables.data()))) return rc;
-        // files: header + scan + EOI per frame; the scans come back with one copy each, one synchronisation per pass
-        for (uint32_t f = 0; f < F; ++f) {
-            const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
-            const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], nullptr);
-            sizes[f0 + f] = hdr + scan + 2;
-            if (!out) continue;
-            uint8_t* dst = out[f0 + f];
-            if (caps[f0 + f] < hdr + scan + 2) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
-            jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], dst);
-            JPGENC_CUDA(c, cudaMemcpyAsync(dst + hdr, c->d_scan + 2 * c->frame_raw_off[f], scan, cudaMemcpyDeviceToHost, c->stream));
-            dst[hdr + scan] = 0xFF;                                  // EOI
-            dst[hdr + scan + 1] = 0xD9;
-        }
-        if (out) JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+        // the previous user of this half (pass p-1) has been synchronised by the time pass p+1 is uploaded
+        for (uint32_t f = 0; f < F; ++f)
+            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + (static_cast<size_t>(half) * per_pass + f) * fstride, frames[f0 + f], fbytes,
+                                           cudaMemcpyHostToDevice, c->copy_stream));
+        JPGENC_CUDA(c, cudaEventRecord(c->ev_band[half], c->copy_stream));
+        return JPGENC_OK;
+    };
+    if ((rc = upload(0, 0))) return rc;
+    int half = 0;
+    for (uint32_t f0 = 0; f0 < n && !rc; f0 += per_pass, half ^= 1) {
+        const uint32_t F = std::min(per_pass, n - f0);
+        if (f0 + per_pass < n && (rc = upload(f0 + per_pass, half ^ 1))) break;
+        for (uint32_t f = 0; f < F; ++f) ptrs[f] = c->d_rgb_owned + (static_cast<size_t>(half) * per_pass + f) * fstride;
+        rc = encode_frames_pass(c, F, ptrs.data(), c->ev_band[half], out ? out + f0 : nullptr, caps ? caps + f0 : nullptr, sizes + f0, tables);
+        if (!rc && !out) JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    c->nframes = 1;                                                  // the context goes back to single-image state
-    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false;
-    c->host_hist.clear();
-    return JPGENC_OK;
+    leave_batch_state(c);
+    c->d_rgb = c->d_rgb_owned;
+    return rc;
 }
 
 int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) {

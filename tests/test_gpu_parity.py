@@ -334,6 +334,11 @@ def test_frames_through_the_kernels_together(encoder, oracle, w, h, n):
         for i in range(n):
             assert outs[i][: sizes[i]].tobytes() == want[i], f"frame {i}"
         assert encoder.encode_frames_device([d + i * fb for i in range(n)], w, h) == sizes      # sizes only
+        # the same batch from host memory (uploads overlapped with the kernels)
+        host = [np.ascontiguousarray(f) for f in frames]
+        outs2 = [np.zeros(cap, np.uint8) for _ in range(n)]
+        sizes2 = encoder.encode_frames_device([f.ctypes.data for f in host], w, h, [o.ctypes.data for o in outs2], [cap] * n, host_frames=True)
+        assert sizes2 == sizes and all(outs2[i][: sizes[i]].tobytes() == want[i] for i in range(n))
         # the context is usable for single images afterwards
         assert encoder.encode_rgb(frames[0]) == want[0]
     finally:
