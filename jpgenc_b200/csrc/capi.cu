@@ -1,6 +1,7 @@
 // C-ABI of the encode path (include/jpgenc_b200.h): context, buffers, stage calls, whole-image driver.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -284,6 +285,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->lane) jpgenc_destroy(c->lane);
     delete c->pool;
     delete c->host_pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
@@ -436,6 +438,15 @@ static size_t meta_bytes(uint32_t F) { return ((F * 16 + (F + 1) * 4 + 15) / 16)
 static size_t stage_totals_off(uint32_t F) { return stage_meta_off(F) + meta_bytes(F); }
 static size_t stage_bytes(uint32_t F) { return stage_totals_off(F) + F * 16 + 64; }
 
+// JPGENC_TRACE=1: host wall-clock of the phases of every batched pass on stderr (development aid)
+static bool trace_on() {
+    static const bool on = [] { const char* v = std::getenv("JPGENC_TRACE"); return v && *v && *v != '0'; }();
+    return on;
+}
+static double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int stats_frames(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     const uint32_t F = c->nframes;
@@ -490,8 +501,10 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     c->frame_bits.assign(F, 0); c->frame_raw_off.assign(F, 0); c->frame_ff.assign(F, 0);
     // exact size of every scan from the statistics the tables were built from: a symbol costs its code length plus
     // (symbol & 15) magnitude bits
-    uint64_t raw_total = 0, k4_tiles = 0;
-    for (uint32_t f = 0; f < F; ++f) {
+    // (per frame: independent work, spread over the batch's host threads; the offsets are a serial prefix afterwards)
+    std::atomic<int> conv_err{0};
+    const double t_conv = trace_on() ? now_us() : 0;
+    auto convert = [&](uint32_t f) {
         const uint32_t* hist = &c->host_hist[static_cast<size_t>(f) * 1024];
         uint64_t bits = 0;
         for (int t = 0; t < 4; ++t) {
@@ -502,14 +515,22 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
                 ht[f].entry[t][s] = len ? (len << 16) | code : 0u;
                 ht[f].fast[t][s] = (len && len + cat <= 27) ? ((len + cat) << 27) | (code << cat) : 0u;
                 if (hist[t * 256 + s]) {
-                    if (!len) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
+                    if (!len) conv_err.store(1);
                     bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + cat);
                 }
             }
         }
-        if (bits == 0) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
-        const uint64_t nbytes = (bits + 7) / 8;
+        if (bits == 0) conv_err.store(2);
         c->frame_bits[f] = bits;
+    };
+    if (c->host_pool && F >= 8) c->host_pool->parallel_for(F, convert);
+    else for (uint32_t f = 0; f < F; ++f) convert(f);
+    if (trace_on()) c->trace_convert_us = now_us() - t_conv;
+    if (conv_err.load() == 1) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
+    if (conv_err.load() == 2) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+    uint64_t raw_total = 0, k4_tiles = 0;
+    for (uint32_t f = 0; f < F; ++f) {
+        const uint64_t nbytes = (c->frame_bits[f] + 7) / 8;
         c->frame_raw_off[f] = raw_total;
         m_off[f] = raw_total;
         m_bytes[f] = nbytes;
@@ -711,6 +732,7 @@ static uint32_t frames_per_pass(const jpgenc_ctx* c) {
 static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_frames, cudaEvent_t ready, uint8_t* const* out,
                               const uint64_t* caps, uint64_t* sizes, std::vector<jpgenc_huff_table>& tables) {
     int rc;
+    const double t_begin = trace_on() ? now_us() : 0;
     c->nframes = F;
     c->have_coef = c->have_scan = c->have_items = false;
     bool aligned = true;
@@ -733,6 +755,7 @@ static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_
     if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
     c->have_coef = true;
     if ((rc = stats_frames(c))) return rc;
+    const double t_stats = trace_on() ? now_us() : 0;
     // 4 * F independent table builds
     tables.resize(static_cast<size_t>(F) * 4);
     const uint8_t* hs = static_cast<const uint8_t*>(c->h_pinned);
@@ -745,21 +768,38 @@ static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_
         if (r) build_rc.store(r);
     });
     if (build_rc.load()) return fail(c, build_rc.load(), "Huffman table build failed");
+    const double t_built = trace_on() ? now_us() : 0;
     if ((rc = entropy_frames(c, tables.data()))) return rc;
+    const double t_entropy = trace_on() ? now_us() : 0;
     // files: header + scan + EOI per frame; the scans come back with one copy each, one synchronisation per pass
-    for (uint32_t f = 0; f < F; ++f) {
+    std::atomic<int> cap_err{0};
+    std::vector<uint32_t>& hdr_len = c->hdr_len;
+    hdr_len.resize(F);
+    auto headers = [&](uint32_t f) {
         const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
         const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], nullptr);
+        hdr_len[f] = static_cast<uint32_t>(hdr);
         sizes[f] = hdr + scan + 2;
-        if (!out) continue;
+        if (!out) return;
+        if (caps[f] < hdr + scan + 2) { cap_err.store(1); return; }
         uint8_t* dst = out[f];
-        if (caps[f] < hdr + scan + 2) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
         jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], dst);
-        JPGENC_CUDA(c, cudaMemcpyAsync(dst + hdr, c->d_scan + 2 * c->frame_raw_off[f], scan, cudaMemcpyDeviceToHost, c->stream));
         dst[hdr + scan] = 0xFF;                                  // EOI
         dst[hdr + scan + 1] = 0xD9;
+    };
+    if (F >= 8) c->host_pool->parallel_for(F, headers);
+    else for (uint32_t f = 0; f < F; ++f) headers(f);
+    if (cap_err.load()) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
+    if (out) {
+        for (uint32_t f = 0; f < F; ++f) {
+            const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
+            JPGENC_CUDA(c, cudaMemcpyAsync(out[f] + hdr_len[f], c->d_scan + 2 * c->frame_raw_off[f], scan, cudaMemcpyDeviceToHost, c->stream));
+        }
+        JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    if (out) JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (trace_on())
+        std::fprintf(stderr, "[jpgenc pass ctx %p F %u] K1+K2+sync %.0f us, tables %.0f us, convert+K3+K4+sync %.0f us (convert %.0f), files %.0f us\n",
+                     static_cast<void*>(c), F, t_stats - t_begin, t_built - t_stats, t_entropy - t_built, c->trace_convert_us, now_us() - t_entropy);
     return JPGENC_OK;
 }
 
@@ -769,56 +809,134 @@ static void leave_batch_state(jpgenc_ctx* c) {
     c->host_hist.clear();
 }
 
+// ---- two pipeline lanes ----------------------------------------------------------------------------------------------
+// A pass is GPU work (K1, refinement, K2), then host work (4 * F table builds), then GPU work (K3, K4) again: on one stream
+// the GPU idles for the host half.  The batch calls therefore cut the batch into passes and run them on TWO lanes -- the
+// context itself and a second, lazily created context on the same device with its own stream and buffers -- each driven
+// by its own host thread: while one lane builds its tables the other lane's kernels run.
+static unsigned pool_threads() { return std::min(15u, std::max(2u, std::thread::hardware_concurrency()) - 1); }
+
+static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, uint32_t maxval) {
+    if (l != c) {
+        std::memcpy(l->qy, c->qy, 64); std::memcpy(l->qc, c->qc, 64);
+        std::memcpy(l->dct_a, c->dct_a, sizeof c->dct_a); std::memcpy(l->dct_s, c->dct_s, sizeof c->dct_s);
+    }
+    const int rc = set_geometry(l, w, h, maxval);
+    if (rc) return rc;
+    if (!l->host_pool) l->host_pool = new HostPool(pool_threads());
+    return JPGENC_OK;
+}
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
+// frames per pass: a pass must be large enough to fill the GPU and amortise its two synchronisations, small enough
+// that the two lanes get several passes each to overlap
+static uint32_t pipelined_pass_frames(const jpgenc_ctx* c, uint32_t n) {
+    const uint32_t cap = frames_per_pass(c);
+    const size_t px = static_cast<size_t>(c->mcu_w) * c->mcu_h * 256;
+    const uint32_t floor_frames = static_cast<uint32_t>(std::max<size_t>(1, (96u << 20) / px));   // >= ~100 Mpx per pass
+    uint32_t per = std::max(floor_frames, (n + 5) / 6);           // measured on 1024 x 1080p: 128..256 per pass are within 4 %
+    per = env_u32("JPGENC_FRAMES_PER_PASS", per);
+    return std::max(1u, std::min(per, cap));
+}
+
+// runs pass(lane, p) for p = 0 .. npasses-1 on up to two lanes; passes are handed out in order
+static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
+                     const std::function<int(jpgenc_ctx*, uint32_t)>& pass) {
+    int rc = prepare_lane(c, c, w, h, maxval);
+    if (rc) return rc;
+    const bool two = npasses > 1 && env_u32("JPGENC_LANES", 2) > 1;
+    if (two) {
+        if (!c->lane && (rc = jpgenc_create(c->device, &c->lane))) return fail(c, rc, jpgenc_last_error(nullptr));
+        if ((rc = prepare_lane(c, c->lane, w, h, maxval))) return fail(c, rc, jpgenc_last_error(c->lane));
+    }
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> first_error{JPGENC_OK};
+    auto work = [&](jpgenc_ctx* l) {
+        cudaSetDevice(c->device);
+        for (;;) {
+            const uint32_t p = next.fetch_add(1);
+            if (p >= npasses || first_error.load() != JPGENC_OK) return;
+            const int r = pass(l, p);
+            if (r != JPGENC_OK) {
+                int expected = JPGENC_OK;
+                if (first_error.compare_exchange_strong(expected, r) && l != c) c->error = l->error;
+                return;
+            }
+        }
+    };
+    if (two) {
+        std::thread helper(work, c->lane);
+        work(c);
+        helper.join();
+        c->launches += c->lane->launches;
+        c->lane->launches = 0;
+        leave_batch_state(c->lane);
+    } else {
+        work(c);
+    }
+    leave_batch_state(c);
+    return first_error.load();
+}
+
 int jpgenc_encode_frames_device(jpgenc_ctx* c, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h, uint32_t maxval,
                                 uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
     if (!c || !dev_frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
-    if (!c->host_pool) c->host_pool = new HostPool(std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
-    const uint32_t per_pass = frames_per_pass(c);
-    std::vector<jpgenc_huff_table> tables;
-    for (uint32_t f0 = 0; f0 < n && !rc; f0 += per_pass)
-        rc = encode_frames_pass(c, std::min(per_pass, n - f0), dev_frames + f0, nullptr, out ? out + f0 : nullptr,
-                                caps ? caps + f0 : nullptr, sizes + f0, tables);
-    leave_batch_state(c);
-    return rc;
+    if (n == 0) return JPGENC_OK;
+    const uint32_t per_pass = pipelined_pass_frames(c, n), npasses = (n + per_pass - 1) / per_pass;
+    return run_lanes(c, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
+        const uint32_t f0 = p * per_pass;
+        return encode_frames_pass(l, std::min(per_pass, n - f0), dev_frames + f0, nullptr, out ? out + f0 : nullptr,
+                                  caps ? caps + f0 : nullptr, sizes + f0, l->pass_tables);
+    });
 }
 
-// The same for frames in host memory (pinned for full PCIe speed): the frames of pass p+1 are uploaded on the copy
-// stream into the other half of a double-buffered staging area while pass p goes through the kernels.
+// The same for frames in host memory (pinned for full PCIe speed): the frames travel on the copy stream into a ring of
+// kRing pass-sized slices of device memory, always a few passes ahead of the kernels; a lane that has finished pass p
+// re-fills p's slice with the frames of pass p + kRing before it takes its next pass.
 int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h, uint32_t maxval,
                          uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
     if (!c || !frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
-    if (!c->host_pool) c->host_pool = new HostPool(std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
+    if (n == 0) return JPGENC_OK;
+    constexpr uint32_t kRing = 4;
     const size_t fbytes = static_cast<size_t>(w) * h * 3, fstride = (fbytes + 255) & ~static_cast<size_t>(255);
     // passes small enough that the first one starts soon and copies overlap compute finely, large enough to amortise
-    const uint32_t per_pass = std::max(1u, std::min<uint32_t>(frames_per_pass(c), static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / fstride))));
-    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, 2 * per_pass * fstride + 16))) return rc;
-    std::vector<jpgenc_huff_table> tables;
-    std::vector<const void*> ptrs(per_pass);
-    auto upload = [&](uint32_t f0, int half) -> int {
-        const uint32_t F = std::min(per_pass, n - f0);
-        // the previous user of this half (pass p-1) has been synchronised by the time pass p+1 is uploaded
+    uint32_t per_pass = std::max(1u, std::min<uint32_t>(frames_per_pass(c), static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / fstride))));
+    per_pass = std::max(1u, std::min(env_u32("JPGENC_FRAMES_PER_PASS", per_pass), frames_per_pass(c)));
+    const uint32_t npasses = (n + per_pass - 1) / per_pass;
+    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, kRing * per_pass * fstride + 16))) return rc;
+    std::mutex copy_mutex;                                       // one pass's copies stay together on the copy stream
+    auto upload = [&](uint32_t p) -> int {
+        const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
+        std::lock_guard<std::mutex> lk(copy_mutex);
         for (uint32_t f = 0; f < F; ++f)
-            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + (static_cast<size_t>(half) * per_pass + f) * fstride, frames[f0 + f], fbytes,
+            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride, frames[f0 + f], fbytes,
                                            cudaMemcpyHostToDevice, c->copy_stream));
-        JPGENC_CUDA(c, cudaEventRecord(c->ev_band[half], c->copy_stream));
+        JPGENC_CUDA(c, cudaEventRecord(c->ev_band[slot], c->copy_stream));
         return JPGENC_OK;
     };
-    if ((rc = upload(0, 0))) return rc;
-    int half = 0;
-    for (uint32_t f0 = 0; f0 < n && !rc; f0 += per_pass, half ^= 1) {
-        const uint32_t F = std::min(per_pass, n - f0);
-        if (f0 + per_pass < n && (rc = upload(f0 + per_pass, half ^ 1))) break;
-        for (uint32_t f = 0; f < F; ++f) ptrs[f] = c->d_rgb_owned + (static_cast<size_t>(half) * per_pass + f) * fstride;
-        rc = encode_frames_pass(c, F, ptrs.data(), c->ev_band[half], out ? out + f0 : nullptr, caps ? caps + f0 : nullptr, sizes + f0, tables);
-        if (!rc && !out) JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
-    leave_batch_state(c);
+    for (uint32_t p = 0; p < std::min(kRing, npasses); ++p)
+        if ((rc = upload(p))) return rc;
+    rc = run_lanes(c, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
+        const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
+        std::vector<const void*>& ptrs = l->pass_ptrs;
+        ptrs.resize(F);
+        for (uint32_t f = 0; f < F; ++f) ptrs[f] = c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride;
+        int r = encode_frames_pass(l, F, ptrs.data(), c->ev_band[slot], out ? out + f0 : nullptr, caps ? caps + f0 : nullptr, sizes + f0,
+                                   l->pass_tables);
+        // every kernel of the pass has finished (its last synchronisation is behind K4): the slice is free again
+        if (!r && p + kRing < npasses && upload(p + kRing)) { l->error = c->error; r = JPGENC_ERR_CUDA; }
+        return r;
+    });
     c->d_rgb = c->d_rgb_owned;
     return rc;
 }

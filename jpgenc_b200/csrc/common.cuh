@@ -86,6 +86,8 @@ struct jpgenc_ctx {
     jpgenc::TablePool* pool = nullptr;    // host worker threads that build the four Huffman tables side by side
     jpgenc::HostPool* host_pool = nullptr;   // parallel table builds of a batch of frames
     bool parallel_tables = true;          // false inside a batch: there the frames run in parallel instead
+    jpgenc_ctx* lane = nullptr;           // second pipeline lane of the batched-frame calls (own stream and buffers): while one
+                                          // lane's pass waits for its Huffman tables on the host, the other lane's kernels run
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-to-device copies of jpgenc_encode_rgb, overlapped with K1 band by band
     cudaEvent_t ev_band[16] = {};
@@ -144,6 +146,11 @@ struct jpgenc_ctx {
     size_t flush_bytes = 0;
     void* h_pinned = nullptr;             // small pinned staging (stats, totals)
     size_t pinned_bytes = 0;
+
+    std::vector<jpgenc_huff_table> pass_tables;   // batched-frame calls: tables of the lane's current pass
+    std::vector<const void*> pass_ptrs;           // ... device pointers of its frames
+    double trace_convert_us = 0;
+    std::vector<uint32_t> hdr_len;                // ... header length of every frame's file
 
     jpgenc_stats stats{};
     jpgenc_huff_table last_tables[4];     // tables of the last whole-image run (for jpgenc_assemble_last)

@@ -343,3 +343,41 @@ def test_frames_through_the_kernels_together(encoder, oracle, w, h, n):
         assert encoder.encode_rgb(frames[0]) == want[0]
     finally:
         encoder.dev_free(d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_pass,lanes", [(3, 2), (1, 2), (4, 1), (7, 2)])
+def test_frames_in_many_passes_on_two_lanes(encoder, oracle, monkeypatch, per_pass, lanes):
+    """The batched-frame calls cut a batch into passes and run them on two pipeline lanes (own streams and buffers, one
+    host thread each; uploads of host frames travel through a ring of slices ahead of the kernels).  Forcing tiny passes
+    makes every hand-over happen many times: the files must not depend on pass size, lane count or which lane ran a pass."""
+    monkeypatch.setenv("JPGENC_FRAMES_PER_PASS", str(per_pass))
+    monkeypatch.setenv("JPGENC_LANES", str(lanes))
+    w, h, n = 176, 104, 23
+    frames = [synth_rgb(w, h, s) if s % 4 else noise_rgb(w, h, s) for s in range(n)]
+    want = [oracle.encode_rgb(f) for f in frames]
+    fb = w * h * 3
+    d = encoder.dev_alloc(n * fb + 64)
+    try:
+        for i, f in enumerate(frames):
+            encoder.h2d(d + i * fb, np.ascontiguousarray(f))
+        cap = max(len(x) for x in want) + 64
+        for rep in range(2):                                      # second round: lanes and their buffers are reused
+            outs = [np.zeros(cap, np.uint8) for _ in range(n)]
+            sizes = encoder.encode_frames_device([d + i * fb for i in range(n)], w, h, [o.ctypes.data for o in outs], [cap] * n)
+            assert sizes == [len(x) for x in want]
+            assert all(outs[i][: sizes[i]].tobytes() == want[i] for i in range(n))
+            assert encoder.encode_frames_device([d + i * fb for i in range(n)], w, h) == sizes
+            host = [np.ascontiguousarray(f) for f in frames]
+            outs2 = [np.zeros(cap, np.uint8) for _ in range(n)]
+            sizes2 = encoder.encode_frames_device([f.ctypes.data for f in host], w, h, [o.ctypes.data for o in outs2], [cap] * n, host_frames=True)
+            assert sizes2 == sizes and all(outs2[i][: sizes[i]].tobytes() == want[i] for i in range(n))
+        # a too-small output buffer in a late pass is reported, and the context keeps working
+        small = [cap] * n
+        small[n - 2] = 16
+        outs = [np.zeros(cap, np.uint8) for _ in range(n)]
+        with pytest.raises(Exception):
+            encoder.encode_frames_device([d + i * fb for i in range(n)], w, h, [o.ctypes.data for o in outs], small)
+        assert encoder.encode_rgb(frames[1]) == want[1]
+    finally:
+        encoder.dev_free(d)
