@@ -175,9 +175,13 @@ int fail(jpgenc_ctx* c, int code, const char* what) {
     return code;
 }
 
+// `headroom`: for buffers whose size follows the data (scan sizes differ from pass to pass): a reallocation frees device
+// memory, which synchronises the whole device -- every lane -- so it should happen a few times, not whenever a pass is
+// slightly larger than the last one
 template <class T>
-int ensure(jpgenc_ctx* c, T** ptr, size_t* cap, size_t need_bytes) {
+int ensure(jpgenc_ctx* c, T** ptr, size_t* cap, size_t need_bytes, bool headroom = false) {
     if (*ptr && *cap >= need_bytes) return JPGENC_OK;
+    if (headroom) need_bytes += need_bytes / 4 + 4096;
     if (*ptr) JPGENC_CUDA(c, cudaFree(*ptr));
     *ptr = nullptr; *cap = 0;
     void* p = nullptr;
@@ -285,7 +289,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->lane) jpgenc_destroy(c->lane);
+    for (jpgenc_ctx* l : c->lanes) jpgenc_destroy(l);
     delete c->pool;
     delete c->host_pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
@@ -540,12 +544,12 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     }
     m_tile0[F] = static_cast<uint32_t>(k4_tiles);
     if (k4_tiles > 0xFFFFFFFFull) return fail(c, JPGENC_ERR_ARG, "scan too large");
-    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, raw_total))) return rc;
-    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * raw_total + 64))) return rc;
+    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, raw_total, true))) return rc;
+    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * raw_total + 64, true))) return rc;
     if ((rc = ensure(c, &c->d_tables, &c->tables_cap, F * sizeof(DeviceTables)))) return rc;
     if ((rc = ensure(c, &c->d_meta, &c->meta_cap, meta_bytes(F)))) return rc;
     size_t lb_bytes = c->lookback_cap;
-    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (2 * static_cast<size_t>(F) + k4_tiles + 8) * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (2 * static_cast<size_t>(F) + k4_tiles + 8) * sizeof(unsigned long long), true))) return rc;
     c->lookback_cap = lb_bytes;
     // tables and meta sit next to each other in the staging buffer: two copies
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables), cudaMemcpyHostToDevice, c->stream));
@@ -809,21 +813,27 @@ static void leave_batch_state(jpgenc_ctx* c) {
     c->host_hist.clear();
 }
 
-// ---- two pipeline lanes ----------------------------------------------------------------------------------------------
+// ---- pipeline lanes --------------------------------------------------------------------------------------------------
 // A pass is GPU work (K1, refinement, K2), then host work (4 * F table builds), then GPU work (K3, K4) again: on one stream
-// the GPU idles for the host half.  The batch calls therefore cut the batch into passes and run them on TWO lanes -- the
-// context itself and a second, lazily created context on the same device with its own stream and buffers -- each driven
-// by its own host thread: while one lane builds its tables the other lane's kernels run.
-static unsigned pool_threads() { return std::min(15u, std::max(2u, std::thread::hardware_concurrency()) - 1); }
+// the GPU idles for the host half.  The batch calls therefore cut the batch into passes and run them on several lanes -- the
+// context itself and further, lazily created contexts on the same device with their own streams and buffers -- each
+// driven by its own host thread: while one lane builds its tables the other lanes' kernels run.
+constexpr uint32_t kDefaultLanes = 3, kMaxLanes = 4;
+// host threads per lane for the table builds: the lanes' host phases overlap, so they share the cores
+static unsigned pool_threads(uint32_t lanes) {
+    const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
+    return std::min(15u, std::max(2u, hc / lanes) - 1);
+}
 
-static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, uint32_t maxval) {
+static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t lanes, uint32_t w, uint32_t h, uint32_t maxval) {
     if (l != c) {
         std::memcpy(l->qy, c->qy, 64); std::memcpy(l->qc, c->qc, 64);
         std::memcpy(l->dct_a, c->dct_a, sizeof c->dct_a); std::memcpy(l->dct_s, c->dct_s, sizeof c->dct_s);
     }
     const int rc = set_geometry(l, w, h, maxval);
     if (rc) return rc;
-    if (!l->host_pool) l->host_pool = new HostPool(pool_threads());
+    if (l->host_pool && l->host_pool_lanes != lanes) { delete l->host_pool; l->host_pool = nullptr; }
+    if (!l->host_pool) { l->host_pool = new HostPool(pool_threads(lanes)); l->host_pool_lanes = lanes; }
     return JPGENC_OK;
 }
 
@@ -838,23 +848,27 @@ static uint32_t pipelined_pass_frames(const jpgenc_ctx* c, uint32_t n) {
     const uint32_t cap = frames_per_pass(c);
     const size_t px = static_cast<size_t>(c->mcu_w) * c->mcu_h * 256;
     const uint32_t floor_frames = static_cast<uint32_t>(std::max<size_t>(1, (96u << 20) / px));   // >= ~100 Mpx per pass
-    uint32_t per = std::max(floor_frames, (n + 5) / 6);           // measured on 1024 x 1080p: 128..256 per pass are within 4 %
+    uint32_t per = std::max(floor_frames, (n + 9) / 10);          // measured on 1024 x 1080p, 3 lanes: 64..128 per pass are within 5 %
     per = env_u32("JPGENC_FRAMES_PER_PASS", per);
     return std::max(1u, std::min(per, cap));
 }
 
-// runs pass(lane, p) for p = 0 .. npasses-1 on up to two lanes; passes are handed out in order
+// runs pass(lane, p) for p = 0 .. npasses-1 on the lanes; passes are handed out in order
 static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
                      const std::function<int(jpgenc_ctx*, uint32_t)>& pass) {
-    int rc = prepare_lane(c, c, w, h, maxval);
+    const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", kDefaultLanes), kMaxLanes, npasses}));
+    int rc = prepare_lane(c, c, nl, w, h, maxval);
     if (rc) return rc;
-    const bool two = npasses > 1 && env_u32("JPGENC_LANES", 2) > 1;
-    if (two) {
-        if (!c->lane && (rc = jpgenc_create(c->device, &c->lane))) return fail(c, rc, jpgenc_last_error(nullptr));
-        if ((rc = prepare_lane(c, c->lane, w, h, maxval))) return fail(c, rc, jpgenc_last_error(c->lane));
+    while (c->lanes.size() + 1 < nl) {
+        jpgenc_ctx* l = nullptr;
+        if ((rc = jpgenc_create(c->device, &l))) return fail(c, rc, jpgenc_last_error(nullptr));
+        c->lanes.push_back(l);
     }
+    for (uint32_t k = 1; k < nl; ++k)
+        if ((rc = prepare_lane(c, c->lanes[k - 1], nl, w, h, maxval))) return fail(c, rc, jpgenc_last_error(c->lanes[k - 1]));
     std::atomic<uint32_t> next{0};
     std::atomic<int> first_error{JPGENC_OK};
+    std::mutex error_mutex;
     auto work = [&](jpgenc_ctx* l) {
         cudaSetDevice(c->device);
         for (;;) {
@@ -862,21 +876,24 @@ static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, ui
             if (p >= npasses || first_error.load() != JPGENC_OK) return;
             const int r = pass(l, p);
             if (r != JPGENC_OK) {
-                int expected = JPGENC_OK;
-                if (first_error.compare_exchange_strong(expected, r) && l != c) c->error = l->error;
+                std::lock_guard<std::mutex> lk(error_mutex);
+                if (first_error.load() == JPGENC_OK) {
+                    first_error.store(r);
+                    if (l != c) c->error = l->error;
+                }
                 return;
             }
         }
     };
-    if (two) {
-        std::thread helper(work, c->lane);
-        work(c);
-        helper.join();
-        c->launches += c->lane->launches;
-        c->lane->launches = 0;
-        leave_batch_state(c->lane);
-    } else {
-        work(c);
+    std::vector<std::thread> helpers;
+    for (uint32_t k = 1; k < nl; ++k) helpers.emplace_back(work, c->lanes[k - 1]);
+    work(c);
+    for (std::thread& t : helpers) t.join();
+    for (uint32_t k = 1; k < nl; ++k) {
+        jpgenc_ctx* l = c->lanes[k - 1];
+        c->launches += l->launches;
+        l->launches = 0;
+        leave_batch_state(l);
     }
     leave_batch_state(c);
     return first_error.load();
@@ -907,7 +924,7 @@ int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames
     int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
     if (n == 0) return JPGENC_OK;
-    constexpr uint32_t kRing = 4;
+    constexpr uint32_t kRing = kMaxLanes + 2;                   // when pass p is handed out, every pass <= p - lanes is complete
     const size_t fbytes = static_cast<size_t>(w) * h * 3, fstride = (fbytes + 255) & ~static_cast<size_t>(255);
     // passes small enough that the first one starts soon and copies overlap compute finely, large enough to amortise
     uint32_t per_pass = std::max(1u, std::min<uint32_t>(frames_per_pass(c), static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / fstride))));
@@ -915,26 +932,39 @@ int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames
     const uint32_t npasses = (n + per_pass - 1) / per_pass;
     if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, kRing * per_pass * fstride + 16))) return rc;
     std::mutex copy_mutex;                                       // one pass's copies stay together on the copy stream
+    std::condition_variable copy_cv;
+    std::vector<char> issued(npasses, 0);                        // pass p's copies and event record have been enqueued
     auto upload = [&](uint32_t p) -> int {
         const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
-        std::lock_guard<std::mutex> lk(copy_mutex);
-        for (uint32_t f = 0; f < F; ++f)
-            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride, frames[f0 + f], fbytes,
-                                           cudaMemcpyHostToDevice, c->copy_stream));
-        JPGENC_CUDA(c, cudaEventRecord(c->ev_band[slot], c->copy_stream));
-        return JPGENC_OK;
+        int r = JPGENC_OK;
+        {
+            std::lock_guard<std::mutex> lk(copy_mutex);
+            for (uint32_t f = 0; f < F && r == JPGENC_OK; ++f)
+                if (cudaMemcpyAsync(c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride, frames[f0 + f], fbytes,
+                                    cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) r = JPGENC_ERR_CUDA;
+            if (r == JPGENC_OK && cudaEventRecord(c->ev_band[slot], c->copy_stream) != cudaSuccess) r = JPGENC_ERR_CUDA;
+            issued[p] = r == JPGENC_OK ? 1 : 2;
+        }
+        copy_cv.notify_all();
+        return r;
     };
     for (uint32_t p = 0; p < std::min(kRing, npasses); ++p)
-        if ((rc = upload(p))) return rc;
+        if ((rc = upload(p))) return fail(c, rc, "host-to-device copy of a frame failed");
     rc = run_lanes(c, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
         const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
+        {   // the lane that finished pass p - kRing enqueues this pass's copies; normally long done
+            std::unique_lock<std::mutex> lk(copy_mutex);
+            copy_cv.wait(lk, [&] { return issued[p] != 0; });
+            if (issued[p] != 1) { l->error = "host-to-device copy of a frame failed"; return JPGENC_ERR_CUDA; }
+        }
         std::vector<const void*>& ptrs = l->pass_ptrs;
         ptrs.resize(F);
         for (uint32_t f = 0; f < F; ++f) ptrs[f] = c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride;
         int r = encode_frames_pass(l, F, ptrs.data(), c->ev_band[slot], out ? out + f0 : nullptr, caps ? caps + f0 : nullptr, sizes + f0,
                                    l->pass_tables);
-        // every kernel of the pass has finished (its last synchronisation is behind K4): the slice is free again
-        if (!r && p + kRing < npasses && upload(p + kRing)) { l->error = c->error; r = JPGENC_ERR_CUDA; }
+        // every kernel of the pass has finished (its last synchronisation is behind K4): the slice is free again.  Also
+        // after a failure: a lane may be waiting for those copies to be enqueued.
+        if (p + kRing < npasses && upload(p + kRing) && !r) { l->error = "host-to-device copy of a frame failed"; r = JPGENC_ERR_CUDA; }
         return r;
     });
     c->d_rgb = c->d_rgb_owned;

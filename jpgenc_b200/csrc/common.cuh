@@ -85,9 +85,11 @@ struct jpgenc_ctx {
     int device = 0;
     jpgenc::TablePool* pool = nullptr;    // host worker threads that build the four Huffman tables side by side
     jpgenc::HostPool* host_pool = nullptr;   // parallel table builds of a batch of frames
+    uint32_t host_pool_lanes = 0;            // ... sized for this many lanes sharing the host cores
     bool parallel_tables = true;          // false inside a batch: there the frames run in parallel instead
-    jpgenc_ctx* lane = nullptr;           // second pipeline lane of the batched-frame calls (own stream and buffers): while one
-                                          // lane's pass waits for its Huffman tables on the host, the other lane's kernels run
+    std::vector<jpgenc_ctx*> lanes;       // further pipeline lanes of the batched-frame calls (contexts on the same device with their own
+                                          // stream and buffers): while one lane's pass waits for its Huffman tables on the host, the
+                                          // other lanes' kernels run
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-to-device copies of jpgenc_encode_rgb, overlapped with K1 band by band
     cudaEvent_t ev_band[16] = {};

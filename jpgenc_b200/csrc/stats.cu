@@ -17,6 +17,7 @@
 // like, the loop body is branch-free and the item stores are coalesced.  The DC and EOB symbols
 // exist exactly once (at most once) per block and stay with the block's own thread.
 #include "blockwalk.cuh"
+#include "ptx.cuh"
 
 namespace jpgenc {
 
@@ -37,36 +38,77 @@ struct StatsParams {
 
 // One histogram update for the whole warp: lanes with the same bin are counted by their lowest lane, so the hot
 // symbols (EOB, +-1 coefficients, the common DC category) cost one shared-memory atomic instead of up to 32.
-__device__ __forceinline__ void warp_count(uint32_t* s_hist, unsigned long long* s_first, bool has, int idx,
-                                           unsigned long long key) {
+//
+// Keys inside a tile are 32-bit and TILE-LOCAL (see local_key_of): shared memory has a native 32-bit atomic minimum,
+// a 64-bit one is a compare-and-swap loop, and a frame of a batch has so few tiles that most of them start before any
+// global minimum exists to pre-empt their updates.
+__device__ __forceinline__ void warp_count(uint32_t* s_hist, uint32_t* s_first, bool has, int idx, uint32_t key) {
     const int lane = threadIdx.x & 31;
     const unsigned grp = __match_any_sync(0xffffffffu, has ? idx : (0x10000 | lane));
-    if (has) {
-        if (lane == __ffs(grp) - 1) atomicAdd(&s_hist[idx], static_cast<uint32_t>(__popc(grp)));
-        if (key < s_first[idx]) atomicMin(&s_first[idx], key);
+    const bool leader = has && lane == __ffs(grp) - 1;
+    if (leader) atomicAdd(&s_hist[idx], static_cast<uint32_t>(__popc(grp)));
+    // first-occurrence key: nothing to do once the minimum is established (the steady state of a large image); where
+    // lanes do improve on it, the matching lanes agree on their smallest key first (REDUX.MIN) so that one lane per
+    // symbol updates shared memory -- 32 lanes hammering one address with atomics is what made small frames slow
+    const bool better = has && key < s_first[idx];
+    if (__any_sync(0xffffffffu, better)) {
+        if (has) {
+            const uint32_t kmin = __reduce_min_sync(grp, better ? key : 0xFFFFFFFFu);
+            if (leader && kmin != 0xFFFFFFFFu) atomicMin(&s_first[idx], kmin);
+        }
     }
 }
+
+// Tile-local first-occurrence keys.  The global key of a symbol is (block index in the reference's text order) * 256 +
+// position key.  Inside one tile (64 consecutive MCUs) the luma text indices lie within a few block rows of the tile's
+// first block, and the chroma ones are the tile's MCU numbers, once for Cb and once -- n_mcu later -- for Cr:
+//   luma    local = (text index - text index of the tile's first Y block) * 256 + position key      (< 2^24)
+//   chroma  local = (is Cr) << 30 | (MCU - first MCU of the tile) * 256 + position key
+// TileKeys converts between the two forms; to_local also maps any global key that no symbol of this tile can beat (or
+// that every symbol of it beats) to a value with exactly that effect.
+struct TileKeys {
+    unsigned long long y_base, cb_base, cr_base;          // global keys of local key 0
+    static constexpr uint32_t kCr = 1u << 30, kSpan = 64u * 256u;
+    __device__ __forceinline__ uint32_t to_local(int table, unsigned long long g) const {
+        if (table < 2) {
+            if (g <= y_base) return 0u;
+            const unsigned long long d = g - y_base;
+            return d > 0xFFFFFFFEull ? 0xFFFFFFFFu : static_cast<uint32_t>(d);
+        }
+        if (g <= cb_base) return 0u;
+        if (g < cb_base + kSpan) return static_cast<uint32_t>(g - cb_base);
+        if (g <= cr_base) return kCr;
+        if (g < cr_base + kSpan) return kCr + static_cast<uint32_t>(g - cr_base);
+        return 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ unsigned long long to_global(int table, uint32_t k) const {
+        if (table < 2) return y_base + k;
+        return ((k & kCr) ? cr_base : cb_base) + (k & (kCr - 1));
+    }
+};
 
 constexpr size_t kStatsBytes = 4096 + 8192;
 
 constexpr int kStatsSmem = kTileSmemBytes                // masks + dc
-                           + kTileBlocks * 8             // text key of the block
+                           + kTileBlocks * 4             // local text key of the block
                            + kTileBlocks * 4             // first item / first AC descriptor of the block
                            + kDescCap * 4                // descriptors
-                           + 4096 + 8192                 // histogram, first-occurrence keys
+                           + 4096 + 8192 + 4096          // histogram, global keys as fetched, local first-occurrence keys
                            + 36 * 4;                     // scan scratch
 
 __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __grid_constant__ StatsParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const TileView tv = tile_view(smem);
     uint8_t* at = smem + kTileSmemBytes;
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(at);    at += kTileBlocks * 8;
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(at);                        at += kTileBlocks * 4;
     uint32_t* s_base = reinterpret_cast<uint32_t*>(at);                       at += kTileBlocks * 4;
     uint32_t* s_desc = reinterpret_cast<uint32_t*>(at);                       at += kDescCap * 4;
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(at);                       at += 4096;
-    unsigned long long* s_first = reinterpret_cast<unsigned long long*>(at);  at += 8192;
+    unsigned long long* s_first_g = reinterpret_cast<unsigned long long*>(at); at += 8192;   // offset 19200: 16-byte aligned
+    uint32_t* s_first = reinterpret_cast<uint32_t*>(at);                      at += 4096;
     uint32_t* s_scan = reinterpret_cast<uint32_t*>(at);
     __shared__ uint32_t s_origin[2];                                      // MCU column / row of the tile's first MCU
+    __shared__ alignas(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t frame = blockIdx.x / p.tiles_per_frame;
@@ -76,16 +118,29 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     uint32_t* __restrict__ g_hist = reinterpret_cast<uint32_t*>(p.g_stats + frame * kStatsBytes);
     unsigned long long* __restrict__ g_first = reinterpret_cast<unsigned long long*>(p.g_stats + frame * kStatsBytes + 4096);
 
-    // the global minima seen so far bound what this tile can still contribute: after the first tiles almost no
-    // key is smaller, so the shared-memory atomicMin below is rarely executed
-    for (int i = tid; i < 1024; i += kTileBlocks) { s_hist[i] = 0; s_first[i] = __ldcg(&g_first[i]); }
-    if (tid == 0) {                                                       // the tile's only division
-        const uint32_t m0 = first / kBlocksPerMcu, y0 = m0 / p.mcu_w;
+    // The global minima seen so far bound what this tile can still contribute (after the first tiles of an image almost
+    // no key is smaller, so the shared-memory atomics below are rarely executed).  They are fetched by one bulk copy
+    // that runs behind the coefficient scan; a stale (larger) value only costs a redundant update.
+    if (tid == 0) {
+        ptx::mbar_init(&s_bar, 1);
+        ptx::mbar_init_fence();
+        ptx::mbar_expect_tx(&s_bar, 8192);
+        ptx::bulk_g2s(s_first_g, g_first, 8192, &s_bar);
+        const uint32_t m0 = first / kBlocksPerMcu, y0 = m0 / p.mcu_w;  // the tile's only division
         s_origin[0] = m0 - y0 * p.mcu_w;
         s_origin[1] = y0;
     }
+    for (int i = tid; i < 1024; i += kTileBlocks) s_hist[i] = 0;
     scan_tile(tv, coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
+    ptx::mbar_wait(&s_bar, 0);
+    const uint32_t m_first = first / kBlocksPerMcu;
+    const uint32_t y_text0 = (s_origin[1] * 2u) * (2u * p.mcu_w) + s_origin[0] * 2u;     // text index of the tile's first Y block
+    TileKeys tk;
+    tk.y_base = 256ull * y_text0;
+    tk.cb_base = 256ull * m_first;
+    tk.cr_base = 256ull * (static_cast<unsigned long long>(p.n_mcu) + m_first);
+    for (int i = tid; i < 1024; i += kTileBlocks) s_first[i] = tk.to_local(i >> 8, s_first_g[i]);   // visible after the scan's barrier below
 
     // ---- per block: mask, DC difference, text key, item counts ----
     const bool live = tid < nb;
@@ -93,17 +148,17 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     const int tdc = k < 4 ? 0 : 2;
     uint32_t lo = 0, hi = 0, nac = 0, eob = 0;
     int diff = 0;
-    unsigned long long key = 0;
+    uint32_t key = 0;
     if (live) {
         load_mask(tv, tid, lo, hi);
         diff = tv.dc[tid] - dc_predictor(tv, coef, first, tid);
         nac = __popc(lo) + __popc(hi);
         eob = (hi >> 31) ? 0u : 1u;                                       // no EOB when coefficient 63 is non-zero
-        const uint32_t lm = tid / kBlocksPerMcu, mcu = first / kBlocksPerMcu + lm;
+        const uint32_t lm = tid / kBlocksPerMcu;
         uint32_t mx = s_origin[0] + lm, my = s_origin[1];
         while (mx >= p.mcu_w) { mx -= p.mcu_w; ++my; }                    // a 64-MCU tile wraps rarely
-        key = 256ull * (k < 4 ? static_cast<unsigned long long>(my * 2 + (k >> 1)) * (2ull * p.mcu_w) + mx * 2 + (k & 1)
-                              : static_cast<unsigned long long>(k - 4) * p.n_mcu + mcu);
+        key = k < 4 ? 256u * ((my * 2 + (k >> 1)) * (2u * p.mcu_w) + mx * 2 + (k & 1) - y_text0)
+                    : (static_cast<uint32_t>(k - 4) << 30) | (256u * lm);
         s_key[tid] = key;
     }
     // one scan for both prefix sums: items (DC + ACs + EOB) in the low half, AC descriptors in the high half
@@ -126,13 +181,22 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     }
     warp_count(s_hist, s_first, live, tdc * 256 + dcat, key);
     {
-        const unsigned by = __ballot_sync(0xffffffffu, eob && k < 4), bc = __ballot_sync(0xffffffffu, eob && k >= 4);
+        const bool ey = eob && k < 4, ec = eob && k >= 4;
+        const unsigned by = __ballot_sync(0xffffffffu, ey), bc = __ballot_sync(0xffffffffu, ec);
         if (lane == 0) {
             if (by) atomicAdd(&s_hist[256], static_cast<uint32_t>(__popc(by)));
             if (bc) atomicAdd(&s_hist[768], static_cast<uint32_t>(__popc(bc)));
         }
         const int ti = (tdc + 1) * 256;
-        if (eob && key + 129 < s_first[ti]) atomicMin(&s_first[ti], key + 129);
+        const bool better = eob && key + 129u < s_first[ti];
+        if (__any_sync(0xffffffffu, better)) {
+            const uint32_t ky = __reduce_min_sync(0xffffffffu, better && k < 4 ? key + 129u : 0xFFFFFFFFu);
+            const uint32_t kc = __reduce_min_sync(0xffffffffu, better && k >= 4 ? key + 129u : 0xFFFFFFFFu);
+            if (lane == 0) {
+                if (ky != 0xFFFFFFFFu) atomicMin(&s_first[256], ky);
+                if (kc != 0xFFFFFFFFu) atomicMin(&s_first[768], kc);
+            }
+        }
     }
 
     // ---- AC coefficients, flattened ----
@@ -164,7 +228,7 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
             const uint32_t j = j0 + tid;
             const bool has = j < n;
             int idx = 0, nzrl = 0, table = 0;
-            unsigned long long ikey = 0;
+            uint32_t ikey = 0;
             if (has) {
                 const uint32_t d = s_desc[j], pos = d & 63u, run = (d >> 6) & 63u, b = (d >> 12) & 511u;
                 nzrl = static_cast<int>(run >> 4);
@@ -181,7 +245,7 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
                 if (nzrl) {
                     const int zi = table * 256 + 0xF0;
                     atomicAdd(&s_hist[zi], static_cast<uint32_t>(nzrl));
-                    const unsigned long long kz = ikey - 1;              // 2*pos: just before the symbol of position pos
+                    const uint32_t kz = ikey - 1;                        // 2*pos: just before the symbol of position pos
                     if (kz < s_first[zi]) atomicMin(&s_first[zi], kz);
                 }
             }
@@ -194,7 +258,7 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
         const uint32_t n = s_hist[i];
         if (n) {
             atomicAdd(&g_hist[i], n);
-            const unsigned long long k = s_first[i];
+            const unsigned long long k = tk.to_global(i >> 8, s_first[i]);
             if (k < __ldcg(&g_first[i])) atomicMin(&g_first[i], k);
         }
     }

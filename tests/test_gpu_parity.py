@@ -346,9 +346,9 @@ def test_frames_through_the_kernels_together(encoder, oracle, w, h, n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("per_pass,lanes", [(3, 2), (1, 2), (4, 1), (7, 2)])
-def test_frames_in_many_passes_on_two_lanes(encoder, oracle, monkeypatch, per_pass, lanes):
-    """The batched-frame calls cut a batch into passes and run them on two pipeline lanes (own streams and buffers, one
+@pytest.mark.parametrize("per_pass,lanes", [(3, 2), (1, 4), (4, 1), (7, 3), (2, 3)])
+def test_frames_in_many_passes_on_several_lanes(encoder, oracle, monkeypatch, per_pass, lanes):
+    """The batched-frame calls cut a batch into passes and run them on several pipeline lanes (own streams and buffers, one
     host thread each; uploads of host frames travel through a ring of slices ahead of the kernels).  Forcing tiny passes
     makes every hand-over happen many times: the files must not depend on pass size, lane count or which lane ran a pass."""
     monkeypatch.setenv("JPGENC_FRAMES_PER_PASS", str(per_pass))
