@@ -529,7 +529,6 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     };
     if (c->host_pool && F >= 8) c->host_pool->parallel_for(F, convert);
     else for (uint32_t f = 0; f < F; ++f) convert(f);
-    if (trace_on()) c->trace_convert_us = now_us() - t_conv;
     if (conv_err.load() == 1) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
     if (conv_err.load() == 2) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
     uint64_t raw_total = 0, k4_tiles = 0;
@@ -551,12 +550,15 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     size_t lb_bytes = c->lookback_cap;
     if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (2 * static_cast<size_t>(F) + k4_tiles + 8) * sizeof(unsigned long long), true))) return rc;
     c->lookback_cap = lb_bytes;
-    // tables and meta sit next to each other in the staging buffer: two copies
+    // tables and meta sit next to each other in the staging buffer: two copies.  (Measured and rejected for one image:
+    // passing the 8 KB of tables as kernel parameters instead -- the launches get slower and the per-thread reads of
+    // the parameter bank serialise; K3+K4 went from 185 to 212 us.)
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables), cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_meta, m_off, meta_bytes(F), cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
     if ((rc = launch_entropy(c, raw_total, static_cast<uint32_t>(k4_tiles)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    if (trace_on()) c->trace_convert_us = now_us() - t_conv;
     // totals: bits written by K3 [F], stuffed FF bytes [F]
     unsigned long long* totals = reinterpret_cast<unsigned long long*>(h + stage_totals_off(F));
     JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback, F * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -616,6 +618,7 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
     int rc;
     uint32_t count[4][256];
     uint64_t first_pos[4][256];
+    const double t0 = trace_on() ? now_us() : 0;
     if (!c->parallel_tables) {
         if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
         for (int t = 0; t < 4; ++t)
@@ -627,9 +630,13 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
             c->pool->build(nullptr, nullptr, nullptr);              // release them again
             return rc;
         }
+        const double t1 = trace_on() ? now_us() : 0;
         if ((rc = c->pool->build(count, first_pos, tables))) return fail(c, rc, "Huffman table build failed");
+        if (trace_on()) std::fprintf(stderr, "[jpgenc image] K2 launch+sync %.1f us, tables %.1f us, ", t1 - t0, now_us() - t1);
     }
+    const double t2 = trace_on() ? now_us() : 0;
     if ((rc = jpgenc_entropy_encode(c, tables, scan))) return rc;
+    if (trace_on()) std::fprintf(stderr, "convert+K3+K4+sync %.1f us (convert+enqueue %.1f)\n", now_us() - t2, c->trace_convert_us);
     std::memcpy(c->last_tables, tables, sizeof c->last_tables);
     c->have_tables = true;
     return JPGENC_OK;

@@ -61,6 +61,7 @@ struct ForwardParams {
     uint32_t real_w, real_h;
     uint32_t mcu_w, mcu_h;
     uint32_t mcu_y0;                      // first MCU row of this launch (band-wise launches behind the H2D copies)
+    uint32_t prefetch_ahead;              // > 0: every CTA pulls the strip of the CTA this many positions later into L2
     ColorConsts color;
     QuantConsts2 luma;
     QuantConsts2 chroma;
