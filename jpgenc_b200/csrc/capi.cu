@@ -197,7 +197,7 @@ int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
     c->real_w = w; c->real_h = h; c->maxval = maxval;
     c->mcu_w = (w + 15) / 16; c->mcu_h = (h + 15) / 16;        // src/Image.cpp:479-489
     c->nframes = 1;
-    c->have_coef = c->have_scan = c->have_items = false;
+    c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
 }
 
@@ -375,7 +375,7 @@ int jpgenc_color_dct_quant(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     c->forward_pending = true;
     c->have_coef = true;
-    c->have_scan = c->have_items = false;
+    c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
 }
 
@@ -404,7 +404,7 @@ int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_coef, coef, bytes, cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_coef = true;
-    c->have_scan = c->have_items = false;
+    c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
 }
 
@@ -430,7 +430,7 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
     if (e != cudaSuccess) { c->error = cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
     if (rc) return rc;
     c->have_coef = true;
-    c->have_scan = c->have_items = false;
+    c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
 }
 
@@ -451,8 +451,8 @@ static double now_us() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int stats_frames(jpgenc_ctx* c) {
-    JPGENC_CUDA(c, cudaSetDevice(c->device));
+// device buffers of K2 / K3 for the frames bound to the context
+static int ensure_stats_buffers(jpgenc_ctx* c) {
     const uint32_t F = c->nframes;
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     int rc;
@@ -463,9 +463,20 @@ static int stats_frames(jpgenc_ctx* c) {
     if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, F * tiles * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, F * (tiles / 8 + tiles / 2048 + 4) * sizeof(unsigned long long)))) return rc;
     if ((rc = ensure(c, &c->d_stats, &c->stats_cap, F * kStatsBytes + 16))) return rc;
-    if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
+    return ensure_pinned(c, stage_bytes(F));
+}
+
+static int stats_frames(jpgenc_ctx* c) {
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t F = c->nframes;
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
+    int rc;
+    if ((rc = ensure_stats_buffers(c))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-    if ((rc = launch_symbol_stats(c))) return rc;
+    // a band-wise upload has already taken the first k2_tiles_done tiles through K2
+    const uint32_t done = F == 1 ? std::min<uint32_t>(c->k2_tiles_done, static_cast<uint32_t>(tiles)) : 0u;
+    c->k2_tiles_done = 0;
+    if ((rc = launch_symbol_stats(c, done, static_cast<uint32_t>(tiles * F) - done, done == 0))) return rc;
     c->have_items = true;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
@@ -663,8 +674,10 @@ static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w
     // bands of at least ~8 MB (a copy that size already runs at full PCIe rate), at most kMaxBands of them
     uint32_t rows_per_band = static_cast<uint32_t>(std::max<size_t>(1, (8u << 20) / (row_bytes * 16)));
     rows_per_band = std::max(rows_per_band, (c->mcu_h + kMaxBands - 1) / kMaxBands);
+    if ((rc = ensure_stats_buffers(c))) return rc;
+    const uint32_t tiles = (c->mcu_w * c->mcu_h * kBlocksPerMcu + 383) / 384;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->copy_stream));
-    uint32_t band = 0;
+    uint32_t band = 0, k2_done = 0;
     for (uint32_t y0 = 0; y0 < c->mcu_h; y0 += rows_per_band, ++band) {
         const uint32_t rows = std::min(rows_per_band, c->mcu_h - y0);
         const size_t px0 = static_cast<size_t>(y0) * 16, px1 = std::min<size_t>(h, static_cast<size_t>(y0 + rows) * 16);
@@ -673,12 +686,23 @@ static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w
                                            cudaMemcpyHostToDevice, c->copy_stream));
         JPGENC_CUDA(c, cudaEventRecord(c->ev_band[band], c->copy_stream));
         JPGENC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_band[band], 0));
-        if ((rc = launch_forward_rows(c, y0, rows, y0 == 0, y0 + rows >= c->mcu_h))) return rc;
+        if ((rc = launch_forward_rows(c, y0, rows, y0 == 0, false))) return rc;
+        // while the next band is on its way: exact refinement of what this band flagged, then K2 for every tile (64 MCUs)
+        // that lies completely inside the rows transformed so far -- after the last byte has crossed PCIe only the last
+        // band's share of K1, refinement and K2 is left before the tables can be built
+        if ((rc = launch_refine_pending(c))) return rc;
+        const bool last = y0 + rows >= c->mcu_h;
+        const uint32_t upto = last ? tiles : static_cast<uint32_t>((static_cast<uint64_t>(y0 + rows) * c->mcu_w) / 64);
+        if (!last && upto > k2_done) {
+            if ((rc = launch_symbol_stats(c, k2_done, upto - k2_done, k2_done == 0))) return rc;
+            k2_done = upto;
+        }
     }
     JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->copy_stream));
     c->upload_pending = true;
     c->have_coef = true;
     c->have_scan = c->have_items = false;
+    c->k2_tiles_done = k2_done;                                  // stats_frames finishes the rest
     return JPGENC_OK;
 }
 
@@ -745,7 +769,7 @@ static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_
     int rc;
     const double t_begin = trace_on() ? now_us() : 0;
     c->nframes = F;
-    c->have_coef = c->have_scan = c->have_items = false;
+    c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     bool aligned = true;
     for (uint32_t f = 0; f < F; ++f) aligned = aligned && (reinterpret_cast<uintptr_t>(dev_frames[f]) % 16 == 0);
     c->frames_aligned = aligned;
@@ -816,7 +840,7 @@ static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_
 
 static void leave_batch_state(jpgenc_ctx* c) {
     c->nframes = 1;                                                  // the context goes back to single-image state
-    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false;
+    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     c->host_hist.clear();
 }
 

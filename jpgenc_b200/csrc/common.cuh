@@ -132,6 +132,7 @@ struct jpgenc_ctx {
     unsigned long long* d_range_base = nullptr; // bits per group of 8 tiles, then per 256 groups (K3a); K3b derives offsets from them
     size_t range_base_cap = 0;
     bool have_items = false;
+    uint32_t k2_tiles_done = 0;           // K2 tiles already processed behind the bands of an upload (jpgenc_encode_rgb)
     std::vector<uint32_t> host_hist;      // K2's histograms as last read back, [nframes][4][256]
     std::vector<uint64_t> frame_bits, frame_raw_off, frame_ff;   // per frame after K3/K4: scan bits, byte offset of its raw scan, stuffed FFs
     bool k2_configured = false;
@@ -176,7 +177,9 @@ int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, b
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
                             uint64_t* refined);
 int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qcb, const int32_t* d_qcr);
-int launch_symbol_stats(jpgenc_ctx* c);
+int launch_refine_pending(jpgenc_ctx* c);
+// K2 over the tiles [tile0, tile0 + ntiles) of the bound image(s); `first` also clears the statistics
+int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
 int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles);
 constexpr uint32_t kK4TileBytes = 16384;   // input bytes per K4 tile (entropy.cu static_asserts it)
 int launch_synth_rgb(jpgenc_ctx* c, uint8_t* d, uint32_t w, uint32_t h, uint32_t seed);

@@ -438,15 +438,16 @@ __constant__ uint8_t c_inv_zigzag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4, 
                                          41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
                                          46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 
+// processes list entries (or, with `all`, block ids) [n0, n)
 template <class Sample>
-__device__ __forceinline__ void refine_loop(uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
+__device__ __forceinline__ void refine_loop(uint32_t n0, uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
                                             uint32_t blocks_per_frame, const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e,
                                             Sample&& sample) {
     const int lane8 = threadIdx.x & 7;
     const uint32_t group = (blockIdx.x * kRefineThreads + threadIdx.x) >> 3, ngroups = (gridDim.x * kRefineThreads) >> 3;
-    const uint32_t rounds = (n + ngroups - 1) / ngroups;             // same trip count for every lane of a warp (shuffles inside)
+    const uint32_t rounds = (n - min(n0, n) + ngroups - 1) / ngroups;   // same trip count for every lane of a warp (shuffles inside)
     for (uint32_t it = 0; it < rounds; ++it) {
-        const uint32_t i = it * ngroups + group;
+        const uint32_t i = n0 + it * ngroups + group;
         const bool valid = i < n;
         const uint32_t id = valid ? (all ? i : list[i]) : 0;
         double x[8], t[8];
@@ -476,8 +477,9 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* _
                                                                     const uint32_t* __restrict__ count, uint32_t cap, int all,
                                                                     uint32_t nblocks, uint32_t real_w, uint32_t real_h,
                                                                     uint32_t mcu_w, const __grid_constant__ ExactConsts e) {
-    const uint32_t n = all ? nblocks : min(*count, cap);
-    refine_loop(n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e, [&](uint32_t id, int r, int c) {
+    // count[0] = entries in the list, count[3] = entries already refined (band-wise encodes refine after every band)
+    const uint32_t n = all ? nblocks : min(count[0], cap), n0 = all ? 0u : count[3];
+    refine_loop(n0, n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e, [&](uint32_t id, int r, int c) {
         const uint32_t f = id / blocks_per_frame;
         return exact_sample(frames ? frames[f] : rgb, real_w, real_h, mcu_w, id - f * blocks_per_frame, r, c, e.scale);
     });
@@ -539,10 +541,13 @@ __global__ void __launch_bounds__(kRefineThreads) refine_blocks_kernel(const flo
                                                                            uint32_t nblocks, int all,
                                                                            const __grid_constant__ ExactConsts e) {
     const uint32_t n = all ? nblocks : min(*count, cap);
-    refine_loop(n, list, all != 0, out, 0xFFFFFFFFu, e.qy, e.qy, e, [&](uint32_t id, int r, int c) {
+    refine_loop(0u, n, list, all != 0, out, 0xFFFFFFFFu, e.qy, e.qy, e, [&](uint32_t id, int r, int c) {
         return static_cast<double>(in[static_cast<size_t>(id) * 64 + r * 8 + c]);
     });
 }
+
+// band-wise encodes: everything in the list so far has been refined
+__global__ void refine_advance_kernel(uint32_t* counters, uint32_t cap) { counters[3] = min(counters[0], cap); }
 
 // reference planar natural-order int32 planes -> MCU-ordered zigzag int16 (test hook behind jpgenc_set_coefficients)
 __global__ void planes_to_mcu_kernel(const int32_t* __restrict__ qy, const int32_t* __restrict__ qcb,
@@ -710,7 +715,7 @@ int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, b
         static const int ahead = [] { const char* v = std::getenv("JPGENC_K1_PREFETCH"); return v && *v ? std::atoi(v) : 256; }();
         p.prefetch_ahead = static_cast<uint32_t>(ahead);
     }
-    if (first) JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
+    if (first) JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(uint32_t), c->stream));   // list length .. refined so far
     bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
     if (c->nframes > 1) aligned = (c->real_w % 16 == 0) && c->frames_aligned;
     const dim3 grid((c->mcu_w + 31) / 32, rows, c->nframes);
@@ -719,6 +724,15 @@ int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, b
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return last ? launch_refine(c, false) : JPGENC_OK;
+}
+
+// exact pass over the list entries that have not been refined yet (after a band of K1), and remember how far it got
+int launch_refine_pending(jpgenc_ctx* c) {
+    const int rc = launch_refine(c, false);
+    if (rc) return rc;
+    refine_advance_kernel<<<1, 1, 0, c->stream>>>(c->d_counters, static_cast<uint32_t>(c->refine_cap));
+    JPGENC_CUDA(c, cudaGetLastError());
+    return JPGENC_OK;
 }
 
 int launch_forward(jpgenc_ctx* c) {

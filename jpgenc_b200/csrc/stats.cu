@@ -26,7 +26,9 @@ constexpr int kDescCap = 2048;                           // descriptors per roun
 struct StatsParams {
     const int16_t* coef;
     uint32_t nblocks;                 // blocks per frame
-    uint32_t tiles_per_frame;         // CTA blockIdx.x handles tile blockIdx.x % tiles_per_frame of frame blockIdx.x / tiles_per_frame
+    uint32_t tiles_per_frame;         // CTA blockIdx.x handles tile t % tiles_per_frame of frame t / tiles_per_frame, t = tile0 + blockIdx.x
+    uint32_t tile0;                   // first tile of this launch (band-wise encodes run K2 behind every band; one frame only)
+    uint32_t tiles_total;
     uint32_t mcu_w;
     uint32_t n_mcu;
     uint8_t* g_stats;                 // per frame kStatsBytes: hist u32[4][256], then first-occurrence keys u64[4][256]
@@ -111,8 +113,9 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     __shared__ alignas(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t frame = blockIdx.x / p.tiles_per_frame;
-    const uint32_t first = (blockIdx.x - frame * p.tiles_per_frame) * kTileBlocks;      // first block of the tile, within its frame
+    const uint32_t gtile = p.tile0 + blockIdx.x;
+    const uint32_t frame = gtile / p.tiles_per_frame;
+    const uint32_t first = (gtile - frame * p.tiles_per_frame) * kTileBlocks;           // first block of the tile, within its frame
     const int nb = static_cast<int>(min(static_cast<uint32_t>(kTileBlocks), p.nblocks - first));
     const int16_t* __restrict__ coef = p.coef + static_cast<size_t>(frame) * p.nblocks * kCoefPerBlock;
     uint32_t* __restrict__ g_hist = reinterpret_cast<uint32_t*>(p.g_stats + frame * kStatsBytes);
@@ -168,10 +171,10 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     const uint32_t base = base2 & 0xFFFFu, total = totals & 0xFFFFu, total_ac = totals >> 16;
     s_base[tid] = base2;
     if (tid == 0) {
-        p.tile_cnt[blockIdx.x] = total;
-        if (blockIdx.x == 0) *p.refine_copy = *p.refine_count;
+        p.tile_cnt[gtile] = total;
+        if (gtile + 1 == p.tiles_total) *p.refine_copy = *p.refine_count;    // the last tile runs in the last launch
     }
-    uint32_t* __restrict__ out = p.items + static_cast<size_t>(blockIdx.x) * kSlabItems;
+    uint32_t* __restrict__ out = p.items + static_cast<size_t>(gtile) * kSlabItems;
 
     // ---- DC and EOB: exactly one (at most one) per block, so the block's own thread handles them ----
     const int dcat = category_of(diff);
@@ -264,18 +267,23 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     }
 }
 
-int launch_symbol_stats(jpgenc_ctx* c) {
+int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
-    const unsigned tiles = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks), grid = tiles * c->nframes;
-    // per frame: histogram = 0, first-occurrence keys = all ones
-    JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats, kStatsBytes, 0, 4096, c->nframes, c->stream));
-    JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats + 4096, kStatsBytes, 0xFF, 8192, c->nframes, c->stream));
-    // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base; clear it off the critical path
-    JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, c->range_base_cap, c->stream));
+    const unsigned tiles = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    if (first) {
+        // per frame: histogram = 0, first-occurrence keys = all ones
+        JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats, kStatsBytes, 0, 4096, c->nframes, c->stream));
+        JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats + 4096, kStatsBytes, 0xFF, 8192, c->nframes, c->stream));
+        // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base; clear it off the critical path
+        JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, c->range_base_cap, c->stream));
+    }
+    if (ntiles == 0) return JPGENC_OK;
     StatsParams p{};
     p.coef = c->d_coef;
     p.nblocks = static_cast<uint32_t>(nblocks);
     p.tiles_per_frame = tiles;
+    p.tile0 = tile0;
+    p.tiles_total = tiles * c->nframes;
     p.mcu_w = c->mcu_w;
     p.n_mcu = static_cast<uint32_t>(n_mcu);
     p.g_stats = c->d_stats;
@@ -287,7 +295,7 @@ int launch_symbol_stats(jpgenc_ctx* c) {
         JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
         c->k2_configured = true;
     }
-    symbol_stats_kernel<<<grid, kTileBlocks, kStatsSmem, c->stream>>>(p);
+    symbol_stats_kernel<<<ntiles, kTileBlocks, kStatsSmem, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return JPGENC_OK;
