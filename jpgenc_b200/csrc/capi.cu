@@ -970,9 +970,16 @@ int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames
         int r = JPGENC_OK;
         {
             std::lock_guard<std::mutex> lk(copy_mutex);
-            for (uint32_t f = 0; f < F && r == JPGENC_OK; ++f)
-                if (cudaMemcpyAsync(c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride, frames[f0 + f], fbytes,
-                                    cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) r = JPGENC_ERR_CUDA;
+            // frames that follow each other in host memory (a video buffer) travel as one strided copy
+            for (uint32_t f = 0; f < F && r == JPGENC_OK;) {
+                uint32_t run = 1;
+                while (f + run < F && frames[f0 + f + run] == frames[f0 + f + run - 1] + fbytes) ++run;
+                uint8_t* dst = c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride;
+                const cudaError_t e = run == 1 ? cudaMemcpyAsync(dst, frames[f0 + f], fbytes, cudaMemcpyHostToDevice, c->copy_stream)
+                                               : cudaMemcpy2DAsync(dst, fstride, frames[f0 + f], fbytes, fbytes, run, cudaMemcpyHostToDevice, c->copy_stream);
+                if (e != cudaSuccess) r = JPGENC_ERR_CUDA;
+                f += run;
+            }
             if (r == JPGENC_OK && cudaEventRecord(c->ev_band[slot], c->copy_stream) != cudaSuccess) r = JPGENC_ERR_CUDA;
             issued[p] = r == JPGENC_OK ? 1 : 2;
         }

@@ -372,6 +372,15 @@ def test_frames_in_many_passes_on_several_lanes(encoder, oracle, monkeypatch, pe
             outs2 = [np.zeros(cap, np.uint8) for _ in range(n)]
             sizes2 = encoder.encode_frames_device([f.ctypes.data for f in host], w, h, [o.ctypes.data for o in outs2], [cap] * n, host_frames=True)
             assert sizes2 == sizes and all(outs2[i][: sizes[i]].tobytes() == want[i] for i in range(n))
+            # frames that follow each other in host memory travel as one strided copy per run (the frame size is not a
+            # multiple of the 256-byte device stride here); a gap after frame 9 splits the run
+            block = np.zeros(n * fb + 512, np.uint8)
+            offs = [i * fb + (512 if i > 9 else 0) for i in range(n)]
+            for i, f in enumerate(frames):
+                block[offs[i]: offs[i] + fb] = f.reshape(-1)
+            outs3 = [np.zeros(cap, np.uint8) for _ in range(n)]
+            sizes3 = encoder.encode_frames_device([block.ctypes.data + o for o in offs], w, h, [o.ctypes.data for o in outs3], [cap] * n, host_frames=True)
+            assert sizes3 == sizes and all(outs3[i][: sizes[i]].tobytes() == want[i] for i in range(n))
         # a too-small output buffer in a late pass is reported, and the context keeps working
         small = [cap] * n
         small[n - 2] = 16
