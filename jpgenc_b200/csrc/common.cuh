@@ -1,6 +1,7 @@
 // Shared declarations for the sm_100a JPEG encode path (kernels + C-ABI).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -65,6 +66,7 @@ struct ForwardParams {
     ColorConsts color;
     QuantConsts2 luma;
     QuantConsts2 chroma;
+    alignas(64) CUtensorMap coef_map;     // coefficient array as rows of 128 bytes, for the tensor store of full strips
 };
 
 __host__ __device__ inline uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }

@@ -180,7 +180,6 @@ __device__ __forceinline__ void stage_block(uint8_t* staging, int slot, const ui
 #pragma unroll
     for (int c = 0; c < 8; ++c) base[c ^ (slot & 7)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
-
 __device__ __forceinline__ void copy_out(const uint8_t* staging, int16_t* gdst, int nslots, int tid, int nthreads) {
     uint4* g = reinterpret_cast<uint4*>(gdst);
     const int chunks = nslots * 8;
@@ -200,14 +199,14 @@ struct ForwardSmem {
     static constexpr int kPitch = kMcus * 48;                 // bytes of RGB per tile row
     static constexpr int kTileBytes = 16 * kPitch;            // == kMcus*6*128: the staging buffer aliases it
     static constexpr int kChromaW = kMcus * 8;
-    alignas(128) uint8_t tile[kTileBytes];
+    alignas(1024) uint8_t tile[kTileBytes];               // 1 KB: the 128-byte swizzle of the tensor store is taken from address bits 7..9
     alignas(16) float chroma[2][8][kChromaW];
     alignas(8) uint64_t bar;
 };
 
 // kAligned: real_w % 16 == 0 and 16-byte aligned base -> rows are staged with bulk copies; otherwise a clamped
 // byte loader fills the tile (odd sizes; right-edge replication, src/Image.cpp:491-530)
-template <int kMcus, bool kAligned>
+template <int kMcus, bool kAligned, bool kBulkOut = false>
 __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(const __grid_constant__ ForwardParams p) {
     using Smem = ForwardSmem<kMcus>;
     __shared__ Smem sm;
@@ -327,6 +326,20 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
             const bool boundary = quantize_pack_packed(v, p.chroma, packed);
             stage_block(sm.tile, m * kBlocksPerMcu + 4 + comp, packed);
             if (boundary) push_refine(p, block_base + m * kBlocksPerMcu + 4 + comp);
+        }
+    }
+    if constexpr (kBulkOut) {
+        // full strips leave as ONE tensor store: the staging layout (16-byte chunk c of row s at c ^ (s & 7)) is exactly
+        // the 128-byte swizzle of a tensor map whose rows are the 128-byte coefficient blocks
+        if (nm == kMcus) {
+            ptx::fence_async_smem();              // this thread's staging writes become visible to the copy engine
+            __syncthreads();
+            if (tid == 0) {
+                ptx::tensor_store_2d(&p.coef_map, sm.tile, 0, static_cast<int>(block_base));
+                ptx::bulk_commit();
+                ptx::bulk_wait_all_read();        // shared memory must stay allocated until the engine has read it
+            }
+            return;
         }
     }
     __syncthreads();
@@ -530,6 +543,8 @@ __global__ void __launch_bounds__(kMbThreads) dct_blocks_kernel(const float* __r
         }
         stage_block(tile, tid, packed);
     }
+    // (a tensor store as in forward_kernel was measured here too: this kernel is bound by HBM, not by instruction issue,
+    // and holding the CTA until the copy engine has read the tile costs more than the saved instructions: 1.06 -> 1.11 ms)
     __syncthreads();
     copy_out(tile, out + first * 64, nb, tid, kMbThreads);
 }
@@ -669,6 +684,31 @@ static void fill_exact(const jpgenc_ctx* c, const uint8_t* qy, const uint8_t* qc
     for (int i = 0; i < 64; ++i) { e->qy[i] = qy[i]; e->qc[i] = qc[i]; }
 }
 
+// tensor map over an array of coefficient blocks as [blocks][64 x int16] with a box of `box_blocks` rows and the 128-byte
+// swizzle: what a CTA has staged in shared memory (stage_block) leaves with one tensor store
+static bool make_block_map(void* base, uint64_t nblocks, uint32_t box_blocks, CUtensorMap* map) {
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = [] {                   // libcuda is not linked: the entry point comes from the runtime
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<Encode>(fn);
+    }();
+    if (!encode || nblocks == 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t gdim[2] = {64, nblocks};
+    const cuuint64_t gstride[1] = {kBlockBytes};
+    const cuuint32_t box[2] = {64, box_blocks};
+    const cuuint32_t estride[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// JPGENC_TENSOR_STORE=0 falls back to the per-thread copy-out (A/B measurements)
+static bool tensor_store_enabled() {
+    static const bool on = [] { const char* v = std::getenv("JPGENC_TENSOR_STORE"); return !(v && *v == '0'); }();
+    return on;
+}
+
 // Everything K1 needs to know about the image(s) bound to the context
 static void fill_forward_params(const jpgenc_ctx* c, ForwardParams* p) {
     p->rgb = c->d_rgb;
@@ -719,7 +759,10 @@ int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, b
     bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
     if (c->nframes > 1) aligned = (c->real_w % 16 == 0) && c->frames_aligned;
     const dim3 grid((c->mcu_w + 31) / 32, rows, c->nframes);
-    if (aligned) forward_kernel<32, true><<<grid, 128, 0, c->stream>>>(p);
+    const bool bulk_out = tensor_store_enabled() && aligned &&
+                          make_block_map(c->d_coef, static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu * c->nframes, 32 * kBlocksPerMcu, &p.coef_map);
+    if (bulk_out) forward_kernel<32, true, true><<<grid, 128, 0, c->stream>>>(p);
+    else if (aligned) forward_kernel<32, true><<<grid, 128, 0, c->stream>>>(p);
     else forward_kernel<32, false><<<grid, 128, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;

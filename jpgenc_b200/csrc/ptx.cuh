@@ -55,6 +55,12 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
                  "r"(bytes)
                  : "memory");
 }
+// shared -> global tensor store of one box of a 2-D tensor map (coordinates: innermost first)
+__device__ __forceinline__ void tensor_store_2d(const void* tensor_map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tensor_map), "r"(smem_u32(smem_src)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // order generic-proxy shared-memory writes before a following async-proxy read of them
