@@ -293,7 +293,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     delete c->pool;
     delete c->host_pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
-    cudaFree(c->d_stats); cudaFree(c->d_meta); cudaFree(c->d_tables); cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
+    cudaFree(c->d_stats); cudaFree(c->d_tables);   /* d_meta lives in the same allocation */ cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -556,16 +556,16 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     if (k4_tiles > 0xFFFFFFFFull) return fail(c, JPGENC_ERR_ARG, "scan too large");
     if ((rc = ensure(c, &c->d_raw, &c->raw_cap, raw_total, true))) return rc;
     if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * raw_total + 64, true))) return rc;
-    if ((rc = ensure(c, &c->d_tables, &c->tables_cap, F * sizeof(DeviceTables)))) return rc;
-    if ((rc = ensure(c, &c->d_meta, &c->meta_cap, meta_bytes(F)))) return rc;
+    // tables and frame geometry share one allocation, in the order of the staging buffer: one copy brings both
+    if ((rc = ensure(c, &c->d_tables, &c->tables_cap, F * sizeof(DeviceTables) + meta_bytes(F)))) return rc;
+    c->d_meta = reinterpret_cast<uint8_t*>(c->d_tables) + F * sizeof(DeviceTables);
     size_t lb_bytes = c->lookback_cap;
     if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (2 * static_cast<size_t>(F) + k4_tiles + 8) * sizeof(unsigned long long), true))) return rc;
     c->lookback_cap = lb_bytes;
-    // tables and meta sit next to each other in the staging buffer: two copies.  (Measured and rejected for one image:
+    // (Measured and rejected for one image:
     // passing the 8 KB of tables as kernel parameters instead -- the launches get slower and the per-thread reads of
     // the parameter bank serialise; K3+K4 went from 185 to 212 us.)
-    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables), cudaMemcpyHostToDevice, c->stream));
-    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_meta, m_off, meta_bytes(F), cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables) + meta_bytes(F), cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
     if ((rc = launch_entropy(c, raw_total, static_cast<uint32_t>(k4_tiles)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
