@@ -38,6 +38,11 @@ def _images():
         "white": (np.full((40, 40, 3), 255, np.uint8), 255),
         "maxval15": (noise_rgb(64, 48, 5) >> 4, 15),
         "maxval100": (noise_rgb(50, 50, 6) % 101, 100),
+        # the largest dimensions a baseline JPEG can declare (SOF0 holds 16-bit sizes): 4096 MCUs in a row / in a column
+        "max_width_65535x16": (synth_rgb(65535, 16, 8), 255),
+        "max_height_16x65535": (synth_rgb(16, 65535, 9), 255),
+        # 129 MCUs per row: four full strips (tensor store) and a partial one (per-thread copy-out) in every MCU row
+        "strips_2064x48": (noise_rgb(2064, 48, 10), 255),
     }
 
 
