@@ -3,6 +3,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <memory>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -22,7 +24,10 @@ int launch_exact_all(jpgenc_ctx* c);
 // worker threads plus the calling thread build them side by side.  Waking a sleeping thread costs about as much as a
 // small table, so the workers are ARMED (woken, then spinning) when the statistics kernel is launched and find the
 // histogram as soon as it arrives; they go back to sleep after every image.
-// parallel_for over n jobs on persistent host threads (the 4 * F table builds of a batch of F frames)
+// parallel_for over n jobs on persistent host threads (the 4 * F table builds of a batch of F frames).  One pool serves
+// all pipeline lanes of a context: several parallel_for calls may be in flight at once, every idle worker helps whichever
+// call still has jobs to hand out, and the caller works on its own call too -- a lane whose tables are due gets all the
+// cores that the other lanes are not using right now.
 class HostPool {
 public:
     explicit HostPool(unsigned workers) {
@@ -38,52 +43,54 @@ public:
     }
     template <class F>
     void parallel_for(uint32_t n, F&& fn) {
-        std::function<void(uint32_t)> job = fn;
+        if (n == 0) return;
+        auto call = std::make_shared<Call>();
+        call->fn = fn;
+        call->n = n;
         {
             std::lock_guard<std::mutex> lk(m_);
-            job_ = &job; n_ = n; next_.store(0); pending_ = static_cast<uint32_t>(threads_.size()); ++generation_;
+            calls_.push_back(call);
         }
         cv_.notify_all();
-        drain(job);
-        std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
-        job_ = nullptr;
+        drain(*call);
+        while (call->done.load(std::memory_order_acquire) < n) std::this_thread::yield();   // the last few jobs, on other threads
     }
 
 private:
-    void drain(const std::function<void(uint32_t)>& job) {
+    struct Call {
+        std::function<void(uint32_t)> fn;
+        uint32_t n = 0;
+        std::atomic<uint32_t> next{0}, done{0};
+    };
+    static void drain(Call& c) {
         for (;;) {
-            const uint32_t i = next_.fetch_add(1);
-            if (i >= n_) return;
-            job(i);
+            const uint32_t i = c.next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= c.n) return;
+            c.fn(i);
+            c.done.fetch_add(1, std::memory_order_release);
         }
     }
     void run() {
-        uint64_t seen = 0;
         for (;;) {
-            const std::function<void(uint32_t)>* job;
+            std::shared_ptr<Call> call;
             {
                 std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return quit_ || generation_ != seen; });
+                for (;;) {
+                    while (!calls_.empty() && calls_.front()->next.load(std::memory_order_relaxed) >= calls_.front()->n) calls_.pop_front();
+                    if (quit_ || !calls_.empty()) break;
+                    cv_.wait(lk);
+                }
                 if (quit_) return;
-                seen = generation_;
-                job = job_;
+                call = calls_.front();
             }
-            drain(*job);
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                if (--pending_ == 0) done_cv_.notify_all();
-            }
+            drain(*call);
         }
     }
     std::vector<std::thread> threads_;
     std::mutex m_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
     bool quit_ = false;
-    uint64_t generation_ = 0;
-    const std::function<void(uint32_t)>* job_ = nullptr;
-    uint32_t n_ = 0, pending_ = 0;
-    std::atomic<uint32_t> next_{0};
+    std::deque<std::shared_ptr<Call>> calls_;
 };
 
 class TablePool {
@@ -291,7 +298,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (jpgenc_ctx* l : c->lanes) jpgenc_destroy(l);
     delete c->pool;
-    delete c->host_pool;
+    if (c->owns_host_pool) delete c->host_pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_stats); cudaFree(c->d_tables);   /* d_meta lives in the same allocation */ cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
@@ -850,22 +857,19 @@ static void leave_batch_state(jpgenc_ctx* c) {
 // context itself and further, lazily created contexts on the same device with their own streams and buffers -- each
 // driven by its own host thread: while one lane builds its tables the other lanes' kernels run.
 constexpr uint32_t kDefaultLanes = 3, kMaxLanes = 4;
-// host threads per lane for the table builds: the lanes' host phases overlap, so they share the cores
-static unsigned pool_threads(uint32_t lanes) {
-    const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
-    return std::min(15u, std::max(2u, hc / lanes) - 1);
-}
 
-static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t lanes, uint32_t w, uint32_t h, uint32_t maxval) {
+static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, uint32_t maxval) {
+    if (!c->host_pool) {                                       // one pool of host threads for all lanes (HostPool)
+        c->host_pool = new HostPool(std::min(15u, std::max(2u, std::thread::hardware_concurrency()) - 1));
+        c->owns_host_pool = true;
+    }
     if (l != c) {
         std::memcpy(l->qy, c->qy, 64); std::memcpy(l->qc, c->qc, 64);
         std::memcpy(l->dct_a, c->dct_a, sizeof c->dct_a); std::memcpy(l->dct_s, c->dct_s, sizeof c->dct_s);
+        l->host_pool = c->host_pool;
+        l->owns_host_pool = false;
     }
-    const int rc = set_geometry(l, w, h, maxval);
-    if (rc) return rc;
-    if (l->host_pool && l->host_pool_lanes != lanes) { delete l->host_pool; l->host_pool = nullptr; }
-    if (!l->host_pool) { l->host_pool = new HostPool(pool_threads(lanes)); l->host_pool_lanes = lanes; }
-    return JPGENC_OK;
+    return set_geometry(l, w, h, maxval);
 }
 
 static uint32_t env_u32(const char* name, uint32_t dflt) {
@@ -888,7 +892,7 @@ static uint32_t pipelined_pass_frames(const jpgenc_ctx* c, uint32_t n) {
 static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
                      const std::function<int(jpgenc_ctx*, uint32_t)>& pass) {
     const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", kDefaultLanes), kMaxLanes, npasses}));
-    int rc = prepare_lane(c, c, nl, w, h, maxval);
+    int rc = prepare_lane(c, c, w, h, maxval);
     if (rc) return rc;
     while (c->lanes.size() + 1 < nl) {
         jpgenc_ctx* l = nullptr;
@@ -896,7 +900,7 @@ static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, ui
         c->lanes.push_back(l);
     }
     for (uint32_t k = 1; k < nl; ++k)
-        if ((rc = prepare_lane(c, c->lanes[k - 1], nl, w, h, maxval))) return fail(c, rc, jpgenc_last_error(c->lanes[k - 1]));
+        if ((rc = prepare_lane(c, c->lanes[k - 1], w, h, maxval))) return fail(c, rc, jpgenc_last_error(c->lanes[k - 1]));
     std::atomic<uint32_t> next{0};
     std::atomic<int> first_error{JPGENC_OK};
     std::mutex error_mutex;

@@ -88,7 +88,7 @@ struct jpgenc_ctx {
     int device = 0;
     jpgenc::TablePool* pool = nullptr;    // host worker threads that build the four Huffman tables side by side
     jpgenc::HostPool* host_pool = nullptr;   // parallel table builds of a batch of frames
-    uint32_t host_pool_lanes = 0;            // ... sized for this many lanes sharing the host cores
+    bool owns_host_pool = false;             // pipeline lanes share their parent context's pool
     bool parallel_tables = true;          // false inside a batch: there the frames run in parallel instead
     std::vector<jpgenc_ctx*> lanes;       // further pipeline lanes of the batched-frame calls (contexts on the same device with their own
                                           // stream and buffers): while one lane's pass waits for its Huffman tables on the host, the

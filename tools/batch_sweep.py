@@ -18,8 +18,8 @@ sizes = enc.encode_frames_device(ptrs, w, h)
 cap = max(sizes) + 64
 out, op = pinned_empty(nf * cap)
 optrs = [op + k * cap for k in range(nf)]
-for lanes in (2, 3, 4):
-    for per in (256, 171, 128, 96, 64):
+for lanes in (1, 2, 3, 4):
+    for per in (171, 128, 103, 64, 48):
         os.environ["JPGENC_LANES"] = str(lanes)
         os.environ["JPGENC_FRAMES_PER_PASS"] = str(per)
         enc.encode_frames_device(ptrs, w, h)

@@ -11,8 +11,9 @@ for k in range(nf):
     enc.synth_rgb(d + k * fb, w, h, k)
 enc.synchronize()
 ptrs = [d + k * fb for k in range(nf)]
-for lanes, per in ((1, 128), (2, 128)):
+for lanes, per in ((3, 103), (4, 64)):
     os.environ["JPGENC_LANES"] = str(lanes); os.environ["JPGENC_FRAMES_PER_PASS"] = str(per)
+    enc.encode_frames_device(ptrs, w, h)
     enc.encode_frames_device(ptrs, w, h)
     print(f"--- lanes {lanes} per_pass {per}", file=sys.stderr, flush=True)
     t = time.perf_counter()
