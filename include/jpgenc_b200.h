@@ -109,6 +109,14 @@ int jpgenc_symbol_stats(jpgenc_ctx* ctx, uint32_t count[4][256], uint64_t first_
 /* ---- host: generateHuffmanCode from the statistics (src/Huffman.cpp:3-66, Huffman.hpp:114-174) ----- */
 int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
 
+/* the same on the device, n tables at once (one warp per table; libstdc++'s container orders restated on arrays).  The
+ * batched-frame calls use it when the process has few host cores for its GPU (8-GPU boxes); identical results. */
+/* the device build's code run on the HOST (no GPU): the array restatement against the container-driven build, for the
+ * CPU test suite */
+int jpgenc_build_huffman_arrays(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
+int jpgenc_build_huffman_device(jpgenc_ctx* ctx, uint32_t n, const uint32_t (*count)[256], const uint64_t (*first_pos)[256],
+                                jpgenc_huff_table* out);
+
 /* ---- K3 + K4: doHuffmanEncoding, MCU interleave, fill(), FF00 stuffing
  *      (src/Image.cpp:737-829, 957-971; BitstreamGeneric.hpp:182-195, 213-224, 242-248) ------------- */
 int jpgenc_entropy_encode(jpgenc_ctx* ctx, const jpgenc_huff_table tables[4], uint64_t* scan_bytes);

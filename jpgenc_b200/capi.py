@@ -63,6 +63,8 @@ _SIGNATURES = {
     "jpgenc_set_coefficients_mcu": (C.c_int, [C.c_void_p, i16p, C.c_uint32, C.c_uint32]),
     "jpgenc_symbol_stats": (C.c_int, [C.c_void_p, u32p, u64p]),
     "jpgenc_build_huffman": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
+    "jpgenc_build_huffman_arrays": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
+    "jpgenc_build_huffman_device": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_entropy_encode": (C.c_int, [C.c_void_p, C.POINTER(HuffTable), u64p]),
     "jpgenc_download_scan": (C.c_int, [C.c_void_p, u8p, C.c_uint64]),
     "jpgenc_ppm_info": (C.c_int, [C.c_char_p, C.c_size_t, u32p, u32p, u32p, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
@@ -205,6 +207,15 @@ class Encoder:
             rc = self.lib.jpgenc_build_huffman(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(tabs[t]))
             if rc != OK:
                 raise JpgencError(rc, f"jpgenc_build_huffman(table {t})")
+        return tabs
+
+    def build_huffman_device(self, count, first):
+        """n tables at once on the device: count (n, 256) u32, first (n, 256) u64 -> HuffTable array"""
+        c = np.ascontiguousarray(count, np.uint32).reshape(-1, 256)
+        f = np.ascontiguousarray(first, np.uint64).reshape(-1, 256)
+        n = c.shape[0]
+        tabs = (HuffTable * n)()
+        self._check(self.lib.jpgenc_build_huffman_device(self.h, n, _np_ptr(c, u32p), _np_ptr(f, u64p), tabs))
         return tabs
 
     def entropy_encode(self, tabs) -> int:

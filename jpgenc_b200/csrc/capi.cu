@@ -302,6 +302,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_stats); cudaFree(c->d_tables);   /* d_meta lives in the same allocation */ cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
     cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
+    cudaFree(c->d_tab_scratch); cudaFree(c->d_built_tables);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
@@ -473,7 +474,22 @@ static int ensure_stats_buffers(jpgenc_ctx* c) {
     return ensure_pinned(c, stage_bytes(F));
 }
 
-static int stats_frames(jpgenc_ctx* c) {
+// Where the 4 * F tables of a batched pass are built.  The host build costs 38 us of CPU per 1080p frame; a process that
+// has fewer than 8 host cores for its GPU (an 8-GPU box with 32 cores) cannot feed the GPU that way, so there the tables
+// are built by build_tables_kernel.  JPGENC_DEVICE_TABLES=0/1 overrides.
+static bool device_tables_enabled() {
+    const char* v = std::getenv("JPGENC_DEVICE_TABLES");
+    if (v && *v) return *v != '0';
+    static const bool few_cores = [] {
+        int ndev = 1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+        return std::max(1u, std::thread::hardware_concurrency()) / static_cast<unsigned>(ndev) < 8u;
+    }();
+    return few_cores;
+}
+
+// built_tables != nullptr: build the 4 * F tables on the device right behind K2 and bring them back with the statistics
+static int stats_frames(jpgenc_ctx* c, jpgenc_huff_table* built_tables = nullptr) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     const uint32_t F = c->nframes;
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
@@ -487,6 +503,14 @@ static int stats_frames(jpgenc_ctx* c) {
     c->have_items = true;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
+    if (built_tables) {
+        const uint32_t nt = 4 * F;
+        if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&c->d_tab_scratch), &c->tab_scratch_cap, nt * table_scratch_bytes()))) return rc;
+        if ((rc = ensure(c, &c->d_built_tables, &c->built_tables_cap, nt * (sizeof(jpgenc_huff_table) + sizeof(uint32_t))))) return rc;
+        uint32_t* d_status = reinterpret_cast<uint32_t*>(c->d_built_tables + nt);
+        if ((rc = launch_build_tables(c, c->d_stats, kStatsBytes, nt, c->d_tab_scratch, c->d_built_tables, d_status))) return rc;
+        JPGENC_CUDA(c, cudaMemcpyAsync(built_tables, c->d_built_tables, nt * sizeof(jpgenc_huff_table), cudaMemcpyDeviceToHost, c->stream));
+    }
     JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_stats, F * kStatsBytes + 16, cudaMemcpyDeviceToHost, c->stream));   // + K2's copy of the refine counter
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->host_hist.resize(static_cast<size_t>(F) * 1024);
@@ -605,6 +629,54 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     const uint8_t* h = static_cast<const uint8_t*>(c->h_pinned);
     std::memcpy(count, h, 4096);
     std::memcpy(first_pos, h + 4096, 8192);
+    return JPGENC_OK;
+}
+
+// the device build's code (array restatement of the container orders) executed on the host, no GPU involved
+int jpgenc_build_huffman_arrays(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
+    if (!count || !first_pos || !out) return JPGENC_ERR_ARG;
+    return build_table_arrays_host(count, first_pos, out);
+}
+
+// generateHuffmanCode on the device (tables_device.cu) for n independent (count, first_pos) pairs; what the batched-frame
+// calls use on hosts with few cores per GPU, exposed so that it can be checked against jpgenc_build_huffman directly
+int jpgenc_build_huffman_device(jpgenc_ctx* c, uint32_t n, const uint32_t (*count)[256], const uint64_t (*first_pos)[256],
+                                jpgenc_huff_table* out) {
+    if (!c || !count || !first_pos || !out || n == 0) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t frames = (n + 3) / 4;                       // the kernel reads K2's layout: 4 tables per frame
+    std::vector<uint8_t> host(static_cast<size_t>(frames) * kStatsBytes, 0);
+    for (uint32_t i = 0; i < frames * 4; ++i) {
+        uint8_t* f = host.data() + static_cast<size_t>(i >> 2) * kStatsBytes;
+        if (i < n) {
+            std::memcpy(f + (i & 3) * 1024, count[i], 1024);
+            std::memcpy(f + 4096 + (i & 3) * 2048, first_pos[i], 2048);
+        } else {
+            std::memset(f + 4096 + (i & 3) * 2048, 0xFF, 2048);
+        }
+    }
+    int rc;
+    uint8_t* d_in = nullptr;
+    size_t cap = 0;
+    if ((rc = ensure(c, &d_in, &cap, host.size()))) return rc;
+    auto cleanup = [&] { cudaFree(d_in); };
+    const uint32_t nt = frames * 4;
+    if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&c->d_tab_scratch), &c->tab_scratch_cap, nt * table_scratch_bytes()))) { cleanup(); return rc; }
+    if ((rc = ensure(c, &c->d_built_tables, &c->built_tables_cap, nt * (sizeof(jpgenc_huff_table) + sizeof(uint32_t))))) { cleanup(); return rc; }
+    std::vector<jpgenc_huff_table> res(nt);
+    cudaError_t e = cudaMemcpyAsync(d_in, host.data(), host.size(), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        rc = launch_build_tables(c, d_in, kStatsBytes, nt, c->d_tab_scratch, c->d_built_tables, reinterpret_cast<uint32_t*>(c->d_built_tables + nt));
+        if (rc) { cleanup(); return rc; }
+        e = cudaMemcpyAsync(res.data(), c->d_built_tables, nt * sizeof(jpgenc_huff_table), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) { c->error = std::string("device table build: ") + cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (res[i].nsymbols <= 0) return fail(c, JPGENC_ERR_ARG, "Huffman table build failed: a table has no symbol");
+        out[i] = res[i];
+    }
     return JPGENC_OK;
 }
 
@@ -796,19 +868,23 @@ static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_
     if (ready) JPGENC_CUDA(c, cudaStreamWaitEvent(c->stream, ready, 0));
     if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
     c->have_coef = true;
-    if ((rc = stats_frames(c))) return rc;
-    const double t_stats = trace_on() ? now_us() : 0;
-    // 4 * F independent table builds
     tables.resize(static_cast<size_t>(F) * 4);
+    const bool on_device = device_tables_enabled();
+    if ((rc = stats_frames(c, on_device ? tables.data() : nullptr))) return rc;
+    const double t_stats = trace_on() ? now_us() : 0;
+    // 4 * F independent table builds (already done when they were built on the device)
     const uint8_t* hs = static_cast<const uint8_t*>(c->h_pinned);
     std::atomic<int> build_rc{JPGENC_OK};
-    c->host_pool->parallel_for(F * 4, [&](uint32_t j) {
+    if (!on_device) c->host_pool->parallel_for(F * 4, [&](uint32_t j) {
         const uint32_t f = j >> 2, t = j & 3;
         const uint32_t* count = reinterpret_cast<const uint32_t*>(hs + f * kStatsBytes) + t * 256;
         const uint64_t* first = reinterpret_cast<const uint64_t*>(hs + f * kStatsBytes + 4096) + t * 256;
         const int r = jpgenc_build_huffman(count, first, &tables[j]);
         if (r) build_rc.store(r);
     });
+    if (on_device)
+        for (size_t j = 0; j < tables.size(); ++j)
+            if (tables[j].nsymbols <= 0) build_rc.store(JPGENC_ERR_ARG);        // the kernel leaves a table zeroed when it has no symbol
     if (build_rc.load()) return fail(c, build_rc.load(), "Huffman table build failed");
     const double t_built = trace_on() ? now_us() : 0;
     if ((rc = entropy_frames(c, tables.data()))) return rc;
@@ -891,7 +967,8 @@ static uint32_t pipelined_pass_frames(const jpgenc_ctx* c, uint32_t n) {
 // runs pass(lane, p) for p = 0 .. npasses-1 on the lanes; passes are handed out in order
 static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
                      const std::function<int(jpgenc_ctx*, uint32_t)>& pass) {
-    const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", kDefaultLanes), kMaxLanes, npasses}));
+    // a device-side table build is a long, thin kernel (one working thread per table): one more lane to overlap it with
+    const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", device_tables_enabled() ? kMaxLanes : kDefaultLanes), kMaxLanes, npasses}));
     int rc = prepare_lane(c, c, w, h, maxval);
     if (rc) return rc;
     while (c->lanes.size() + 1 < nl) {

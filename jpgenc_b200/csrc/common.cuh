@@ -138,6 +138,10 @@ struct jpgenc_ctx {
     std::vector<uint32_t> host_hist;      // K2's histograms as last read back, [nframes][4][256]
     std::vector<uint64_t> frame_bits, frame_raw_off, frame_ff;   // per frame after K3/K4: scan bits, byte offset of its raw scan, stuffed FFs
     bool k2_configured = false;
+    void* d_tab_scratch = nullptr;        // device-side table build (tables_device.cu): work space, one slab per table
+    size_t tab_scratch_cap = 0;
+    jpgenc_huff_table* d_built_tables = nullptr;   // ... its results [4 * nframes], and one status word per table behind them
+    size_t built_tables_cap = 0;
     jpgenc::DeviceTables* d_tables = nullptr;   // [nframes]
     size_t tables_cap = 0;
     unsigned long long* d_lookback = nullptr;  // total_bits u64[F] | total_ff u64[F] | one look-back word per K4 tile
@@ -184,6 +188,10 @@ int launch_refine_pending(jpgenc_ctx* c);
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
 int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles);
 constexpr uint32_t kK4TileBytes = 16384;   // input bytes per K4 tile (entropy.cu static_asserts it)
+size_t table_scratch_bytes();
+int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
+int launch_build_tables(jpgenc_ctx* c, const uint8_t* d_stats, uint32_t stats_stride, uint32_t ntables, void* d_scratch,
+                        jpgenc_huff_table* d_out, uint32_t* d_status);
 int launch_synth_rgb(jpgenc_ctx* c, uint8_t* d, uint32_t w, uint32_t h, uint32_t seed);
 int launch_synth_blocks(jpgenc_ctx* c, float* d, uint64_t nblocks);
 int launch_flush(jpgenc_ctx* c);

@@ -1,0 +1,369 @@
+// Huffman table construction ON THE DEVICE, for batches of frames.
+//
+// Produces exactly what the reference's generateHuffmanCode(text) produces (src/Huffman.cpp:3-66,
+// include/Huffman.hpp:114-174), like the host build in host/huffman_build.cpp, from the same inputs (K2's symbol
+// histogram and first-occurrence keys).  The host build gets the two library-defined orders the result depends on --
+// std::unordered_map<int,int> iteration order and std::priority_queue's heap layout -- by driving the
+// real libstdc++ containers; device code cannot, so both are restated here on plain arrays:
+//   * OrderedMap: libstdc++'s _Hashtable for int keys (identity hash): one forward list threaded through the buckets,
+//     a new node goes to the front of its bucket (or, for an empty bucket, to the front of the whole list),
+//     _Prime_rehash_policy growth (1 -> 13 -> 29 -> 59 -> 127 -> 257 -> 541 buckets), _M_rehash_aux re-threading;
+//   * heap_push / heap_pop: std::push_heap / std::pop_heap (bits/stl_heap.h: __push_heap, __adjust_heap) with the
+//     reference's comparator "weight greater" (Huffman.hpp:117-119).
+// tests/test_gpu_parity.py compares the result with the host build on every test image and on random histograms.
+//
+// Why it exists: a 1080p frame costs 38 us of host CPU for its four tables.  With one GPU and 16 cores that hides
+// behind the other pipeline lanes' kernels; on an 8-GPU box with 32 cores it is what limits a batch (8 x fewer
+// cores per GPU).  On the device a table is a serial chain of ~6 k (27 symbols) to ~50 k (162 symbols) dependent heap
+// steps -- one thread, ~40 ns per step -- but all 4 * F tables of a pass run side by side (one warp each, lane 0
+// working) and the other lanes' kernels fill the SMs meanwhile.  A single image keeps the host build: 16 us there
+// against >= 250 us here.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace jpgenc {
+
+namespace {
+
+constexpr int kMaxSyms = 256;
+constexpr int kMaxBuckets = 600;
+constexpr int kLimit = 15;                                     // package_merge(symbol_frequency, 15)
+constexpr int kMaxNodes = kMaxSyms * (kLimit + 2) + 16;        // leaves + at most one package per pair of items per level
+constexpr int kBeforeBegin = -2;
+constexpr int kSharedSyms = 64;                               // heaps of up to this many symbols fit the CTA's shared memory
+
+struct HeapItem {
+    long long w;
+    int node;
+};
+struct Node {
+    short left, right, sym;                                    // sym >= 0: leaf
+    short pad;
+};
+
+struct OrderedMap {                                            // libstdc++ unordered_map<int, T> iteration order
+    short key[kMaxSyms], nxt[kMaxSyms], slot_of[kMaxSyms];
+    short bucket[kMaxBuckets];                                 // node BEFORE the bucket's first node; -1 = empty bucket
+    int nb, n, next_resize, head;
+};
+
+struct TableScratch {
+    OrderedMap map;
+    short syms[kMaxSyms];
+    unsigned freq[kMaxSyms];
+    unsigned short len_of[kMaxSyms], cnt[kMaxSyms];
+    unsigned char per_len[18][kMaxSyms];
+    int per_len_n[18];
+    HeapItem blueprint[kMaxSyms], heap_a[2 * kMaxSyms + 16], heap_b[2 * kMaxSyms + 16];
+    Node nodes[kMaxNodes];
+    unsigned char order[kMaxSyms];
+};
+
+__host__ __device__ void um_init(OrderedMap& m) {
+    m.nb = 1; m.n = 0; m.next_resize = 0; m.head = -1;
+    for (int i = 0; i < kMaxSyms; ++i) m.slot_of[i] = -1;
+    m.bucket[0] = -1;
+}
+
+__host__ __device__ int um_next_bkt(OrderedMap& m, int want) {         // _Prime_rehash_policy::_M_next_bkt
+    const unsigned char fast[14] = {2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13};
+    const short primes[46] = {17,  19,  23,  29,  31,  37,  41,  43,  47,  53,  59,  61,  67,  71,  73,  79,
+                              83,  89,  97,  103, 109, 113, 127, 137, 139, 149, 157, 167, 179, 193, 199, 211,
+                              227, 241, 257, 277, 293, 313, 337, 359, 383, 409, 439, 467, 503, 541};
+    if (want < 14) {
+        if (want == 0) return 1;
+        m.next_resize = fast[want];
+        return fast[want];
+    }
+    for (int i = 0; i < 46; ++i)
+        if (primes[i] >= want) { m.next_resize = primes[i]; return primes[i]; }
+    m.next_resize = 541;
+    return 541;                                                // unreachable: at most 256 keys
+}
+
+__host__ __device__ int um_get_next(const OrderedMap& m, int node) { return node == kBeforeBegin ? m.head : m.nxt[node]; }
+__host__ __device__ void um_set_next(OrderedMap& m, int node, int v) { if (node == kBeforeBegin) m.head = v; else m.nxt[node] = static_cast<short>(v); }
+
+__host__ __device__ void um_rehash(OrderedMap& m, int nb) {            // _M_rehash_aux(n, true_type)
+    int p = m.head, bbegin_bkt = 0;
+    for (int i = 0; i < nb; ++i) m.bucket[i] = -1;
+    m.head = -1;
+    while (p >= 0) {
+        const int next = m.nxt[p];
+        const int bkt = m.key[p] % nb;
+        if (m.bucket[bkt] == -1) {
+            m.nxt[p] = static_cast<short>(m.head);
+            m.head = p;
+            m.bucket[bkt] = kBeforeBegin;
+            if (m.nxt[p] >= 0) m.bucket[bbegin_bkt] = static_cast<short>(p);
+            bbegin_bkt = bkt;
+        } else {
+            const int before = m.bucket[bkt];
+            m.nxt[p] = static_cast<short>(um_get_next(m, before));
+            um_set_next(m, before, p);
+        }
+        p = next;
+    }
+    m.nb = nb;
+}
+
+// operator[]: the node of `key`, inserted when new
+__host__ __device__ int um_touch(OrderedMap& m, int key) {
+    if (m.slot_of[key] >= 0) return m.slot_of[key];
+    if (m.n + 1 > m.next_resize) {                             // _M_need_rehash(n_bkt, n_elt, 1)
+        int min_bkts = m.n + 1;
+        if (m.next_resize == 0 && min_bkts < 11) min_bkts = 11;
+        if (min_bkts >= m.nb) {
+            int want = min_bkts + 1;
+            if (want < m.nb * 2) want = m.nb * 2;
+            um_rehash(m, um_next_bkt(m, want));
+        } else {
+            m.next_resize = m.nb;
+        }
+    }
+    const int node = m.n++;
+    m.key[node] = static_cast<short>(key);
+    m.slot_of[key] = static_cast<short>(node);
+    const int bkt = key % m.nb;
+    if (m.bucket[bkt] != -1) {                                 // _M_insert_bucket_begin
+        const int before = m.bucket[bkt];
+        m.nxt[node] = static_cast<short>(um_get_next(m, before));
+        um_set_next(m, before, node);
+    } else {
+        m.nxt[node] = static_cast<short>(m.head);
+        m.head = node;
+        if (m.nxt[node] >= 0) m.bucket[m.key[m.nxt[node]] % m.nb] = static_cast<short>(node);
+        m.bucket[bkt] = kBeforeBegin;
+    }
+    return node;
+}
+
+__host__ __device__ void heap_push_hole(HeapItem* v, int hole, int top, long long val_w, int val_node) {      // std::__push_heap
+    int parent = (hole - 1) / 2;
+    while (hole > top && v[parent].w > val_w) {
+        v[hole].w = v[parent].w;
+        v[hole].node = v[parent].node;
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    v[hole].w = val_w;
+    v[hole].node = val_node;
+}
+__host__ __device__ void heap_push(HeapItem* v, int& n, long long w, int node) { ++n; heap_push_hole(v, n - 1, 0, w, node); }
+// top(), then std::pop_heap + pop_back
+__host__ __device__ void heap_pop(HeapItem* v, int& n, long long& top_w, int& top_node) {
+    top_w = v[0].w;
+    top_node = v[0].node;
+    if (n > 1) {
+        const int len = n - 1;                                                       // std::__pop_heap -> std::__adjust_heap
+        const long long val_w = v[len].w;
+        const int val_node = v[len].node;
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (v[child].w > v[child - 1].w) --child;
+            v[hole].w = v[child].w;
+            v[hole].node = v[child].node;
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            v[hole].w = v[child - 1].w;
+            v[hole].node = v[child - 1].node;
+            hole = child - 1;
+        }
+        heap_push_hole(v, hole, 0, val_w, val_node);
+    }
+    --n;
+}
+
+// occurrences of every symbol among the leaves of package `root`: cnt[] is incremented, the symbols seen are flagged in
+// the 256-bit mask
+__host__ __device__ void count_leaves(const Node* nodes, int root, unsigned short* cnt, unsigned (&mask)[8]) {
+    int stack[40], sp = 0;                                     // a package is at most kLimit levels deep: <= 17 pending nodes
+    stack[sp++] = root;
+    while (sp) {
+        const int k = stack[--sp];
+        const int sym = nodes[k].sym;
+        if (sym >= 0) { ++cnt[sym]; mask[sym >> 5] |= 1u << (sym & 31); continue; }
+        stack[sp++] = nodes[k].left;
+        stack[sp++] = nodes[k].right;
+    }
+}
+
+__host__ __device__ void write_table(const TableScratch& s, int nsymbols, jpgenc_huff_table* t) {     // generateCodes, src/Huffman.cpp:50-66
+    unsigned code = 0;
+    int k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        t->counts[len - 1] = static_cast<uint8_t>(s.per_len_n[len]);
+        for (int i = 0; i < s.per_len_n[len]; ++i) {
+            const int sym = s.per_len[len][i];
+            t->code_msb[sym] = code << (32 - len);
+            t->length[sym] = static_cast<uint8_t>(len);
+            t->symbols[k++] = static_cast<uint8_t>(sym);
+            ++code;
+        }
+        code <<= 1;
+    }
+    t->nsymbols = nsymbols;
+}
+
+// The serial part: s.order[0..n) = the distinct symbols in order of first appearance, count[256] their frequencies;
+// *tab has been zeroed.  Runs on one device thread -- and, for tests without a GPU, on the host.
+// The three heaps (leaves, current level, next level) live where the caller says: in shared memory for alphabets of up
+// to kSharedSyms symbols (a heap step is two dependent loads and a store; from global memory a 27-symbol table took
+// 700 us), otherwise in the table's scratch slab.
+__host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* count, int n, jpgenc_huff_table* tab,
+                                            HeapItem* blueprint, HeapItem* heap_a, HeapItem* heap_b) {
+    um_init(s.map);
+    for (int i = 0; i < n; ++i) um_touch(s.map, s.order[i]);
+    int m = 0;
+    for (int p = s.map.head; p >= 0; p = s.map.nxt[p]) { s.syms[m] = s.map.key[p]; s.freq[m] = count[s.map.key[p]]; ++m; }
+    for (int l = 0; l < 18; ++l) s.per_len_n[l] = 0;
+
+    if (n == 1) {                                              // src/Huffman.cpp:17-25: the lone symbol gets code "0"
+        s.per_len[1][s.per_len_n[1]++] = static_cast<unsigned char>(s.syms[0]);
+        write_table(s, n, tab);
+        return;
+    }
+    int nn = 0, nb = 0;
+    for (int i = 0; i < n; ++i) {                              // map iteration order feeds the first heap
+        s.nodes[nn] = Node{-1, -1, s.syms[i], 0};
+        heap_push(blueprint, nb, static_cast<long long>(static_cast<int>(s.freq[i])), nn);   // the reference counts in int
+        ++nn;
+    }
+    HeapItem *cur = heap_a, *nxt = heap_b;
+    int ncur = n, nnxt = 0;
+    for (int i = 0; i < n; ++i) cur[i] = blueprint[i];
+    for (int lvl = 0; lvl < kLimit; ++lvl) {
+        if (lvl + 1 < kLimit) {                                // every level but the last starts as a copy of the leaves
+            for (int i = 0; i < n; ++i) nxt[i] = blueprint[i];
+            nnxt = n;
+        } else {
+            nnxt = 0;
+        }
+        while (ncur > 1) {
+            long long aw, bw;
+            int an, bn;
+            heap_pop(cur, ncur, aw, an);
+            heap_pop(cur, ncur, bw, bn);
+            s.nodes[nn] = Node{static_cast<short>(an), static_cast<short>(bn), -1, 0};
+            heap_push(nxt, nnxt, aw + bw, nn);
+            ++nn;
+        }
+        HeapItem* sw = cur; cur = nxt; nxt = sw;
+        ncur = nnxt;
+    }
+    // drain the last level: a symbol's code length is the number of times it occurs in the surviving packages; the
+    // lengths map is touched package by package, symbols of a package in ascending order
+    um_init(s.map);
+    for (int i = 0; i < 256; ++i) { s.len_of[i] = 0; s.cnt[i] = 0; }
+    while (ncur) {
+        long long pw;
+        int pn;
+        heap_pop(cur, ncur, pw, pn);
+        unsigned mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        count_leaves(s.nodes, pn, s.cnt, mask);
+#pragma unroll 1
+        for (int w = 0; w < 8; ++w) {                          // ascending symbol order, only the symbols that occur
+            unsigned bits = mask[w];
+            while (bits) {
+                int b = 0;
+                while (!((bits >> b) & 1u)) ++b;               // lowest set bit (portable: this function also runs on the host)
+                const int sym = w * 32 + b;
+                bits &= bits - 1;
+                um_touch(s.map, sym);
+                s.len_of[sym] += s.cnt[sym];
+                s.cnt[sym] = 0;
+            }
+        }
+    }
+    for (int p = s.map.head; p >= 0; p = s.map.nxt[p]) {
+        const int sym = s.map.key[p], len = s.len_of[sym];
+        s.per_len[len][s.per_len_n[len]++] = static_cast<unsigned char>(sym);
+    }
+    // preventOnlyOnesCode (src/Huffman.cpp:37-48): the last symbol of the deepest level moves one level down
+    int deepest = 16;
+    while (deepest > 0 && s.per_len_n[deepest] == 0) --deepest;
+    const int moved = s.per_len[deepest][--s.per_len_n[deepest]];
+    s.per_len[deepest + 1][s.per_len_n[deepest + 1]++] = static_cast<unsigned char>(moved);
+    write_table(s, n, tab);
+}
+
+}  // namespace
+
+// One warp per table.  All lanes clear the output and rank the symbols by first occurrence; lane 0 then runs the
+// (inherently serial) container operations.  status[table] = 0 ok, 1 = no symbol at all.
+// (No __restrict__ on these parameters: with it nvcc 12.9 -O3 treated the two level heaps -- members of one scratch
+// object whose pointers swap roles every level -- as never aliasing, and a popped weight read back as 0.  Found by the
+// parity test; -G, -Xcicc -O1 and non-inlined heap functions all gave the right tables.)
+__global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, uint32_t stats_stride, uint32_t ntables,
+                                                          TableScratch* scratch, jpgenc_huff_table* out, uint32_t* status) {
+    __shared__ HeapItem sh_heap[3][2 * kSharedSyms + 16];
+    const uint32_t table = blockIdx.x, lane = threadIdx.x;
+    if (table >= ntables) return;
+    const uint32_t frame = table >> 2, t = table & 3;
+    const uint32_t* count = reinterpret_cast<const uint32_t*>(stats + static_cast<size_t>(frame) * stats_stride) + t * 256;
+    const unsigned long long* first =
+        reinterpret_cast<const unsigned long long*>(stats + static_cast<size_t>(frame) * stats_stride + 4096) + t * 256;
+    TableScratch& s = scratch[table];
+    jpgenc_huff_table* tab = out + table;
+    {
+        uint32_t* w = reinterpret_cast<uint32_t*>(tab);
+        for (uint32_t i = lane; i < sizeof(jpgenc_huff_table) / 4; i += 32) w[i] = 0;
+    }
+    // distinct symbols in order of first appearance == the order the reference's counting loop creates map entries
+    // (keys are unique: one text position holds one symbol); rank = number of present symbols that appear earlier
+    int n = 0;
+    for (int base = 0; base < 256; base += 32) {
+        const int sym = base + lane;
+        const bool here = count[sym] != 0;
+        if (here) {
+            const unsigned long long k = first[sym];
+            int rank = 0;
+            for (int o = 0; o < 256; ++o) rank += (count[o] != 0 && first[o] < k) ? 1 : 0;
+            s.order[rank] = static_cast<unsigned char>(sym);
+        }
+        n += __popc(__ballot_sync(0xffffffffu, here));
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    if (n == 0) { status[table] = 1; return; }                 // the reference asserts text.size() > 0
+    status[table] = 0;
+    if (n <= kSharedSyms) build_table_serial(s, count, n, tab, sh_heap[0], sh_heap[1], sh_heap[2]);
+    else build_table_serial(s, count, n, tab, s.blueprint, s.heap_a, s.heap_b);
+}
+
+size_t table_scratch_bytes() { return sizeof(TableScratch); }
+
+// the same code on the host (no GPU involved): lets the array restatement be checked against the container-driven build
+// in the CPU test suite
+int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
+    TableScratch* s = new TableScratch;
+    std::memset(s, 0xA5, sizeof *s);            // device scratch is not initialised either: nothing may be read before it is written
+    std::memset(out, 0, sizeof *out);
+    int n = 0;
+    for (int sym = 0; sym < 256; ++sym) {
+        if (!count[sym]) continue;
+        int rank = 0;
+        for (int o = 0; o < 256; ++o) rank += (count[o] != 0 && first_pos[o] < first_pos[sym]) ? 1 : 0;
+        s->order[rank] = static_cast<unsigned char>(sym);
+        ++n;
+    }
+    if (n) build_table_serial(*s, count, n, out, s->blueprint, s->heap_a, s->heap_b);
+    delete s;
+    return n ? JPGENC_OK : JPGENC_ERR_ARG;
+}
+
+// tables [ntables] (device) from the statistics of ntables / 4 frames laid out as K2 leaves them (stats_stride bytes per
+// frame: histogram u32[4][256], first-occurrence keys u64[4][256]); scratch: ntables * table_scratch_bytes()
+int launch_build_tables(jpgenc_ctx* c, const uint8_t* d_stats, uint32_t stats_stride, uint32_t ntables, void* d_scratch,
+                        jpgenc_huff_table* d_out, uint32_t* d_status) {
+    build_tables_kernel<<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return JPGENC_OK;
+}
+
+}  // namespace jpgenc

@@ -51,3 +51,23 @@ def encoder():
 def table_fields(t):
     n = int(sum(t.counts))
     return (bytes(t.length), bytes(t.code_msb), bytes(t.counts), bytes(t.symbols[:n]))
+
+
+def random_symbol_stats(rng, nsym, max_count):
+    """a histogram with nsym distinct symbols and a first-occurrence order (unique keys), as K2 would deliver them"""
+    import numpy as np
+    syms = rng.choice(256, nsym, replace=False)
+    count = np.zeros(256, np.uint32)
+    first = np.full(256, np.iinfo(np.uint64).max, np.uint64)
+    shape = rng.integers(0, 4)
+    for rank, s in enumerate(rng.permutation(syms)):
+        if shape == 0:
+            count[s] = rng.integers(1, max_count)                     # arbitrary
+        elif shape == 1:
+            count[s] = rng.integers(1, 4)                             # many ties
+        elif shape == 2:
+            count[s] = max(1, int(max_count * 0.6 ** rank))           # geometric: the length limit of 15 binds
+        else:
+            count[s] = 1 << min(rank, 30)                             # powers of two: maximally deep tree
+        first[s] = np.uint64(rank * 256 + int(rng.integers(0, 130)))
+    return count, first

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import table_fields
+from conftest import random_symbol_stats, table_fields
 from jpgenc_b200.synth import noise_rgb, synth_rgb
 
 pytestmark = pytest.mark.gpu
@@ -395,3 +395,52 @@ def test_frames_in_many_passes_on_several_lanes(encoder, oracle, monkeypatch, pe
         assert encoder.encode_rgb(frames[1]) == want[1]
     finally:
         encoder.dev_free(d)
+
+
+@pytest.mark.gpu
+def test_device_table_build_equals_host_build(encoder):
+    """build_tables_kernel restates libstdc++'s unordered_map iteration order and heap order on arrays; the host build drives
+    the real containers.  Same tables -- codes, lengths, DHT symbol order -- for every alphabet size and weight pattern."""
+    rng = np.random.default_rng(2024)
+    counts, firsts = [], []
+    for nsym in list(range(1, 40)) + [47, 59, 60, 64, 100, 127, 128, 129, 162, 200, 255, 256] + list(rng.integers(2, 257, 120)):
+        c, f = random_symbol_stats(rng, int(nsym), int(rng.choice([5, 1000, 10 ** 6, 2 ** 31 - 1])))
+        counts.append(c); firsts.append(f)
+    dev = encoder.build_huffman_device(np.stack(counts), np.stack(firsts))
+    for i, (c, f) in enumerate(zip(counts, firsts)):
+        host = encoder.build_huffman([c] * 4, [f] * 4)[0]
+        assert table_fields(dev[i]) == table_fields(host), f"table {i} ({int(np.count_nonzero(c))} symbols) differs"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["synth_512", "noise_256", "odd_203x117", "one_pixel", "stripes", "maxval15"])
+def test_device_table_build_on_image_statistics(encoder, name):
+    rgb, maxval = IMAGES[name]
+    encoder.upload_rgb(rgb, maxval)
+    encoder.color_dct_quant()
+    count, first = encoder.symbol_stats()
+    host = encoder.build_huffman(count, first)
+    dev = encoder.build_huffman_device(count, first)
+    for t in range(4):
+        assert table_fields(dev[t]) == table_fields(host[t]), f"table {t}"
+
+
+@pytest.mark.gpu
+def test_frames_with_tables_built_on_the_device(oracle, monkeypatch):
+    """the batched-frame path with JPGENC_DEVICE_TABLES=1 (what hosts with few cores per GPU use): same files"""
+    from jpgenc_b200.capi import Encoder
+    monkeypatch.setenv("JPGENC_DEVICE_TABLES", "1")
+    monkeypatch.setenv("JPGENC_FRAMES_PER_PASS", "5")
+    enc = Encoder(0)
+    try:
+        w, h, n = 208, 120, 17
+        frames = [synth_rgb(w, h, s) if s % 3 else noise_rgb(w, h, s) for s in range(n)]
+        want = [oracle.encode_rgb(f) for f in frames]
+        host = [np.ascontiguousarray(f) for f in frames]
+        cap = max(len(x) for x in want) + 64
+        outs = [np.zeros(cap, np.uint8) for _ in range(n)]
+        sizes = enc.encode_frames_device([f.ctypes.data for f in host], w, h, [o.ctypes.data for o in outs], [cap] * n, host_frames=True)
+        assert sizes == [len(x) for x in want]
+        assert all(outs[i][: sizes[i]].tobytes() == want[i] for i in range(n))
+    finally:
+        enc.close()

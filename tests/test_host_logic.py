@@ -149,3 +149,26 @@ def test_golden_ppm_headers(golden, oracle):
         rc, info = _ppm_info(lib, data)
         orc, oh = oracle.ppm_parse(data)
         assert rc == 0 and info == (oh.magic, oh.width, oh.height, oh.maxval, oh.payload)
+
+
+def test_array_restatement_of_the_table_build_equals_the_container_driven_build():
+    """The device-side table build (csrc/tables_device.cu) restates libstdc++'s unordered_map iteration order and heap
+    order on plain arrays.  Its code also runs on the host (jpgenc_build_huffman_arrays): every alphabet size, tie-heavy,
+    geometric (length limit binds) and maximally deep weight patterns must give the tables of jpgenc_build_huffman, which
+    drives the real containers and is itself pinned against the reference (test_oracle_vs_reference)."""
+    import ctypes as C
+    import numpy as np
+    from conftest import random_symbol_stats, table_fields
+    from jpgenc_b200.capi import HuffTable, _np_ptr, u32p, u64p
+    _, lib = _lib()
+    rng = np.random.default_rng(7)
+    sizes = list(range(1, 70)) + [100, 127, 128, 129, 161, 162, 200, 255, 256] + [int(x) for x in rng.integers(1, 257, 700)]
+    for n in sizes:
+        c, f = random_symbol_stats(rng, n, int(rng.choice([5, 1000, 10 ** 6, 2 ** 31 - 1])))
+        a, b = HuffTable(), HuffTable()
+        assert lib.jpgenc_build_huffman(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(a)) == 0
+        assert lib.jpgenc_build_huffman_arrays(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(b)) == 0
+        assert table_fields(a) == table_fields(b) and a.nsymbols == b.nsymbols, f"{n} symbols: {c[c > 0].tolist()}"
+    empty = np.zeros(256, np.uint32)
+    none = np.full(256, np.iinfo(np.uint64).max, np.uint64)
+    assert lib.jpgenc_build_huffman_arrays(_np_ptr(empty, u32p), _np_ptr(none, u64p), C.byref(HuffTable())) != 0
