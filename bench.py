@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(row)
             except Exception:
                 pass
-            self.stop_flag.wait(0.005 if self.nvml else 0.05)
+            self.stop_flag.wait(0.02 if self.nvml else 0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -384,7 +384,7 @@ def run_batch(args):
         enc.synth_rgb(d_all + i * fbytes, w, h, k)
     enc.synchronize()
     dev_ptrs = [d_all + i * fbytes for i in range(nf)]
-    workers = min(16, os.cpu_count() or 1)
+    workers = max(2, (os.cpu_count() or 1) // max(1, torch.cuda.device_count()))      # the library's default share of the host per GPU process
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -412,7 +412,9 @@ def run_batch(args):
             "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": desc, "frames": BATCH_FRAMES, "frames_per_gpu": nf, "width": w, "height": h,
                        "mode": "all frames of a pass through every kernel together, passes on three pipeline lanes (jpgenc_encode_frames[_device])",
-                       "host_threads_for_tables": workers, "timing": "host wall clock around the synchronous batch call, max over ranks",
+                       "host_threads_for_tables": workers,
+                       "tables_built_on": ("device" if (os.environ.get("JPGENC_DEVICE_TABLES", "") or ("1" if workers < 8 else "0")) != "0" else "host"),
+                       "timing": "host wall clock around the synchronous batch call, max over ranks",
                        "l2": "inputs larger than L2 (%.1f GB of frames per GPU)" % (nf * fbytes / 1e9)},
             "e2e": {"value": round(mpx / dt_e2e, 1), "unit": UNIT, "h2d_bytes_per_step": nf * fbytes, "d2h_bytes_per_step": int(sum(sizes)),
                     "ms_per_step": round(dt_e2e * 1e3, 3), "frames_per_s": round(BATCH_FRAMES / dt_e2e, 1)},

@@ -53,7 +53,10 @@ public:
         }
         cv_.notify_all();
         drain(*call);
-        while (call->done.load(std::memory_order_acquire) < n) std::this_thread::yield();   // the last few jobs, on other threads
+        if (call->done.load(std::memory_order_acquire) < n) {   // the last few jobs are still running on other threads
+            std::unique_lock<std::mutex> lk(m_);
+            done_cv_.wait(lk, [&] { return call->done.load(std::memory_order_acquire) >= n; });
+        }
     }
 
 private:
@@ -62,12 +65,15 @@ private:
         uint32_t n = 0;
         std::atomic<uint32_t> next{0}, done{0};
     };
-    static void drain(Call& c) {
+    void drain(Call& c) {
         for (;;) {
             const uint32_t i = c.next.fetch_add(1, std::memory_order_relaxed);
             if (i >= c.n) return;
             c.fn(i);
-            c.done.fetch_add(1, std::memory_order_release);
+            if (c.done.fetch_add(1, std::memory_order_acq_rel) + 1 == c.n) {     // the call is complete: wake its owner
+                std::lock_guard<std::mutex> lk(m_);
+                done_cv_.notify_all();
+            }
         }
     }
     void run() {
@@ -88,7 +94,7 @@ private:
     }
     std::vector<std::thread> threads_;
     std::mutex m_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, done_cv_;
     bool quit_ = false;
     std::deque<std::shared_ptr<Call>> calls_;
 };
@@ -934,9 +940,20 @@ static void leave_batch_state(jpgenc_ctx* c) {
 // driven by its own host thread: while one lane builds its tables the other lanes' kernels run.
 constexpr uint32_t kDefaultLanes = 3, kMaxLanes = 4;
 
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
 static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, uint32_t maxval) {
     if (!c->host_pool) {                                       // one pool of host threads for all lanes (HostPool)
-        c->host_pool = new HostPool(std::min(15u, std::max(2u, std::thread::hardware_concurrency()) - 1));
+        // this process's share of the host: the cores divided by the visible GPUs (one process per GPU is the deployment
+        // this library is written for); JPGENC_HOST_THREADS overrides
+        int ndev = 1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+        const unsigned share = std::max(2u, std::thread::hardware_concurrency() / static_cast<unsigned>(ndev));
+        const unsigned workers = std::max(1u, std::min(15u, env_u32("JPGENC_HOST_THREADS", share) - 1));
+        c->host_pool = new HostPool(workers);
         c->owns_host_pool = true;
     }
     if (l != c) {
@@ -946,11 +963,6 @@ static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, ui
         l->owns_host_pool = false;
     }
     return set_geometry(l, w, h, maxval);
-}
-
-static uint32_t env_u32(const char* name, uint32_t dflt) {
-    const char* v = std::getenv(name);
-    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
 }
 
 // frames per pass: a pass must be large enough to fill the GPU and amortise its two synchronisations, small enough

@@ -2,7 +2,7 @@
 import os, sys, time
 sys.path.insert(0, ".")
 from jpgenc_b200.capi import Encoder
-w, h, nf = 1920, 1080, 1024
+w, h, nf = 1920, 1080, int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 fb = w * h * 3
 enc = Encoder(0)
 d = enc.dev_alloc(nf * fb)
@@ -24,6 +24,6 @@ os.environ["JPGENC_TRACE"] = "1"
 os.environ["JPGENC_LANES"] = "1"; os.environ["JPGENC_FRAMES_PER_PASS"] = "103"
 for dev in ("0", "1"):
     os.environ["JPGENC_DEVICE_TABLES"] = dev
-    enc.encode_frames_device(ptrs[:206], w, h)
+    enc.encode_frames_device(ptrs[:min(nf, 206)], w, h)
     print("--- trace, one lane, device tables", dev, file=sys.stderr, flush=True)
-    enc.encode_frames_device(ptrs[:206], w, h)
+    enc.encode_frames_device(ptrs[:min(nf, 206)], w, h)
