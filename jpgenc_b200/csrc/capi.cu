@@ -474,8 +474,9 @@ static int ensure_stats_buffers(jpgenc_ctx* c) {
     // touch a few percent of it
     if ((rc = ensure(c, &c->d_items, &c->items_cap, F * tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, F * tiles * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, F * tiles * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, F * (tiles / 8 + tiles / 2048 + 4) * sizeof(unsigned long long)))) return rc;
+    // K3 may cut a tile into four ranges (small images, launch_entropy): sized for that
+    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, F * tiles * 4 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, F * (tiles * 4 / 8 + tiles * 4 / 2048 + 4) * sizeof(unsigned long long)))) return rc;
     if ((rc = ensure(c, &c->d_stats, &c->stats_cap, F * kStatsBytes + 16))) return rc;
     return ensure_pinned(c, stage_bytes(F));
 }

@@ -56,7 +56,8 @@ struct EntropyParams {
     const uint32_t* items;              // K2's symbol items: range R = the first range_cnt[R] slots of slab R
     const uint32_t* range_cnt;          // [nframes * ranges_per_frame]
     uint32_t nframes;
-    uint32_t ranges_per_frame;          // K2 tiles per frame
+    uint32_t split;                     // ranges per K2 tile: 1, or 4 for small images (more warps at work; see launch_entropy)
+    uint32_t ranges_per_frame;          // K2 tiles per frame * split
     uint32_t groups_per_frame;          // ceil(ranges_per_frame / 8): one CTA of K3a/K3b each
     uint32_t supers_per_frame;          // ceil(groups_per_frame / 256)
     const DeviceTables* tables;         // [nframes]
@@ -101,6 +102,16 @@ __device__ __forceinline__ uint32_t item_fast(uint32_t item, const uint32_t* s_f
     return ((item >> 10) & 3u) || !e ? 0u : e | (item >> 12);
 }
 
+// items of range `range` of frame `frame`: with split == 1 a range is a K2 tile's item slab, with split == 4 a quarter of it
+__device__ __forceinline__ const uint32_t* range_items(const EntropyParams& p, uint32_t frame, uint32_t range, uint32_t* n) {
+    const uint32_t tile = range / p.split, q = range - tile * p.split;
+    const size_t slab = static_cast<size_t>(frame) * (p.ranges_per_frame / p.split) + tile;
+    const uint32_t nt = p.range_cnt[slab], begin = static_cast<uint32_t>((static_cast<uint64_t>(nt) * q) / p.split),
+                   end = static_cast<uint32_t>((static_cast<uint64_t>(nt) * (q + 1)) / p.split);
+    *n = end - begin;
+    return p.items + slab * kSlabItems + begin;
+}
+
 constexpr int kPackThreads = 256;                       // 8 warps, one item range each
 constexpr int kPackWarps = kPackThreads / 32;
 
@@ -131,8 +142,8 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
     uint32_t bits = 0;
     if (range < p.ranges_per_frame) {
         const size_t slab = static_cast<size_t>(frame) * p.ranges_per_frame + range;
-        const uint32_t n = p.range_cnt[slab];
-        const uint32_t* __restrict__ items = p.items + slab * kSlabItems;
+        uint32_t n;
+        const uint32_t* __restrict__ items = range_items(p, frame, range, &n);
         for (uint32_t i = lane; i < n; i += 32) {
             const uint32_t item = __ldg(items + i), w = item_fast(item, s_fast);
             bits += w ? w >> 27 : item_bits(item, s_tab);
@@ -199,8 +210,8 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     for (int w = 0; w < warp; ++w)
         if (group * kPackWarps + w < p.ranges_per_frame) cur += __ldcg(p.range_bits + slab0 + w);
     if (range >= p.ranges_per_frame) return;
-    const uint32_t n = p.range_cnt[slab0 + warp];
-    const uint32_t* __restrict__ items = p.items + (slab0 + warp) * kSlabItems;
+    uint32_t n;
+    const uint32_t* __restrict__ items = range_items(p, frame, range, &n);
     uint32_t* it = s_items[warp];
     uint32_t* bitbuf = s_bits[warp];
 
@@ -387,7 +398,11 @@ int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles) {
     p.items = c->d_items;
     p.range_cnt = c->d_tile_cnt;
     p.nframes = F;
-    p.ranges_per_frame = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    const uint32_t tiles = static_cast<uint32_t>((nblocks + kTileBlocks - 1) / kTileBlocks);
+    // one warp walks one range; a small image has too few tiles to occupy the GPU (3840x2160: 507 tiles = 64 CTAs, and every
+    // warp walks ~1600 items one after the other), so its tiles are cut into four ranges each
+    p.split = static_cast<uint64_t>(tiles) * F < 4096 ? 4u : 1u;
+    p.ranges_per_frame = tiles * p.split;
     p.groups_per_frame = (p.ranges_per_frame + kPackWarps - 1) / kPackWarps;
     p.supers_per_frame = (p.groups_per_frame + 255) / 256;
     p.tables = c->d_tables;
