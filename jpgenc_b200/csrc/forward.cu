@@ -15,6 +15,7 @@
 //    coefficients are the reference's, bit for bit;
 //  * coefficients leave through a bank-conflict-free swizzled staging buffer as full 512-byte warp stores,
 //    already in the MCU-interleaved order the entropy coder consumes.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -735,7 +736,10 @@ static int launch_refine(jpgenc_ctx* c, bool all) {
     ExactConsts e;
     fill_exact(c, c->qy, c->qc, 255. / c->maxval, &e);
     const uint32_t bpf = c->mcu_w * c->mcu_h * kBlocksPerMcu;
-    refine_kernel<<<c->sm_count * 16, kRefineThreads, 0, c->stream>>>(
+    // grid-stride over the list; a small image does not need (and should not wait for) 2368 mostly empty CTAs
+    const uint64_t total = static_cast<uint64_t>(bpf) * c->nframes;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(c->sm_count, std::min<uint64_t>(c->sm_count * 16, total / 256 + 1)));
+    refine_kernel<<<grid, kRefineThreads, 0, c->stream>>>(
         c->d_rgb, c->nframes > 1 ? c->d_frame_ptrs : nullptr, bpf, c->d_coef, c->d_refine_list, c->d_counters,
         all ? 0u : static_cast<uint32_t>(c->refine_cap), all ? 1 : 0, bpf * c->nframes, c->real_w, c->real_h, c->mcu_w, e);
     JPGENC_CUDA(c, cudaGetLastError());

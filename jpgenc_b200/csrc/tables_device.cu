@@ -209,17 +209,28 @@ __host__ __device__ void write_table(const TableScratch& s, int nsymbols, jpgenc
     t->nsymbols = nsymbols;
 }
 
+// where the serial part keeps its hot state: in the CTA's shared memory for small alphabets, in the scratch slab otherwise
+struct Work {
+    OrderedMap* map;
+    Node* nodes;
+    HeapItem *blueprint, *heap_a, *heap_b;
+    unsigned short *len_of, *cnt;
+};
+
 // The serial part: s.order[0..n) = the distinct symbols in order of first appearance, count[256] their frequencies;
 // *tab has been zeroed.  Runs on one device thread -- and, for tests without a GPU, on the host.
-// The three heaps (leaves, current level, next level) live where the caller says: in shared memory for alphabets of up
-// to kSharedSyms symbols (a heap step is two dependent loads and a store; from global memory a 27-symbol table took
-// 700 us), otherwise in the table's scratch slab.
-__host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* count, int n, jpgenc_huff_table* tab,
-                                            HeapItem* blueprint, HeapItem* heap_a, HeapItem* heap_b) {
-    um_init(s.map);
-    for (int i = 0; i < n; ++i) um_touch(s.map, s.order[i]);
+// The container state (map, three heaps, package nodes, counters) lives where `wk` says: in shared memory for alphabets of
+// up to kSharedSyms symbols -- every container operation is a chain of dependent loads; from global memory a 27-symbol
+// table took 700 us -- otherwise in the table's scratch slab.
+__host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* count, int n, jpgenc_huff_table* tab, const Work& wk) {
+    OrderedMap& map = *wk.map;
+    Node* nodes = wk.nodes;
+    HeapItem *blueprint = wk.blueprint, *heap_a = wk.heap_a, *heap_b = wk.heap_b;
+    unsigned short *len_of = wk.len_of, *cnt = wk.cnt;
+    um_init(map);
+    for (int i = 0; i < n; ++i) um_touch(map, s.order[i]);
     int m = 0;
-    for (int p = s.map.head; p >= 0; p = s.map.nxt[p]) { s.syms[m] = s.map.key[p]; s.freq[m] = count[s.map.key[p]]; ++m; }
+    for (int p = map.head; p >= 0; p = map.nxt[p]) { s.syms[m] = map.key[p]; s.freq[m] = count[map.key[p]]; ++m; }
     for (int l = 0; l < 18; ++l) s.per_len_n[l] = 0;
 
     if (n == 1) {                                              // src/Huffman.cpp:17-25: the lone symbol gets code "0"
@@ -229,7 +240,7 @@ __host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* cou
     }
     int nn = 0, nb = 0;
     for (int i = 0; i < n; ++i) {                              // map iteration order feeds the first heap
-        s.nodes[nn] = Node{-1, -1, s.syms[i], 0};
+        nodes[nn] = Node{-1, -1, s.syms[i], 0};
         heap_push(blueprint, nb, static_cast<long long>(static_cast<int>(s.freq[i])), nn);   // the reference counts in int
         ++nn;
     }
@@ -248,7 +259,7 @@ __host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* cou
             int an, bn;
             heap_pop(cur, ncur, aw, an);
             heap_pop(cur, ncur, bw, bn);
-            s.nodes[nn] = Node{static_cast<short>(an), static_cast<short>(bn), -1, 0};
+            nodes[nn] = Node{static_cast<short>(an), static_cast<short>(bn), -1, 0};
             heap_push(nxt, nnxt, aw + bw, nn);
             ++nn;
         }
@@ -257,14 +268,14 @@ __host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* cou
     }
     // drain the last level: a symbol's code length is the number of times it occurs in the surviving packages; the
     // lengths map is touched package by package, symbols of a package in ascending order
-    um_init(s.map);
-    for (int i = 0; i < 256; ++i) { s.len_of[i] = 0; s.cnt[i] = 0; }
+    um_init(map);
+    for (int i = 0; i < 256; ++i) { len_of[i] = 0; cnt[i] = 0; }
     while (ncur) {
         long long pw;
         int pn;
         heap_pop(cur, ncur, pw, pn);
         unsigned mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        count_leaves(s.nodes, pn, s.cnt, mask);
+        count_leaves(nodes, pn, cnt, mask);
 #pragma unroll 1
         for (int w = 0; w < 8; ++w) {                          // ascending symbol order, only the symbols that occur
             unsigned bits = mask[w];
@@ -273,14 +284,14 @@ __host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* cou
                 while (!((bits >> b) & 1u)) ++b;               // lowest set bit (portable: this function also runs on the host)
                 const int sym = w * 32 + b;
                 bits &= bits - 1;
-                um_touch(s.map, sym);
-                s.len_of[sym] += s.cnt[sym];
-                s.cnt[sym] = 0;
+                um_touch(map, sym);
+                len_of[sym] += cnt[sym];
+                cnt[sym] = 0;
             }
         }
     }
-    for (int p = s.map.head; p >= 0; p = s.map.nxt[p]) {
-        const int sym = s.map.key[p], len = s.len_of[sym];
+    for (int p = map.head; p >= 0; p = map.nxt[p]) {
+        const int sym = map.key[p], len = len_of[sym];
         s.per_len[len][s.per_len_n[len]++] = static_cast<unsigned char>(sym);
     }
     // preventOnlyOnesCode (src/Huffman.cpp:37-48): the last symbol of the deepest level moves one level down
@@ -301,6 +312,9 @@ __host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* cou
 __global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, uint32_t stats_stride, uint32_t ntables,
                                                           TableScratch* scratch, jpgenc_huff_table* out, uint32_t* status) {
     __shared__ HeapItem sh_heap[3][2 * kSharedSyms + 16];
+    __shared__ Node sh_nodes[kSharedSyms * (kLimit + 2) + 16];
+    __shared__ OrderedMap sh_map;
+    __shared__ unsigned short sh_len[2][kMaxSyms];
     const uint32_t table = blockIdx.x, lane = threadIdx.x;
     if (table >= ntables) return;
     const uint32_t frame = table >> 2, t = table & 3;
@@ -331,8 +345,9 @@ __global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, 
     if (lane != 0) return;
     if (n == 0) { status[table] = 1; return; }                 // the reference asserts text.size() > 0
     status[table] = 0;
-    if (n <= kSharedSyms) build_table_serial(s, count, n, tab, sh_heap[0], sh_heap[1], sh_heap[2]);
-    else build_table_serial(s, count, n, tab, s.blueprint, s.heap_a, s.heap_b);
+    const Work in_shared{&sh_map, sh_nodes, sh_heap[0], sh_heap[1], sh_heap[2], sh_len[0], sh_len[1]};
+    const Work in_scratch{&s.map, s.nodes, s.blueprint, s.heap_a, s.heap_b, s.len_of, s.cnt};
+    build_table_serial(s, count, n, tab, n <= kSharedSyms ? in_shared : in_scratch);
 }
 
 size_t table_scratch_bytes() { return sizeof(TableScratch); }
@@ -351,7 +366,7 @@ int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[
         s->order[rank] = static_cast<unsigned char>(sym);
         ++n;
     }
-    if (n) build_table_serial(*s, count, n, out, s->blueprint, s->heap_a, s->heap_b);
+    if (n) build_table_serial(*s, count, n, out, Work{&s->map, s->nodes, s->blueprint, s->heap_a, s->heap_b, s->len_of, s->cnt});
     delete s;
     return n ? JPGENC_OK : JPGENC_ERR_ARG;
 }
