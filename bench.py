@@ -413,7 +413,7 @@ def run_batch(args):
             "config": {"workload": desc, "frames": BATCH_FRAMES, "frames_per_gpu": nf, "width": w, "height": h,
                        "mode": "all frames of a pass through every kernel together, passes on three pipeline lanes (jpgenc_encode_frames[_device])",
                        "host_threads_for_tables": workers,
-                       "tables_built_on": ("device" if (os.environ.get("JPGENC_DEVICE_TABLES", "") or ("1" if workers < 8 else "0")) != "0" else "host"),
+                       "tables_built_on": ("device" if (os.environ.get("JPGENC_DEVICE_TABLES", "") or ("1" if workers < 8 and nf >= 256 else "0")) != "0" else "host"),
                        "timing": "host wall clock around the synchronous batch call, max over ranks",
                        "l2": "inputs larger than L2 (%.1f GB of frames per GPU)" % (nf * fbytes / 1e9)},
             "e2e": {"value": round(mpx / dt_e2e, 1), "unit": UNIT, "h2d_bytes_per_step": nf * fbytes, "d2h_bytes_per_step": int(sum(sizes)),

@@ -483,10 +483,14 @@ static int ensure_stats_buffers(jpgenc_ctx* c) {
 
 // Where the 4 * F tables of a batched pass are built.  The host build costs 38 us of CPU per 1080p frame; a process that
 // has fewer than 8 host cores for its GPU (an 8-GPU box with 32 cores) cannot feed the GPU that way, so there the tables
-// are built by build_tables_kernel.  JPGENC_DEVICE_TABLES=0/1 overrides.
-static bool device_tables_enabled() {
+// of a large batch are built by build_tables_kernel (measured with 4 cores: 66 k -> 107 k frames/s for 1024 frames).  A
+// small batch (a few passes, nothing to overlap the longer device build with) keeps the host build: 128 frames per GPU
+// on such a box ran at 218 k frames/s over 8 GPUs with host tables, 200 k with device tables.
+// JPGENC_DEVICE_TABLES=0/1 overrides.
+static bool device_tables_enabled(uint32_t batch_frames) {
     const char* v = std::getenv("JPGENC_DEVICE_TABLES");
     if (v && *v) return *v != '0';
+    if (batch_frames < 256) return false;
     static const bool few_cores = [] {
         int ndev = 1;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
@@ -876,7 +880,7 @@ static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_
     if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
     c->have_coef = true;
     tables.resize(static_cast<size_t>(F) * 4);
-    const bool on_device = device_tables_enabled();
+    const bool on_device = c->batch_device_tables;
     if ((rc = stats_frames(c, on_device ? tables.data() : nullptr))) return rc;
     const double t_stats = trace_on() ? now_us() : 0;
     // 4 * F independent table builds (already done when they were built on the device)
@@ -962,6 +966,7 @@ static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, ui
         std::memcpy(l->dct_a, c->dct_a, sizeof c->dct_a); std::memcpy(l->dct_s, c->dct_s, sizeof c->dct_s);
         l->host_pool = c->host_pool;
         l->owns_host_pool = false;
+        l->batch_device_tables = c->batch_device_tables;
     }
     return set_geometry(l, w, h, maxval);
 }
@@ -978,10 +983,12 @@ static uint32_t pipelined_pass_frames(const jpgenc_ctx* c, uint32_t n) {
 }
 
 // runs pass(lane, p) for p = 0 .. npasses-1 on the lanes; passes are handed out in order
-static int run_lanes(jpgenc_ctx* c, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
+static int run_lanes(jpgenc_ctx* c, uint32_t batch_frames, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
                      const std::function<int(jpgenc_ctx*, uint32_t)>& pass) {
     // a device-side table build is a long, thin kernel (one working thread per table): one more lane to overlap it with
-    const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", device_tables_enabled() ? kMaxLanes : kDefaultLanes), kMaxLanes, npasses}));
+    const bool device_tables = device_tables_enabled(batch_frames);
+    const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", device_tables ? kMaxLanes : kDefaultLanes), kMaxLanes, npasses}));
+    c->batch_device_tables = device_tables;
     int rc = prepare_lane(c, c, w, h, maxval);
     if (rc) return rc;
     while (c->lanes.size() + 1 < nl) {
@@ -1032,7 +1039,7 @@ int jpgenc_encode_frames_device(jpgenc_ctx* c, uint32_t n, const void* const* de
     if (rc) return rc;
     if (n == 0) return JPGENC_OK;
     const uint32_t per_pass = pipelined_pass_frames(c, n), npasses = (n + per_pass - 1) / per_pass;
-    return run_lanes(c, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
+    return run_lanes(c, n, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
         const uint32_t f0 = p * per_pass;
         return encode_frames_pass(l, std::min(per_pass, n - f0), dev_frames + f0, nullptr, out ? out + f0 : nullptr,
                                   caps ? caps + f0 : nullptr, sizes + f0, l->pass_tables);
@@ -1082,7 +1089,7 @@ int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames
     };
     for (uint32_t p = 0; p < std::min(kRing, npasses); ++p)
         if ((rc = upload(p))) return fail(c, rc, "host-to-device copy of a frame failed");
-    rc = run_lanes(c, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
+    rc = run_lanes(c, n, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
         const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
         {   // the lane that finished pass p - kRing enqueues this pass's copies; normally long done
             std::unique_lock<std::mutex> lk(copy_mutex);

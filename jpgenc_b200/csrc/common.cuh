@@ -89,6 +89,7 @@ struct jpgenc_ctx {
     jpgenc::TablePool* pool = nullptr;    // host worker threads that build the four Huffman tables side by side
     jpgenc::HostPool* host_pool = nullptr;   // parallel table builds of a batch of frames
     bool owns_host_pool = false;             // pipeline lanes share their parent context's pool
+    bool batch_device_tables = false;        // the current batched-frame call builds its tables on the device
     bool parallel_tables = true;          // false inside a batch: there the frames run in parallel instead
     std::vector<jpgenc_ctx*> lanes;       // further pipeline lanes of the batched-frame calls (contexts on the same device with their own
                                           // stream and buffers): while one lane's pass waits for its Huffman tables on the host, the
