@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t gtile = p.tile0 + blockIdx.x;
-    const uint32_t frame = gtile / p.tiles_per_frame;
+    const uint32_t frame = p.tiles_total == p.tiles_per_frame ? 0u : gtile / p.tiles_per_frame;   // one image: no division
     const uint32_t first = (gtile - frame * p.tiles_per_frame) * kTileBlocks;           // first block of the tile, within its frame
     const int nb = static_cast<int>(min(static_cast<uint32_t>(kTileBlocks), p.nblocks - first));
     const int16_t* __restrict__ coef = p.coef + static_cast<size_t>(frame) * p.nblocks * kCoefPerBlock;
