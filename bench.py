@@ -39,6 +39,8 @@ WORKLOADS = {
 }
 BATCH_FRAMES = 1024
 CPU_SAMPLE = (2048, 2048)          # bounded sample of the same generator for the CPU arms (~0.7 s per encode)
+if os.environ.get("JPGENC_BENCH_CPU_SAMPLE"):                      # tests use a smaller one
+    CPU_SAMPLE = tuple(int(x) for x in os.environ["JPGENC_BENCH_CPU_SAMPLE"].split("x"))
 METRIC, UNIT = "encode_throughput", "Mpx/s"
 
 

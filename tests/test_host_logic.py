@@ -172,3 +172,22 @@ def test_array_restatement_of_the_table_build_equals_the_container_driven_build(
     empty = np.zeros(256, np.uint32)
     none = np.full(256, np.iinfo(np.uint64).max, np.uint64)
     assert lib.jpgenc_build_huffman_arrays(_np_ptr(empty, u32p), _np_ptr(none, u64p), C.byref(HuffTable())) != 0
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) needs no GPU: exactly one JSON line on stdout
+    with the contract's keys, whatever the libraries print while loading"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, JPGENC_BENCH_CPU_SAMPLE="512x512")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "encode_throughput" and d["unit"] == "Mpx/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
