@@ -13,6 +13,8 @@
 #include <cstring>
 #include <vector>
 
+#include <unistd.h>
+
 #include "common.cuh"
 #include "../host/ppm_reader.hpp"
 
@@ -311,6 +313,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_tab_scratch); cudaFree(c->d_built_tables);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_file_pinned) cudaFreeHost(c->h_file_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -748,10 +751,41 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     return rc ? rc : run_entropy_stages(c, tables, scan);
 }
 
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
+// the context's pool of host threads (HostPool): this process's share of the host -- the cores divided by the visible GPUs
+// (one process per GPU is the deployment this library is written for); JPGENC_HOST_THREADS overrides
+static void ensure_host_pool(jpgenc_ctx* c) {
+    if (c->host_pool) return;
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const unsigned share = std::max(2u, std::thread::hardware_concurrency() / static_cast<unsigned>(ndev));
+    const unsigned workers = std::max(1u, std::min(15u, env_u32("JPGENC_HOST_THREADS", share) - 1));
+    c->host_pool = new HostPool(workers);
+    c->owns_host_pool = true;
+}
+
+// pinned staging for streamed inputs (jpgenc_encode_ppm_file), grown on demand
+static int ensure_file_staging(jpgenc_ctx* c, size_t bytes) {
+    if (c->file_pinned_bytes >= bytes) return JPGENC_OK;
+    if (c->h_file_pinned) JPGENC_CUDA(c, cudaFreeHost(c->h_file_pinned));
+    c->h_file_pinned = nullptr; c->file_pinned_bytes = 0;
+    JPGENC_CUDA(c, cudaMallocHost(&c->h_file_pinned, bytes));
+    c->file_pinned_bytes = bytes;
+    return JPGENC_OK;
+}
+
 // Host pixels -> coefficients with the upload hidden behind K1: the image is cut into bands of MCU rows, every band
 // is copied on the copy stream and transformed on the compute stream as soon as its copy has landed, so after the last
 // byte has crossed PCIe only one band of K1 work (plus the refinement) is left.
-static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
+// `fill` (optional): instead of reading the pixels from `host_rgb`, every band is first produced by fill(dst, byte offset in
+// the image, bytes) into one of two pinned staging buffers (a file read, for instance) and uploaded from there: bounded
+// pinned memory, full PCIe rate, and the production of band b+1 overlaps the upload of band b.
+static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval,
+                              const std::function<int(uint8_t*, size_t, size_t)>* fill = nullptr) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
@@ -771,9 +805,21 @@ static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w
     for (uint32_t y0 = 0; y0 < c->mcu_h; y0 += rows_per_band, ++band) {
         const uint32_t rows = std::min(rows_per_band, c->mcu_h - y0);
         const size_t px0 = static_cast<size_t>(y0) * 16, px1 = std::min<size_t>(h, static_cast<size_t>(y0 + rows) * 16);
-        if (px1 > px0)
-            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + px0 * row_bytes, host_rgb + px0 * row_bytes, (px1 - px0) * row_bytes,
-                                           cudaMemcpyHostToDevice, c->copy_stream));
+        if (px1 > px0) {
+            const uint8_t* src = host_rgb ? host_rgb + px0 * row_bytes : nullptr;
+            if (fill) {
+                const size_t band_bytes = static_cast<size_t>(rows_per_band) * 16 * row_bytes;
+                if (band == 0) {
+                    if ((rc = ensure_file_staging(c, 2 * band_bytes))) return rc;
+                } else if (band >= 2) {
+                    JPGENC_CUDA(c, cudaEventSynchronize(c->ev_band[band - 2]));     // this slot's previous upload has left it
+                }
+                uint8_t* slot = static_cast<uint8_t*>(c->h_file_pinned) + (band & 1) * band_bytes;
+                if ((rc = (*fill)(slot, px0 * row_bytes, (px1 - px0) * row_bytes))) return fail(c, rc, "truncated PPM payload");
+                src = slot;
+            }
+            JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + px0 * row_bytes, src, (px1 - px0) * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        }
         JPGENC_CUDA(c, cudaEventRecord(c->ev_band[band], c->copy_stream));
         JPGENC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_band[band], 0));
         if ((rc = launch_forward_rows(c, y0, rows, y0 == 0, false))) return rc;
@@ -945,22 +991,9 @@ static void leave_batch_state(jpgenc_ctx* c) {
 // driven by its own host thread: while one lane builds its tables the other lanes' kernels run.
 constexpr uint32_t kDefaultLanes = 3, kMaxLanes = 4;
 
-static uint32_t env_u32(const char* name, uint32_t dflt) {
-    const char* v = std::getenv(name);
-    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
-}
 
 static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, uint32_t maxval) {
-    if (!c->host_pool) {                                       // one pool of host threads for all lanes (HostPool)
-        // this process's share of the host: the cores divided by the visible GPUs (one process per GPU is the deployment
-        // this library is written for); JPGENC_HOST_THREADS overrides
-        int ndev = 1;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
-        const unsigned share = std::max(2u, std::thread::hardware_concurrency() / static_cast<unsigned>(ndev));
-        const unsigned workers = std::max(1u, std::min(15u, env_u32("JPGENC_HOST_THREADS", share) - 1));
-        c->host_pool = new HostPool(workers);
-        c->owns_host_pool = true;
-    }
+    ensure_host_pool(c);                                       // one pool of host threads for all lanes
     if (l != c) {
         std::memcpy(l->qy, c->qy, 64); std::memcpy(l->qc, c->qc, 64);
         std::memcpy(l->dct_a, c->dct_a, sizeof c->dct_a); std::memcpy(l->dct_s, c->dct_s, sizeof c->dct_s);
@@ -1110,19 +1143,55 @@ int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames
     return rc;
 }
 
+// main.cpp:8-32.  A binary (P6) payload is streamed: the header is parsed from the first bytes, then every band of rows is
+// read straight into pinned staging and uploaded while the next band is being read and the previous ones go through
+// K1/refinement/K2 (loadPPM's pixel path, src/Image.cpp:411-418, without ever holding the image in host memory).  ASCII
+// (P3) files are parsed on the host first (src/Image.cpp:393-408) and then take the same banded upload.
 int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) {
     if (!c || !ppm_path || !jpg_path) return JPGENC_ERR_ARG;
-    std::vector<uint8_t> file, p3;
-    int rc = slurp_file(ppm_path, &file);
-    if (rc) return fail(c, rc, "Failed to open input file");
+    std::FILE* in = std::fopen(ppm_path, "rb");
+    if (!in) return fail(c, JPGENC_ERR_IO, "Failed to open input file");
+    struct Closer { std::FILE* f; ~Closer() { if (f) std::fclose(f); } } closer{in};
+    std::vector<uint8_t> head(1 << 16);
+    head.resize(std::fread(head.data(), 1, head.size(), in));
     PpmHeader h;
-    if ((rc = parse_ppm_header(file.data(), file.size(), &h))) return fail(c, rc, "Only P3 and P6 format is supported!");
-    const uint8_t* samples = nullptr;
-    if ((rc = ppm_samples(file.data(), file.size(), h, &p3, &samples))) return fail(c, rc, "truncated PPM payload");
-    if ((rc = jpgenc_upload_rgb(c, samples, h.width, h.height, h.maxval))) return rc;
+    int rc = parse_ppm_header(head.data(), head.size(), &h);
+    if (rc) return fail(c, rc, "Only P3 and P6 format is supported!");
+    if (h.magic == 6 && h.maxval <= 255) {
+        const size_t need = static_cast<size_t>(h.width) * h.height * 3;
+        // a band is read by several threads at once (positional reads): one thread copies from the page cache at ~6 GB/s,
+        // which would leave the 55 GB/s link waiting
+        ensure_host_pool(c);
+        const int fd = fileno(in);
+        const std::function<int(uint8_t*, size_t, size_t)> fill = [&](uint8_t* dst, size_t off, size_t n) -> int {
+            constexpr size_t kPart = 8u << 20;
+            const uint32_t parts = static_cast<uint32_t>((n + kPart - 1) / kPart);
+            std::atomic<int> bad{0};
+            c->host_pool->parallel_for(parts, [&](uint32_t k) {
+                size_t at = static_cast<size_t>(k) * kPart;
+                const size_t end = std::min(n, at + kPart);
+                while (at < end) {
+                    const ssize_t got = pread(fd, dst + at, end - at, static_cast<off_t>(h.payload + off + at));
+                    if (got <= 0) { bad.store(1); return; }         // a short payload is an error (the reference's reader
+                    at += static_cast<size_t>(got);                  // would run past the end of its buffer)
+                }
+            });
+            (void)need;
+            return bad.load() ? JPGENC_ERR_FORMAT : JPGENC_OK;
+        };
+        if ((rc = upload_and_forward(c, nullptr, h.width, h.height, h.maxval, &fill))) return rc;
+    } else {
+        std::vector<uint8_t> file, p3;
+        std::fclose(in);
+        closer.f = nullptr;
+        if ((rc = slurp_file(ppm_path, &file))) return fail(c, rc, "Failed to open input file");
+        const uint8_t* samples = nullptr;
+        if ((rc = ppm_samples(file.data(), file.size(), h, &p3, &samples))) return fail(c, rc, "truncated PPM payload");
+        if ((rc = upload_and_forward(c, samples, h.width, h.height, h.maxval))) return rc;
+    }
     jpgenc_huff_table tables[4];
     uint64_t scan = 0;
-    if ((rc = run_pipeline(c, tables, &scan))) return rc;
+    if ((rc = run_entropy_stages(c, tables, &scan))) return rc;
     const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, nullptr);
     std::vector<uint8_t> out(hdr + scan + 2);
     if ((rc = assemble(c, tables, scan, out.data(), out.size()))) return rc;

@@ -155,6 +155,8 @@ struct jpgenc_ctx {
     size_t stuff_cap = 0;
     void* d_flush = nullptr;              // L2 eviction scratch
     size_t flush_bytes = 0;
+    void* h_file_pinned = nullptr;        // two band-sized pinned buffers for streamed inputs (jpgenc_encode_ppm_file)
+    size_t file_pinned_bytes = 0;
     void* h_pinned = nullptr;             // small pinned staging (stats, totals)
     size_t pinned_bytes = 0;
 

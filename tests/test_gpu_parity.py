@@ -444,3 +444,31 @@ def test_frames_with_tables_built_on_the_device(oracle, monkeypatch):
         assert all(outs[i][: sizes[i]].tobytes() == want[i] for i in range(n))
     finally:
         enc.close()
+
+
+@pytest.mark.gpu
+def test_ppm_file_streamed_band_by_band(encoder, oracle, tmp_path):
+    """jpgenc_encode_ppm_file streams a P6 payload: every band of rows is read (by several threads) into pinned staging,
+    uploaded, and taken through K1 / refinement / K2 while the next band is read.  A file with several bands, a header
+    with a comment, an odd width (clamped loader), a truncated payload (error), and an ASCII file through the same call."""
+    from jpgenc_b200.capi import ERR_FORMAT, JpgencError
+    from jpgenc_b200.synth import write_ppm
+    for w, h, seed in ((4096, 2304, 3), (3001, 2999, 4)):
+        rgb = synth_rgb(w, h, seed)
+        src, dst = tmp_path / f"in_{w}.ppm", tmp_path / f"out_{w}.jpg"
+        src.write_bytes(b"P6\n# streamed\n%d %d\n255\n" % (w, h) + rgb.tobytes())
+        encoder.encode_ppm_file(str(src), str(dst))
+        assert dst.read_bytes() == oracle.encode_rgb(rgb)
+        data = src.read_bytes()
+        cut = tmp_path / f"cut_{w}.ppm"
+        cut.write_bytes(data[:-1000])
+        with pytest.raises(JpgencError) as e:
+            encoder.encode_ppm_file(str(cut), str(tmp_path / "never.jpg"))
+        assert e.value.code == ERR_FORMAT
+    small = noise_rgb(37, 21, 5)
+    p3 = tmp_path / "ascii.ppm"
+    p3.write_text("P3\n37 21\n255\n" + "\n".join(" ".join(str(int(v)) for v in row.reshape(-1)) for row in small) + "\n")
+    encoder.encode_ppm_file(str(p3), str(tmp_path / "ascii.jpg"))
+    assert (tmp_path / "ascii.jpg").read_bytes() == oracle.encode_rgb(small)
+    # the context still works for in-memory images afterwards
+    assert encoder.encode_rgb(small) == oracle.encode_rgb(small)
