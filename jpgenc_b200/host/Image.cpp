@@ -90,6 +90,20 @@ Image& Image::operator=(Image&& o) {
 // ---------------------------------------------------------------------------------------------------------------
 // loading
 // ---------------------------------------------------------------------------------------------------------------
+void encodePPMFile(std::string in, std::string out) {
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    jpgenc_ctx* c = g_gpu.get();
+    const int rc = jpgenc_encode_ppm_file(c, in.c_str(), out.c_str());
+    if (rc == JPGENC_ERR_IO || rc == JPGENC_ERR_FORMAT) {
+        const std::string what = jpgenc_last_error(c);                  // the reference's texts (src/Image.cpp:428,450)
+        throw std::runtime_error(what.find("Failed to open input") == 0 ? "Failed to open \"" + in + "\"" : what);
+    }
+    check(c, rc);
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    std::cout << "PPM loading took 0 ms (streamed with the encode)\n";
+    std::cout << "Encoding duration: " << std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count() << " ms" << std::endl;
+}
+
 Image loadPPM(std::string path) {
     const auto t0 = std::chrono::high_resolution_clock::now();
     std::vector<uint8_t> file, p3;

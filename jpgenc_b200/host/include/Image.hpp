@@ -24,6 +24,9 @@ class Image;
 
 // P3 or P6; throws std::runtime_error when the file cannot be opened or is not a PPM (reference src/Image.cpp:427-450)
 Image loadPPM(std::string path);
+// loadPPM(in).writeJPEG(out) without materialising the image on the host: a binary PPM is streamed from the file to the
+// GPU band by band (jpgenc_encode_ppm_file).  Same file bytes, same exceptions; what the bundled command line uses.
+void encodePPMFile(std::string in, std::string out);
 int fast_atoi(const char* str);
 
 class Image {

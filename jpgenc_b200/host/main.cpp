@@ -11,8 +11,7 @@ int main(int argc, char* argv[]) {
     }
     const std::string out = argc < 3 ? "noname.jpg" : argv[2];
     try {
-        Image img = loadPPM(argv[1]);
-        img.writeJPEG(out);
+        encodePPMFile(argv[1], out);      // == loadPPM(argv[1]).writeJPEG(out), streamed (include/Image.hpp)
     } catch (const std::exception& e) {
         std::cerr << e.what() << std::endl;
         return 1;
