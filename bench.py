@@ -475,7 +475,7 @@ def extra_workloads(enc, args, peak):
         out["frame4k"] = {"ms_per_frame": round(tot / reps, 4), "mpx_per_s": round(w * h / 1e6 / (tot / reps / 1e3), 1),
                           "k1_ms": round(s.ms_k1, 4), "l2": "flushed between iterations (256 MB write)"}
         enc.dev_free(d)
-    # configs[4] in small: 256 frames of 1920x1080 through the batch API (8 contexts on this GPU)
+    # configs[4] in small: 256 frames of 1920x1080 through the batched-frame calls
     try:
         from jpgenc_b200.capi import pinned_empty, pinned_free
         w, h, nf = 1920, 1080, 256
@@ -492,7 +492,7 @@ def extra_workloads(enc, args, peak):
         fps_e2e, _, _ = batch_frames_per_s(enc.device, [host_ptr + k * fbytes for k in range(nf)], w, h, 8, False,
                                            [out_ptr + k * cap for k in range(nf)], [cap] * nf, reps=2, enc=enc)
         pinned_free(host_ptr); pinned_free(out_ptr); enc.dev_free(d_all)
-        out["batch1080p_256"] = {"frames": nf, "mode": "one pass through every kernel for all frames", "device_resident_frames_per_s": round(fps_dev, 1),
+        out["batch1080p_256"] = {"frames": nf, "mode": "frames batched through the kernels in passes on pipeline lanes (jpgenc_encode_frames[_device])", "device_resident_frames_per_s": round(fps_dev, 1),
                                  "device_resident_mpx_per_s": round(fps_dev * w * h / 1e6, 1),
                                  "e2e_frames_per_s": round(fps_e2e, 1), "e2e_mpx_per_s": round(fps_e2e * w * h / 1e6, 1),
                                  "timing": "host wall clock around the synchronous batch call"}
