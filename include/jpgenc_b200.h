@@ -61,6 +61,10 @@ typedef struct {
     float    ms_stats;            /* last K2 */
     float    ms_entropy;          /* last K3 + K4 */
     float    ms_h2d, ms_d2h;
+    /* running sums of the four stage times over every whole-image encode on this context since it was created, and their
+     * number: a caller that times many encodes reads them once before and once after instead of polling every encode */
+    double   sum_ms_k1, sum_ms_forward, sum_ms_stats, sum_ms_entropy;
+    uint64_t timed_encodes;
 } jpgenc_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------ */

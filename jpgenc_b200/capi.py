@@ -42,6 +42,8 @@ class Stats(C.Structure):
         ("scan_bytes", C.c_uint64), ("stuffed_ff", C.c_uint64),
         ("ms_k1", C.c_float), ("ms_forward", C.c_float), ("ms_stats", C.c_float), ("ms_entropy", C.c_float),
         ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+        ("sum_ms_k1", C.c_double), ("sum_ms_forward", C.c_double), ("sum_ms_stats", C.c_double), ("sum_ms_entropy", C.c_double),
+        ("timed_encodes", C.c_uint64),
     ]
 
 

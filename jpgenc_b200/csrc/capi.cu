@@ -630,6 +630,11 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     c->stats.stuffed_ff = c->frame_ff[0];
     c->stats.scan_bytes = (c->frame_bits[0] + 7) / 8 + c->frame_ff[0];
     JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_t0, c->ev_t1));
+    if (F == 1) {                                                // one whole-image encode has gone through all four stages
+        c->stats.sum_ms_k1 += c->stats.ms_k1; c->stats.sum_ms_forward += c->stats.ms_forward;
+        c->stats.sum_ms_stats += c->stats.ms_stats; c->stats.sum_ms_entropy += c->stats.ms_entropy;
+        c->stats.timed_encodes += 1;
+    }
     c->have_scan = true;
     return JPGENC_OK;
 }
