@@ -386,6 +386,7 @@ def test_frames_in_many_passes_on_several_lanes(encoder, oracle, monkeypatch, pe
             outs3 = [np.zeros(cap, np.uint8) for _ in range(n)]
             sizes3 = encoder.encode_frames_device([block.ctypes.data + o for o in offs], w, h, [o.ctypes.data for o in outs3], [cap] * n, host_frames=True)
             assert sizes3 == sizes and all(outs3[i][: sizes[i]].tobytes() == want[i] for i in range(n))
+            assert encoder.encode_frames_device([f.ctypes.data for f in host], w, h, host_frames=True) == sizes   # sizes only
         # a too-small output buffer in a late pass is reported, and the context keeps working
         small = [cap] * n
         small[n - 2] = 16
