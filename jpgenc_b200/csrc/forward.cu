@@ -762,8 +762,8 @@ int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, b
     if (first) JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(uint32_t), c->stream));   // list length .. refined so far
     bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
     if (c->nframes > 1) aligned = (c->real_w % 16 == 0) && c->frames_aligned;
-    // (strips of 24 MCUs, which divide 1920- and 3840-pixel rows evenly, were measured: no gain on those frames, 7 % slower
-    // where 32 divides the row)
+    // (strips of 24 and of 40 MCUs, which divide 1920- and 3840-pixel rows evenly, were measured: no gain on those frames
+    // -- the partial fourth strip is not what costs -- and 24 is 7 % slower where 32 divides the row)
     const dim3 grid((c->mcu_w + 31) / 32, rows, c->nframes);
     const bool bulk_out = tensor_store_enabled() && aligned &&
                           make_block_map(c->d_coef, static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu * c->nframes, 32 * kBlocksPerMcu, &p.coef_map);
