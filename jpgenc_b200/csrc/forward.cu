@@ -234,14 +234,17 @@ __global__ void __launch_bounds__(kMcus * 4, 640 / (kMcus * 4)) forward_kernel(c
             ptx::bulk_g2s(sm.tile + tid * Smem::kPitch, rgb + (static_cast<size_t>(sy) * p.real_w + mcu0 * 16) * 3, row_bytes, &sm.bar);
         }
         if (p.prefetch_ahead && tid >= 32 && tid < 48) {
-            // the CTAs are dispatched in linear order: by the time the CTA `prefetch_ahead` positions later starts, its
-            // strip is in L2 and its bulk copies wait for L2 instead of DRAM
-            const uint32_t lin = blockIdx.y * gridDim.x + blockIdx.x + p.prefetch_ahead;
+            // the CTAs are dispatched in linear order (x, then y, then frame): by the time the CTA `prefetch_ahead`
+            // positions later starts, its strip is in L2 and its bulk copies wait for L2 instead of DRAM
+            const uint32_t per_frame = gridDim.x * gridDim.y;
+            uint32_t lin = blockIdx.y * gridDim.x + blockIdx.x + p.prefetch_ahead, pz = blockIdx.z;
+            while (lin >= per_frame && pz + 1 < gridDim.z) { lin -= per_frame; ++pz; }    // at most a few frames ahead
             const uint32_t pby = lin / gridDim.x, pbx = lin - pby * gridDim.x;
             if (pby < gridDim.y) {
+                const uint8_t* __restrict__ prgb = p.frames ? p.frames[pz] : p.rgb;
                 const uint32_t pm0 = pbx * kMcus, pnm = min(static_cast<uint32_t>(kMcus), p.mcu_w - pm0);
                 const uint32_t sy = min((p.mcu_y0 + pby) * 16 + (tid - 32), p.real_h - 1);
-                ptx::bulk_prefetch_l2(rgb + (static_cast<size_t>(sy) * p.real_w + pm0 * 16) * 3, pnm * 48);
+                ptx::bulk_prefetch_l2(prgb + (static_cast<size_t>(sy) * p.real_w + pm0 * 16) * 3, pnm * 48);
             }
         }
         ptx::mbar_wait(&sm.bar, 0);
