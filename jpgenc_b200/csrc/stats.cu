@@ -49,15 +49,16 @@ __device__ __forceinline__ void warp_count(uint32_t* s_hist, uint32_t* s_first, 
     const unsigned grp = __match_any_sync(0xffffffffu, has ? idx : (0x10000 | lane));
     const bool leader = has && lane == __ffs(grp) - 1;
     if (leader) atomicAdd(&s_hist[idx], static_cast<uint32_t>(__popc(grp)));
-    // first-occurrence key: nothing to do once the minimum is established (the steady state of a large image); where
-    // lanes do improve on it, the matching lanes agree on their smallest key first (REDUX.MIN) so that one lane per
-    // symbol updates shared memory -- 32 lanes hammering one address with atomics is what made small frames slow
+    // first-occurrence key: nothing to do once the minimum is established (the steady state of a large image).  Where
+    // lanes do improve on it, 32 lanes hammering one address with atomics is what made small frames slow, and a minimum
+    // over the matching lanes (__reduce_min_sync with a partial mask) is a software loop of ~40 instructions.  Lanes hold
+    // consecutive symbols of the scan, so the lowest matching lane nearly always holds the smallest key: it updates first,
+    // and only lanes that still beat the stored value afterwards (block rows out of text order) follow.
     const bool better = has && key < s_first[idx];
     if (__any_sync(0xffffffffu, better)) {
-        if (has) {
-            const uint32_t kmin = __reduce_min_sync(grp, better ? key : 0xFFFFFFFFu);
-            if (leader && kmin != 0xFFFFFFFFu) atomicMin(&s_first[idx], kmin);
-        }
+        if (leader && better) atomicMin(&s_first[idx], key);
+        __syncwarp();
+        if (better && !leader && key < s_first[idx]) atomicMin(&s_first[idx], key);
     }
 }
 
