@@ -218,10 +218,18 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     for (uint32_t c0 = 0; c0 < n; c0 += kChunkItems) {
         const uint32_t m = min(static_cast<uint32_t>(kChunkItems), n - c0);
         const uint32_t rows = (m + 31) >> 5;
+        if (m == kChunkItems) {                                  // full chunk: all 16 row loads in flight at once
+            uint32_t v[kChunkRows];
+#pragma unroll
+            for (int r = 0; r < kChunkRows; ++r) v[r] = __ldg(items + c0 + r * 32 + lane);
+#pragma unroll
+            for (int r = 0; r < kChunkRows; ++r) it[r * 33 + lane] = v[r];
+        } else {
 #pragma unroll 4
-        for (uint32_t r = 0; r < rows; ++r) {
-            const uint32_t j = r * 32 + lane;
-            if (j < m) it[j + r] = __ldg(items + c0 + j);
+            for (uint32_t r = 0; r < rows; ++r) {
+                const uint32_t j = r * 32 + lane;
+                if (j < m) it[j + r] = __ldg(items + c0 + j);
+            }
         }
         __syncwarp();
         const uint32_t j0 = min(m, lane * rows), j1 = min(m, j0 + rows);   // this lane's consecutive items
