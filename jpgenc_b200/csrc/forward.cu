@@ -397,18 +397,26 @@ __device__ __forceinline__ double exact_pixel(const uint8_t* rgb, uint32_t real_
                          dmul(static_cast<double>(px[2]), scale));
 }
 
-// spatial sample (r, c) of block `id` (mcu*6+k) in the reference's arithmetic
-__device__ __forceinline__ double exact_sample(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uint32_t mcu_w,
-                                               uint32_t id, int r, int c, double scale) {
+// Column c of block `id` (mcu*6+k) of an image: located once per thread (the divisions), then sampled row by row
+struct ExactColumn {
+    const uint8_t* rgb;
+    uint32_t x, y;          // top pixel of the column (luma) / of the column's 2x2 cells (chroma)
+    int comp;               // 0 = Y, 1 = Cb, 2 = Cr
+};
+__device__ __forceinline__ ExactColumn exact_locate(const uint8_t* rgb, uint32_t mcu_w, uint32_t id, int c) {
     const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu;
-    const uint32_t mx = mcu % mcu_w, my = mcu / mcu_w;
-    if (k < 4) return exact_pixel(rgb, real_w, real_h, mx * 16 + (k & 1) * 8 + c, my * 16 + (k >> 1) * 8 + r, 0, scale);
-    const int comp = k - 3;                                                     // S420_m, src/Image.cpp:207-226
-    const uint32_t x = mx * 16 + 2 * c, y = my * 16 + 2 * r;
-    const double top = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y, comp, scale)),
-                            exact_pixel(rgb, real_w, real_h, x + 1, y, comp, scale));
-    const double bot = dadd(dadd(0.0, exact_pixel(rgb, real_w, real_h, x, y + 1, comp, scale)),
-                            exact_pixel(rgb, real_w, real_h, x + 1, y + 1, comp, scale));
+    const uint32_t my = mcu / mcu_w, mx = mcu - my * mcu_w;
+    if (k < 4) return ExactColumn{rgb, mx * 16 + (k & 1) * 8 + c, my * 16 + (k >> 1) * 8, 0};
+    return ExactColumn{rgb, mx * 16 + 2 * c, my * 16, static_cast<int>(k) - 3};
+}
+// spatial sample of row r in the reference's arithmetic
+__device__ __forceinline__ double exact_sample(const ExactColumn& b, uint32_t real_w, uint32_t real_h, int r, double scale) {
+    if (b.comp == 0) return exact_pixel(b.rgb, real_w, real_h, b.x, b.y + r, 0, scale);
+    const uint32_t x = b.x, y = b.y + 2 * r;                                    // S420_m, src/Image.cpp:207-226
+    const double top = dadd(dadd(0.0, exact_pixel(b.rgb, real_w, real_h, x, y, b.comp, scale)),
+                            exact_pixel(b.rgb, real_w, real_h, x + 1, y, b.comp, scale));
+    const double bot = dadd(dadd(0.0, exact_pixel(b.rgb, real_w, real_h, x, y + 1, b.comp, scale)),
+                            exact_pixel(b.rgb, real_w, real_h, x + 1, y + 1, b.comp, scale));
     return __ddiv_rn(dadd(top, bot), 4.0);
 }
 
@@ -456,10 +464,11 @@ __constant__ uint8_t c_inv_zigzag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4, 
                                          46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 
 // processes list entries (or, with `all`, block ids) [n0, n)
-template <class Sample>
+// locate(id, column) finds the thread's column once; sample(column, r) returns its row r
+template <class Locate, class Sample>
 __device__ __forceinline__ void refine_loop(uint32_t n0, uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
                                             uint32_t blocks_per_frame, const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e,
-                                            Sample&& sample) {
+                                            Locate&& locate, Sample&& sample) {
     const int lane8 = threadIdx.x & 7;
     const uint32_t group = (blockIdx.x * kRefineThreads + threadIdx.x) >> 3, ngroups = (gridDim.x * kRefineThreads) >> 3;
     const uint32_t rounds = (n - min(n0, n) + ngroups - 1) / ngroups;   // same trip count for every lane of a warp (shuffles inside)
@@ -468,8 +477,9 @@ __device__ __forceinline__ void refine_loop(uint32_t n0, uint32_t n, const uint3
         const bool valid = i < n;
         const uint32_t id = valid ? (all ? i : list[i]) : 0;
         double x[8], t[8];
+        const auto col = locate(id, lane8);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) x[r] = valid ? sample(id, r, lane8) : 0.0;
+        for (int r = 0; r < 8; ++r) x[r] = valid ? sample(col, r) : 0.0;
         aan8_exact_regs(x, t, e);                                     // t[k] = temporary(row lane8, column k)
         transpose_stage<1>(t, lane8);
         transpose_stage<2>(t, lane8);
@@ -496,10 +506,12 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* _
                                                                     uint32_t mcu_w, const __grid_constant__ ExactConsts e) {
     // count[0] = entries in the list, count[3] = entries already refined (band-wise encodes refine after every band)
     const uint32_t n = all ? nblocks : min(count[0], cap), n0 = all ? 0u : count[3];
-    refine_loop(n0, n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e, [&](uint32_t id, int r, int c) {
-        const uint32_t f = id / blocks_per_frame;
-        return exact_sample(frames ? frames[f] : rgb, real_w, real_h, mcu_w, id - f * blocks_per_frame, r, c, e.scale);
-    });
+    refine_loop(n0, n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e,
+                [&](uint32_t id, int c) {
+                    const uint32_t f = frames ? id / blocks_per_frame : 0u;
+                    return exact_locate(frames ? frames[f] : rgb, mcu_w, id - f * blocks_per_frame, c);
+                },
+                [&](const ExactColumn& col, int r) { return exact_sample(col, real_w, real_h, r, e.scale); });
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -560,9 +572,9 @@ __global__ void __launch_bounds__(kRefineThreads) refine_blocks_kernel(const flo
                                                                            uint32_t nblocks, int all,
                                                                            const __grid_constant__ ExactConsts e) {
     const uint32_t n = all ? nblocks : min(*count, cap);
-    refine_loop(0u, n, list, all != 0, out, 0xFFFFFFFFu, e.qy, e.qy, e, [&](uint32_t id, int r, int c) {
-        return static_cast<double>(in[static_cast<size_t>(id) * 64 + r * 8 + c]);
-    });
+    refine_loop(0u, n, list, all != 0, out, 0xFFFFFFFFu, e.qy, e.qy, e,
+                [&](uint32_t id, int c) { return in + static_cast<size_t>(id) * 64 + c; },
+                [](const float* col, int r) { return static_cast<double>(col[r * 8]); });
 }
 
 // band-wise encodes: everything in the list so far has been refined
