@@ -8,7 +8,7 @@ CU := $(wildcard jpgenc_b200/csrc/*.cu)
 HOSTSRC := jpgenc_b200/host/huffman_build.cpp jpgenc_b200/host/jfif_writer.cpp jpgenc_b200/host/ppm_reader.cpp \
            jpgenc_b200/host/Image.cpp jpgenc_b200/host/Huffman.cpp
 OBJ := $(patsubst jpgenc_b200/csrc/%.cu,build/%.o,$(CU)) $(patsubst jpgenc_b200/host/%.cpp,build/host_%.o,$(HOSTSRC))
-HDR := $(wildcard jpgenc_b200/csrc/*.cuh) $(wildcard jpgenc_b200/host/*.hpp) $(wildcard jpgenc_b200/host/include/*.hpp) include/jpgenc_b200.h
+HDR := $(wildcard jpgenc_b200/csrc/*.cuh) $(wildcard jpgenc_b200/csrc/*.hpp) $(wildcard jpgenc_b200/host/*.hpp) $(wildcard jpgenc_b200/host/include/*.hpp) include/jpgenc_b200.h
 
 all: $(LIBDIR)/libjpgenc_b200.so jpgenc_b200/bin/jpgEnc
 
