@@ -173,6 +173,16 @@ int jpgenc_encode_frames_device(jpgenc_ctx* ctx, uint32_t n, const void* const* 
 int jpgenc_encode_frames(jpgenc_ctx* ctx, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h,
                          uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
 
+/* The same batch with the output as the reference's file writer would leave it on disk, one file after the other
+ * (src/Image.cpp:933-972 per frame): the complete JFIF files -- SOI..SOS headers, stuffed scan, EOI -- are assembled ON THE
+ * DEVICE back to back and every pass of the batch comes home with ONE device-to-host copy into `out` (pinned for full PCIe
+ * speed; `cap` bytes).  File i occupies out[offsets[i] .. offsets[i] + sizes[i]); files are in frame order without gaps,
+ * *total_bytes (optional) is the end of the last one.  frames_on_device: 0 = host pointers (uploads overlap the kernels),
+ * 1 = device pointers.  out may be NULL: nothing is copied, offsets/sizes are still reported. */
+int jpgenc_encode_frames_packed(jpgenc_ctx* ctx, uint32_t n, const void* const* frames, int frames_on_device, uint32_t w,
+                                uint32_t h, uint32_t maxval, uint8_t* out, uint64_t cap, uint64_t* offsets, uint64_t* sizes,
+                                uint64_t* total_bytes);
+
 /* ---- config-1 microbenchmark: dctArai + quantize + zigzag on stand-alone blocks -------------------- */
 /* dev_in: nblocks*64 fp32 samples (row-major 8x8 per block); dev_out: nblocks*64 int16 zigzag.
  * Same exactness contract as K1 (FP32 fast path + exact FP64 refinement of boundary cases). */

@@ -93,6 +93,8 @@ _SIGNATURES = {
                                               C.POINTER(C.c_void_p), u64p, u64p]),
     "jpgenc_encode_frames": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.POINTER(C.c_void_p), u64p, u64p]),
+    "jpgenc_encode_frames_packed": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_uint64, u64p, u64p, u64p]),
     "jpgenc_batch_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "jpgenc_batch_destroy": (None, [C.c_void_p]),
     "jpgenc_batch_last_error": (C.c_char_p, [C.c_void_p]),
@@ -278,6 +280,18 @@ class Encoder:
         fn = self.lib.jpgenc_encode_frames if host_frames else self.lib.jpgenc_encode_frames_device
         self._check(fn(self.h, n, frames, w, h, maxval, outs, capv, sizes))
         return [int(x) for x in sizes]
+
+    def encode_frames_packed(self, frame_ptrs, w: int, h: int, out_ptr: int | None, cap: int, maxval: int = 255, host_frames=False):
+        """equally sized frames -> complete files back to back in ONE buffer (one device-to-host copy per pass);
+        returns (offsets, sizes, total bytes)"""
+        n = len(frame_ptrs)
+        frames = (C.c_void_p * n)(*frame_ptrs)
+        sizes = (C.c_uint64 * n)()
+        offs = (C.c_uint64 * n)()
+        total = C.c_uint64()
+        self._check(self.lib.jpgenc_encode_frames_packed(self.h, n, frames, 0 if host_frames else 1, w, h, maxval, out_ptr, cap,
+                                                         offs, sizes, C.byref(total)))
+        return [int(x) for x in offs], [int(x) for x in sizes], int(total.value)
 
     def encode_ppm_file(self, src: str, dst: str):
         self._check(self.lib.jpgenc_encode_ppm_file(self.h, src.encode(), dst.encode()))

@@ -20,15 +20,20 @@
 
 #include "host_pools.hpp"
 
+#include "internal.hpp"
+
 namespace jpgenc {
 int launch_exact_all(jpgenc_ctx* c);
 }
 
 using namespace jpgenc;
+using namespace jpgenc::detail;
 
 namespace {
-
 thread_local std::string g_create_error;
+}
+
+namespace jpgenc { namespace detail {
 
 const uint8_t kAnnexKLuma[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
                                  14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
@@ -44,11 +49,7 @@ int fail(jpgenc_ctx* c, int code, const char* what) {
     return code;
 }
 
-// `headroom`: for buffers whose size follows the data (scan sizes differ from pass to pass): a reallocation frees device
-// memory, which synchronises the whole device -- every lane -- so it should happen a few times, not whenever a pass is
-// slightly larger than the last one
-template <class T>
-int ensure(jpgenc_ctx* c, T** ptr, size_t* cap, size_t need_bytes, bool headroom = false) {
+int ensure_bytes(jpgenc_ctx* c, void** ptr, size_t* cap, size_t need_bytes, bool headroom) {
     if (*ptr && *cap >= need_bytes) return JPGENC_OK;
     if (headroom) need_bytes += need_bytes / 4 + 4096;
     if (*ptr) JPGENC_CUDA(c, cudaFree(*ptr));
@@ -56,7 +57,7 @@ int ensure(jpgenc_ctx* c, T** ptr, size_t* cap, size_t need_bytes, bool headroom
     void* p = nullptr;
     const size_t bytes = (need_bytes + 255) & ~static_cast<size_t>(255);
     JPGENC_CUDA(c, cudaMalloc(&p, bytes));
-    *ptr = static_cast<T*>(p);
+    *ptr = p;
     *cap = bytes;
     return JPGENC_OK;
 }
@@ -69,8 +70,6 @@ int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
     c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
 }
-
-constexpr size_t kStatsBytes = 4096 + 8192;                    // per frame: histogram + first-occurrence keys (stats.cu)
 
 // pinned host staging, grown on demand
 int ensure_pinned(jpgenc_ctx* c, size_t bytes) {
@@ -102,7 +101,77 @@ int ensure_coef(jpgenc_ctx* c) {
     return rc;
 }
 
-}  // namespace
+// JPGENC_TRACE=1: host wall-clock of the phases of every batched pass on stderr (development aid)
+bool trace_on() {
+    static const bool on = [] { const char* v = std::getenv("JPGENC_TRACE"); return v && *v && *v != '0'; }();
+    return on;
+}
+double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// device buffers of K2 / K3 for the frames bound to the context
+int ensure_stats_buffers(jpgenc_ctx* c) {
+    const uint32_t F = c->nframes;
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
+    int rc;
+    // one fixed slab of item slots per tile, sized for the worst case (every coefficient non-zero); typical images
+    // touch a few percent of it
+    if ((rc = ensure(c, &c->d_items, &c->items_cap, F * tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, F * tiles * sizeof(uint32_t)))) return rc;
+    // K3 may cut a tile into four ranges (small images, launch_entropy): sized for that
+    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, F * tiles * 4 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, F * (tiles * 4 / 8 + tiles * 4 / 2048 + 4) * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, &c->d_stats, &c->stats_cap, F * kStatsBytes + 16))) return rc;
+    return ensure_pinned(c, stage_bytes(F));
+}
+
+// device buffers of K3 / K4 for `raw_total` bytes of raw scan, `out_total` bytes of output and `k4_tiles` K4 tiles
+int ensure_entropy_buffers(jpgenc_ctx* c, uint64_t raw_total, uint64_t out_total, uint64_t k4_tiles) {
+    const uint32_t F = c->nframes;
+    int rc;
+    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, raw_total, true))) return rc;
+    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, out_total + 64, true))) return rc;
+    // tables and frame geometry share one allocation, in the order of the staging buffer: one copy brings both
+    if ((rc = ensure(c, &c->d_tables, &c->tables_cap, F * sizeof(DeviceTables) + pass_meta_bytes(F)))) return rc;
+    c->d_meta = reinterpret_cast<uint8_t*>(c->d_tables) + F * sizeof(DeviceTables);
+    size_t lb_bytes = c->lookback_cap;
+    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (k4_tiles + 8) * sizeof(unsigned long long), true))) return rc;
+    c->lookback_cap = lb_bytes;
+    return JPGENC_OK;
+}
+
+uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
+// the context's pool of host threads (HostPool): this process's share of the host -- the cores divided by the visible GPUs
+// (one process per GPU is the deployment this library is written for); JPGENC_HOST_THREADS overrides
+void ensure_host_pool(jpgenc_ctx* c) {
+    if (c->host_pool) return;
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const unsigned share = std::max(2u, std::thread::hardware_concurrency() / static_cast<unsigned>(ndev));
+    const unsigned workers = std::min(15u, std::max(2u, env_u32("JPGENC_HOST_THREADS", share)) - 1);   // the caller works too
+    c->host_pool = new HostPool(workers);
+    c->owns_host_pool = true;
+}
+
+// pinned staging: [statistics F * kStatsBytes + 16][device tables F * 8 KB][PassMeta block (common.cuh)]
+size_t stage_tables_off(uint32_t F) { return ((F * kStatsBytes + 16 + 255) / 256) * 256; }
+size_t stage_meta_off(uint32_t F) { return stage_tables_off(F) + F * sizeof(DeviceTables); }
+size_t stage_bytes(uint32_t F) { return stage_meta_off(F) + pass_meta_bytes(F) + 64; }
+
+
+void leave_batch_state(jpgenc_ctx* c) {
+    c->nframes = 1;                                                  // the context goes back to single-image state
+    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
+    c->file_mode = false;
+    c->host_hist.clear();
+}
+
+}}  // namespace jpgenc::detail
 
 extern "C" {
 
@@ -145,9 +214,9 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     std::memcpy(c->qc, kAnnexKChroma, 64);
     default_dct_constants(c->dct_a, c->dct_s);
     void* p = nullptr;
-    if ((e = cudaMalloc(&p, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&p, kCounterWords * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
     c->d_counters = static_cast<uint32_t*>(p);
-    if ((e = cudaMemset(p, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+    if ((e = cudaMemset(p, 0, kCounterWords * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
     c->pinned_bytes = 64 * 1024;
     if ((e = cudaMallocHost(&c->h_pinned, c->pinned_bytes)) != cudaSuccess) return bail("cudaMallocHost", e);
     *out = c;
@@ -163,13 +232,14 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (c->owns_host_pool) delete c->host_pool;
     cudaFree(c->d_rgb_owned); cudaFree(c->d_coef); cudaFree(c->d_refine_list); cudaFree(c->d_counters);
     cudaFree(c->d_stats); cudaFree(c->d_tables);   /* d_meta lives in the same allocation */ cudaFree(c->d_frame_ptrs); cudaFree(c->d_lookback); cudaFree(c->d_raw);
-    cudaFree(c->d_scan); cudaFree(c->d_stuff_state); cudaFree(c->d_flush);
+    cudaFree(c->d_scan); cudaFree(c->d_hdr_prefix); cudaFree(c->d_flush);
     cudaFree(c->d_tab_scratch); cudaFree(c->d_built_tables);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_file_pinned) cudaFreeHost(c->h_file_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -306,58 +376,7 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
 }
 
 // ---- K2 and K3/K4 for all frames bound to the context (one image = one frame) ------------------------------------
-// pinned staging: [statistics F * kStatsBytes + 16][device tables F * 8 KB][meta][totals F * 16]
-static size_t stage_tables_off(uint32_t F) { return ((F * kStatsBytes + 16 + 255) / 256) * 256; }
-static size_t stage_meta_off(uint32_t F) { return stage_tables_off(F) + F * sizeof(DeviceTables); }
-static size_t meta_bytes(uint32_t F) { return ((F * 16 + (F + 1) * 4 + 15) / 16) * 16; }
-static size_t stage_totals_off(uint32_t F) { return stage_meta_off(F) + meta_bytes(F); }
-static size_t stage_bytes(uint32_t F) { return stage_totals_off(F) + F * 16 + 64; }
-
-// JPGENC_TRACE=1: host wall-clock of the phases of every batched pass on stderr (development aid)
-static bool trace_on() {
-    static const bool on = [] { const char* v = std::getenv("JPGENC_TRACE"); return v && *v && *v != '0'; }();
-    return on;
-}
-static double now_us() {
-    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
-// device buffers of K2 / K3 for the frames bound to the context
-static int ensure_stats_buffers(jpgenc_ctx* c) {
-    const uint32_t F = c->nframes;
-    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
-    int rc;
-    // one fixed slab of item slots per tile, sized for the worst case (every coefficient non-zero); typical images
-    // touch a few percent of it
-    if ((rc = ensure(c, &c->d_items, &c->items_cap, F * tiles * 384 * 64 * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_tile_cnt, &c->tile_cnt_cap, F * tiles * sizeof(uint32_t)))) return rc;
-    // K3 may cut a tile into four ranges (small images, launch_entropy): sized for that
-    if ((rc = ensure(c, &c->d_range_bits, &c->range_bits_cap, F * tiles * 4 * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(c, &c->d_range_base, &c->range_base_cap, F * (tiles * 4 / 8 + tiles * 4 / 2048 + 4) * sizeof(unsigned long long)))) return rc;
-    if ((rc = ensure(c, &c->d_stats, &c->stats_cap, F * kStatsBytes + 16))) return rc;
-    return ensure_pinned(c, stage_bytes(F));
-}
-
-// Where the 4 * F tables of a batched pass are built.  The host build costs 38 us of CPU per 1080p frame; a process that
-// has fewer than 8 host cores for its GPU (an 8-GPU box with 32 cores) cannot feed the GPU that way, so there the tables
-// of a large batch are built by build_tables_kernel (measured with 4 cores: 66 k -> 107 k frames/s for 1024 frames).  A
-// small batch (a few passes, nothing to overlap the longer device build with) keeps the host build: 128 frames per GPU
-// on such a box ran at 218 k frames/s over 8 GPUs with host tables, 200 k with device tables.
-// JPGENC_DEVICE_TABLES=0/1 overrides.
-static bool device_tables_enabled(uint32_t batch_frames) {
-    const char* v = std::getenv("JPGENC_DEVICE_TABLES");
-    if (v && *v) return *v != '0';
-    if (batch_frames < 256) return false;
-    static const bool few_cores = [] {
-        int ndev = 1;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
-        return std::max(1u, std::thread::hardware_concurrency()) / static_cast<unsigned>(ndev) < 8u;
-    }();
-    return few_cores;
-}
-
-// built_tables != nullptr: build the 4 * F tables on the device right behind K2 and bring them back with the statistics
-static int stats_frames(jpgenc_ctx* c, jpgenc_huff_table* built_tables = nullptr) {
+static int stats_frames(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     const uint32_t F = c->nframes;
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
@@ -371,14 +390,6 @@ static int stats_frames(jpgenc_ctx* c, jpgenc_huff_table* built_tables = nullptr
     c->have_items = true;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    if (built_tables) {
-        const uint32_t nt = 4 * F;
-        if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&c->d_tab_scratch), &c->tab_scratch_cap, nt * table_scratch_bytes()))) return rc;
-        if ((rc = ensure(c, &c->d_built_tables, &c->built_tables_cap, nt * (sizeof(jpgenc_huff_table) + sizeof(uint32_t))))) return rc;
-        uint32_t* d_status = reinterpret_cast<uint32_t*>(c->d_built_tables + nt);
-        if ((rc = launch_build_tables(c, c->d_stats, kStatsBytes, nt, c->d_tab_scratch, c->d_built_tables, d_status))) return rc;
-        JPGENC_CUDA(c, cudaMemcpyAsync(built_tables, c->d_built_tables, nt * sizeof(jpgenc_huff_table), cudaMemcpyDeviceToHost, c->stream));
-    }
     JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_stats, F * kStatsBytes + 16, cudaMemcpyDeviceToHost, c->stream));   // + K2's copy of the refine counter
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->host_hist.resize(static_cast<size_t>(F) * 1024);
@@ -399,8 +410,8 @@ static int stats_frames(jpgenc_ctx* c, jpgenc_huff_table* built_tables = nullptr
     return JPGENC_OK;
 }
 
-// tables: [F][4].  Afterwards c->frame_bits / frame_raw_off / frame_ff describe every frame's scan in d_scan
-// (frame f's stuffed scan starts at byte 2 * frame_raw_off[f]).
+// tables: [F][4], built on the host.  Afterwards c->frame_bits / frame_out_off / frame_ff describe every frame's scan
+// in d_scan (frame f's stuffed scan starts at byte frame_out_off[f]).
 static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     const uint32_t F = c->nframes;
@@ -409,10 +420,8 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
     DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + stage_tables_off(F));
-    unsigned long long* m_off = reinterpret_cast<unsigned long long*>(h + stage_meta_off(F));
-    unsigned long long* m_bytes = m_off + F;
-    uint32_t* m_tile0 = reinterpret_cast<uint32_t*>(m_bytes + F);
-    c->frame_bits.assign(F, 0); c->frame_raw_off.assign(F, 0); c->frame_ff.assign(F, 0);
+    const PassMeta m = pass_meta_view(h + stage_meta_off(F), F);
+    c->frame_bits.assign(F, 0); c->frame_out_off.assign(F, 0); c->frame_ff.assign(F, 0);
     // exact size of every scan from the statistics the tables were built from: a symbol costs its code length plus
     // (symbol & 15) magnitude bits
     // (per frame: independent work, spread over the batch's host threads; the offsets are a serial prefix afterwards)
@@ -441,44 +450,48 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     else for (uint32_t f = 0; f < F; ++f) convert(f);
     if (conv_err.load() == 1) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
     if (conv_err.load() == 2) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
-    uint64_t raw_total = 0, k4_tiles = 0;
+    uint64_t raw_total = 0, out_total = 0, k4_tiles = 0;
     for (uint32_t f = 0; f < F; ++f) {
         const uint64_t nbytes = (c->frame_bits[f] + 7) / 8;
-        c->frame_raw_off[f] = raw_total;
-        m_off[f] = raw_total;
-        m_bytes[f] = nbytes;
-        m_tile0[f] = static_cast<uint32_t>(k4_tiles);
-        raw_total += ((nbytes + 15) & ~15ull) + 64;              // 16-byte aligned, with slack for the last words
+        m.raw_off[f] = raw_total;
+        m.raw_bytes[f] = nbytes;
+        m.frame_bits[f] = c->frame_bits[f];
+        m.file_base[f] = out_total;                              // bare scans, back to back
+        m.k4_tile0[f] = static_cast<uint32_t>(k4_tiles);
+        m.hdr_len[f] = 0;
+        raw_total += raw_slot_bytes(nbytes);
+        out_total += nbytes;
         k4_tiles += (nbytes + kK4TileBytes - 1) / kK4TileBytes;
     }
-    m_tile0[F] = static_cast<uint32_t>(k4_tiles);
+    m.k4_tile0[F] = static_cast<uint32_t>(k4_tiles);
     if (k4_tiles > 0xFFFFFFFFull) return fail(c, JPGENC_ERR_ARG, "scan too large");
-    if ((rc = ensure(c, &c->d_raw, &c->raw_cap, raw_total, true))) return rc;
-    if ((rc = ensure(c, &c->d_scan, &c->scan_cap, 2 * raw_total + 64, true))) return rc;
-    // tables and frame geometry share one allocation, in the order of the staging buffer: one copy brings both
-    if ((rc = ensure(c, &c->d_tables, &c->tables_cap, F * sizeof(DeviceTables) + meta_bytes(F)))) return rc;
-    c->d_meta = reinterpret_cast<uint8_t*>(c->d_tables) + F * sizeof(DeviceTables);
-    size_t lb_bytes = c->lookback_cap;
-    if ((rc = ensure(c, &c->d_lookback, &lb_bytes, (2 * static_cast<size_t>(F) + k4_tiles + 8) * sizeof(unsigned long long), true))) return rc;
-    c->lookback_cap = lb_bytes;
+    *m.hdr = PassHeader{};
+    m.hdr->raw_total = raw_total;
+    m.hdr->out_total = out_total;
+    m.hdr->raw_sum = out_total;
+    m.hdr->k4_tiles = static_cast<uint32_t>(k4_tiles);
+    m.hdr->nframes = F;
+    c->file_mode = false;
+    if ((rc = ensure_entropy_buffers(c, raw_total, 2 * out_total, k4_tiles))) return rc;
     // (Measured and rejected for one image:
     // passing the 8 KB of tables as kernel parameters instead -- the launches get slower and the per-thread reads of
     // the parameter bank serialise; K3+K4 went from 185 to 212 us.)
-    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables) + meta_bytes(F), cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables) + pass_meta_input_bytes(F), cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-    if ((rc = launch_entropy(c, raw_total, static_cast<uint32_t>(k4_tiles)))) return rc;
+    if ((rc = launch_entropy(c, static_cast<uint32_t>(k4_tiles)))) return rc;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     if (trace_on()) c->trace_convert_us = now_us() - t_conv;
-    // totals: bits written by K3 [F], stuffed FF bytes [F]
-    unsigned long long* totals = reinterpret_cast<unsigned long long*>(h + stage_totals_off(F));
-    JPGENC_CUDA(c, cudaMemcpyAsync(totals, c->d_lookback, F * 16, cudaMemcpyDeviceToHost, c->stream));
+    // results: bits written by K3 [F], running count of stuffed FF bytes [F]
+    JPGENC_CUDA(c, cudaMemcpyAsync(m.total_bits, c->d_meta + pass_meta_input_bytes(F), F * 16, cudaMemcpyDeviceToHost, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     for (uint32_t f = 0; f < F; ++f) {
-        if (totals[f] != c->frame_bits[f]) {
-            c->error = "entropy coder wrote " + std::to_string(totals[f]) + " bits, statistics predicted " + std::to_string(c->frame_bits[f]);
+        if (m.total_bits[f] != c->frame_bits[f]) {
+            c->error = "entropy coder wrote " + std::to_string(m.total_bits[f]) + " bits, statistics predicted " + std::to_string(c->frame_bits[f]);
             return JPGENC_ERR_ARG;
         }
-        c->frame_ff[f] = totals[F + f];
+        const uint64_t before = f ? m.ff_incl[f - 1] : 0;
+        c->frame_ff[f] = m.ff_incl[f] - before;
+        c->frame_out_off[f] = m.file_base[f] + before;
     }
     c->stats.scan_bits = c->frame_bits[0];
     c->stats.stuffed_ff = c->frame_ff[0];
@@ -610,23 +623,6 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     return rc ? rc : run_entropy_stages(c, tables, scan);
 }
 
-static uint32_t env_u32(const char* name, uint32_t dflt) {
-    const char* v = std::getenv(name);
-    return v && *v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : dflt;
-}
-
-// the context's pool of host threads (HostPool): this process's share of the host -- the cores divided by the visible GPUs
-// (one process per GPU is the deployment this library is written for); JPGENC_HOST_THREADS overrides
-static void ensure_host_pool(jpgenc_ctx* c) {
-    if (c->host_pool) return;
-    int ndev = 1;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
-    const unsigned share = std::max(2u, std::thread::hardware_concurrency() / static_cast<unsigned>(ndev));
-    const unsigned workers = std::max(1u, std::min(15u, env_u32("JPGENC_HOST_THREADS", share) - 1));
-    c->host_pool = new HostPool(workers);
-    c->owns_host_pool = true;
-}
-
 // pinned staging for streamed inputs (jpgenc_encode_ppm_file), grown on demand
 static int ensure_file_staging(jpgenc_ctx* c, size_t bytes) {
     if (c->file_pinned_bytes >= bytes) return JPGENC_OK;
@@ -744,262 +740,6 @@ int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
     if (!dst) return JPGENC_OK;
     return assemble(c, tables, scan, dst, cap);
-}
-
-// ---- batches of equally sized frames, taken through every kernel together ---------------------------------------
-// One K1 launch over all frames of a pass, one K2, the 4 * F tables built in parallel on the host, one K3a/K3b/K4: launch
-// count and host synchronisations are per PASS (a slice of the batch sized to a few GB of scratch), not per frame.
-static uint32_t frames_per_pass(const jpgenc_ctx* c) {
-    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
-    // item slabs (worst-case reservation, 96 KB per tile) within ~4 GB, block ids within 31 bits
-    size_t per_pass = std::max<size_t>(1, (4ull << 30) / (tiles * 384 * 64 * 4));
-    per_pass = std::min<size_t>(per_pass, 0x7FFFFFFFull / nblocks);
-    return static_cast<uint32_t>(std::min<size_t>(per_pass, 1024));
-}
-
-// F frames at the device pointers `dev_frames` (host array); geometry is already set.  `ready` (optional): event on
-// another stream after which the pixels are valid.
-static int encode_frames_pass(jpgenc_ctx* c, uint32_t F, const void* const* dev_frames, cudaEvent_t ready, uint8_t* const* out,
-                              const uint64_t* caps, uint64_t* sizes, std::vector<jpgenc_huff_table>& tables) {
-    int rc;
-    const double t_begin = trace_on() ? now_us() : 0;
-    c->nframes = F;
-    c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
-    bool aligned = true;
-    for (uint32_t f = 0; f < F; ++f) aligned = aligned && (reinterpret_cast<uintptr_t>(dev_frames[f]) % 16 == 0);
-    c->frames_aligned = aligned;
-    c->d_rgb = static_cast<const uint8_t*>(dev_frames[0]);
-    c->have_pixels = true;
-    {
-        size_t cap = c->frame_ptrs_cap;
-        void* p = c->d_frame_ptrs;
-        if ((rc = ensure(c, reinterpret_cast<uint8_t**>(&p), &cap, F * sizeof(void*)))) return rc;
-        c->d_frame_ptrs = static_cast<const uint8_t**>(p);
-        c->frame_ptrs_cap = cap;
-    }
-    // the pointer array is staged through pinned memory so that the copy is truly asynchronous
-    if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
-    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_frame_ptrs, dev_frames, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = ensure_coef(c))) return rc;
-    if (ready) JPGENC_CUDA(c, cudaStreamWaitEvent(c->stream, ready, 0));
-    if ((rc = launch_forward_rows(c, 0, c->mcu_h, true, true))) return rc;
-    c->have_coef = true;
-    tables.resize(static_cast<size_t>(F) * 4);
-    const bool on_device = c->batch_device_tables;
-    if ((rc = stats_frames(c, on_device ? tables.data() : nullptr))) return rc;
-    const double t_stats = trace_on() ? now_us() : 0;
-    // 4 * F independent table builds (already done when they were built on the device)
-    const uint8_t* hs = static_cast<const uint8_t*>(c->h_pinned);
-    std::atomic<int> build_rc{JPGENC_OK};
-    if (!on_device) c->host_pool->parallel_for(F * 4, [&](uint32_t j) {
-        const uint32_t f = j >> 2, t = j & 3;
-        const uint32_t* count = reinterpret_cast<const uint32_t*>(hs + f * kStatsBytes) + t * 256;
-        const uint64_t* first = reinterpret_cast<const uint64_t*>(hs + f * kStatsBytes + 4096) + t * 256;
-        const int r = jpgenc_build_huffman(count, first, &tables[j]);
-        if (r) build_rc.store(r);
-    });
-    if (on_device)
-        for (size_t j = 0; j < tables.size(); ++j)
-            if (tables[j].nsymbols <= 0) build_rc.store(JPGENC_ERR_ARG);        // the kernel leaves a table zeroed when it has no symbol
-    if (build_rc.load()) return fail(c, build_rc.load(), "Huffman table build failed");
-    const double t_built = trace_on() ? now_us() : 0;
-    if ((rc = entropy_frames(c, tables.data()))) return rc;
-    const double t_entropy = trace_on() ? now_us() : 0;
-    // files: header + scan + EOI per frame; the scans come back with one copy each, one synchronisation per pass
-    std::atomic<int> cap_err{0};
-    std::vector<uint32_t>& hdr_len = c->hdr_len;
-    hdr_len.resize(F);
-    auto headers = [&](uint32_t f) {
-        const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
-        const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], nullptr);
-        hdr_len[f] = static_cast<uint32_t>(hdr);
-        sizes[f] = hdr + scan + 2;
-        if (!out) return;
-        if (caps[f] < hdr + scan + 2) { cap_err.store(1); return; }
-        uint8_t* dst = out[f];
-        jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, &tables[f * 4], dst);
-        dst[hdr + scan] = 0xFF;                                  // EOI
-        dst[hdr + scan + 1] = 0xD9;
-    };
-    if (F >= 8) c->host_pool->parallel_for(F, headers);
-    else for (uint32_t f = 0; f < F; ++f) headers(f);
-    if (cap_err.load()) return fail(c, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
-    if (out) {
-        for (uint32_t f = 0; f < F; ++f) {
-            const uint64_t scan = (c->frame_bits[f] + 7) / 8 + c->frame_ff[f];
-            JPGENC_CUDA(c, cudaMemcpyAsync(out[f] + hdr_len[f], c->d_scan + 2 * c->frame_raw_off[f], scan, cudaMemcpyDeviceToHost, c->stream));
-        }
-        JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
-    if (trace_on())
-        std::fprintf(stderr, "[jpgenc pass ctx %p F %u] K1+K2+sync %.0f us, tables %.0f us, convert+K3+K4+sync %.0f us (convert %.0f), files %.0f us\n",
-                     static_cast<void*>(c), F, t_stats - t_begin, t_built - t_stats, t_entropy - t_built, c->trace_convert_us, now_us() - t_entropy);
-    return JPGENC_OK;
-}
-
-static void leave_batch_state(jpgenc_ctx* c) {
-    c->nframes = 1;                                                  // the context goes back to single-image state
-    c->have_pixels = c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
-    c->host_hist.clear();
-}
-
-// ---- pipeline lanes --------------------------------------------------------------------------------------------------
-// A pass is GPU work (K1, refinement, K2), then host work (4 * F table builds), then GPU work (K3, K4) again: on one stream
-// the GPU idles for the host half.  The batch calls therefore cut the batch into passes and run them on several lanes -- the
-// context itself and further, lazily created contexts on the same device with their own streams and buffers -- each
-// driven by its own host thread: while one lane builds its tables the other lanes' kernels run.
-constexpr uint32_t kDefaultLanes = 3, kMaxLanes = 4;
-
-
-static int prepare_lane(jpgenc_ctx* c, jpgenc_ctx* l, uint32_t w, uint32_t h, uint32_t maxval) {
-    ensure_host_pool(c);                                       // one pool of host threads for all lanes
-    if (l != c) {
-        std::memcpy(l->qy, c->qy, 64); std::memcpy(l->qc, c->qc, 64);
-        std::memcpy(l->dct_a, c->dct_a, sizeof c->dct_a); std::memcpy(l->dct_s, c->dct_s, sizeof c->dct_s);
-        l->host_pool = c->host_pool;
-        l->owns_host_pool = false;
-        l->batch_device_tables = c->batch_device_tables;
-    }
-    return set_geometry(l, w, h, maxval);
-}
-
-// frames per pass: a pass must be large enough to fill the GPU and amortise its two synchronisations, small enough
-// that the two lanes get several passes each to overlap
-static uint32_t pipelined_pass_frames(const jpgenc_ctx* c, uint32_t n) {
-    const uint32_t cap = frames_per_pass(c);
-    const size_t px = static_cast<size_t>(c->mcu_w) * c->mcu_h * 256;
-    const uint32_t floor_frames = static_cast<uint32_t>(std::max<size_t>(1, (96u << 20) / px));   // >= ~100 Mpx per pass
-    uint32_t per = std::max(floor_frames, (n + 9) / 10);          // measured on 1024 x 1080p, 3 lanes: 64..128 per pass are within 5 %
-    per = env_u32("JPGENC_FRAMES_PER_PASS", per);
-    return std::max(1u, std::min(per, cap));
-}
-
-// runs pass(lane, p) for p = 0 .. npasses-1 on the lanes; passes are handed out in order
-static int run_lanes(jpgenc_ctx* c, uint32_t batch_frames, uint32_t npasses, uint32_t w, uint32_t h, uint32_t maxval,
-                     const std::function<int(jpgenc_ctx*, uint32_t)>& pass) {
-    // a device-side table build is a long, thin kernel (one working thread per table): one more lane to overlap it with
-    const bool device_tables = device_tables_enabled(batch_frames);
-    const uint32_t nl = std::max(1u, std::min({env_u32("JPGENC_LANES", device_tables ? kMaxLanes : kDefaultLanes), kMaxLanes, npasses}));
-    c->batch_device_tables = device_tables;
-    int rc = prepare_lane(c, c, w, h, maxval);
-    if (rc) return rc;
-    while (c->lanes.size() + 1 < nl) {
-        jpgenc_ctx* l = nullptr;
-        if ((rc = jpgenc_create(c->device, &l))) return fail(c, rc, jpgenc_last_error(nullptr));
-        c->lanes.push_back(l);
-    }
-    for (uint32_t k = 1; k < nl; ++k)
-        if ((rc = prepare_lane(c, c->lanes[k - 1], w, h, maxval))) return fail(c, rc, jpgenc_last_error(c->lanes[k - 1]));
-    std::atomic<uint32_t> next{0};
-    std::atomic<int> first_error{JPGENC_OK};
-    std::mutex error_mutex;
-    auto work = [&](jpgenc_ctx* l) {
-        cudaSetDevice(c->device);
-        for (;;) {
-            const uint32_t p = next.fetch_add(1);
-            if (p >= npasses || first_error.load() != JPGENC_OK) return;
-            const int r = pass(l, p);
-            if (r != JPGENC_OK) {
-                std::lock_guard<std::mutex> lk(error_mutex);
-                if (first_error.load() == JPGENC_OK) {
-                    first_error.store(r);
-                    if (l != c) c->error = l->error;
-                }
-                return;
-            }
-        }
-    };
-    std::vector<std::thread> helpers;
-    for (uint32_t k = 1; k < nl; ++k) helpers.emplace_back(work, c->lanes[k - 1]);
-    work(c);
-    for (std::thread& t : helpers) t.join();
-    for (uint32_t k = 1; k < nl; ++k) {
-        jpgenc_ctx* l = c->lanes[k - 1];
-        c->launches += l->launches;
-        l->launches = 0;
-        leave_batch_state(l);
-    }
-    leave_batch_state(c);
-    return first_error.load();
-}
-
-int jpgenc_encode_frames_device(jpgenc_ctx* c, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h, uint32_t maxval,
-                                uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
-    if (!c || !dev_frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
-    JPGENC_CUDA(c, cudaSetDevice(c->device));
-    int rc = set_geometry(c, w, h, maxval);
-    if (rc) return rc;
-    if (n == 0) return JPGENC_OK;
-    const uint32_t per_pass = pipelined_pass_frames(c, n), npasses = (n + per_pass - 1) / per_pass;
-    return run_lanes(c, n, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
-        const uint32_t f0 = p * per_pass;
-        return encode_frames_pass(l, std::min(per_pass, n - f0), dev_frames + f0, nullptr, out ? out + f0 : nullptr,
-                                  caps ? caps + f0 : nullptr, sizes + f0, l->pass_tables);
-    });
-}
-
-// The same for frames in host memory (pinned for full PCIe speed): the frames travel on the copy stream into a ring of
-// kRing pass-sized slices of device memory, always a few passes ahead of the kernels; a lane that has finished pass p
-// re-fills p's slice with the frames of pass p + kRing before it takes its next pass.
-int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h, uint32_t maxval,
-                         uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
-    if (!c || !frames || !sizes || (out && !caps)) return JPGENC_ERR_ARG;
-    JPGENC_CUDA(c, cudaSetDevice(c->device));
-    int rc = set_geometry(c, w, h, maxval);
-    if (rc) return rc;
-    if (n == 0) return JPGENC_OK;
-    constexpr uint32_t kRing = kMaxLanes + 2;                   // when pass p is handed out, every pass <= p - lanes is complete
-    const size_t fbytes = static_cast<size_t>(w) * h * 3, fstride = (fbytes + 255) & ~static_cast<size_t>(255);
-    // passes small enough that the first one starts soon and copies overlap compute finely, large enough to amortise
-    uint32_t per_pass = std::max(1u, std::min<uint32_t>(frames_per_pass(c), static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / fstride))));
-    per_pass = std::max(1u, std::min(env_u32("JPGENC_FRAMES_PER_PASS", per_pass), frames_per_pass(c)));
-    const uint32_t npasses = (n + per_pass - 1) / per_pass;
-    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, kRing * per_pass * fstride + 16))) return rc;
-    std::mutex copy_mutex;                                       // one pass's copies stay together on the copy stream
-    std::condition_variable copy_cv;
-    std::vector<char> issued(npasses, 0);                        // pass p's copies and event record have been enqueued
-    auto upload = [&](uint32_t p) -> int {
-        const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
-        int r = JPGENC_OK;
-        {
-            std::lock_guard<std::mutex> lk(copy_mutex);
-            // frames that follow each other in host memory (a video buffer) travel as one strided copy
-            for (uint32_t f = 0; f < F && r == JPGENC_OK;) {
-                uint32_t run = 1;
-                while (f + run < F && frames[f0 + f + run] == frames[f0 + f + run - 1] + fbytes) ++run;
-                uint8_t* dst = c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride;
-                const cudaError_t e = run == 1 ? cudaMemcpyAsync(dst, frames[f0 + f], fbytes, cudaMemcpyHostToDevice, c->copy_stream)
-                                               : cudaMemcpy2DAsync(dst, fstride, frames[f0 + f], fbytes, fbytes, run, cudaMemcpyHostToDevice, c->copy_stream);
-                if (e != cudaSuccess) r = JPGENC_ERR_CUDA;
-                f += run;
-            }
-            if (r == JPGENC_OK && cudaEventRecord(c->ev_band[slot], c->copy_stream) != cudaSuccess) r = JPGENC_ERR_CUDA;
-            issued[p] = r == JPGENC_OK ? 1 : 2;
-        }
-        copy_cv.notify_all();
-        return r;
-    };
-    for (uint32_t p = 0; p < std::min(kRing, npasses); ++p)
-        if ((rc = upload(p))) return fail(c, rc, "host-to-device copy of a frame failed");
-    rc = run_lanes(c, n, npasses, w, h, maxval, [&](jpgenc_ctx* l, uint32_t p) {
-        const uint32_t f0 = p * per_pass, F = std::min(per_pass, n - f0), slot = p % kRing;
-        {   // the lane that finished pass p - kRing enqueues this pass's copies; normally long done
-            std::unique_lock<std::mutex> lk(copy_mutex);
-            copy_cv.wait(lk, [&] { return issued[p] != 0; });
-            if (issued[p] != 1) { l->error = "host-to-device copy of a frame failed"; return JPGENC_ERR_CUDA; }
-        }
-        std::vector<const void*>& ptrs = l->pass_ptrs;
-        ptrs.resize(F);
-        for (uint32_t f = 0; f < F; ++f) ptrs[f] = c->d_rgb_owned + (static_cast<size_t>(slot) * per_pass + f) * fstride;
-        int r = encode_frames_pass(l, F, ptrs.data(), c->ev_band[slot], out ? out + f0 : nullptr, caps ? caps + f0 : nullptr, sizes + f0,
-                                   l->pass_tables);
-        // every kernel of the pass has finished (its last synchronisation is behind K4): the slice is free again.  Also
-        // after a failure: a lane may be waiting for those copies to be enqueued.
-        if (p + kRing < npasses && upload(p + kRing) && !r) { l->error = "host-to-device copy of a frame failed"; r = JPGENC_ERR_CUDA; }
-        return r;
-    });
-    c->d_rgb = c->d_rgb_owned;
-    return rc;
 }
 
 // main.cpp:8-32.  A binary (P6) payload is streamed: the header is parsed from the first bytes, then every band of rows is

@@ -80,6 +80,53 @@ struct DeviceTables {
     uint32_t fast[4][256];
 };
 
+// ---- entropy-stage geometry of a pass (one image = a pass of one frame), device resident -------------------------
+// Produced either by the host (single image: the tables are built on the host, so the sizes are known there) or by
+// finalize_tables_kernel (batches: tables, sizes and offsets never leave the device); K3a/K3b/K4 read it from device
+// memory and take no size from the host.  One block of memory, in this order:
+//   PassHeader | raw_off u64[F] | raw_bytes u64[F] | frame_bits u64[F] | file_base u64[F] | k4_tile0 u32[F+1] | hdr_len u32[F]
+//   | (8-byte aligned) total_bits u64[F] | ff_incl u64[F]
+// The part up to hdr_len is input of K3/K4; total_bits (K3b) and ff_incl (K4) are their results.
+struct PassHeader {
+    unsigned long long raw_total;    // bytes of `raw` in use: every frame's scan padded to 16 bytes, plus slack
+    unsigned long long out_total;    // bytes of the pass's output before byte stuffing: sum of hdr_len + raw_bytes + tail
+    unsigned long long raw_sum;      // sum of raw_bytes (an upper bound of the FF bytes K4 can stuff)
+    uint32_t k4_tiles;               // K4 tiles of all frames
+    uint32_t error;                  // kPass* below; when set, K3a/K3b/K4 return at once
+    uint32_t error_frame;
+    uint32_t nframes;
+    unsigned long long pad[3];
+};
+static_assert(sizeof(PassHeader) == 64, "PassHeader is copied as 64 bytes");
+constexpr uint32_t kPassOk = 0, kPassMissingSymbol = 1, kPassNoSymbols = 2, kPassRawOverflow = 4, kPassOutOverflow = 8;
+
+struct PassMeta {
+    PassHeader* hdr;
+    unsigned long long *raw_off, *raw_bytes, *frame_bits, *file_base;
+    uint32_t *k4_tile0, *hdr_len;
+    unsigned long long *total_bits, *ff_incl;
+};
+__host__ __device__ inline size_t pass_meta_input_bytes(uint32_t F) {
+    return (sizeof(PassHeader) + static_cast<size_t>(F) * 32 + (static_cast<size_t>(F) + 1) * 4 + static_cast<size_t>(F) * 4 + 7) & ~static_cast<size_t>(7);
+}
+__host__ __device__ inline size_t pass_meta_bytes(uint32_t F) { return pass_meta_input_bytes(F) + static_cast<size_t>(F) * 16; }
+__host__ __device__ inline PassMeta pass_meta_view(void* base, uint32_t F) {
+    uint8_t* b = static_cast<uint8_t*>(base);
+    PassMeta m;
+    m.hdr = reinterpret_cast<PassHeader*>(b);
+    m.raw_off = reinterpret_cast<unsigned long long*>(b + sizeof(PassHeader));
+    m.raw_bytes = m.raw_off + F;
+    m.frame_bits = m.raw_bytes + F;
+    m.file_base = m.frame_bits + F;
+    m.k4_tile0 = reinterpret_cast<uint32_t*>(m.file_base + F);
+    m.hdr_len = m.k4_tile0 + F + 1;
+    m.total_bits = reinterpret_cast<unsigned long long*>(b + pass_meta_input_bytes(F));
+    m.ff_incl = m.total_bits + F;
+    return m;
+}
+// a frame's raw (un-stuffed) scan occupies its bytes rounded up to 16, plus slack for the last words K3b touches
+__host__ __device__ inline unsigned long long raw_slot_bytes(unsigned long long nbytes) { return ((nbytes + 15) & ~15ull) + 64; }
+
 }  // namespace jpgenc
 
 namespace jpgenc { class TablePool; class HostPool; }
@@ -89,7 +136,6 @@ struct jpgenc_ctx {
     jpgenc::TablePool* pool = nullptr;    // host worker threads that build the four Huffman tables side by side
     jpgenc::HostPool* host_pool = nullptr;   // parallel table builds of a batch of frames
     bool owns_host_pool = false;             // pipeline lanes share their parent context's pool
-    bool batch_device_tables = false;        // the current batched-frame call builds its tables on the device
     bool parallel_tables = true;          // false inside a batch: there the frames run in parallel instead
     std::vector<jpgenc_ctx*> lanes;       // further pipeline lanes of the batched-frame calls (contexts on the same device with their own
                                           // stream and buffers): while one lane's pass waits for its Huffman tables on the host, the
@@ -121,11 +167,17 @@ struct jpgenc_ctx {
     size_t coef_cap = 0;
     uint32_t* d_refine_list = nullptr;
     size_t refine_cap = 0;
-    uint32_t* d_counters = nullptr;       // [0] refine count, [1] lookback ticket, [2..3] spare
+    uint32_t* d_counters = nullptr;       // kCounterWords words, see kCnt* below
     uint8_t* d_stats = nullptr;           // per frame: hist u32[4][256] + first-occurrence keys u64[4][256]; then a copy of the refine counter
     size_t stats_cap = 0;
-    uint8_t* d_meta = nullptr;            // per-frame entropy geometry: raw_off u64[F] | raw_bytes u64[F] | k4_tile0 u32[F+1]
-    size_t meta_cap = 0;
+    uint8_t* d_meta = nullptr;            // PassMeta block of the frames bound to the context (lives behind d_tables, same allocation)
+    uint32_t entropy_runs = 0;            // K3/K4 passes over the current symbol items (reset by K2)
+    bool file_mode = false;               // K4 writes complete files (header + scan + EOI per frame) instead of bare scans
+    uint8_t* d_hdr_prefix = nullptr;      // SOI .. SOF0 of the frames of a batch (identical for all of them)
+    uint32_t hdr_prefix_len = 0;
+    uint64_t raw_limit = 0, out_limit = 0;   // what finalize_tables_kernel may use of d_raw / d_scan
+    uint64_t batch_raw_per_frame = 0;     // batched calls: raw-scan bytes reserved per frame (1.5 x the largest seen so far; 0 = nothing seen yet)
+    cudaEvent_t ev_done = nullptr;        // batched calls: end of the slot's current pass
     uint32_t* d_items = nullptr;          // K2's symbol stream (blockwalk.cuh), consumed by K3
     size_t items_cap = 0;
     uint32_t* d_tile_cnt = nullptr;             // per K2 tile: number of items in its slab
@@ -137,7 +189,7 @@ struct jpgenc_ctx {
     bool have_items = false;
     uint32_t k2_tiles_done = 0;           // K2 tiles already processed behind the bands of an upload (jpgenc_encode_rgb)
     std::vector<uint32_t> host_hist;      // K2's histograms as last read back, [nframes][4][256]
-    std::vector<uint64_t> frame_bits, frame_raw_off, frame_ff;   // per frame after K3/K4: scan bits, byte offset of its raw scan, stuffed FFs
+    std::vector<uint64_t> frame_bits, frame_out_off, frame_ff;   // per frame after K3/K4: scan bits, byte offset of its stuffed scan in d_scan, stuffed FFs
     bool k2_configured = false;
     void* d_tab_scratch = nullptr;        // device-side table build (tables_device.cu): work space, one slab per table
     size_t tab_scratch_cap = 0;
@@ -145,14 +197,12 @@ struct jpgenc_ctx {
     size_t built_tables_cap = 0;
     jpgenc::DeviceTables* d_tables = nullptr;   // [nframes]
     size_t tables_cap = 0;
-    unsigned long long* d_lookback = nullptr;  // total_bits u64[F] | total_ff u64[F] | one look-back word per K4 tile
+    unsigned long long* d_lookback = nullptr;  // one look-back word per K4 tile
     size_t lookback_cap = 0;
     uint32_t* d_raw = nullptr;            // un-stuffed scan, 32-bit words, bytes in stream order
     size_t raw_cap = 0;
-    uint8_t* d_scan = nullptr;            // stuffed scan
+    uint8_t* d_scan = nullptr;            // K4's output: the stuffed scan, or (file_mode) the complete files of a pass back to back
     size_t scan_cap = 0;
-    unsigned long long* d_stuff_state = nullptr;   // lookback words of K4 + totals
-    size_t stuff_cap = 0;
     void* d_flush = nullptr;              // L2 eviction scratch
     size_t flush_bytes = 0;
     void* h_file_pinned = nullptr;        // two band-sized pinned buffers for streamed inputs (jpgenc_encode_ppm_file)
@@ -181,6 +231,14 @@ struct jpgenc_ctx {
 
 // launchers implemented in the kernel translation units
 namespace jpgenc {
+// words of jpgenc_ctx::d_counters
+constexpr int kCntRefine = 0;      // entries in the refinement list (K1)
+constexpr int kCntK4Ticket = 2;    // K4's tile ticket (zeroed by K3a)
+constexpr int kCntRefined = 3;     // list entries already refined (band-wise encodes)
+constexpr int kCntFinalize = 4;    // finalize_tables_kernel's CTA ticket (resets itself)
+constexpr int kCntK2Done = 5;      // K2 tiles finished (single image: the last one publishes the statistics to the host)
+constexpr int kCntK4Done = 6;      // K4 tiles finished
+constexpr int kCounterWords = 16;
 int launch_forward(jpgenc_ctx* c);
 int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, bool last);
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
@@ -189,7 +247,9 @@ int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qc
 int launch_refine_pending(jpgenc_ctx* c);
 // K2 over the tiles [tile0, tile0 + ntiles) of the bound image(s); `first` also clears the statistics
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
-int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles);
+int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid);
+// batches: built tables + K2's histograms -> DeviceTables and the PassMeta block, all on the device
+int launch_finalize_tables(jpgenc_ctx* c);
 constexpr uint32_t kK4TileBytes = 16384;   // input bytes per K4 tile (entropy.cu static_asserts it)
 size_t table_scratch_bytes();
 int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);

@@ -51,7 +51,8 @@ struct BitWriter {
 };
 
 // Per-frame geometry of the entropy stage.  One image is the batch of one frame; in a batch every frame has its own
-// tables, its own stretch of the raw and of the stuffed scan, and its own totals.
+// tables, its own stretch of the raw scan, its own place in the output and its own totals.  Sizes and offsets are read
+// from device memory (PassMeta, common.cuh): for a batch they are computed on the device and never visit the host.
 struct EntropyParams {
     const uint32_t* items;              // K2's symbol items: range R = the first range_cnt[R] slots of slab R
     const uint32_t* range_cnt;          // [nframes * ranges_per_frame]
@@ -65,15 +66,21 @@ struct EntropyParams {
     unsigned long long* group_bits;     // [nframes * groups_per_frame] bits of the 8 ranges one CTA handles (K3a)
     unsigned long long* super_bits;     // [nframes * supers_per_frame] bits of 256 consecutive groups (K3a, atomics; zeroed before K2)
     uint32_t* raw;                      // all frames' un-stuffed scans; K3a zeroes it, K3b fills it
-    unsigned long long raw_words16;     // size of raw in 16-byte units
-    const unsigned long long* raw_off;  // [nframes] byte offset of the frame's raw scan (multiple of 16); its stuffed scan starts at twice that
+    const PassHeader* hdr;              // raw_total, k4_tiles, error
+    const unsigned long long* raw_off;  // [nframes] byte offset of the frame's raw scan (multiple of 16)
     const unsigned long long* raw_bytes;// [nframes] bytes of the frame's raw scan = ceil(bits / 8), known from the histogram
     const uint32_t* k4_tile0;           // [nframes + 1] first K4 tile of the frame
+    const unsigned long long* file_base;// [nframes] where the frame's output starts, not counting the FFs stuffed before it
+    const uint32_t* hdr_len;            // [nframes] bytes of JFIF header in front of the frame's scan (0: scan only)
     unsigned long long* total_bits;     // [nframes] out: bits of the scan (before padding)
-    unsigned long long* total_ff;       // [nframes] out: FF bytes K4 stuffed
-    unsigned long long* k4_status;      // K4's look-back words, one per tile
-    uint32_t k4_tiles;
-    uint32_t* counters;                 // [1] K4's tile ticket
+    unsigned long long* ff_incl;        // [nframes] out: FF bytes K4 stuffed in frames 0..f of the pass
+    unsigned long long* k4_status;      // K4's look-back words, one per tile (all frames of the pass form ONE sequence)
+    uint32_t* counters;                 // [0] K4's tile ticket
+    // output as complete files (batches): every frame = header + scan + EOI, frames back to back
+    const jpgenc_huff_table* built;     // [nframes * 4] tables as the device build left them (DHT segments); null = scan only
+    const uint8_t* hdr_prefix;          // SOI .. SOF0, identical for every frame of the pass
+    uint32_t hdr_prefix_len;
+    uint32_t tail;                      // 2 (EOI) behind every scan, or 0
 };
 
 // code bits of one item: `nz` ZRL codes first, then the symbol's code with the magnitude bits appended
@@ -123,6 +130,7 @@ constexpr int kPackWarps = kPackThreads / 32;
 __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_constant__ EntropyParams p) {
     __shared__ uint32_t s_tab[1024], s_fast[1024];
     __shared__ uint32_t s_wbits[kPackWarps];
+    if (p.hdr->error) return;                                  // the pass was refused (finalize_tables_kernel): the host re-runs it
     const uint32_t frame = blockIdx.x / p.groups_per_frame, group = blockIdx.x - frame * p.groups_per_frame;
     const DeviceTables* tables = p.tables + frame;
     for (int i = threadIdx.x; i < 1024; i += kPackThreads) {
@@ -132,10 +140,11 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
     {   // housekeeping, spread over the grid
         const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * kPackThreads + threadIdx.x;
         const unsigned long long gsize = static_cast<unsigned long long>(gridDim.x) * kPackThreads;
+        const unsigned long long raw_words16 = p.hdr->raw_total / 16, k4_tiles = p.hdr->k4_tiles;
         uint4* raw16 = reinterpret_cast<uint4*>(p.raw);
-        for (unsigned long long i = gtid; i < p.raw_words16; i += gsize) raw16[i] = make_uint4(0, 0, 0, 0);
-        for (unsigned long long i = gtid; i < p.k4_tiles; i += gsize) p.k4_status[i] = 0ull;
-        if (gtid == 0) p.counters[1] = 0u;
+        for (unsigned long long i = gtid; i < raw_words16; i += gsize) raw16[i] = make_uint4(0, 0, 0, 0);
+        for (unsigned long long i = gtid; i < k4_tiles; i += gsize) p.k4_status[i] = 0ull;
+        if (gtid == 0) p.counters[0] = 0u;
     }
     __syncthreads();
     const uint32_t range = group * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     __shared__ uint32_t s_bits[kPackWarps][kWarpBitWords + 2];
     __shared__ unsigned long long s_part[kPackWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (p.hdr->error) return;
     const uint32_t frame = blockIdx.x / p.groups_per_frame, group = blockIdx.x - frame * p.groups_per_frame;
     const DeviceTables* tables = p.tables + frame;
     for (int i = tid; i < 1024; i += kPackThreads) {
@@ -305,16 +315,49 @@ constexpr int kStuffBytesPerThread = 16;
 constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
 static_assert(kStuffTile == kK4TileBytes, "capi.cu numbers K4 tiles with kK4TileBytes");
 
+// header of frame `frame`'s file at `dst`: the common prefix (SOI .. SOF0), the four DHT segments from the tables as the
+// device build left them, SOS (src/Image.cpp:933-954, JpegSegments.hpp:188-218; host twin: host/jfif_writer.cpp)
+__device__ __forceinline__ void write_file_header(uint8_t* dst, const EntropyParams& p, uint32_t frame, int tid, int nthreads) {
+    for (uint32_t i = tid; i < p.hdr_prefix_len; i += nthreads) dst[i] = p.hdr_prefix[i];
+    uint32_t at = p.hdr_prefix_len;
+    const jpgenc_huff_table* tabs = p.built + static_cast<size_t>(frame) * 4;
+    for (int t = 0; t < 4; ++t) {
+        uint32_t nsym = 0;
+        for (int i = 0; i < 16; ++i) nsym += tabs[t].counts[i];
+        const uint32_t seg = 21 + nsym;                        // marker 2, length 2, table info 1, counts 16, symbols
+        for (uint32_t i = tid; i < seg; i += nthreads) {
+            uint32_t b;
+            if (i == 0) b = 0xFF;
+            else if (i == 1) b = 0xC4;
+            else if (i == 2) b = (19 + nsym) >> 8;
+            else if (i == 3) b = (19 + nsym) & 0xFFu;
+            else if (i == 4) b = ((t & 1) << 4) | (t >> 1);    // (class << 4) | destination: Y_DC 00, Y_AC 10, C_DC 01, C_AC 11
+            else if (i < 21) b = tabs[t].counts[i - 5];
+            else b = tabs[t].symbols[i - 21];
+            dst[at + i] = static_cast<uint8_t>(b);
+        }
+        at += seg;
+    }
+    // SOS: Y -> tables 0/0, Cb and Cr -> 1/1, Ss = 0, Se = 63, Ah/Al = 0
+    if (tid < 14) {
+        // FF DA 00 0C | 03 01 00 02 | 11 03 11 00 | 3F 00
+        const uint32_t w = tid < 4 ? 0x0C00DAFFu : tid < 8 ? 0x02000103u : tid < 12 ? 0x00110311u : 0x0000003Fu;
+        dst[at + tid] = static_cast<uint8_t>(w >> (8 * (tid & 3)));
+    }
+}
+
 __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_constant__ EntropyParams p, uint8_t* __restrict__ scan) {
     __shared__ alignas(16) uint8_t s_out[2 * kStuffTile + 16];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tile, s_frame;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
+    if (p.hdr->error) return;
     if (tid == 0) {
-        // tiles are numbered frame by frame; tickets are handed out in start order, so every tile a look-back waits for
-        // is already running
-        const uint32_t t = atomicAdd(&p.counters[1], 1u);
+        // tiles are numbered frame by frame through the whole pass; tickets are handed out in start order, so every tile
+        // a look-back waits for is already running.  The grid is an upper bound (the exact count is only known on the
+        // device): surplus CTAs leave at once.
+        const uint32_t t = atomicAdd(&p.counters[0], 1u);
         uint32_t lo = 0, hi = p.nframes;                       // frame f owns tiles [k4_tile0[f], k4_tile0[f + 1])
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
@@ -324,11 +367,12 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_const
         s_frame = lo;
     }
     __syncthreads();
-    const uint32_t frame = s_frame, tile0 = p.k4_tile0[frame], tile = s_tile - tile0;
+    if (s_tile >= p.hdr->k4_tiles) return;
+    const uint32_t frame = s_frame, gtile = s_tile, tile = gtile - p.k4_tile0[frame];
     const uint64_t nbytes = p.raw_bytes[frame];
     const uint8_t* __restrict__ raw = reinterpret_cast<const uint8_t*>(p.raw) + p.raw_off[frame];
-    uint8_t* __restrict__ out = scan + 2 * p.raw_off[frame];
-    unsigned long long* status = p.k4_status + tile0;
+    uint8_t* __restrict__ file = scan + p.file_base[frame];       // + the FFs stuffed before this frame: part of s_base
+    uint8_t* __restrict__ out = file + p.hdr_len[frame];
     const uint64_t tile_at = static_cast<uint64_t>(tile) * kStuffTile;
     const uint64_t at = tile_at + static_cast<uint64_t>(tid) * kStuffBytesPerThread;
     uint4 q = make_uint4(0, 0, 0, 0);
@@ -348,7 +392,7 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_const
     uint32_t tile_ff;
     const uint32_t local = block_exclusive_scan(ff, s_scan, &tile_ff);
     if (tid >= kStuffThreads - 32) {                           // the last warp resolves the global position meanwhile
-        const unsigned long long b = lookback_exclusive(status, tile, tile_ff);
+        const unsigned long long b = lookback_exclusive(p.k4_status, gtile, tile_ff);   // FFs of all earlier tiles of the PASS
         if (tid == kStuffThreads - 32) s_base = b;
     }
     // ---- assemble the tile's output at tile-relative positions ----
@@ -394,12 +438,17 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_const
         gw[w] = head ? __funnelshift_r(sw[w], sw[w + 1], 8 * head) : sw[w];
     const uint32_t tail0 = head + 4 * nwords;
     if (tid < len - tail0) g[tail0 + tid] = s_out[tail0 + tid];
-    if (tid == 0 && tile_at + kStuffTile >= nbytes) p.total_ff[frame] = s_base + tile_ff;
+    if (tile_at + kStuffTile >= nbytes) {                      // the frame's last tile
+        if (tid == 0) p.ff_incl[frame] = s_base + tile_ff;
+        if (tid < p.tail) g[len + tid] = tid ? 0xD9 : 0xFF;   // EOI (JpegSegments.hpp:361-377)
+    }
+    if (tile == 0 && p.hdr_len[frame]) write_file_header(file + s_base, p, frame, tid, kStuffThreads);
 }
 
-// Frame geometry (raw offsets, sizes, K4 tile numbering) comes from the caller: it is computed on the host from the
-// histograms and code lengths and already sits in device memory (c->d_meta, layout below).
-int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles) {
+// Frame geometry (raw offsets, sizes, K4 tile numbering, output positions) is read from the PassMeta block in device
+// memory (c->d_meta): written there by the host for one image, by finalize_tables_kernel for a batch.  `k4_grid` is an
+// upper bound of the number of K4 tiles (exact when the host computed the geometry).
+int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
     const uint32_t F = c->nframes;
     EntropyParams p{};
@@ -417,25 +466,37 @@ int launch_entropy(jpgenc_ctx* c, uint64_t raw_bytes_total, uint32_t k4_tiles) {
     p.range_bits = c->d_range_bits;
     p.group_bits = c->d_range_base;                                  // [F * groups] then [F * supers]
     p.super_bits = c->d_range_base + static_cast<size_t>(F) * p.groups_per_frame;
+    if (c->entropy_runs) {
+        // K3a ADDS into the super-group sums, which launch_symbol_stats cleared: a second entropy pass over the same
+        // symbol items (other tables) must start from zero again
+        JPGENC_CUDA(c, cudaMemsetAsync(p.super_bits, 0, static_cast<size_t>(F) * p.supers_per_frame * sizeof(unsigned long long), c->stream));
+    }
+    ++c->entropy_runs;
     p.raw = c->d_raw;
-    p.raw_words16 = raw_bytes_total / 16;
-    // d_meta: raw_off u64[F] | raw_bytes u64[F] | k4_tile0 u32[F + 1]
-    p.raw_off = reinterpret_cast<const unsigned long long*>(c->d_meta);
-    p.raw_bytes = p.raw_off + F;
-    p.k4_tile0 = reinterpret_cast<const uint32_t*>(p.raw_bytes + F);
-    // d_lookback: total_bits u64[F] | total_ff u64[F] | K4 status words
-    p.total_bits = c->d_lookback;
-    p.total_ff = c->d_lookback + F;
-    p.k4_status = c->d_lookback + 2 * static_cast<size_t>(F);
-    p.k4_tiles = k4_tiles;
-    p.counters = c->d_counters + 1;                                  // d_counters[2] is K4's ticket
+    const PassMeta m = pass_meta_view(c->d_meta, F);
+    p.hdr = m.hdr;
+    p.raw_off = m.raw_off;
+    p.raw_bytes = m.raw_bytes;
+    p.k4_tile0 = m.k4_tile0;
+    p.file_base = m.file_base;
+    p.hdr_len = m.hdr_len;
+    p.total_bits = m.total_bits;
+    p.ff_incl = m.ff_incl;
+    p.k4_status = c->d_lookback;
+    p.counters = c->d_counters + kCntK4Ticket;
+    if (c->file_mode) {
+        p.built = c->d_built_tables;
+        p.hdr_prefix = c->d_hdr_prefix;
+        p.hdr_prefix_len = c->hdr_prefix_len;
+        p.tail = 2;
+    }
     const unsigned grid = p.groups_per_frame * F;
     range_bits_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     huffman_pack_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
-    if (k4_tiles) {
-        stuff_kernel<<<k4_tiles, kStuffThreads, 0, c->stream>>>(p, c->d_scan);
+    if (k4_grid) {
+        stuff_kernel<<<k4_grid, kStuffThreads, 0, c->stream>>>(p, c->d_scan);
         JPGENC_CUDA(c, cudaGetLastError());
     }
     c->launches += 3;

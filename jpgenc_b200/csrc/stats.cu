@@ -277,6 +277,7 @@ int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool fir
         JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats + 4096, kStatsBytes, 0xFF, 8192, c->nframes, c->stream));
         // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base; clear it off the critical path
         JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, c->range_base_cap, c->stream));
+        c->entropy_runs = 0;
     }
     if (ntiles == 0) return JPGENC_OK;
     StatsParams p{};

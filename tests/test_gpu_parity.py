@@ -198,9 +198,13 @@ def test_device_generator_matches_host_generator(encoder):
 @pytest.mark.parametrize("w,h", [(3840, 2160), (16384, 16384)])
 def test_full_size_properties(encoder, oracle, w, h):
     """configs 2 and 3.  (a) K1 on random MCU rows == oracle; (b) the device scan == the oracle's entropy coder run on
-    the DEVICE's coefficients (table build, Huffman pack, padding, stuffing at full size); (c) JPEG size == the
-    reference pin of SURVEY.md 8(c); (d) FF count consistent with the stuffed length."""
+    the DEVICE's coefficients (table build, Huffman pack, padding, stuffing at full size); (c) JPEG size AND SHA-256 ==
+    the pins the compiled reference produced for these files: the whole file is byte-identical to the
+    reference's, not only the sampled rows; (d) FF count consistent with the stuffed length."""
+    import hashlib
     pins = {(3840, 2160): 339813, (16384, 16384): 10898928}
+    sha = {(3840, 2160): "6a1f9d77ee80e71282e563eda740758fc48cc0962e2f7acaeba6318855a7435d",
+           (16384, 16384): "6eddc10c5db418a6be99f0d61ba5ee3643c0c8e93994e45131e868f54b2568fd"}
     d = encoder.dev_alloc(w * h * 3)
     try:
         encoder.synth_rgb(d, w, h, 0)
@@ -208,6 +212,7 @@ def test_full_size_properties(encoder, oracle, w, h):
         out = np.empty(pins[(w, h)] + 1024, np.uint8)
         n = encoder.encode_bound(out)
         assert n == pins[(w, h)]
+        assert hashlib.sha256(out[:n].tobytes()).hexdigest() == sha[(w, h)]
         st = encoder.stats()
         coef = encoder.get_coefficients()
         mw, mh = st.mcu_w, st.mcu_h
@@ -427,24 +432,118 @@ def test_device_table_build_on_image_statistics(encoder, name):
 
 
 @pytest.mark.gpu
-def test_frames_with_tables_built_on_the_device(oracle, monkeypatch):
-    """the batched-frame path with JPGENC_DEVICE_TABLES=1 (what hosts with few cores per GPU use): same files"""
-    from jpgenc_b200.capi import Encoder
-    monkeypatch.setenv("JPGENC_DEVICE_TABLES", "1")
+@pytest.mark.parametrize("guess", ["12", "0"])
+def test_frames_packed_output_and_refused_passes(oracle, monkeypatch, guess):
+    """jpgenc_encode_frames_packed: complete files (headers written on the device, stuffed scan, EOI) back to back in ONE
+    buffer, one device-to-host copy per pass.  With JPGENC_RAW_GUESS_PER_BLOCK=0 the first passes reserve too little scan
+    space: finalize_tables_kernel refuses them and the host re-runs their entropy stage with what they asked for."""
+    from jpgenc_b200.capi import Encoder, pinned_empty, pinned_free
+    monkeypatch.setenv("JPGENC_RAW_GUESS_PER_BLOCK", guess)
     monkeypatch.setenv("JPGENC_FRAMES_PER_PASS", "5")
     enc = Encoder(0)
     try:
-        w, h, n = 208, 120, 17
+        w, h, n = 208, 120, 23
         frames = [synth_rgb(w, h, s) if s % 3 else noise_rgb(w, h, s) for s in range(n)]
         want = [oracle.encode_rgb(f) for f in frames]
         host = [np.ascontiguousarray(f) for f in frames]
-        cap = max(len(x) for x in want) + 64
-        outs = [np.zeros(cap, np.uint8) for _ in range(n)]
-        sizes = enc.encode_frames_device([f.ctypes.data for f in host], w, h, [o.ctypes.data for o in outs], [cap] * n, host_frames=True)
-        assert sizes == [len(x) for x in want]
-        assert all(outs[i][: sizes[i]].tobytes() == want[i] for i in range(n))
+        total_want = sum(len(x) for x in want)
+        buf, ptr = pinned_empty(total_want + 64)
+        try:
+            for rep in range(2):
+                buf[:] = 0
+                offs, sizes, total = enc.encode_frames_packed([f.ctypes.data for f in host], w, h, ptr, buf.size, host_frames=True)
+                assert sizes == [len(x) for x in want] and total == total_want
+                assert offs == [sum(sizes[:i]) for i in range(n)]             # frame order, no gaps
+                assert all(buf[offs[i]: offs[i] + sizes[i]].tobytes() == want[i] for i in range(n))
+            # device-resident frames, and sizes/offsets only
+            fb = w * h * 3
+            d = enc.dev_alloc(n * fb + 64)
+            try:
+                for i, f in enumerate(host):
+                    enc.h2d(d + i * fb, f)
+                buf[:] = 0
+                offs2, sizes2, total2 = enc.encode_frames_packed([d + i * fb for i in range(n)], w, h, ptr, buf.size)
+                assert (offs2, sizes2, total2) == (offs, sizes, total)
+                assert buf[:total].tobytes() == b"".join(want)
+                assert enc.encode_frames_packed([d + i * fb for i in range(n)], w, h, None, 0) == (offs, sizes, total)
+                with pytest.raises(Exception):                              # capacity is checked before anything is copied past it
+                    enc.encode_frames_packed([d + i * fb for i in range(n)], w, h, ptr, total - 1)
+                assert enc.encode_rgb(frames[2]) == want[2]
+            finally:
+                enc.dev_free(d)
+        finally:
+            pinned_free(ptr)
     finally:
         enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slots,per_pass", [(None, None), (2, 48)])
+def test_batch_of_1080p_frames_at_its_real_size(oracle, monkeypatch, slots, per_pass):
+    """BASELINE config 4 at its real frame size and a GPU's share of it: 160 frames of 1920x1080 (1080 -> 1088 bottom
+    clamp, a partial fourth strip in every MCU row, K1's prefetch running across frame boundaries, several passes on
+    several slots, device-built tables) -- every file is compared with the oracle's, through the per-frame and the packed
+    output."""
+    from concurrent.futures import ThreadPoolExecutor
+    from jpgenc_b200.capi import Encoder, pinned_empty, pinned_free
+    if slots:
+        monkeypatch.setenv("JPGENC_SLOTS", str(slots))
+        monkeypatch.setenv("JPGENC_FRAMES_PER_PASS", str(per_pass))
+    enc = Encoder(0)
+    w, h, n = 1920, 1080, 160
+    fb = w * h * 3
+    d = enc.dev_alloc(n * fb)
+    host, host_ptr = pinned_empty(n * fb)
+    try:
+        for k in range(n):
+            enc.synth_rgb(d + k * fb, w, h, k)                   # the device generator is checked against synth.py elsewhere
+        enc.synchronize()
+        enc.d2h(host, d)
+        frames = host.reshape(n, h, w, 3)
+        with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+            want = list(ex.map(oracle.encode_rgb, frames))
+        assert np.array_equal(frames[7], synth_rgb(w, h, 7))
+        total_want = sum(len(x) for x in want)
+        out, out_ptr = pinned_empty(total_want + 4096)
+        try:
+            offs, sizes, total = enc.encode_frames_packed([d + k * fb for k in range(n)], w, h, out_ptr, out.size)
+            assert sizes == [len(x) for x in want] and total == total_want
+            bad = [k for k in range(n) if out[offs[k]: offs[k] + sizes[k]].tobytes() != want[k]]
+            assert not bad, f"frames {bad[:8]} differ from the oracle (device-resident, packed)"
+            out[:] = 0
+            offs2, sizes2, _ = enc.encode_frames_packed([host_ptr + k * fb for k in range(n)], w, h, out_ptr, out.size, host_frames=True)
+            assert (offs2, sizes2) == (offs, sizes)
+            assert out[:total].tobytes() == b"".join(want), "host frames, packed"
+            cap = max(sizes) + 64
+            outs = [np.zeros(cap, np.uint8) for _ in range(n)]
+            sizes3 = enc.encode_frames_device([d + k * fb for k in range(n)], w, h, [o.ctypes.data for o in outs], [cap] * n)
+            assert sizes3 == sizes and all(outs[k][: sizes[k]].tobytes() == want[k] for k in range(n)), "per-frame buffers"
+        finally:
+            pinned_free(out_ptr)
+    finally:
+        pinned_free(host_ptr)
+        enc.dev_free(d)
+        enc.close()
+
+
+def test_entropy_stage_can_run_twice_on_a_large_image(encoder, oracle):
+    """K3a accumulates bit counts per 256 groups with atomics into words that K2's launch cleared: a second
+    jpgenc_entropy_encode over the same symbol items (here: the same tables again) must not see them doubled.  4096x2304
+    has 576 K2 tiles = 2304 item ranges = 288 groups, i.e. more than one super-group."""
+    w, h = 4096, 2304
+    rgb = synth_rgb(w, h, 11)
+    want = oracle.encode_rgb(rgb)
+    encoder.upload_rgb(rgb)
+    encoder.color_dct_quant()
+    count, first = encoder.symbol_stats()
+    tabs = encoder.build_huffman(count, first)
+    n1 = encoder.entropy_encode(tabs)
+    scan1 = encoder.download_scan().copy()
+    n2 = encoder.entropy_encode(tabs)
+    scan2 = encoder.download_scan().copy()
+    assert n1 == n2 and np.array_equal(scan1, scan2)
+    hdr = encoder.headers(tabs, w, h, oracle.qy, oracle.qc)
+    assert hdr.tobytes() + scan2.tobytes() + b"\xff\xd9" == want
 
 
 @pytest.mark.gpu
