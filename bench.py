@@ -14,8 +14,14 @@ e2e     = Mpx/s through jpgenc_encode_rgb with pinned HOST buffers: H2D of the p
           timed region
 roofline= the K1 kernel (fused colour+subsample+DCT+quant+zigzag): 6 algorithmic bytes per padded pixel / its
           CUDA-event duration, against the measured copy bandwidth in MEASURED_PEAKS.json
-cpu_baseline / --impl reference = the reference encoder itself (oracle/_ref, built from /root/reference by
-          oracle/build_ref.sh) on the box's host cores, on a bounded sample of the same synthetic.
+extra.batch1080p = BASELINE configs[4] on EVERY N: the 1024 frames of 1920x1080 are partitioned over the ranks (strong
+          scaling, no data-path collective) and timed resident, with the files returned, and end to end from pinned host
+          memory; sizes of all frames and the SHA-256 of frame 0 are checked against tests/golden/batch1080p.json.
+cpu_baseline = the reference encoder itself (oracle/_ref, built from /root/reference by oracle/build_ref.sh) on the box's
+          host cores, OMP_NUM_THREADS=1, on a bounded sample (2048x2048) of the same synthetic.
+--impl reference = the same binary on the headline workload itself: the 16384x16384 file, OMP_NUM_THREADS=1 (north_star:
+          "single-threaded"; its three std::async channel tasks still run), ONE timed encode whatever --steps says (an
+          encode takes ~45 s + ~9 s of PPM loading); the best multi-threaded figure is reported beside it.
 """
 from __future__ import annotations
 
@@ -121,21 +127,32 @@ def _ref_binary():
     return p if os.path.exists(p) else None
 
 
-def _cpu_sample_file():
-    from jpgenc_b200.synth import synth_rgb, write_ppm
-    w, h = CPU_SAMPLE
-    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    path = os.path.join(d, f"jpgenc_bench_{w}x{h}_{os.getpid()}.ppm")
-    write_ppm(path, synth_rgb(w, h, 0))
+def _shm_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+
+
+def _write_synth_ppm(w: int, h: int, seed: int = 0) -> str:
+    """the synthetic image as a P6 file, generated band by band (a 16384x16384 image is 805 MB)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from jpgenc_b200.synth import synth_rgb
+    path = os.path.join(_shm_dir(), f"jpgenc_bench_{w}x{h}_{os.getpid()}.ppm")
+    band = max(16, (8 << 20) // max(1, w * 3))
+    starts = list(range(0, h, band))
+    with open(path, "wb") as f, ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as ex:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        for part in ex.map(lambda y0: synth_rgb(w, h, seed, rows=slice(y0, min(h, y0 + band))).tobytes(), starts):
+            f.write(part)
     return path
 
 
-def _run_reference_once(path: str, omp_threads: int) -> float:
-    """seconds of Image::writeJPEG ("Encoding duration", src/Image.cpp:975) for one encode by the reference CLI"""
+def _run_reference_once(path: str, omp_threads: int):
+    """(seconds of Image::writeJPEG -- "Encoding duration", src/Image.cpp:975 --, seconds of loadPPM) for one run of the
+    reference CLI"""
     env = dict(os.environ, OMP_NUM_THREADS=str(omp_threads))
     out = subprocess.run([_ref_binary(), path, path + ".jpg"], capture_output=True, text=True, env=env, check=True).stdout
     m = re.search(r"Encoding duration: (\d+) ms", out)
-    return int(m.group(1)) / 1e3
+    ld = re.search(r"PPM loading took (\d+) ms", out)
+    return int(m.group(1)) / 1e3, (int(ld.group(1)) / 1e3 if ld else None)
 
 
 def _run_port_once(rgb) -> float:
@@ -146,54 +163,74 @@ def _run_port_once(rgb) -> float:
     return time.perf_counter() - t
 
 
-def cpu_arm(steps: int, warmup: int):
-    """-> (Mpx/s, ms_per_step, dict cpu_baseline)"""
-    w, h = CPU_SAMPLE
+def cpu_arm(w: int, h: int, steps: int, warmup: int, what: str):
+    """The reference on host cores, on a w x h image of the bench's generator (seed 0).
+    -> (Mpx/s at OMP_NUM_THREADS=1, ms per encode, dict cpu_baseline).  north_star asks for the single-threaded encoder;
+    the figure with all host threads is reported beside it (on small hosts the six OpenMP regions cost more than they
+    save: BASELINE.md)."""
     mpx = w * h / 1e6
     nproc = os.cpu_count() or 1
     if _ref_binary():
-        path = _cpu_sample_file()
+        path = _write_synth_ppm(w, h, 0)
         try:
-            # the reference parallelises with OpenMP over block rows + 3 std::async channel tasks; on small hosts the
-            # OpenMP regions cost more than they save (BASELINE.md), so take whichever thread setting is faster
-            cand = {1: _run_reference_once(path, 1)}
-            if nproc > 1:
-                cand[nproc] = _run_reference_once(path, nproc)
-            omp = min(cand, key=cand.get)
-            for _ in range(max(0, warmup - 1)):
-                _run_reference_once(path, omp)
-            times = [_run_reference_once(path, omp) for _ in range(steps)]
+            for _ in range(warmup):
+                _run_reference_once(path, 1)
+            runs = [_run_reference_once(path, 1) for _ in range(steps)]
+            multi = _run_reference_once(path, nproc) if nproc > 1 else None
         finally:
             for p in (path, path + ".jpg"):
                 if os.path.exists(p):
                     os.remove(p)
-        kind, cores = "reference", (3 if omp == 1 else omp)
-        sample = (f"reference CLI (oracle/_ref/jpgEnc_ref) writeJPEG time on a {w}x{h} crop-size synthetic (same generator, seed 0), "
-                  f"OMP_NUM_THREADS={omp} + its 3 std::async channel tasks, {steps} encodes")
+        sec = sum(r[0] for r in runs) / len(runs)
+        load = [r[1] for r in runs if r[1] is not None]
+        cb = {"value": round(mpx / sec, 3), "unit": UNIT, "cores": 1, "kind": "reference",
+              "sample": (f"{what}: reference CLI (oracle/_ref/jpgEnc_ref), Image::writeJPEG time ('Encoding duration') on the {w}x{h} synthetic "
+                         f"(bench generator, seed 0), OMP_NUM_THREADS=1 (its 3 std::async channel tasks still run), {steps} timed encode(s), {warmup} warm-up"),
+              "encode_s": round(sec, 3), "ppm_load_s": round(sum(load) / len(load), 3) if load else None,
+              "host_cores_available": nproc}
+        if multi:
+            cb["all_threads"] = {"value": round(mpx / multi[0], 3), "unit": UNIT, "cores": nproc, "encode_s": round(multi[0], 3),
+                                 "note": f"same file, OMP_NUM_THREADS={nproc}, one encode"}
     else:
         from jpgenc_b200.synth import synth_rgb
         rgb = synth_rgb(w, h, 0)
         for _ in range(max(1, warmup)):
             _run_port_once(rgb)
         times = [_run_port_once(rgb) for _ in range(steps)]
-        kind, cores = "port", 1
-        sample = f"oracle C port (oracle/liboracle.so, oracle/_ref absent) on a {w}x{h} synthetic, single thread, {steps} encodes"
-    sec = sum(times) / len(times)
-    return mpx / sec, sec * 1e3, {"value": round(mpx / sec, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
-                                 "host_cores_available": nproc}
+        sec = sum(times) / len(times)
+        cb = {"value": round(mpx / sec, 3), "unit": UNIT, "cores": 1, "kind": "port",
+              "sample": f"{what}: oracle C port (oracle/liboracle.so; oracle/_ref absent) on the {w}x{h} synthetic, single thread, {steps} encodes",
+              "host_cores_available": nproc}
+    return mpx / sec, sec * 1e3, cb
+
+
+def headline_config(workload: str, world: int) -> dict:
+    """the `config` object of the JSON line -- the same for our arm and for the reference arm"""
+    w, h, desc = WORKLOADS[workload]
+    return {"workload": desc, "width": w, "height": h, "images_per_gpu": 1,
+            "l2": "inputs larger than L2 (805 MB RGB + 805 MB coefficients per step)" if w * h > 50e6 else "inputs smaller than L2",
+            "parallelism": f"independent images x{world}", "subsampling": "4:2:0 mean",
+            "tables": "image-optimal length-limited Huffman per image"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, h, desc = WORKLOADS[args.workload]
-    v, ms, cb = cpu_arm(args.steps, args.warmup)
+    w, h, _ = WORKLOADS[args.workload]
+    if os.environ.get("JPGENC_BENCH_REF_SIZE"):                    # tests use a small image
+        w, h = (int(x) for x in os.environ["JPGENC_BENCH_REF_SIZE"].split("x"))
+    # ONE timed encode of the workload's own image (268 Mpx: ~45 s + ~9 s load at OMP_NUM_THREADS=1), no warm-up run
+    big = w * h > 50e6
+    steps_timed = 1 if big else max(1, min(args.steps, 5))
+    v, ms, cb = cpu_arm(w, h, steps_timed, 0 if big else 1, "the headline workload itself")
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "cpu_sample": f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} synthetic per step (bounded sample of the workload)"},
+            "warmup": args.warmup, "steps_timed": steps_timed, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": headline_config(args.workload, int(os.environ.get("WORLD_SIZE", str(args.gpus)))),
             "cpu_baseline": cb,
+            "note": "same image as our arm (same generator, seed 0, full size); steps_timed encodes were timed -- one encode of this image takes "
+                    "about a minute on one thread, so --steps is not honoured beyond that",
             "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -297,15 +334,32 @@ def run_ours(args):
         except Exception:
             pass
 
+    # the other stages against the same peak, from the bytes they must move: K2 reads the coefficients
+    # (128 B per block) and writes one 4-byte item per symbol (~4.2 per block on this image); K3a/K3b read the items twice and
+    # write the raw scan, K4 reads and writes the scan
+    n_blocks = int(stats.n_blocks)
+    st_k2, st_k34 = sum(st_ms) / len(st_ms), sum(en_ms) / len(en_ms)
+    scan_b = int(jpeg_bytes)
+    k2_bytes = n_blocks * 128
+    roofline["other_kernels"] = {
+        "k2_symbol_stats": {"algorithmic_bytes": k2_bytes, "ms": round(st_k2, 4), "achieved": round(k2_bytes / (st_k2 / 1e3) / 1e9, 1),
+                            "frac": round(k2_bytes / (st_k2 / 1e3) / 1e9 / peak, 4), "note": "coefficient read only; its item writes (4 B per symbol) not counted"},
+        "k3_k4_entropy": {"algorithmic_bytes": 3 * scan_b, "ms": round(st_k34, 4), "achieved": round(3 * scan_b / (st_k34 / 1e3) / 1e9, 1),
+                          "frac": round(3 * scan_b / (st_k34 / 1e3) / 1e9 / peak, 4),
+                          "note": "raw scan written once, read once, stuffed scan written once; the item reads (~10x the scan) not counted: latency- and issue-bound stage, not HBM-bound"},
+        "whole_encode": {"algorithmic_bytes": npx * 3 + scan_b, "ms": round(ms_step, 4), "achieved": round((npx * 3 + scan_b) / (ms_step / 1e3) / 1e9, 1),
+                         "frac": round((npx * 3 + scan_b) / (ms_step / 1e3) / 1e9 / peak, 4),
+                         "two_pass_floor_bytes": 9 * padded_px, "frac_of_two_pass_floor": round(9 * padded_px / (ms_step / 1e3) / 1e9 / peak, 4)},
+    }
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic",
-        "config": {"workload": desc, "width": w, "height": h, "images_per_gpu": 1, "l2": "inputs larger than L2 (805 MB RGB + 805 MB coefficients per step)"
-                   if npx > 50e6 else "inputs smaller than L2", "parallelism": f"independent images x{world}",
-                   "subsampling": "4:2:0 mean", "tables": "image-optimal length-limited Huffman (host build per image)"},
+        "config": headline_config(args.workload, world),
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": npx * 3, "d2h_bytes_per_step": int(n),
-                "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps, "ms_h2d": round(st_e2e.ms_h2d, 3), "ms_d2h": round(st_e2e.ms_d2h, 3)},
+                "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps, "ms_h2d": round(st_e2e.ms_h2d, 3), "ms_d2h": round(st_e2e.ms_d2h, 3),
+                "h2d_gbps_per_gpu": round(npx * 3 / max(st_e2e.ms_h2d, 1e-6) / 1e6, 2),
+                "ms_not_h2d": round(ms_e2e - st_e2e.ms_h2d, 3)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -318,12 +372,24 @@ def run_ours(args):
     pinned_free(out_ptr)
     enc.dev_free(d_rgb)
 
+    # BASELINE configs[4] on every N (all ranks take part: strong scaling over the ranks); the other single-GPU
+    # configurations and the CPU baseline on rank 0 at N = 1 only
+    extra = {}
+    if args.workload == "image16k" and not os.environ.get("JPGENC_BENCH_NO_BATCH"):
+        try:
+            extra["batch1080p"] = batch_section(enc, rank, world, barrier, max_over_ranks, reps=3)
+        except AssertionError:
+            raise
+        except Exception as ex:
+            extra["batch1080p"] = {"error": repr(ex)}
     if rank == 0 and world == 1:
         try:
-            line["extra"] = extra_workloads(enc, args, peak)
+            extra.update(extra_workloads(enc, args, peak))
         except Exception as ex:          # extras never invalidate the headline line
-            line["extra"] = {"error": repr(ex)}
-        _, _, line["cpu_baseline"] = cpu_arm(steps=max(3, min(args.steps, 10)), warmup=1)
+            extra["error"] = repr(ex)
+        _, _, line["cpu_baseline"] = cpu_arm(CPU_SAMPLE[0], CPU_SAMPLE[1], steps=3, warmup=1,
+                                             what="bounded sample of the workload (the full 16384x16384 image is what --impl reference times)")
+    line["extra"] = extra
     enc.close()
     if dist is not None:
         dist.barrier()
@@ -332,33 +398,93 @@ def run_ours(args):
         emit(line)
 
 
-def batch_frames_per_s(local, frames_ptrs, w, h, workers, device_frames, out_ptrs=None, caps=None, reps=1, enc=None):
-    """frames/s of one synchronous batch call on this rank, host wall clock around it.  Equally sized frames go through
-    every kernel together (jpgenc_encode_frames / jpgenc_encode_frames_device on one context); `workers` is reported for
-    the host threads that build the Huffman tables."""
-    from jpgenc_b200.capi import Encoder
-    own = enc is None
-    if own:
-        enc = Encoder(local)
+def batch_golden():
     try:
-        # warm-up with the full batch: the context sizes its buffers for the largest pass it has seen
-        enc.encode_frames_device(frames_ptrs, w, h, out_ptrs, caps, host_frames=not device_frames)
-        t = time.perf_counter()
+        with open(os.path.join(ROOT, "tests", "golden", "batch1080p.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def batch_section(enc, rank, world, barrier, max_over_ranks, reps=3, frames_total=BATCH_FRAMES):
+    """BASELINE configs[4]: `frames_total` synthetic 1920x1080 frames (frame k = seed k), frame k encoded by the rank that
+    owns it (contiguous shards, no data-path collective) -> strong scaling over the ranks.  Every figure is the host wall
+    clock around ONE synchronous library call on this rank's shard, between barriers, max over ranks, mean of `reps`.
+      resident        frames in HBM, files left in HBM (sizes and offsets reported)
+      files_returned  frames in HBM, complete files back in ONE pinned host buffer (one device-to-host copy per pass)
+      e2e             frames in pinned host memory, files back in pinned host memory (H2D + D2H inside)"""
+    import hashlib
+    import numpy as np
+    from jpgenc_b200.capi import pinned_empty, pinned_free
+    from jpgenc_b200.sharding import frames_for_rank
+    w, h, _ = WORKLOADS["batch1080p"]
+    mine = frames_for_rank(frames_total, rank, world)
+    nf, fbytes = len(mine), w * h * 3
+    d_all = enc.dev_alloc(max(1, nf) * fbytes)
+    for i, k in enumerate(mine):
+        enc.synth_rgb(d_all + i * fbytes, w, h, k)
+    enc.synchronize()
+    dev_ptrs = [d_all + i * fbytes for i in range(nf)]
+
+    def timed(fn):
+        fn()                                           # warm-up with the full shard: buffers are sized by the largest pass seen
+        tot = 0.0
         for _ in range(reps):
-            sizes = enc.encode_frames_device(frames_ptrs, w, h, out_ptrs, caps, host_frames=not device_frames)
-        dt = (time.perf_counter() - t) / reps
-    finally:
-        if own:
-            enc.close()
-    return len(frames_ptrs) / dt, dt, sizes
+            barrier()
+            t = time.perf_counter()
+            res = fn()
+            tot += max_over_ranks(time.perf_counter() - t)
+        barrier()
+        return tot / reps, res
+
+    launches0 = enc.launch_count()
+    dt_res, (offs, sizes, total) = timed(lambda: enc.encode_frames_packed(dev_ptrs, w, h, None, 0))
+    launches = (enc.launch_count() - launches0) // (reps + 1)
+    out, out_ptr = pinned_empty(total + 4096)
+    dt_files, res2 = timed(lambda: enc.encode_frames_packed(dev_ptrs, w, h, out_ptr, out.size))
+    host, host_ptr = pinned_empty(max(1, nf) * fbytes)
+    enc.d2h(host, d_all)
+    out[:] = 0
+    dt_e2e, res3 = timed(lambda: enc.encode_frames_packed([host_ptr + i * fbytes for i in range(nf)], w, h, out_ptr, out.size, host_frames=True))
+    # ---- parity, outside the timed regions: golden sizes of this rank's frames, SHA-256 of frame 0 (rank 0), JFIF framing
+    gold = batch_golden()
+    parity = {"checked": False}
+    ok = res2 == (offs, sizes, total) and res3 == (offs, sizes, total)
+    if gold and gold.get("frames", 0) >= frames_total:
+        ok = ok and sizes == [gold["sizes"][k] for k in mine]
+        parity = {"checked": True, "sizes_equal_golden": sizes == [gold["sizes"][k] for k in mine], "frames_checked": nf}
+        if rank == 0 and nf:
+            sha0 = hashlib.sha256(out[offs[0]: offs[0] + sizes[0]].tobytes()).hexdigest()
+            parity["frame0_sha256_equals_reference_pin"] = sha0 == gold["sha256_frame0"]
+            ok = ok and sha0 == gold["sha256_frame0"]
+            if world == 1 and frames_total == gold["frames"]:
+                hs = "".join(hashlib.sha256(out[offs[k]: offs[k] + sizes[k]].tobytes()).hexdigest() for k in range(nf))
+                parity["all_files_sha256_equal_golden"] = hashlib.sha256(hs.encode()).hexdigest() == gold["sha256_of_frame_sha256s"]
+                ok = ok and parity["all_files_sha256_equal_golden"]
+    for k in range(nf):
+        ok = ok and out[offs[k]] == 0xFF and out[offs[k] + 1] == 0xD8 and out[offs[k] + sizes[k] - 1] == 0xD9
+    parity["ok"] = bool(ok)
+    assert ok, f"batch output differs from the golden/reference data: {parity}"
+    pinned_free(host_ptr); pinned_free(out_ptr); enc.dev_free(d_all)
+    mpx = frames_total * w * h / 1e6
+    sec = {"resident": dt_res, "files_returned": dt_files, "e2e": dt_e2e}
+    res = {"frames": frames_total, "frames_per_gpu": nf, "width": w, "height": h, "n_gpus": world, "scaling": "strong",
+           "mode": "passes of ~32 frames, each one asynchronous chain K1 > K2 > device table build > device sizes/offsets > K3 > K4 (files "
+                   "assembled on the device), rotating over 4 streams driven by one host thread; one host synchronisation per pass",
+           "timing": f"host wall clock around one synchronous call per rank, barrier before, max over ranks, mean of {reps}",
+           "gpu_launches_per_call": int(launches), "jpeg_bytes_total_this_rank": int(total), "parity": parity}
+    for k, dt in sec.items():
+        res[k] = {"frames_per_s": round(frames_total / dt, 1), "mpx_per_s": round(mpx / dt, 1), "ms": round(dt * 1e3, 3)}
+    res["e2e"]["h2d_bytes_per_gpu"] = nf * fbytes
+    res["e2e"]["h2d_gbps_per_gpu"] = round(nf * fbytes / dt_e2e / 1e9, 2)
+    return res
 
 
 def run_batch(args):
-    """BASELINE config 4: 1024 frames of 1920x1080, frame k (seed k) encoded by rank owner_of(k); no collective on the
-    data path.  value = frames resident in HBM; e2e = frames in pinned host memory, files back in pinned host memory."""
+    """--workload batch1080p: BASELINE configs[4] as the headline line (the default workload carries the same measurement in
+    extra.batch1080p)."""
     import torch
-    from jpgenc_b200.capi import Encoder, pinned_empty, pinned_free
-    from jpgenc_b200.sharding import frames_for_rank
+    from jpgenc_b200.capi import Encoder
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
@@ -379,53 +505,23 @@ def run_batch(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    w, h, desc = WORKLOADS["batch1080p"]
-    mine = frames_for_rank(BATCH_FRAMES, rank, world)
-    nf, fbytes = len(mine), w * h * 3
     enc = Encoder(local)
-    d_all = enc.dev_alloc(nf * fbytes)
-    for i, k in enumerate(mine):
-        enc.synth_rgb(d_all + i * fbytes, w, h, k)
-    enc.synchronize()
-    dev_ptrs = [d_all + i * fbytes for i in range(nf)]
-    workers = max(2, (os.cpu_count() or 1) // max(1, torch.cuda.device_count()))      # the library's default share of the host per GPU process
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
-    launches0 = enc.launch_count()
-    reps_dev = max(3, args.steps // 20)
-    fps_dev, dt_dev, sizes = batch_frames_per_s(local, dev_ptrs, w, h, workers, True, reps=reps_dev, enc=enc)
-    launches = enc.launch_count() - launches0
-    barrier()
+    reps = max(3, args.steps // 20)
+    b = batch_section(enc, rank, world, barrier, max_over_ranks, reps=reps)
     clocks = sampler.summary()
-    dt_dev = max_over_ranks(dt_dev)
-    # end to end: the same frames in pinned host memory, complete files written to pinned host memory
-    host, host_ptr = pinned_empty(nf * fbytes)
-    enc.d2h(host, d_all)
-    cap = max(sizes) + 4096
-    out, out_ptr = pinned_empty(nf * cap)
-    barrier()
-    fps_e2e, dt_e2e, sizes2 = batch_frames_per_s(local, [host_ptr + i * fbytes for i in range(nf)], w, h, workers, False,
-                                                 [out_ptr + i * cap for i in range(nf)], [cap] * nf, enc=enc)
-    barrier()
-    dt_e2e = max_over_ranks(dt_e2e)
-    assert sizes2 == sizes and out[0] == 0xFF and out[1] == 0xD8
-    mpx = BATCH_FRAMES * w * h / 1e6
-    line = {"metric": METRIC, "value": round(mpx / dt_dev, 1), "unit": UNIT, "n_gpus": world, "steps": reps_dev, "warmup": 1,
-            "ms_per_step": round(dt_dev * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    w, h, desc = WORKLOADS["batch1080p"]
+    line = {"metric": METRIC, "value": b["resident"]["mpx_per_s"], "unit": UNIT, "n_gpus": world, "steps": reps, "warmup": 1,
+            "ms_per_step": b["resident"]["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": desc, "frames": BATCH_FRAMES, "frames_per_gpu": nf, "width": w, "height": h,
-                       "mode": "all frames of a pass through every kernel together, passes on three pipeline lanes (jpgenc_encode_frames[_device])",
-                       "host_threads_for_tables": workers,
-                       "tables_built_on": ("device" if (os.environ.get("JPGENC_DEVICE_TABLES", "") or ("1" if workers < 8 and nf >= 256 else "0")) != "0" else "host"),
-                       "timing": "host wall clock around the synchronous batch call, max over ranks",
-                       "l2": "inputs larger than L2 (%.1f GB of frames per GPU)" % (nf * fbytes / 1e9)},
-            "e2e": {"value": round(mpx / dt_e2e, 1), "unit": UNIT, "h2d_bytes_per_step": nf * fbytes, "d2h_bytes_per_step": int(sum(sizes)),
-                    "ms_per_step": round(dt_e2e * 1e3, 3), "frames_per_s": round(BATCH_FRAMES / dt_e2e, 1)},
-            "frames_per_s": round(BATCH_FRAMES / dt_dev, 1), "gpu_launches": int(launches), "gpu_launches_note": "6 kernels per pass (a sixth of the rank's frames each), passes are handed to three pipeline lanes; includes the warm-up call",
-            "clocks": clocks,
-            "jpeg_bytes_per_frame": int(sum(sizes) / max(nf, 1))}
-    pinned_free(host_ptr); pinned_free(out_ptr); enc.dev_free(d_all); enc.close()
+            "config": {"workload": desc, "frames": BATCH_FRAMES, "frames_per_gpu": b["frames_per_gpu"], "width": w, "height": h,
+                       "mode": b["mode"], "timing": b["timing"], "l2": "inputs larger than L2 (%.1f GB of frames per GPU)" % (b["frames_per_gpu"] * w * h * 3 / 1e9)},
+            "e2e": {"value": b["e2e"]["mpx_per_s"], "unit": UNIT, "h2d_bytes_per_step": b["e2e"]["h2d_bytes_per_gpu"],
+                    "d2h_bytes_per_step": b["jpeg_bytes_total_this_rank"], "ms_per_step": b["e2e"]["ms"], "frames_per_s": b["e2e"]["frames_per_s"]},
+            "frames_per_s": b["resident"]["frames_per_s"], "files_returned": b["files_returned"],
+            "gpu_launches": b["gpu_launches_per_call"] * reps, "clocks": clocks, "parity": b["parity"]}
+    enc.close()
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
     if rank == 0:
@@ -477,29 +573,6 @@ def extra_workloads(enc, args, peak):
         out["frame4k"] = {"ms_per_frame": round(tot / reps, 4), "mpx_per_s": round(w * h / 1e6 / (tot / reps / 1e3), 1),
                           "k1_ms": round(s.ms_k1, 4), "l2": "flushed between iterations (256 MB write)"}
         enc.dev_free(d)
-    # configs[4] in small: 256 frames of 1920x1080 through the batched-frame calls
-    try:
-        from jpgenc_b200.capi import pinned_empty, pinned_free
-        w, h, nf = 1920, 1080, 256
-        fbytes = w * h * 3
-        d_all = enc.dev_alloc(nf * fbytes)
-        for k in range(nf):
-            enc.synth_rgb(d_all + k * fbytes, w, h, k)
-        enc.synchronize()
-        fps_dev, _, sizes = batch_frames_per_s(enc.device, [d_all + k * fbytes for k in range(nf)], w, h, 8, True, reps=2, enc=enc)
-        host, host_ptr = pinned_empty(nf * fbytes)
-        enc.d2h(host, d_all)
-        cap = max(sizes) + 4096
-        outb, out_ptr = pinned_empty(nf * cap)
-        fps_e2e, _, _ = batch_frames_per_s(enc.device, [host_ptr + k * fbytes for k in range(nf)], w, h, 8, False,
-                                           [out_ptr + k * cap for k in range(nf)], [cap] * nf, reps=2, enc=enc)
-        pinned_free(host_ptr); pinned_free(out_ptr); enc.dev_free(d_all)
-        out["batch1080p_256"] = {"frames": nf, "mode": "frames batched through the kernels in passes on pipeline lanes (jpgenc_encode_frames[_device])", "device_resident_frames_per_s": round(fps_dev, 1),
-                                 "device_resident_mpx_per_s": round(fps_dev * w * h / 1e6, 1),
-                                 "e2e_frames_per_s": round(fps_e2e, 1), "e2e_mpx_per_s": round(fps_e2e * w * h / 1e6, 1),
-                                 "timing": "host wall clock around the synchronous batch call"}
-    except Exception as ex:
-        out["batch1080p_256"] = {"error": repr(ex)}
     return out
 
 

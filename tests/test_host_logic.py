@@ -180,7 +180,7 @@ def test_bench_reference_arm_prints_one_json_line(tmp_path):
     import json
     import subprocess
     import sys
-    env = dict(os.environ, JPGENC_BENCH_CPU_SAMPLE="512x512")
+    env = dict(os.environ, JPGENC_BENCH_REF_SIZE="512x512")        # the real arm encodes the 16384x16384 file itself (~1 min)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr[-2000:]
@@ -190,4 +190,8 @@ def test_bench_reference_arm_prints_one_json_line(tmp_path):
     assert d["impl"] == "reference" and d["metric"] == "encode_throughput" and d["unit"] == "Mpx/s" and d["value"] > 0
     assert d["higher_is_better"] is True and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["cpu_baseline"]["cores"] == 1
+    # same `config` object as our arm prints for this workload
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.headline_config("image16k", 1)
