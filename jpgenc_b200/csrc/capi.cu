@@ -240,6 +240,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->ev_wide) cudaEventDestroy(c->ev_wide);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -178,6 +178,9 @@ struct jpgenc_ctx {
     uint64_t raw_limit = 0, out_limit = 0;   // what finalize_tables_kernel may use of d_raw / d_scan
     uint64_t batch_raw_per_frame = 0;     // batched calls: raw-scan bytes reserved per frame (1.5 x the largest seen so far; 0 = nothing seen yet)
     cudaEvent_t ev_done = nullptr;        // batched calls: end of the slot's current pass
+    cudaEvent_t ev_wide = nullptr;        // ... its K1/refinement/K2 are through (the next pass's wide kernels wait for it)
+    uint8_t hdr_prefix_host[256] = {};    // what d_hdr_prefix holds
+    uint32_t debug_tables_valid = 0;      // JPGENC_DEBUG_SKIP_TABLES (development): tables in d_built_tables from an earlier call
     uint32_t* d_items = nullptr;          // K2's symbol stream (blockwalk.cuh), consumed by K3
     size_t items_cap = 0;
     uint32_t* d_tile_cnt = nullptr;             // per K2 tile: number of items in its slab

@@ -79,10 +79,14 @@ int prepare_slot(jpgenc_ctx* root, jpgenc_ctx* l, const Job& job, const uint8_t*
     int rc = set_geometry(l, job.w, job.h, job.maxval);
     if (rc) return rc;
     if (!l->d_hdr_prefix) JPGENC_CUDA(l, cudaMalloc(reinterpret_cast<void**>(&l->d_hdr_prefix), 256));
-    JPGENC_CUDA(l, cudaMemcpyAsync(l->d_hdr_prefix, prefix, prefix_len, cudaMemcpyHostToDevice, l->stream));
-    JPGENC_CUDA(l, cudaStreamSynchronize(l->stream));          // `prefix` lives on the caller's stack
-    l->hdr_prefix_len = prefix_len;
+    if (l->hdr_prefix_len != prefix_len || std::memcmp(l->hdr_prefix_host, prefix, prefix_len) != 0) {   // new size or quantisers
+        JPGENC_CUDA(l, cudaMemcpyAsync(l->d_hdr_prefix, prefix, prefix_len, cudaMemcpyHostToDevice, l->stream));
+        JPGENC_CUDA(l, cudaStreamSynchronize(l->stream));      // `prefix` lives on the caller's stack
+        std::memcpy(l->hdr_prefix_host, prefix, prefix_len);
+        l->hdr_prefix_len = prefix_len;
+    }
     if (!l->ev_done) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming));
+    if (!l->ev_wide) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_wide, cudaEventDisableTiming));
     return JPGENC_OK;
 }
 
@@ -103,7 +107,8 @@ int enqueue_entropy(jpgenc_ctx* l, Pass& ps) {
 }
 
 // the whole chain of one pass on slot `l`; `ready` (optional): event after which the pixels are valid
-int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* dev_frames, cudaEvent_t ready) {
+// `after` (optional): the previous pass's "wide kernels done" event (see run_passes)
+int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* dev_frames, cudaEvent_t ready, cudaEvent_t after) {
     const uint32_t F = ps.F;
     int rc;
     l->nframes = F;
@@ -128,16 +133,23 @@ int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* d
     std::memcpy(l->h_pinned, dev_frames, F * sizeof(void*));
     JPGENC_CUDA(l, cudaMemcpyAsync(l->d_frame_ptrs, l->h_pinned, F * sizeof(void*), cudaMemcpyHostToDevice, l->stream));
     if (ready) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, ready, 0));
+    if (after) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, after, 0));
     if ((rc = launch_forward_rows(l, 0, l->mcu_h, true, true))) return rc;                       // K1 + exact refinement
     l->have_coef = true;
     const size_t nblocks = static_cast<size_t>(l->mcu_w) * l->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     if ((rc = launch_symbol_stats(l, 0, static_cast<uint32_t>(tiles * F), true))) return rc;     // K2
     l->have_items = true;
+    JPGENC_CUDA(l, cudaEventRecord(l->ev_wide, l->stream));
     const uint32_t nt = 4 * F;
     if ((rc = ensure(l, reinterpret_cast<uint8_t**>(&l->d_tab_scratch), &l->tab_scratch_cap, nt * table_scratch_bytes()))) return rc;
     if ((rc = ensure(l, &l->d_built_tables, &l->built_tables_cap, nt * (sizeof(jpgenc_huff_table) + sizeof(uint32_t))))) return rc;
-    if ((rc = launch_build_tables(l, l->d_stats, static_cast<uint32_t>(kStatsBytes), nt, l->d_tab_scratch, l->d_built_tables,
-                                  reinterpret_cast<uint32_t*>(l->d_built_tables + nt)))) return rc;
+    // (JPGENC_DEBUG_SKIP_TABLES=1, development only: keep the tables of the previous call -- valid output only when the same
+    // frames are encoded again; shows what the pipeline would do with a free table build)
+    static const bool skip_tables = env_u32("JPGENC_DEBUG_SKIP_TABLES", 0) != 0;
+    if (!(skip_tables && l->debug_tables_valid >= nt))
+        if ((rc = launch_build_tables(l, l->d_stats, static_cast<uint32_t>(kStatsBytes), nt, l->d_tab_scratch, l->d_built_tables,
+                                      reinterpret_cast<uint32_t*>(l->d_built_tables + nt)))) return rc;
+    l->debug_tables_valid = nt;
     // how much raw scan / output the pass may use: 1.5 x the largest frame the batch has produced so far
     // (root->batch_raw_per_frame), before the first pass has finished a guess of 12 bytes per block; a pass that needs more
     // is refused by finalize_tables_kernel and its entropy stage re-run with what it asked for (finish_pass)
@@ -230,6 +242,7 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
         if ((rc = prepare_slot(c, slot[k], job, hdr, prefix_len))) return k ? fail(c, rc, jpgenc_last_error(slot[k])) : rc;
     }
     std::vector<Pass> pass(npasses);
+    const bool stagger = env_u32("JPGENC_STAGGER", 1) != 0;
     rc = JPGENC_OK;
     jpgenc_ctx* failed = nullptr;
     const double t0 = trace_on() ? now_us() : 0;
@@ -249,7 +262,11 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
             const void* const* ptrs = nullptr;
             cudaEvent_t ready = nullptr;
             rc = frames_of(p, l, &ptrs, &ready);
-            if (rc == JPGENC_OK) rc = enqueue_pass(c, l, pass[p], ptrs, ready);
+            // Staggering: the wide kernels of pass p (K1, refinement, K2) start when those of pass p - 1 are through.  Left
+            // alone, the streams run the same stage of all passes side by side, every table build then starts at the same
+            // (late) moment and nothing wide is left to run beside it.
+            cudaEvent_t after = (stagger && p > 0 && nslots > 1) ? slot[(p - 1) % nslots]->ev_wide : nullptr;
+            if (rc == JPGENC_OK) rc = enqueue_pass(c, l, pass[p], ptrs, ready, after);
             if (rc) { failed = l; break; }
         }
     }
