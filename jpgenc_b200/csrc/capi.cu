@@ -241,6 +241,8 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->ev_wide) cudaEventDestroy(c->ev_wide);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->out_stream) { cudaStreamSynchronize(c->out_stream); cudaStreamDestroy(c->out_stream); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -179,6 +179,9 @@ struct jpgenc_ctx {
     uint64_t batch_raw_per_frame = 0;     // batched calls: raw-scan bytes reserved per frame (1.5 x the largest seen so far; 0 = nothing seen yet)
     cudaEvent_t ev_done = nullptr;        // batched calls: end of the slot's current pass
     cudaEvent_t ev_wide = nullptr;        // ... its K1/refinement/K2 are through (the next pass's wide kernels wait for it)
+    cudaEvent_t ev_copied = nullptr;      // ... its files have left d_scan (recorded on out_stream)
+    cudaStream_t out_stream = nullptr;    // device-to-host copies of finished passes, beside the slot's kernels
+    bool copy_pending = false;
     uint8_t hdr_prefix_host[256] = {};    // what d_hdr_prefix holds
     uint32_t debug_tables_valid = 0;      // JPGENC_DEBUG_SKIP_TABLES (development): tables in d_built_tables from an earlier call
     uint32_t* d_items = nullptr;          // K2's symbol stream (blockwalk.cuh), consumed by K3

@@ -59,14 +59,15 @@ uint32_t frames_per_pass_cap(const jpgenc_ctx* c) {
     return static_cast<uint32_t>(std::min<size_t>(per_pass, 1024));
 }
 
-// frames per pass: large enough that every kernel fills the GPU for a few waves and the ~12 enqueues + 1 wait per pass
-// are noise, small enough that a batch gives every slot several passes (the table build of one pass hides behind the
-// wide kernels of the next ones; the last pass's build is the tail nobody hides)
+// Frames per pass.  A pass costs ~0.1 ms of launch gaps and one host wait whatever its size, and its table build (~0.35 ms,
+// independent of the number of frames) only hides behind OTHER passes' wide kernels: passes should be large, but a batch
+// should still give every slot about two of them.  Measured on 1920x1080 frames, 4 slots (frames per pass -> ms per call):
+// 1024 frames: 32 -> 9.0, 64 -> 7.6, 128 -> 6.9;  128 frames: 16 -> 1.71, 32 -> 1.26, 64 -> 1.24.
 uint32_t pass_frames(const jpgenc_ctx* c, uint32_t n, uint32_t slots) {
     const size_t px = static_cast<size_t>(c->mcu_w) * c->mcu_h * 256;
-    uint32_t per = static_cast<uint32_t>(std::max<size_t>(1, (64u << 20) / px));          // ~64 Mpx: 32 frames of 1920x1080
-    per = std::min(per, std::max(1u, (n + 2 * slots - 1) / (2 * slots)));               // at least two passes per slot ...
-    per = std::max(per, static_cast<uint32_t>(std::max<size_t>(1, (16u << 20) / px)));   // ... but no pass under ~16 Mpx
+    const uint32_t lo = static_cast<uint32_t>(std::max<size_t>(1, (64u << 20) / px));     // ~64 Mpx: 32 frames of 1920x1080
+    const uint32_t hi = static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / px));    // ~256 Mpx: 128 such frames
+    uint32_t per = std::min(hi, std::max(lo, (n + 2 * slots - 1) / (2 * slots)));
     per = env_u32("JPGENC_FRAMES_PER_PASS", per);
     return std::max(1u, std::min({per, frames_per_pass_cap(c), n}));
 }
@@ -87,6 +88,9 @@ int prepare_slot(jpgenc_ctx* root, jpgenc_ctx* l, const Job& job, const uint8_t*
     }
     if (!l->ev_done) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming));
     if (!l->ev_wide) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_wide, cudaEventDisableTiming));
+    if (!l->ev_copied) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_copied, cudaEventDisableTiming));
+    if (!l->out_stream) JPGENC_CUDA(l, cudaStreamCreateWithFlags(&l->out_stream, cudaStreamNonBlocking));
+    l->copy_pending = false;
     return JPGENC_OK;
 }
 
@@ -97,6 +101,10 @@ int enqueue_entropy(jpgenc_ctx* l, Pass& ps) {
     const uint64_t k4_grid = l->raw_limit / kK4TileBytes + F;
     if ((rc = ensure_entropy_buffers(l, l->raw_limit, l->out_limit, k4_grid))) return rc;
     ps.k4_grid = static_cast<uint32_t>(k4_grid);
+    if (l->copy_pending) {                                     // the previous pass's files are still leaving d_scan
+        JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, l->ev_copied, 0));
+        l->copy_pending = false;
+    }
     if ((rc = launch_finalize_tables(l))) return rc;
     if ((rc = launch_entropy(l, ps.k4_grid))) return rc;
     uint8_t* h = static_cast<uint8_t*>(l->h_pinned) + stage_meta_off(F);
@@ -194,13 +202,17 @@ int finish_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, Job& job) {
         // later passes reserve 1.5 x the largest frame seen so far
         root->batch_raw_per_frame = std::max<uint64_t>(root->batch_raw_per_frame, max_raw + max_raw / 2 + 4096);
         const uint64_t total = hd.out_total + m.ff_incl[F - 1];
+        // The files go home on the slot's OUTPUT stream (behind ev_done, i.e. behind K4), so that the slot's next pass can
+        // start its K1/K2/table build meanwhile; only its K3/K4, which overwrite d_scan, wait for the copy (enqueue_entropy).
         uint64_t base = 0;
+        const bool copies = job.packed || job.out_ptrs;
+        if (copies) JPGENC_CUDA(l, cudaStreamWaitEvent(l->out_stream, l->ev_done, 0));
         if (job.packed_mode) {                                       // passes finish in order: the files end up in frame order
             base = job.packed_at;
             job.packed_at += total;
             if (job.packed) {
                 if (job.packed_at > job.packed_cap) return fail(l, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
-                JPGENC_CUDA(l, cudaMemcpyAsync(job.packed + base, l->d_scan, total, cudaMemcpyDeviceToHost, l->stream));
+                JPGENC_CUDA(l, cudaMemcpyAsync(job.packed + base, l->d_scan, total, cudaMemcpyDeviceToHost, l->out_stream));
             }
         }
         for (uint32_t f = 0; f < F; ++f) {
@@ -211,8 +223,12 @@ int finish_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, Job& job) {
             if (job.offsets) job.offsets[ps.f0 + f] = base + off;
             if (job.out_ptrs) {
                 if (job.caps[ps.f0 + f] < size) return fail(l, JPGENC_ERR_CAPACITY, "JPEG buffer too small");
-                JPGENC_CUDA(l, cudaMemcpyAsync(job.out_ptrs[ps.f0 + f], l->d_scan + off, size, cudaMemcpyDeviceToHost, l->stream));
+                JPGENC_CUDA(l, cudaMemcpyAsync(job.out_ptrs[ps.f0 + f], l->d_scan + off, size, cudaMemcpyDeviceToHost, l->out_stream));
             }
+        }
+        if (copies) {
+            JPGENC_CUDA(l, cudaEventRecord(l->ev_copied, l->out_stream));
+            l->copy_pending = true;
         }
         return JPGENC_OK;
     }
@@ -242,7 +258,9 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
         if ((rc = prepare_slot(c, slot[k], job, hdr, prefix_len))) return k ? fail(c, rc, jpgenc_last_error(slot[k])) : rc;
     }
     std::vector<Pass> pass(npasses);
-    const bool stagger = env_u32("JPGENC_STAGGER", 1) != 0;
+    // (measured: 128 frames 1.26 -> 1.33 ms, 1024 frames 6.9 -> 7.2 ms: the cross-stream waits cost more than the earlier
+    // table builds gain; kept as a switch)
+    const bool stagger = env_u32("JPGENC_STAGGER", 0) != 0;
     rc = JPGENC_OK;
     jpgenc_ctx* failed = nullptr;
     const double t0 = trace_on() ? now_us() : 0;
@@ -272,7 +290,9 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
     }
     // the files' copies are still in flight; also after a failure: nothing may run once the caller's buffers are gone
     for (uint32_t k = 0; k < nslots; ++k) {
-        const cudaError_t e = cudaStreamSynchronize(slot[k]->stream);
+        cudaError_t e = cudaStreamSynchronize(slot[k]->stream);
+        if (e == cudaSuccess && slot[k]->out_stream) e = cudaStreamSynchronize(slot[k]->out_stream);
+        slot[k]->copy_pending = false;
         if (e != cudaSuccess && rc == JPGENC_OK) { rc = JPGENC_ERR_CUDA; c->error = std::string("batched pass: ") + cudaGetErrorString(e); }
     }
     if (failed && failed != c) c->error = failed->error;

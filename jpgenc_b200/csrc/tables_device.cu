@@ -18,6 +18,7 @@
 // steps -- one thread, ~40 ns per step -- but all 4 * F tables of a pass run side by side (one warp each, lane 0
 // working) and the other lanes' kernels fill the SMs meanwhile.  A single image keeps the host build: 16 us there
 // against >= 250 us here.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -304,17 +305,247 @@ __host__ __device__ void build_table_serial(TableScratch& s, const uint32_t* cou
 
 }  // namespace
 
-// One warp per table.  All lanes clear the output and rank the symbols by first occurrence; lane 0 then runs the
-// (inherently serial) container operations.  status[table] = 0 ok, 1 = no symbol at all.
+// ---------------------------------------------------------------------------------------------------------------------
+// The same construction with the whole warp working on one table.
+//
+// A table is a chain of heap operations that depend on each other (15 levels x ~2n pops and ~n pushes); one thread spends
+// ~400 cycles on a pop because every step of the sift-down is a round trip through shared memory followed by dependent
+// address arithmetic (measured: 0.59 ms for the four tables of a 1920x1080 frame, 28 symbols in the luma AC table, 70 % of
+// a batched pass).  The operations themselves are easy to spread over the lanes without changing their result:
+//   * pop  = libstdc++'s __adjust_heap: the hole at the root walks down to a leaf position, always to the lighter child
+//            (the right one on a tie), then the former last element is sifted up from there.  Which child is the lighter
+//            one is decided for ALL nodes at once (one 16-byte load per lane, one ballot); the walk is then bit arithmetic
+//            on the ballot word, the moves along the path are one load and one store by one lane each, and where the
+//            sift-up stops is a ballot over the path.
+//   * push = __push_heap: the ancestors of the new position are loaded by one lane each; a ballot tells how far the new
+//            element rises.
+// Heap items are packed into one 64-bit word (weight << 16 | node) and stored at slot index + 1, so that the two children
+// of a node are one aligned 16-byte pair.  The container emulation (unordered_map order) stays on lane 0: n insertions.
+// The walk over the final packages (which symbol occurs how often = its code length, and which package touches it first
+// = its place in the reference's second unordered_map) runs one package per lane.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace {
+
+constexpr int kHeapSlots = 2 * kMaxSyms + 18;                 // element i lives in slot i + 1; +1 so that a pair load never leaves the array
+
+struct WarpShared {
+    alignas(16) unsigned long long heap[3][kHeapSlots];
+    OrderedMap map;
+    short syms[kMaxSyms];                                      // map iteration order -> symbol (= leaf node id -> symbol)
+    unsigned freq[kMaxSyms];
+    unsigned short cnt[kMaxSyms];                              // occurrences in the final packages = code length
+    unsigned short first[kMaxSyms];                            // pop index of the first final package that holds the symbol
+    unsigned short root[kMaxSyms];                             // final packages in pop order
+    unsigned char order[kMaxSyms];
+    unsigned char present[kMaxSyms];
+};
+
+__device__ __forceinline__ unsigned long long item_w(unsigned long long it) { return it >> 16; }
+
+// std::push_heap of `item` onto a heap of `len` elements (len grows by one)
+__device__ __forceinline__ void warp_push(unsigned long long* H, int& len, unsigned long long item, int lane) {
+    const int p = len;                                         // new position
+    // lane j >= 1 looks at ancestor j of p: a_j = ((p + 1) >> j) - 1, while it exists
+    const int a = static_cast<int>((static_cast<unsigned>(p) + 1u) >> lane) - 1;
+    const bool has = lane >= 1 && a >= 0;
+    const unsigned long long anc = has ? H[a + 1] : 0ull;
+    const unsigned up = __ballot_sync(0xffffffffu, has && item_w(anc) > item_w(item)) >> 1;   // bit j-1: ancestor j is heavier
+    const int r = __ffs(~up) - 1;                              // the element rises past r ancestors
+    if (has && lane <= r) H[(lane == 1 ? p : static_cast<int>((static_cast<unsigned>(p) + 1u) >> (lane - 1)) - 1) + 1] = anc;   // ancestor j moves to a_{j-1}
+    if (lane == 0) H[(r == 0 ? p : static_cast<int>((static_cast<unsigned>(p) + 1u) >> r) - 1) + 1] = item;
+    len = p + 1;
+    __syncwarp();
+}
+
+// top() followed by std::pop_heap + pop_back on a heap of `len` elements (len shrinks by one); returns the top item
+__device__ __forceinline__ unsigned long long warp_pop(unsigned long long* H, int& len, int lane) {
+    const unsigned long long top = H[1];
+    const int m = len - 1;                                     // elements that stay
+    len = m;
+    if (m == 0) { __syncwarp(); return top; }
+    const unsigned long long val = H[m + 1];                   // the former last element looks for its place
+    const int k2 = (m - 1) / 2;                                // nodes 0 .. k2-1 have both children among the m elements
+    // which child is lighter, for every such node: bit = 1 -> left (the right child is strictly heavier)
+    unsigned word0 = 0, mine = 0;                              // ballot of nodes 0..31 (every lane), of nodes 32g .. 32g+31 (lane g)
+    for (int g = 0; g * 32 < k2; ++g) {
+        const int k = g * 32 + lane;
+        bool left = false;
+        if (k < k2) {
+            const ulonglong2 pair = *reinterpret_cast<const ulonglong2*>(H + 2 * k + 2);   // elements 2k+1 (left), 2k+2 (right)
+            left = item_w(pair.y) > item_w(pair.x);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, left);
+        if (g == 0) word0 = b;
+        if (lane == g) mine = b;
+    }
+    // the hole's way down; lane j remembers step j: the element at `from` moves up to `to`
+    int h = 0, steps = 0, from = 0, to = 0;
+    while (h < k2) {
+        const unsigned w = h < 32 ? word0 : __shfl_sync(0xffffffffu, mine, h >> 5);
+        const int c = 2 * h + 2 - static_cast<int>((w >> (h & 31)) & 1u);
+        if (lane == steps) { to = h; from = c; }
+        h = c;
+        ++steps;
+    }
+    if ((m & 1) == 0 && h == (m - 2) / 2) {                    // a last node with a left child only
+        const int c = 2 * h + 1;
+        if (lane == steps) { to = h; from = c; }
+        h = c;
+        ++steps;
+    }
+    // sift-up of val from the final hole: it passes every moved element that is heavier, from the bottom of the path
+    const bool on_path = lane < steps;
+    const unsigned long long moved = on_path ? H[from + 1] : 0ull;
+    const unsigned heavier = __ballot_sync(0xffffffffu, on_path && item_w(moved) > item_w(val));
+    const unsigned stops = ~heavier & (steps >= 32 ? 0xffffffffu : ((1u << steps) - 1u));     // path steps val does NOT pass
+    const int jstar = stops ? 32 - __clz(stops) : 0;           // val lands at path[jstar]; steps below it keep their elements
+    __syncwarp();
+    if (on_path && lane < jstar) H[to + 1] = moved;
+    if (lane == jstar) H[(jstar == steps ? h : to) + 1] = val;  // lane jstar < steps holds path[jstar] in `to`; jstar == steps: the final hole
+    __syncwarp();
+    return top;
+}
+
+// The table `tab` (zeroed) from count[] / first[]; ws = the warp's shared memory, s = its scratch slab in global memory.
+__device__ void build_table_warp(WarpShared& ws, TableScratch& s, const uint32_t* count, const unsigned long long* first,
+                                 jpgenc_huff_table* tab, int lane, uint32_t* status) {
+    // ---- distinct symbols in order of first appearance (= the order the reference's counting loop creates map entries) ----
+    int n = 0;
+    for (int base = 0; base < 256; base += 32) {
+        const int sym = base + lane;
+        const bool here = count[sym] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, here);
+        if (here) ws.present[n + __popc(b & ((1u << lane) - 1u))] = static_cast<unsigned char>(sym);
+        n += __popc(b);
+    }
+    __syncwarp();
+    if (n == 0) { if (lane == 0) *status = 1; return; }        // the reference asserts text.size() > 0
+    if (lane == 0) *status = 0;
+    for (int i = lane; i < n; i += 32) {                       // rank among the present symbols (keys are unique)
+        const int sym = ws.present[i];
+        const unsigned long long k = first[sym];
+        int rank = 0;
+        for (int o = 0; o < n; ++o) rank += first[ws.present[o]] < k ? 1 : 0;
+        ws.order[rank] = static_cast<unsigned char>(sym);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        um_init(ws.map);
+        for (int i = 0; i < n; ++i) um_touch(ws.map, ws.order[i]);
+        int m = 0;
+        for (int p = ws.map.head; p >= 0; p = ws.map.nxt[p]) { ws.syms[m] = ws.map.key[p]; ws.freq[m] = count[ws.map.key[p]]; ++m; }
+        for (int l = 0; l < 18; ++l) s.per_len_n[l] = 0;
+    }
+    __syncwarp();
+    if (n == 1) {                                              // src/Huffman.cpp:17-25: the lone symbol gets code "0"
+        if (lane == 0) {
+            s.per_len[1][s.per_len_n[1]++] = static_cast<unsigned char>(ws.syms[0]);
+            write_table(s, n, tab);
+        }
+        return;
+    }
+    // ---- package-merge (Huffman.hpp:114-160): leaf i = node i; packages are nodes n, n+1, ... with two children ----
+    uint32_t* nodes = reinterpret_cast<uint32_t*>(s.nodes);    // left | right << 16
+    unsigned long long *bp = ws.heap[0], *cur = ws.heap[1], *nxt = ws.heap[2];
+    int nb = 0;
+    for (int i = 0; i < n; ++i)                                // map iteration order feeds the first heap; the reference counts in int
+        warp_push(bp, nb, (static_cast<unsigned long long>(static_cast<unsigned>(static_cast<int>(ws.freq[i]))) << 16) | static_cast<unsigned>(i), lane);
+    int nn = n, ncur = n, nnxt = 0;
+    for (int i = lane; i < n; i += 32) cur[i + 1] = bp[i + 1];
+    __syncwarp();
+    for (int lvl = 0; lvl < kLimit; ++lvl) {
+        if (lvl + 1 < kLimit) {                                // every level but the last starts as a copy of the leaves
+            for (int i = lane; i < n; i += 32) nxt[i + 1] = bp[i + 1];
+            nnxt = n;
+            __syncwarp();
+        } else {
+            nnxt = 0;
+        }
+        while (ncur > 1) {
+            const unsigned long long a = warp_pop(cur, ncur, lane), b = warp_pop(cur, ncur, lane);
+            if (lane == 0) nodes[nn] = static_cast<uint32_t>(a & 0xFFFFu) | (static_cast<uint32_t>(b & 0xFFFFu) << 16);
+            warp_push(nxt, nnxt, ((item_w(a) + item_w(b)) << 16) | static_cast<unsigned>(nn), lane);
+            ++nn;
+        }
+        unsigned long long* sw = cur; cur = nxt; nxt = sw;
+        ncur = nnxt;
+    }
+    // ---- drain the last level: packages in pop order ----
+    int npk = 0;
+    while (ncur) {
+        const unsigned long long pk = warp_pop(cur, ncur, lane);
+        if (lane == 0) ws.root[npk] = static_cast<unsigned short>(pk & 0xFFFFu);
+        ++npk;
+    }
+    for (int i = lane; i < n; i += 32) { ws.cnt[i] = 0; ws.first[i] = 0xFFFFu; }
+    __syncwarp();
+    __threadfence_block();                                     // lane 0's node records are visible to every lane
+    // a symbol's code length is the number of times it occurs in the surviving packages; the reference's lengths map is
+    // touched package by package (pop order), symbols of a package in ascending order -> remember the first package
+    for (int k = lane; k < npk; k += 32) {
+        int stack[20], sp = 0;                                 // a package is at most kLimit levels deep
+        stack[sp++] = ws.root[k];
+        while (sp) {
+            const int id = stack[--sp];
+            if (id < n) {                                      // leaf: node id = position in map iteration order
+                atomicAdd(reinterpret_cast<unsigned*>(ws.cnt) + (id >> 1), (id & 1) ? 0x10000u : 1u);
+                unsigned* w = reinterpret_cast<unsigned*>(ws.first) + (id >> 1);
+                // 16-bit minimum inside a 32-bit word: compare-and-swap (rarely more than one round)
+                unsigned old = *w;
+                for (;;) {
+                    const unsigned cur16 = (id & 1) ? old >> 16 : old & 0xFFFFu;
+                    if (cur16 <= static_cast<unsigned>(k)) break;
+                    const unsigned want = (id & 1) ? (old & 0xFFFFu) | (static_cast<unsigned>(k) << 16) : (old & 0xFFFF0000u) | static_cast<unsigned>(k);
+                    const unsigned seen = atomicCAS(w, old, want);
+                    if (seen == old) break;
+                    old = seen;
+                }
+                continue;
+            }
+            const uint32_t nd = nodes[id];
+            stack[sp++] = static_cast<int>(nd & 0xFFFFu);
+            stack[sp++] = static_cast<int>(nd >> 16);
+        }
+    }
+    __syncwarp();
+    // touch order of the lengths map: (first package, symbol value) ascending
+    for (int i = lane; i < n; i += 32) {
+        const unsigned key = (static_cast<unsigned>(ws.first[i]) << 16) | static_cast<unsigned>(ws.syms[i]);
+        int rank = 0;
+        for (int o = 0; o < n; ++o) rank += ((static_cast<unsigned>(ws.first[o]) << 16) | static_cast<unsigned>(ws.syms[o])) < key ? 1 : 0;
+        ws.order[rank] = static_cast<unsigned char>(i);        // leaf ids in touch order
+    }
+    __syncwarp();
+    if (lane == 0) {
+        um_init(ws.map);
+        for (int i = 0; i < n; ++i) um_touch(ws.map, ws.syms[ws.order[i]]);
+        // symbol -> code length: cnt is indexed by leaf id; the map holds symbols
+        for (int i = 0; i < n; ++i) s.len_of[ws.syms[i]] = ws.cnt[i];
+        for (int p = ws.map.head; p >= 0; p = ws.map.nxt[p]) {
+            const int sym = ws.map.key[p], len = s.len_of[sym];
+            s.per_len[len][s.per_len_n[len]++] = static_cast<unsigned char>(sym);
+        }
+        // preventOnlyOnesCode (src/Huffman.cpp:37-48): the last symbol of the deepest level moves one level down
+        int deepest = 16;
+        while (deepest > 0 && s.per_len_n[deepest] == 0) --deepest;
+        const int moved = s.per_len[deepest][--s.per_len_n[deepest]];
+        s.per_len[deepest + 1][s.per_len_n[deepest + 1]++] = static_cast<unsigned char>(moved);
+        write_table(s, n, tab);
+    }
+}
+
+}  // namespace
+#endif
+
+// One warp per table.  status[table] = 0 ok, 1 = no symbol at all.  kCooperative = false runs the one-thread version
+// (build_table_serial, the code the CPU tests execute) for A/B checks: JPGENC_TABLES_SERIAL=1.
 // (No __restrict__ on these parameters: with it nvcc 12.9 -O3 treated the two level heaps -- members of one scratch
 // object whose pointers swap roles every level -- as never aliasing, and a popped weight read back as 0.  Found by the
 // parity test; -G, -Xcicc -O1 and non-inlined heap functions all gave the right tables.)
+template <bool kCooperative>
 __global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, uint32_t stats_stride, uint32_t ntables,
                                                           TableScratch* scratch, jpgenc_huff_table* out, uint32_t* status) {
-    __shared__ HeapItem sh_heap[3][2 * kSharedSyms + 16];
-    __shared__ Node sh_nodes[kSharedSyms * (kLimit + 2) + 16];
-    __shared__ OrderedMap sh_map;
-    __shared__ unsigned short sh_len[2][kMaxSyms];
     const uint32_t table = blockIdx.x, lane = threadIdx.x;
     if (table >= ntables) return;
     const uint32_t frame = table >> 2, t = table & 3;
@@ -327,27 +558,37 @@ __global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, 
         uint32_t* w = reinterpret_cast<uint32_t*>(tab);
         for (uint32_t i = lane; i < sizeof(jpgenc_huff_table) / 4; i += 32) w[i] = 0;
     }
-    // distinct symbols in order of first appearance == the order the reference's counting loop creates map entries
-    // (keys are unique: one text position holds one symbol); rank = number of present symbols that appear earlier
-    int n = 0;
-    for (int base = 0; base < 256; base += 32) {
-        const int sym = base + lane;
-        const bool here = count[sym] != 0;
-        if (here) {
-            const unsigned long long k = first[sym];
-            int rank = 0;
-            for (int o = 0; o < 256; ++o) rank += (count[o] != 0 && first[o] < k) ? 1 : 0;
-            s.order[rank] = static_cast<unsigned char>(sym);
+    if constexpr (kCooperative) {
+        __shared__ WarpShared ws;
+        __syncwarp();
+        build_table_warp(ws, s, count, first, tab, static_cast<int>(lane), status + table);
+    } else {
+        __shared__ HeapItem sh_heap[3][2 * kSharedSyms + 16];
+        __shared__ Node sh_nodes[kSharedSyms * (kLimit + 2) + 16];
+        __shared__ OrderedMap sh_map;
+        __shared__ unsigned short sh_len[2][kMaxSyms];
+        // distinct symbols in order of first appearance == the order the reference's counting loop creates map entries
+        // (keys are unique: one text position holds one symbol); rank = number of present symbols that appear earlier
+        int n = 0;
+        for (int base = 0; base < 256; base += 32) {
+            const int sym = base + lane;
+            const bool here = count[sym] != 0;
+            if (here) {
+                const unsigned long long k = first[sym];
+                int rank = 0;
+                for (int o = 0; o < 256; ++o) rank += (count[o] != 0 && first[o] < k) ? 1 : 0;
+                s.order[rank] = static_cast<unsigned char>(sym);
+            }
+            n += __popc(__ballot_sync(0xffffffffu, here));
         }
-        n += __popc(__ballot_sync(0xffffffffu, here));
+        __syncwarp();
+        if (lane != 0) return;
+        if (n == 0) { status[table] = 1; return; }                 // the reference asserts text.size() > 0
+        status[table] = 0;
+        const Work in_shared{&sh_map, sh_nodes, sh_heap[0], sh_heap[1], sh_heap[2], sh_len[0], sh_len[1]};
+        const Work in_scratch{&s.map, s.nodes, s.blueprint, s.heap_a, s.heap_b, s.len_of, s.cnt};
+        build_table_serial(s, count, n, tab, n <= kSharedSyms ? in_shared : in_scratch);
     }
-    __syncwarp();
-    if (lane != 0) return;
-    if (n == 0) { status[table] = 1; return; }                 // the reference asserts text.size() > 0
-    status[table] = 0;
-    const Work in_shared{&sh_map, sh_nodes, sh_heap[0], sh_heap[1], sh_heap[2], sh_len[0], sh_len[1]};
-    const Work in_scratch{&s.map, s.nodes, s.blueprint, s.heap_a, s.heap_b, s.len_of, s.cnt};
-    build_table_serial(s, count, n, tab, n <= kSharedSyms ? in_shared : in_scratch);
 }
 
 size_t table_scratch_bytes() { return sizeof(TableScratch); }
@@ -375,7 +616,9 @@ int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[
 // frame: histogram u32[4][256], first-occurrence keys u64[4][256]); scratch: ntables * table_scratch_bytes()
 int launch_build_tables(jpgenc_ctx* c, const uint8_t* d_stats, uint32_t stats_stride, uint32_t ntables, void* d_scratch,
                         jpgenc_huff_table* d_out, uint32_t* d_status) {
-    build_tables_kernel<<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status);
+    static const bool serial = [] { const char* v = std::getenv("JPGENC_TABLES_SERIAL"); return v && *v && *v != '0'; }();
+    if (serial) build_tables_kernel<false><<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status);
+    else build_tables_kernel<true><<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return JPGENC_OK;
