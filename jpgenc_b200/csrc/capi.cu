@@ -59,6 +59,7 @@ int ensure_bytes(jpgenc_ctx* c, void** ptr, size_t* cap, size_t need_bytes, bool
     JPGENC_CUDA(c, cudaMalloc(&p, bytes));
     *ptr = p;
     *cap = bytes;
+    ++c->alloc_gen;
     return JPGENC_OK;
 }
 
@@ -78,6 +79,7 @@ int ensure_pinned(jpgenc_ctx* c, size_t bytes) {
     c->h_pinned = nullptr; c->pinned_bytes = 0;
     JPGENC_CUDA(c, cudaMallocHost(&c->h_pinned, bytes));
     c->pinned_bytes = bytes;
+    ++c->alloc_gen;
     return JPGENC_OK;
 }
 
@@ -164,6 +166,49 @@ size_t stage_meta_off(uint32_t F) { return stage_tables_off(F) + F * sizeof(Devi
 size_t stage_bytes(uint32_t F) { return stage_meta_off(F) + pass_meta_bytes(F) + 64; }
 
 
+// K3/K4 time of the last single-image encode (its events complete while the host is already elsewhere): read it now and,
+// when that encode went through all four stages, add its stage times to the running sums
+int flush_entropy_time(jpgenc_ctx* c) {
+    if (!c->ent_pending) return JPGENC_OK;
+    JPGENC_CUDA(c, cudaEventSynchronize(c->ev_e1));
+    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_e0, c->ev_e1));
+    c->ent_pending = false;
+    if (c->last_whole) {
+        c->stats.sum_ms_k1 += c->last_k1; c->stats.sum_ms_forward += c->last_fwd;
+        c->stats.sum_ms_stats += c->last_st; c->stats.sum_ms_entropy += c->stats.ms_entropy;
+        c->stats.timed_encodes += 1;
+        c->last_whole = false;
+    }
+    return JPGENC_OK;
+}
+
+// Waits until the kernels of the current encode have raised mailbox word `flag_word` (K2: statistics complete, K4: scan
+// complete).  The word is written over PCIe into page-locked host memory: polling it costs a microsecond where a
+// device-to-host copy plus cudaStreamSynchronize cost 20-30.  The stream is queried every now and then so that a failed
+// launch is reported instead of waited for; long waits (the pixels of a large image still crossing PCIe) yield the core.
+int poll_mailbox(jpgenc_ctx* c, int flag_word) {
+    volatile uint32_t* flag = c->h_mailbox + flag_word;
+    const uint32_t seq = c->mailbox_seq;
+    const double t0 = now_us();
+    for (uint32_t spins = 1;; ++spins) {
+        if (*flag == seq) break;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0x3FFu) == 0) {
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (*flag == seq) break;
+                return fail(c, JPGENC_ERR_CUDA, "the kernels finished without delivering their result");
+            }
+            if (e != cudaErrorNotReady) { c->error = std::string("kernel failed: ") + cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
+            if (now_us() - t0 > 2000.0) usleep(50);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return JPGENC_OK;
+}
+
 void leave_batch_state(jpgenc_ctx* c) {
     c->nframes = 1;                                                  // the context goes back to single-image state
     c->have_pixels = c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
@@ -192,7 +237,7 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     c->device = device;
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
-        delete c;
+        jpgenc_destroy(c);                                         // null-safe on every member: releases what exists so far
         return JPGENC_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
@@ -200,7 +245,7 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     if (prop.major < 10) {
         g_create_error = "device is not sm_100 (Blackwell); the kernels are built for sm_100a only";
-        delete c;
+        jpgenc_destroy(c);
         return JPGENC_ERR_NO_DEVICE;
     }
     c->sm_count = prop.multiProcessorCount;
@@ -219,6 +264,12 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     if ((e = cudaMemset(p, 0, kCounterWords * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
     c->pinned_bytes = 64 * 1024;
     if ((e = cudaMallocHost(&c->h_pinned, c->pinned_bytes)) != cudaSuccess) return bail("cudaMallocHost", e);
+    for (cudaEvent_t* ev : {&c->ev_e0, &c->ev_e1})
+        if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    // the mailbox: page-locked host memory the kernels write into directly (results of one image, a few KB)
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_mailbox), kMailWords * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    std::memset(c->h_mailbox, 0, kMailWords * sizeof(uint32_t));
+    if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_mailbox), c->h_mailbox, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     *out = c;
     return JPGENC_OK;
 }
@@ -227,6 +278,7 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (jpgenc_ctx* l : c->lanes) jpgenc_destroy(l);
     delete c->pool;
     if (c->owns_host_pool) delete c->host_pool;
@@ -236,6 +288,11 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     cudaFree(c->d_tab_scratch); cudaFree(c->d_built_tables);
     cudaFree(c->d_items); cudaFree(c->d_tile_cnt); cudaFree(c->d_range_bits); cudaFree(c->d_range_base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_mailbox) cudaFreeHost(c->h_mailbox);
+    if (c->ev_e0) cudaEventDestroy(c->ev_e0);
+    if (c->ev_e1) cudaEventDestroy(c->ev_e1);
+    if (c->graph_a.exec) cudaGraphExecDestroy(c->graph_a.exec);
+    if (c->graph_b.exec) cudaGraphExecDestroy(c->graph_b.exec);
     if (c->h_file_pinned) cudaFreeHost(c->h_file_pinned);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1, c->ev_u0, c->ev_u1, c->ev_k0, c->ev_k1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
@@ -260,6 +317,8 @@ int jpgenc_synchronize(jpgenc_ctx* c) {
 
 int jpgenc_get_stats(jpgenc_ctx* c, jpgenc_stats* out) {
     if (!c || !out) return JPGENC_ERR_ARG;
+    const int rf = flush_entropy_time(c);
+    if (rf) return rf;
     c->stats.real_w = c->real_w; c->stats.real_h = c->real_h; c->stats.mcu_w = c->mcu_w; c->stats.mcu_h = c->mcu_h;
     c->stats.n_blocks = static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
     *out = c->stats;
@@ -272,6 +331,7 @@ int jpgenc_set_qtables(jpgenc_ctx* c, const uint8_t qy[64], const uint8_t qc[64]
         if (qy[i] == 0 || qc[i] == 0) return fail(c, JPGENC_ERR_ARG, "quantiser entries must be >= 1");
     std::memcpy(c->qy, qy, 64);
     std::memcpy(c->qc, qc, 64);
+    ++c->alloc_gen;
     return JPGENC_OK;
 }
 
@@ -279,6 +339,7 @@ int jpgenc_set_dct_constants(jpgenc_ctx* c, const double a[5], const double s[8]
     if (!c || !a || !s) return JPGENC_ERR_ARG;
     std::memcpy(c->dct_a, a, sizeof c->dct_a);
     std::memcpy(c->dct_s, s, sizeof c->dct_s);
+    ++c->alloc_gen;
     return JPGENC_OK;
 }
 
@@ -289,9 +350,9 @@ int jpgenc_upload_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     if (rc) return rc;
     const size_t bytes = static_cast<size_t>(w) * h * 3;
     if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, bytes + 16))) return rc;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_a));
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned, host_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_b));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));            // the caller may reuse host_rgb as soon as we return
     JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
     c->d_rgb = c->d_rgb_owned;
@@ -308,15 +369,16 @@ int jpgenc_bind_device_rgb(jpgenc_ctx* c, const void* dev_rgb, uint32_t w, uint3
     return JPGENC_OK;
 }
 
+static int enqueue_forward(jpgenc_ctx* c);
+
 int jpgenc_color_dct_quant(jpgenc_ctx* c) {
     if (!c) return JPGENC_ERR_ARG;
     if (!c->have_pixels) return fail(c, JPGENC_ERR_ARG, "no pixels bound: call jpgenc_upload_rgb / jpgenc_bind_device_rgb first");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_coef(c);
     if (rc) return rc;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
-    if ((rc = launch_forward(c))) return rc;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    if ((rc = flush_entropy_time(c))) return rc;
+    if ((rc = enqueue_forward(c))) return rc;
     c->forward_pending = true;
     c->have_coef = true;
     c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
@@ -379,134 +441,166 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
 }
 
 // ---- K2 and K3/K4 for all frames bound to the context (one image = one frame) ------------------------------------
-static int stats_frames(jpgenc_ctx* c) {
-    JPGENC_CUDA(c, cudaSetDevice(c->device));
-    const uint32_t F = c->nframes;
+// ---- one image: the GPU work of an encode as two enqueue-only phases (no host waits inside: they can be captured) ----
+// K1 + exact refinement, between the forward-stage events
+static int enqueue_forward(jpgenc_ctx* c) {
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_a));
+    const int rc = launch_forward(c);
+    if (rc) return rc;
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_b));
+    return JPGENC_OK;
+}
+// K2 over the tiles [done, tiles) and the hand-over of the statistics to the host's mailbox
+static int enqueue_stats(jpgenc_ctx* c, uint32_t done) {
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
-    int rc;
-    if ((rc = ensure_stats_buffers(c))) return rc;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-    // a band-wise upload has already taken the first k2_tiles_done tiles through K2
-    const uint32_t done = F == 1 ? std::min<uint32_t>(c->k2_tiles_done, static_cast<uint32_t>(tiles)) : 0u;
-    c->k2_tiles_done = 0;
-    if ((rc = launch_symbol_stats(c, done, static_cast<uint32_t>(tiles * F) - done, done == 0))) return rc;
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_t0));
+    int rc = launch_symbol_stats(c, done, static_cast<uint32_t>(tiles) - done, done == 0);
+    if (rc) return rc;
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_t1));
+    return launch_publish_stats(c);
+}
+// the host's half: wait for the mailbox, take the histogram
+static int wait_stats(jpgenc_ctx* c) {
     c->have_items = true;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
-    uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    JPGENC_CUDA(c, cudaMemcpyAsync(h, c->d_stats, F * kStatsBytes + 16, cudaMemcpyDeviceToHost, c->stream));   // + K2's copy of the refine counter
-    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->host_hist.resize(static_cast<size_t>(F) * 1024);
-    for (uint32_t f = 0; f < F; ++f) std::memcpy(&c->host_hist[f * 1024], h + f * kStatsBytes, 4096);
-    const uint32_t refined = *reinterpret_cast<const uint32_t*>(h + F * kStatsBytes);
-    if (c->upload_pending) {          // banded upload of jpgenc_encode_rgb: the compute stream waited for every band
-        c->stats.refined_blocks = refined;
-        JPGENC_CUDA(c, cudaEventSynchronize(c->ev_b));           // recorded on the copy stream right after the last band
-        JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
-        c->upload_pending = false;
-    }
-    if (c->forward_pending) {
-        c->stats.refined_blocks = refined;
-        const int rs = refresh_forward_stats(c);
-        if (rs) return rs;
-    }
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_stats, c->ev_t0, c->ev_t1));
+    int rc = flush_entropy_time(c);                               // the previous encode's K3/K4 time, while K2 runs
+    if (rc) return rc;
+    if ((rc = poll_mailbox(c, kMailK2Flag))) return rc;          // the statistics are in the mailbox
+    c->host_hist.assign(c->h_mailbox + kMailStats, c->h_mailbox + kMailStats + 1024);
+    if (c->upload_pending || c->forward_pending) c->stats.refined_blocks = c->h_mailbox[kMailRefined];
+    c->stats_pending = true;
     return JPGENC_OK;
 }
 
-// tables: [F][4], built on the host.  Afterwards c->frame_bits / frame_out_off / frame_ff describe every frame's scan
-// in d_scan (frame f's stuffed scan starts at byte frame_out_off[f]).
-static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
+// K2 for the image bound to the context; the statistics arrive in the host mailbox
+static int stats_frames(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaSetDevice(c->device));
-    const uint32_t F = c->nframes;
-    if (c->host_hist.size() != static_cast<size_t>(F) * 1024) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+    if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
+    const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     int rc;
-    if ((rc = ensure_pinned(c, stage_bytes(F)))) return rc;
+    if ((rc = ensure_stats_buffers(c))) return rc;
+    // a band-wise upload has already taken the first k2_tiles_done tiles through K2
+    const uint32_t done = std::min<uint32_t>(c->k2_tiles_done, static_cast<uint32_t>(tiles));
+    c->k2_tiles_done = 0;
+    if ((rc = enqueue_stats(c, done))) return rc;
+    return wait_stats(c);
+}
+
+// stage times whose events are complete once K3/K4 have been enqueued (called while those run): K1 and refinement, the
+// upload, K2 of the current encode, K3/K4 of the previous one
+static int read_completed_times(jpgenc_ctx* c) {
+    int rc = flush_entropy_time(c);
+    if (rc) return rc;
+    const bool whole = c->forward_pending && c->stats_pending;
+    if (c->upload_pending) {          // banded upload of jpgenc_encode_rgb: ev_b was recorded on the copy stream behind the last band
+        JPGENC_CUDA(c, cudaEventSynchronize(c->ev_b));
+        JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_h2d, c->ev_a, c->ev_b));
+        c->upload_pending = false;
+    }
+    if (c->forward_pending && (rc = refresh_forward_stats(c))) return rc;
+    if (c->stats_pending) {
+        JPGENC_CUDA(c, cudaEventSynchronize(c->ev_t1));            // recorded right behind K2, whose flag the host has seen long ago
+        JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_stats, c->ev_t0, c->ev_t1));
+        c->stats_pending = false;
+    }
+    c->last_whole = whole;
+    c->last_k1 = c->stats.ms_k1; c->last_fwd = c->stats.ms_forward; c->last_st = c->stats.ms_stats;
+    return JPGENC_OK;
+}
+
+// ---- K3/K4 of one image with tables built on the host ----
+// Host part: the tables in the lookup form K3 reads, and -- from histogram x code length -- the exact geometry of the
+// scan (the PassMeta block a batch computes on the device, finalize.cu), both into pinned staging; buffers sized for it.
+// *k4_tiles = the exact number of K4 tiles.
+static int prepare_entropy(jpgenc_ctx* c, const jpgenc_huff_table* tables, uint32_t* k4_tiles) {
+    if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
+    if (c->host_hist.size() != 1024) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+    int rc;
+    if ((rc = ensure_pinned(c, stage_bytes(1)))) return rc;
     uint8_t* h = static_cast<uint8_t*>(c->h_pinned);
-    DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + stage_tables_off(F));
-    const PassMeta m = pass_meta_view(h + stage_meta_off(F), F);
-    c->frame_bits.assign(F, 0); c->frame_out_off.assign(F, 0); c->frame_ff.assign(F, 0);
-    // exact size of every scan from the statistics the tables were built from: a symbol costs its code length plus
+    DeviceTables* ht = reinterpret_cast<DeviceTables*>(h + stage_tables_off(1));
+    const PassMeta m = pass_meta_view(h + stage_meta_off(1), 1);
+    // exact size of the scan from the statistics the tables were built from: a symbol costs its code length plus
     // (symbol & 15) magnitude bits
-    // (per frame: independent work, spread over the batch's host threads; the offsets are a serial prefix afterwards)
-    std::atomic<int> conv_err{0};
-    const double t_conv = trace_on() ? now_us() : 0;
-    auto convert = [&](uint32_t f) {
-        const uint32_t* hist = &c->host_hist[static_cast<size_t>(f) * 1024];
-        uint64_t bits = 0;
-        for (int t = 0; t < 4; ++t) {
-            const jpgenc_huff_table& tab = tables[f * 4 + t];
-            for (int s = 0; s < 256; ++s) {
-                const uint32_t len = tab.length[s];
-                const uint32_t code = len ? tab.code_msb[s] >> (32 - len) : 0u, cat = s & 15;
-                ht[f].entry[t][s] = len ? (len << 16) | code : 0u;
-                ht[f].fast[t][s] = (len && len + cat <= 27) ? ((len + cat) << 27) | (code << cat) : 0u;
-                if (hist[t * 256 + s]) {
-                    if (!len) conv_err.store(1);
-                    bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + cat);
-                }
+    const uint32_t* hist = c->host_hist.data();
+    uint64_t bits = 0;
+    for (int t = 0; t < 4; ++t) {
+        const jpgenc_huff_table& tab = tables[t];
+        for (int s = 0; s < 256; ++s) {
+            const uint32_t len = tab.length[s];
+            const uint32_t code = len ? tab.code_msb[s] >> (32 - len) : 0u, cat = s & 15;
+            ht->entry[t][s] = len ? (len << 16) | code : 0u;
+            ht->fast[t][s] = (len && len + cat <= 27) ? ((len + cat) << 27) | (code << cat) : 0u;
+            if (hist[t * 256 + s]) {
+                if (!len) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
+                bits += static_cast<uint64_t>(hist[t * 256 + s]) * (len + cat);
             }
         }
-        if (bits == 0) conv_err.store(2);
-        c->frame_bits[f] = bits;
-    };
-    if (c->host_pool && F >= 8) c->host_pool->parallel_for(F, convert);
-    else for (uint32_t f = 0; f < F; ++f) convert(f);
-    if (conv_err.load() == 1) return fail(c, JPGENC_ERR_ARG, "Huffman table lacks a symbol that occurs in the image");
-    if (conv_err.load() == 2) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
-    uint64_t raw_total = 0, out_total = 0, k4_tiles = 0;
-    for (uint32_t f = 0; f < F; ++f) {
-        const uint64_t nbytes = (c->frame_bits[f] + 7) / 8;
-        m.raw_off[f] = raw_total;
-        m.raw_bytes[f] = nbytes;
-        m.frame_bits[f] = c->frame_bits[f];
-        m.file_base[f] = out_total;                              // bare scans, back to back
-        m.k4_tile0[f] = static_cast<uint32_t>(k4_tiles);
-        m.hdr_len[f] = 0;
-        raw_total += raw_slot_bytes(nbytes);
-        out_total += nbytes;
-        k4_tiles += (nbytes + kK4TileBytes - 1) / kK4TileBytes;
     }
-    m.k4_tile0[F] = static_cast<uint32_t>(k4_tiles);
-    if (k4_tiles > 0xFFFFFFFFull) return fail(c, JPGENC_ERR_ARG, "scan too large");
+    if (bits == 0) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
+    const uint64_t nbytes = (bits + 7) / 8, tiles = (nbytes + kK4TileBytes - 1) / kK4TileBytes;
+    if (tiles > 0x7FFFFFFFull) return fail(c, JPGENC_ERR_ARG, "scan too large");
+    c->frame_bits.assign(1, bits); c->frame_out_off.assign(1, 0); c->frame_ff.assign(1, 0);
+    m.raw_off[0] = 0;
+    m.raw_bytes[0] = nbytes;
+    m.frame_bits[0] = bits;
+    m.file_base[0] = 0;                                          // the bare scan
+    m.k4_tile0[0] = 0;
+    m.k4_tile0[1] = static_cast<uint32_t>(tiles);
+    m.hdr_len[0] = 0;
     *m.hdr = PassHeader{};
-    m.hdr->raw_total = raw_total;
-    m.hdr->out_total = out_total;
-    m.hdr->raw_sum = out_total;
-    m.hdr->k4_tiles = static_cast<uint32_t>(k4_tiles);
-    m.hdr->nframes = F;
+    m.hdr->raw_total = raw_slot_bytes(nbytes);
+    m.hdr->out_total = nbytes;
+    m.hdr->raw_sum = nbytes;
+    m.hdr->k4_tiles = static_cast<uint32_t>(tiles);
+    m.hdr->nframes = 1;
     c->file_mode = false;
-    if ((rc = ensure_entropy_buffers(c, raw_total, 2 * out_total, k4_tiles))) return rc;
-    // (Measured and rejected for one image:
-    // passing the 8 KB of tables as kernel parameters instead -- the launches get slower and the per-thread reads of
-    // the parameter bank serialise; K3+K4 went from 185 to 212 us.)
-    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, ht, F * sizeof(DeviceTables) + pass_meta_input_bytes(F), cudaMemcpyHostToDevice, c->stream));
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-    if ((rc = launch_entropy(c, static_cast<uint32_t>(k4_tiles)))) return rc;
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
-    if (trace_on()) c->trace_convert_us = now_us() - t_conv;
-    // results: bits written by K3 [F], running count of stuffed FF bytes [F]
-    JPGENC_CUDA(c, cudaMemcpyAsync(m.total_bits, c->d_meta + pass_meta_input_bytes(F), F * 16, cudaMemcpyDeviceToHost, c->stream));
-    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (uint32_t f = 0; f < F; ++f) {
-        if (m.total_bits[f] != c->frame_bits[f]) {
-            c->error = "entropy coder wrote " + std::to_string(m.total_bits[f]) + " bits, statistics predicted " + std::to_string(c->frame_bits[f]);
-            return JPGENC_ERR_ARG;
-        }
-        const uint64_t before = f ? m.ff_incl[f - 1] : 0;
-        c->frame_ff[f] = m.ff_incl[f] - before;
-        c->frame_out_off[f] = m.file_base[f] + before;
+    *k4_tiles = static_cast<uint32_t>(tiles);
+    // the look-back words are sized for the largest K4 grid the raw buffer allows (graph replays launch that many CTAs)
+    if ((rc = ensure_entropy_buffers(c, m.hdr->raw_total, 2 * nbytes, tiles))) return rc;
+    return ensure_entropy_buffers(c, m.hdr->raw_total, 2 * nbytes, c->raw_cap / kK4TileBytes + 1);
+}
+// GPU part, enqueue only: tables + geometry to the device, K3a, K3b, K4, totals into the mailbox
+static int enqueue_entropy_phase(jpgenc_ctx* c, uint32_t k4_grid) {
+    const uint8_t* h = static_cast<const uint8_t*>(c->h_pinned);
+    // (Measured and rejected: passing the 8 KB of tables as kernel parameters instead -- the launches get slower and the
+    // per-thread reads of the parameter bank serialise; K3+K4 went from 185 to 212 us.)
+    JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, h + stage_tables_off(1), sizeof(DeviceTables) + pass_meta_input_bytes(1), cudaMemcpyHostToDevice, c->stream));
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_e0));
+    const int rc = launch_entropy(c, k4_grid);
+    if (rc) return rc;
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_e1));
+    return JPGENC_OK;
+}
+// the host's half: stage times that are final by now, then the totals from the mailbox
+static int wait_entropy(jpgenc_ctx* c) {
+    int rc = read_completed_times(c);                            // K3/K4 are running: the host has nothing else to do
+    if (rc) return rc;
+    c->ent_pending = true;
+    if ((rc = poll_mailbox(c, kMailK4Flag))) return rc;          // the totals are in the mailbox (launch_entropy's last kernel)
+    const volatile unsigned long long* totals = reinterpret_cast<const volatile unsigned long long*>(c->h_mailbox + kMailTotals);
+    const unsigned long long bits = totals[0], ff = totals[1];
+    if (bits != c->frame_bits[0]) {
+        c->error = "entropy coder wrote " + std::to_string(bits) + " bits, statistics predicted " + std::to_string(c->frame_bits[0]);
+        return JPGENC_ERR_ARG;
     }
-    c->stats.scan_bits = c->frame_bits[0];
-    c->stats.stuffed_ff = c->frame_ff[0];
-    c->stats.scan_bytes = (c->frame_bits[0] + 7) / 8 + c->frame_ff[0];
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_t0, c->ev_t1));
-    if (F == 1) {                                                // one whole-image encode has gone through all four stages
-        c->stats.sum_ms_k1 += c->stats.ms_k1; c->stats.sum_ms_forward += c->stats.ms_forward;
-        c->stats.sum_ms_stats += c->stats.ms_stats; c->stats.sum_ms_entropy += c->stats.ms_entropy;
-        c->stats.timed_encodes += 1;
-    }
+    c->frame_ff[0] = ff;
+    c->stats.scan_bits = bits;
+    c->stats.stuffed_ff = ff;
+    c->stats.scan_bytes = (bits + 7) / 8 + ff;
     c->have_scan = true;
     return JPGENC_OK;
+}
+
+// tables[4], built on the host.  Afterwards the stuffed scan is in d_scan, its size in c->stats.
+static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    const double t_conv = trace_on() ? now_us() : 0;
+    uint32_t k4_tiles = 0;
+    int rc = prepare_entropy(c, tables, &k4_tiles);
+    if (rc) return rc;
+    if ((rc = enqueue_entropy_phase(c, k4_tiles))) return rc;
+    if (trace_on()) c->trace_convert_us = now_us() - t_conv;
+    return wait_entropy(c);
 }
 
 int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_pos[4][256]) {
@@ -515,9 +609,8 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
     const int rc = stats_frames(c);
     if (rc) return rc;
-    const uint8_t* h = static_cast<const uint8_t*>(c->h_pinned);
-    std::memcpy(count, h, 4096);
-    std::memcpy(first_pos, h + 4096, 8192);
+    std::memcpy(count, c->h_mailbox + kMailStats, 4096);
+    std::memcpy(first_pos, c->h_mailbox + kMailStats + 1024, 8192);
     return JPGENC_OK;
 }
 
@@ -584,9 +677,9 @@ int jpgenc_download_scan(jpgenc_ctx* c, uint8_t* dst, uint64_t cap) {
     if (!c || !dst) return JPGENC_ERR_ARG;
     if (!c->have_scan) return fail(c, JPGENC_ERR_ARG, "no scan yet: run jpgenc_entropy_encode first");
     if (cap < c->stats.scan_bytes) return fail(c, JPGENC_ERR_CAPACITY, "scan buffer too small");
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_t0));
     JPGENC_CUDA(c, cudaMemcpyAsync(dst, c->d_scan, c->stats.scan_bytes, cudaMemcpyDeviceToHost, c->stream));
-    JPGENC_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    JPGENC_CUDA(c, jpgenc_record(c, c->ev_t1));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_d2h, c->ev_t0, c->ev_t1));
     return JPGENC_OK;
@@ -598,7 +691,9 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
     uint32_t count[4][256];
     uint64_t first_pos[4][256];
     const double t0 = trace_on() ? now_us() : 0;
-    if (!c->parallel_tables) {
+    // the pool's workers spin from arm() until the statistics arrive: fine for the ~0.2 ms of K2 on resident pixels, not for
+    // the milliseconds an upload takes (3 spinning workers x 8 ranks on a 32-core host)
+    if (!c->parallel_tables || c->upload_pending) {
         if ((rc = jpgenc_symbol_stats(c, count, first_pos))) return rc;
         for (int t = 0; t < 4; ++t)
             if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
@@ -621,9 +716,110 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
     return JPGENC_OK;
 }
 
+// ---- whole encode of the pixels bound to the context, its two GPU phases replayed as CUDA graphs ----------------------
+// A small frame is launch-bound: phase A is 8 stream operations (counters, K1, refinement, 3 clears, K2, publish) plus
+// their events, phase B 5 (tables upload, K3a, K3b, K4, publish); at ~4-5 us of host time per call the GPU waits for its
+// next kernel (3840x2160: 35 us of enqueueing in front of 38 us of K3/K4).  Nothing in either phase depends on the
+// content of the image: sizes that do (scan length, number of K4 tiles) are read from device memory by the kernels, the
+// mailbox sequence number lives in device memory, K4's grid is the upper bound the raw buffer allows.  So a phase is
+// captured once per configuration (pixels pointer, geometry, buffers: the key) and replayed with one launch.  A
+// configuration is captured when it is encoded the second time in a row; JPGENC_GRAPHS=0 disables it.
+static bool graphs_enabled() {
+    static const bool on = [] { const char* v = std::getenv("JPGENC_GRAPHS"); return !(v && *v == '0'); }();
+    return on;
+}
+
+// replays (capturing first, if the key is new for the second time) the phase that `enqueue` puts on the stream
+static int run_phase(jpgenc_ctx* c, jpgenc_ctx::PhaseGraph& g, const uint64_t (&key)[5], const std::function<int()>& enqueue) {
+    const bool same_as_graph = g.exec && std::memcmp(g.key, key, sizeof key) == 0;
+    if (!same_as_graph) {
+        const bool repeat = std::memcmp(g.seen, key, sizeof key) == 0;
+        std::memcpy(g.seen, key, sizeof key);
+        if (!graphs_enabled() || !repeat) return enqueue();          // first sight of this configuration: plain launches
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        const uint64_t launches0 = c->launches;
+        const uint32_t seq0 = c->mailbox_seq;
+        JPGENC_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true;
+        const int rc = enqueue();
+        c->capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        g.launches = static_cast<uint32_t>(c->launches - launches0);
+        c->launches = launches0;                                     // nothing has run yet
+        const uint32_t publishes = c->mailbox_seq - seq0;
+        c->mailbox_seq = seq0;
+        if (rc || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            (void)cudaGetLastError();
+            return rc ? rc : fail(c, JPGENC_ERR_CUDA, "stream capture of an encode phase failed");
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { g.exec = nullptr; c->error = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei); return JPGENC_ERR_CUDA; }
+        std::memcpy(g.key, key, sizeof key);
+        g.publishes = publishes;
+    }
+    JPGENC_CUDA(c, cudaGraphLaunch(g.exec, c->stream));
+    c->launches += g.launches;
+    c->mailbox_seq += g.publishes;                                   // what the replayed publish kernels will announce
+    return JPGENC_OK;
+}
+
 static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* scan) {
-    const int rc = jpgenc_color_dct_quant(c);
-    return rc ? rc : run_entropy_stages(c, tables, scan);
+    if (!c->have_pixels) return fail(c, JPGENC_ERR_ARG, "no pixels bound: call jpgenc_upload_rgb / jpgenc_bind_device_rgb first");
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
+    int rc;
+    if ((rc = ensure_coef(c))) return rc;
+    if ((rc = ensure_stats_buffers(c))) return rc;
+    const double t0 = trace_on() ? now_us() : 0;
+    // ---- phase A: K1, refinement, K2, statistics into the mailbox ----
+    c->k2_tiles_done = 0;
+    const uint64_t key_a[5] = {c->alloc_gen, reinterpret_cast<uint64_t>(c->d_rgb), (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, c->maxval, 1};
+    const bool pool = c->parallel_tables;
+    if (pool) {
+        if (!c->pool) c->pool = new TablePool();
+        c->pool->arm();                                             // the table builders wake up while K1 / K2 run
+    }
+    rc = run_phase(c, c->graph_a, key_a, [&]() -> int {
+        const int r = enqueue_forward(c);
+        return r ? r : enqueue_stats(c, 0);
+    });
+    c->forward_pending = true;
+    c->have_coef = true;
+    c->have_scan = false;
+    if (!rc) rc = wait_stats(c);
+    if (rc) {
+        if (pool) c->pool->build(nullptr, nullptr, nullptr);        // release the workers again
+        return rc;
+    }
+    const double t1 = trace_on() ? now_us() : 0;
+    // ---- host: the four tables ----
+    const uint32_t(*count)[256] = reinterpret_cast<const uint32_t(*)[256]>(c->h_mailbox + kMailStats);
+    const uint64_t(*first_pos)[256] = reinterpret_cast<const uint64_t(*)[256]>(c->h_mailbox + kMailStats + 1024);
+    if (pool) {
+        if ((rc = c->pool->build(count, first_pos, tables))) return fail(c, rc, "Huffman table build failed");
+    } else {
+        for (int t = 0; t < 4; ++t)
+            if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
+    }
+    const double t2 = trace_on() ? now_us() : 0;
+    // ---- phase B: tables to the device, K3a, K3b, K4, totals into the mailbox ----
+    uint32_t k4_tiles = 0;
+    if ((rc = prepare_entropy(c, tables, &k4_tiles))) return rc;
+    const uint32_t k4_grid = static_cast<uint32_t>(c->raw_cap / kK4TileBytes + 1);      // >= k4_tiles: the raw buffer holds the scan
+    const uint64_t key_b[5] = {c->alloc_gen, k4_grid, (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, 0, 1};
+    if ((rc = run_phase(c, c->graph_b, key_b, [&]() -> int { return enqueue_entropy_phase(c, k4_grid); }))) return rc;
+    const double t3 = trace_on() ? now_us() : 0;
+    if ((rc = wait_entropy(c))) return rc;
+    if (trace_on())
+        std::fprintf(stderr, "[jpgenc image] phase A + wait %.1f us, tables %.1f us, convert + phase B enqueue %.1f us, wait %.1f us\n", t1 - t0, t2 - t1,
+                     t3 - t2, now_us() - t3);
+    if (scan) *scan = c->stats.scan_bytes;
+    std::memcpy(c->last_tables, tables, sizeof c->last_tables);
+    c->have_tables = true;
+    return JPGENC_OK;
 }
 
 // pinned staging for streamed inputs (jpgenc_encode_ppm_file), grown on demand

@@ -144,9 +144,24 @@ struct jpgenc_ctx {
     cudaStream_t copy_stream = nullptr;   // host-to-device copies of jpgenc_encode_rgb, overlapped with K1 band by band
     cudaEvent_t ev_band[16] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_u0 = nullptr, ev_u1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    // K3/K4 of one image: the time of encode N is read while K2 of encode N + 1 runs (or by jpgenc_get_stats)
+    cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;
+    bool ent_pending = false, stats_pending = false, last_whole = false;
+    float last_k1 = 0, last_fwd = 0, last_st = 0;
     std::string error;
     int sm_count = 148;
     uint64_t launches = 0;
+    bool capturing = false;               // the stream is being captured into a graph (run_phase): events are recorded as external event nodes
+    uint64_t alloc_gen = 0;               // bumped whenever a buffer of the context is (re)allocated or a parameter changes: captured graphs are stale then
+    // whole-image encodes of pixels that stay bound: the two GPU phases (K1 .. K2 + publish; tables upload .. K4 + publish) as
+    // CUDA graphs, captured when the same configuration is encoded a second time
+    struct PhaseGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t key[5] = {0, 0, 0, 0, 0};
+        uint64_t seen[5] = {0, 0, 0, 0, 0};   // key of the previous encode (a graph is captured when it repeats)
+        uint32_t launches = 0;                // kernels per replay
+        uint32_t publishes = 0;               // mailbox announcements per replay
+    } graph_a, graph_b;
 
     // parameters
     uint8_t qy[64], qc[64];
@@ -213,6 +228,11 @@ struct jpgenc_ctx {
     size_t flush_bytes = 0;
     void* h_file_pinned = nullptr;        // two band-sized pinned buffers for streamed inputs (jpgenc_encode_ppm_file)
     size_t file_pinned_bytes = 0;
+    // mailbox: mapped pinned memory the kernels of ONE image write their results into (the host polls a flag word instead of
+    // synchronising the stream): u32[3072] K2 statistics | refine count | K2 flag | pad | u64 scan bits | u64 stuffed FFs | K4 flag
+    uint32_t* h_mailbox = nullptr;        // host view
+    uint32_t* d_mailbox = nullptr;        // device view of the same memory
+    uint32_t mailbox_seq = 0;             // announced by K2 / K4 of the current encode
     void* h_pinned = nullptr;             // small pinned staging (stats, totals)
     size_t pinned_bytes = 0;
 
@@ -225,6 +245,12 @@ struct jpgenc_ctx {
     jpgenc_huff_table last_tables[4];     // tables of the last whole-image run (for jpgenc_assemble_last)
     bool have_tables = false;
 };
+
+// event on the context's stream; inside a stream capture it becomes an event-record NODE of the graph (a plain record there
+// only marks a dependency and leaves an event that cannot be waited for or timed)
+inline cudaError_t jpgenc_record(jpgenc_ctx* c, cudaEvent_t ev) {
+    return cudaEventRecordWithFlags(ev, c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 
 #define JPGENC_CUDA(ctx, expr)                                                                       \
     do {                                                                                             \
@@ -242,9 +268,15 @@ constexpr int kCntRefine = 0;      // entries in the refinement list (K1)
 constexpr int kCntK4Ticket = 2;    // K4's tile ticket (zeroed by K3a)
 constexpr int kCntRefined = 3;     // list entries already refined (band-wise encodes)
 constexpr int kCntFinalize = 4;    // finalize_tables_kernel's CTA ticket (resets itself)
-constexpr int kCntK2Done = 5;      // K2 tiles finished (single image: the last one publishes the statistics to the host)
-constexpr int kCntK4Done = 6;      // K4 tiles finished
+constexpr int kCntSeq = 5;         // mailbox sequence number (mailbox_publish_kernel increments it; never cleared)
 constexpr int kCounterWords = 16;
+// words of the host mailbox (jpgenc_ctx::h_mailbox)
+constexpr int kMailStats = 0;        // u32[3072]: K2's histogram and first-occurrence keys of the image
+constexpr int kMailRefined = 3072;   // K1's refinement counter
+constexpr int kMailK2Flag = 3073;    // == mailbox_seq: the statistics are complete
+constexpr int kMailTotals = 3076;    // u64 scan bits, u64 stuffed FF bytes
+constexpr int kMailK4Flag = 3080;    // == mailbox_seq: the scan is complete
+constexpr int kMailWords = 4096;
 int launch_forward(jpgenc_ctx* c);
 int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, bool last);
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
@@ -254,6 +286,8 @@ int launch_refine_pending(jpgenc_ctx* c);
 // K2 over the tiles [tile0, tile0 + ntiles) of the bound image(s); `first` also clears the statistics
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
 int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid);
+int launch_publish_stats(jpgenc_ctx* c);
+int launch_publish_totals(jpgenc_ctx* c);
 // batches: built tables + K2's histograms -> DeviceTables and the PassMeta block, all on the device
 int launch_finalize_tables(jpgenc_ctx* c);
 constexpr uint32_t kK4TileBytes = 16384;   // input bytes per K4 tile (entropy.cu static_asserts it)

@@ -500,6 +500,7 @@ int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
         JPGENC_CUDA(c, cudaGetLastError());
     }
     c->launches += 3;
+    if (F == 1 && !c->file_mode) return launch_publish_totals(c);    // one image: the totals go to the host's mailbox
     return JPGENC_OK;
 }
 

@@ -268,6 +268,24 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     }
 }
 
+// One image: hand results to the host through its mailbox (mapped pinned memory) -- `nwords` words from `src`, one extra
+// word, then the flag word that the host polls.  A kernel of its own, in stream order behind the producer: making the last
+// CTA of K2 do this needs a __threadfence per CTA behind its histogram atomics, which cost K2 24 us at 16384 tiles.
+// The flag value is a sequence number kept in device memory (*dseq, incremented here) and mirrored by the host
+// (jpgenc_ctx::mailbox_seq): it is not a kernel parameter, so a captured CUDA graph of the encode can be replayed as is.
+__global__ void mailbox_publish_kernel(const uint32_t* __restrict__ src, uint32_t nwords, uint32_t* mailbox, const uint32_t* extra,
+                                       uint32_t extra_word, uint32_t flag_word, uint32_t* dseq) {
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) mailbox[i] = __ldcg(src + i);
+    if (threadIdx.x == 0 && extra) mailbox[extra_word] = *extra;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t seq = *dseq + 1u;
+        *dseq = seq;
+        *reinterpret_cast<volatile uint32_t*>(mailbox + flag_word) = seq;
+    }
+}
+
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
     const unsigned tiles = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
@@ -293,13 +311,34 @@ int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool fir
     p.tile_cnt = c->d_tile_cnt;
     p.refine_count = c->d_counters;
     p.refine_copy = reinterpret_cast<uint32_t*>(c->d_stats + c->nframes * kStatsBytes);
-    if (!c->k2_configured) {
+    if (!c->k2_configured) {                                   // (the first encode of a context is never graph-captured)
         JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
         c->k2_configured = true;
     }
     symbol_stats_kernel<<<ntiles, kTileBlocks, kStatsSmem, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    return JPGENC_OK;
+}
+
+// one image, behind its last K2 launch: statistics + K1's refinement counter into the host mailbox, then the flag
+int launch_publish_stats(jpgenc_ctx* c) {
+    mailbox_publish_kernel<<<1, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->d_stats), static_cast<uint32_t>(kStatsBytes / 4),
+                                                     c->d_mailbox, c->d_counters + kCntRefine, kMailRefined, kMailK2Flag, c->d_counters + kCntSeq);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    ++c->mailbox_seq;                                          // the value the kernel will announce
+    return JPGENC_OK;
+}
+
+// one image, behind K4: scan bits and stuffed FF bytes (the results part of the PassMeta block), then the flag
+int launch_publish_totals(jpgenc_ctx* c) {
+    const PassMeta m = pass_meta_view(c->d_meta, 1);
+    mailbox_publish_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(m.total_bits), 4u, c->d_mailbox + kMailTotals, nullptr, 0u,
+                                                    kMailK4Flag - kMailTotals, c->d_counters + kCntSeq);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    ++c->mailbox_seq;
     return JPGENC_OK;
 }
 

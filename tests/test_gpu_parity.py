@@ -526,6 +526,60 @@ def test_batch_of_1080p_frames_at_its_real_size(oracle, monkeypatch, slots, per_
         enc.close()
 
 
+@pytest.mark.parametrize("graphs", ["1", "0"])
+def test_repeated_encodes_of_bound_pixels_replay_graphs(oracle, monkeypatch, graphs):
+    """jpgenc_encode_bound on pixels that stay bound: from the third encode of a configuration on, both GPU phases are
+    replayed as CUDA graphs (captured at the second).  The bytes must not depend on that -- also when the CONTENT behind
+    the same pointer changes (other scan length, other tables, other number of K4 tiles), when another size is encoded in
+    between, and when the quantisers change."""
+    from jpgenc_b200.capi import Encoder
+    monkeypatch.setenv("JPGENC_GRAPHS", graphs)
+    enc = Encoder(0)
+    try:
+        w, h = 400, 304
+        a, b = synth_rgb(w, h, 1), noise_rgb(w, h, 2)            # very different scan lengths
+        want_a, want_b = oracle.encode_rgb(a), oracle.encode_rgb(b)
+        d = enc.dev_alloc(w * h * 3)
+        out = np.zeros(max(len(want_a), len(want_b)) + 64, np.uint8)
+        try:
+            enc.h2d(d, a)
+            enc.bind_device_rgb(d, w, h)
+            for _ in range(5):
+                n = enc.encode_bound(out)
+                assert out[:n].tobytes() == want_a
+            enc.h2d(d, b)                                        # same pointer, new content: the captured graphs stay valid
+            for _ in range(4):
+                n = enc.encode_bound(out)
+                assert out[:n].tobytes() == want_b
+            enc.h2d(d, a)
+            n = enc.encode_bound(out)
+            assert out[:n].tobytes() == want_a
+            other = synth_rgb(208, 120, 5)                       # another size in between (upload path), then back
+            assert enc.encode_rgb(other) == oracle.encode_rgb(other)
+            enc.bind_device_rgb(d, w, h)
+            for _ in range(4):
+                n = enc.encode_bound(out)
+                assert out[:n].tobytes() == want_a
+            q = np.full(64, 3, np.uint8)
+            enc.set_qtables(q, q)
+            out = np.zeros(w * h * 3, np.uint8)
+            for _ in range(3):
+                n = enc.encode_bound(out)
+                got_q = out[:n].tobytes()
+            assert got_q != want_a and got_q[:2] == b"\xff\xd8" and got_q[-2:] == b"\xff\xd9"
+            # the same quantisers on a fresh context (no graph): identical bytes
+            enc2 = Encoder(0)
+            try:
+                enc2.set_qtables(q, q)
+                assert enc2.encode_rgb(a) == got_q
+            finally:
+                enc2.close()
+        finally:
+            enc.dev_free(d)
+    finally:
+        enc.close()
+
+
 def test_entropy_stage_can_run_twice_on_a_large_image(encoder, oracle):
     """K3a accumulates bit counts per 256 groups with atomics into words that K2's launch cleared: a second
     jpgenc_entropy_encode over the same symbol items (here: the same tables again) must not see them doubled.  4096x2304
