@@ -266,6 +266,10 @@ def run_ours(args):
         return float(t.item())
 
     w, h, desc = WORKLOADS[args.workload]
+    numa = (-1, 0)
+    if world > 1 and not os.environ.get("JPGENC_BENCH_NO_NUMA"):
+        from jpgenc_b200.capi import bind_host_to_device_numa
+        numa = bind_host_to_device_numa(local)       # before any pinned allocation: node-local staging buffers
     enc = Encoder(local)
     npx = w * h
     padded_px = ((w + 15) // 16 * 16) * ((h + 15) // 16 * 16)
@@ -361,6 +365,7 @@ def run_ours(args):
                 "h2d_gbps_per_gpu": round(npx * 3 / max(st_e2e.ms_h2d, 1e-6) / 1e6, 2),
                 "ms_not_h2d": round(ms_e2e - st_e2e.ms_h2d, 3)},
         "gpu_launches": int(launches),
+        "host": {"cores": os.cpu_count(), "numa_node_rank0": numa[0], "cpus_bound_rank0": numa[1]},
         "clocks": clocks,
         "roofline": roofline,
         "stage_ms": {"k1_forward": round(k1, 4), "k1_plus_refine": round(sum(fwd_ms) / len(fwd_ms), 4),

@@ -189,6 +189,13 @@ int jpgenc_encode_frames_packed(jpgenc_ctx* ctx, uint32_t n, const void* const* 
 int jpgenc_dct_quant_blocks(jpgenc_ctx* ctx, const float* dev_in, int16_t* dev_out, uint64_t nblocks,
                             const uint8_t q[64], uint64_t* refined_blocks);
 
+/* ---- deployment helper: one process per GPU on a multi-socket host ------------------------------------------------- */
+/* Restricts the calling thread to the CPUs of the NUMA node `device` is attached to (sysfs), so that pinned buffers it
+ * allocates afterwards are node-local and its uploads do not cross the socket interconnect.  *numa_node = that node, or
+ * -1 when the topology is unknown or the node's CPUs are not available to the process (then nothing is changed);
+ * *cpus_bound = CPUs in the new mask.  Call before allocating pinned memory. */
+int jpgenc_bind_host_to_device_numa(int device, int* numa_node, int* cpus_bound);
+
 /* ---- plain device-memory helpers so a Python/C harness needs no other CUDA binding ---------------- */
 int jpgenc_dev_alloc(jpgenc_ctx* ctx, size_t bytes, void** dev_ptr);
 int jpgenc_dev_free(jpgenc_ctx* ctx, void* dev_ptr);

@@ -77,6 +77,7 @@ _SIGNATURES = {
     "jpgenc_encode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_ppm_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "jpgenc_dct_quant_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u8p, u64p]),
+    "jpgenc_bind_host_to_device_numa": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "jpgenc_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "jpgenc_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jpgenc_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -398,6 +399,13 @@ class Batch:
         outs = [np.empty(cap, np.uint8) for _ in frames]
         sizes = self.encode_ptrs([f.ctypes.data for f in frames], w, h, [o.ctypes.data for o in outs], [cap] * len(frames), maxval)
         return [o[:n].tobytes() for o, n in zip(outs, sizes)]
+
+
+def bind_host_to_device_numa(device: int):
+    """-> (numa node or -1, CPUs in the new affinity mask); see jpgenc_bind_host_to_device_numa"""
+    node, cpus = C.c_int(-1), C.c_int(0)
+    load_library().jpgenc_bind_host_to_device_numa(device, C.byref(node), C.byref(cpus))
+    return node.value, cpus.value
 
 
 def pinned_empty(nbytes: int):

@@ -13,7 +13,9 @@
 #include <cstring>
 #include <vector>
 
+#include <sched.h>
 #include <unistd.h>
+#include <cctype>
 
 #include "common.cuh"
 #include "../host/ppm_reader.hpp"
@@ -1035,6 +1037,50 @@ int jpgenc_dct_quant_blocks(jpgenc_ctx* c, const float* dev_in, int16_t* dev_out
     c->refine_cap = cap_bytes / sizeof(uint32_t);
     if (rc) return rc;
     return launch_dct_quant_blocks(c, dev_in, dev_out, nblocks, q, refined_blocks);
+}
+
+// One process per GPU on a multi-socket host: pixels that cross the socket interconnect on their way to the GPU share it with
+// every other rank.  Restricting the calling thread to the CPUs of the GPU's NUMA node makes the pinned buffers it allocates
+// afterwards node-local (first touch) and keeps the threads it starts there.
+int jpgenc_bind_host_to_device_numa(int device, int* numa_node, int* cpus_bound) {
+    if (numa_node) *numa_node = -1;
+    if (cpus_bound) *cpus_bound = 0;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return JPGENC_ERR_CUDA;
+    for (char* p = bus; *p; ++p) *p = static_cast<char>(std::tolower(static_cast<unsigned char>(*p)));
+    int node = -1;
+    {
+        const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+        std::FILE* f = std::fopen(path.c_str(), "r");
+        if (!f) return JPGENC_OK;                                    // no topology information: nothing to do
+        if (std::fscanf(f, "%d", &node) != 1) node = -1;
+        std::fclose(f);
+    }
+    if (node < 0) return JPGENC_OK;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return JPGENC_OK;
+    {
+        const std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+        std::FILE* f = std::fopen(path.c_str(), "r");
+        if (!f) return JPGENC_OK;
+        int a = 0, b = 0, n = 0;
+        for (;;) {                                                   // "0-15,32-47"
+            if (std::fscanf(f, "%d", &a) != 1) break;
+            b = a;
+            int ch = std::fgetc(f);
+            if (ch == '-') { if (std::fscanf(f, "%d", &b) != 1) break; ch = std::fgetc(f); }
+            for (int k = a; k <= b && k < CPU_SETSIZE; ++k)
+                if (CPU_ISSET(k, &allowed)) { CPU_SET(k, &want); ++n; }
+            if (ch != ',') break;
+        }
+        std::fclose(f);
+        if (n == 0) return JPGENC_OK;                                // the node's CPUs are not ours to use (cpuset): leave it
+        if (sched_setaffinity(0, sizeof want, &want) != 0) return JPGENC_OK;
+        if (cpus_bound) *cpus_bound = n;
+    }
+    if (numa_node) *numa_node = node;
+    return JPGENC_OK;
 }
 
 int jpgenc_dev_alloc(jpgenc_ctx* c, size_t bytes, void** p) {
