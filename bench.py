@@ -347,8 +347,13 @@ def run_ours(args):
     if os.path.exists(tr):
         try:
             t = json.load(open(tr))
-            if t.get("workload") == args.workload:
+            # the capture is only quoted while K1's source is the one that was profiled: a changed forward.cu makes it null
+            import hashlib
+            with open(os.path.join(ROOT, "jpgenc_b200", "csrc", "forward.cu"), "rb") as f:
+                same_k1 = hashlib.sha256(f.read()).hexdigest() == t.get("k1_source_sha256_at_capture")
+            if t.get("workload") == args.workload and same_k1:
                 roofline["traffic"] = t.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = t.get("source")
         except Exception:
             pass
 
