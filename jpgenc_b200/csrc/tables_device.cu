@@ -407,9 +407,149 @@ __device__ __forceinline__ unsigned long long warp_pop(unsigned long long* H, in
     return top;
 }
 
+// ---- heap items: two encodings behind one interface ----------------------------------------------------------------
+// Wide: weight << 16 | node (48-bit weights), the general case.  Lean<W>: weight << 32 | node for heaps of at most 64 W
+// elements whose weights fit 32 bits -- every table of an ordinary frame (a level holds at most 2 n - 1 items; the sum of
+// the packages of a level is at most 15 x the number of symbols in the text) -- with a pop that has no loop at all.
+struct WideHeap {
+    static __device__ __forceinline__ unsigned long long make(unsigned long long w, unsigned node) { return (w << 16) | node; }
+    static __device__ __forceinline__ unsigned long long weight(unsigned long long it) { return it >> 16; }
+    static __device__ __forceinline__ unsigned node(unsigned long long it) { return static_cast<unsigned>(it & 0xFFFFu); }
+    static __device__ __forceinline__ void push(unsigned long long* H, int& len, unsigned long long item, int lane) { warp_push(H, len, item, lane); }
+    static __device__ __forceinline__ unsigned long long pop(unsigned long long* H, int& len, int lane) { return warp_pop(H, len, lane); }
+};
+
+// Element i (1-based) lives in slot i; its children are 2 i and 2 i + 1: one aligned 16-byte pair.  Lane l owns the nodes
+// k = l + 32 t (t < W) -- that is, it holds node k's two children in registers after ONE load.
+//   pop  = __adjust_heap: the hole walks from the root to a leaf, always to the lighter child (the right one on a tie),
+//          then the former last element `val` rises from there past every heavier element (__push_heap).
+//          Every node decides "left or right" at once (ballot Lw).  Node k lies on the hole's way iff the decisions of its
+//          ancestors spell the bits of k below its leading one -- each lane tests that for its own nodes with a few shifts
+//          of Lw, no walk.  The lanes whose node is on the way hold the elements that move (their chosen child); a ballot
+//          of "heavier than val" over them tells where val stops: the deepest such child that is not heavier.  Children
+//          at or above that depth move up into their parent, val takes the place of the deepest mover, the rest stays.
+//   push = __push_heap: lane j looks at ancestor j of the new position; a ballot tells how far the new element rises.
+template <int W>
+struct LeanHeap {
+    static constexpr unsigned kFull = 0xffffffffu;
+    static constexpr int kDepth = W == 1 ? 4 : 5;              // a node index below 32 W has at most this many bits below its leading one
+    static __device__ __forceinline__ unsigned long long make(unsigned long long w, unsigned node) { return (w << 32) | node; }
+    static __device__ __forceinline__ unsigned long long weight(unsigned long long it) { return it >> 32; }
+    static __device__ __forceinline__ unsigned node(unsigned long long it) { return static_cast<unsigned>(it); }
+    static __device__ __forceinline__ unsigned wt(unsigned long long it) { return static_cast<unsigned>(it >> 32); }
+
+    static __device__ __forceinline__ void push(unsigned long long* H, int& len, unsigned long long item, int lane) {
+        const int p = len + 1;                                  // the new position
+        const int a = p >> lane;                                // lane j >= 1: ancestor j of p (0 = none)
+        const bool has = lane >= 1 && a >= 1;
+        const unsigned long long anc = has ? H[a] : 0ull;
+        const unsigned up = __ballot_sync(kFull, has && wt(anc) > wt(item)) >> 1;   // bit j-1: ancestor j is heavier
+        const int r = __ffs(~up) - 1;                           // the element rises past r ancestors
+        if (has && lane <= r) H[p >> (lane - 1)] = anc;         // ancestor j moves down to where ancestor j-1 was
+        if (lane == 0) H[p >> r] = item;
+        len = p;
+        __syncwarp();
+    }
+
+    static __device__ __forceinline__ unsigned long long pop(unsigned long long* H, int& len, int lane) {
+        const unsigned long long top = H[1];
+        const int m = len - 1;                                  // elements that stay: 1 .. m
+        len = m;
+        if (m == 0) { __syncwarp(); return top; }
+        const unsigned long long val = H[m + 1];                // the former last element looks for its place
+        const unsigned vw = wt(val);
+        ulonglong2 pr[W];
+        bool left[W];
+        unsigned Lw[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int k = lane + 32 * t;
+            pr[t] = *reinterpret_cast<const ulonglong2*>(H + 2 * k);             // children 2k (x) and 2k+1 (y); k = 0 reads slots 0, 1: unused
+            const bool hasl = k >= 1 && 2 * k <= m, hasr = 2 * k + 1 <= m;
+            left[t] = hasl && (!hasr || wt(pr[t].y) > wt(pr[t].x));              // left only when the right child is strictly heavier (or absent)
+            Lw[t] = __ballot_sync(kFull, left[t]);
+        }
+        unsigned pc[W], hv[W];
+        unsigned long long child[W];
+        bool onp[W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int k = lane + 32 * t;
+            unsigned x = 0;                                     // bit j = "ancestor k >> (j+1) goes left"
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j) {
+                const int a = k >> (j + 1);
+                const unsigned word = (W > 1 && a >= 32) ? Lw[W - 1] : Lw[0];
+                x |= ((word >> (a & 31)) & 1u) << j;
+            }
+            const unsigned mask = k >= 1 ? (1u << (31 - __clz(k))) - 1u : 0u;
+            // going left means bit 0: the way to k is taken iff every ancestor's decision differs from k's bit
+            onp[t] = k >= 1 && 2 * k <= m && (((x ^ static_cast<unsigned>(k)) & mask) == mask);
+            child[t] = left[t] ? pr[t].x : pr[t].y;
+            pc[t] = __ballot_sync(kFull, onp[t]);
+            hv[t] = __ballot_sync(kFull, onp[t] && wt(child[t]) > vw);
+        }
+        // deepest element on the way that val does not pass (deeper = larger node index); none: val goes to the root
+        int kstar = 0;
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const unsigned stops = pc[t] & ~hv[t];
+            if (stops) kstar = 32 * t + 31 - __clz(stops);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+            const int k = lane + 32 * t;
+            if (onp[t] && k <= kstar) H[k] = child[t];          // the chosen child moves up into its parent
+            if (onp[t] && k == kstar) H[2 * k + (left[t] ? 0 : 1)] = val;
+        }
+        if (kstar == 0 && lane == 0) H[1] = val;
+        __syncwarp();
+        return top;
+    }
+};
+
+// package_merge (Huffman.hpp:114-160) on the warp's three heaps: leaf i = node i, packages are nodes n, n+1, ... with two
+// children; returns the number of packages of the last level and leaves their node ids, in pop order, in ws.root
+template <class HP>
+__device__ int package_merge_warp(WarpShared& ws, uint32_t* nodes, int n, int lane) {
+    unsigned long long *bp = ws.heap[0], *cur = ws.heap[1], *nxt = ws.heap[2];
+    int nb = 0;
+    for (int i = 0; i < n; ++i)                                // map iteration order feeds the first heap; the reference counts in int
+        HP::push(bp, nb, HP::make(static_cast<unsigned long long>(static_cast<unsigned>(static_cast<int>(ws.freq[i]))), static_cast<unsigned>(i)), lane);
+    int nn = n, ncur = n, nnxt = 0;
+    for (int i = lane; i < n; i += 32) cur[i + 1] = bp[i + 1];
+    __syncwarp();
+    for (int lvl = 0; lvl < kLimit; ++lvl) {
+        if (lvl + 1 < kLimit) {                                // every level but the last starts as a copy of the leaves
+            for (int i = lane; i < n; i += 32) nxt[i + 1] = bp[i + 1];
+            nnxt = n;
+            __syncwarp();
+        } else {
+            nnxt = 0;
+        }
+        while (ncur > 1) {
+            const unsigned long long a = HP::pop(cur, ncur, lane), b = HP::pop(cur, ncur, lane);
+            if (lane == 0) nodes[nn] = HP::node(a) | (HP::node(b) << 16);
+            HP::push(nxt, nnxt, HP::make(HP::weight(a) + HP::weight(b), static_cast<unsigned>(nn)), lane);
+            ++nn;
+        }
+        unsigned long long* sw = cur; cur = nxt; nxt = sw;
+        ncur = nnxt;
+    }
+    // ---- drain the last level: packages in pop order ----
+    int npk = 0;
+    while (ncur) {
+        const unsigned long long pk = HP::pop(cur, ncur, lane);
+        if (lane == 0) ws.root[npk] = static_cast<unsigned short>(HP::node(pk));
+        ++npk;
+    }
+    return npk;
+}
+
 // The table `tab` (zeroed) from count[] / first[]; ws = the warp's shared memory, s = its scratch slab in global memory.
 __device__ void build_table_warp(WarpShared& ws, TableScratch& s, const uint32_t* count, const unsigned long long* first,
-                                 jpgenc_huff_table* tab, int lane, uint32_t* status) {
+                                 jpgenc_huff_table* tab, int lane, uint32_t* status, bool lean_ok) {
     // ---- distinct symbols in order of first appearance (= the order the reference's counting loop creates map entries) ----
     int n = 0;
     for (int base = 0; base < 256; base += 32) {
@@ -447,37 +587,15 @@ __device__ void build_table_warp(WarpShared& ws, TableScratch& s, const uint32_t
     }
     // ---- package-merge (Huffman.hpp:114-160): leaf i = node i; packages are nodes n, n+1, ... with two children ----
     uint32_t* nodes = reinterpret_cast<uint32_t*>(s.nodes);    // left | right << 16
-    unsigned long long *bp = ws.heap[0], *cur = ws.heap[1], *nxt = ws.heap[2];
-    int nb = 0;
-    for (int i = 0; i < n; ++i)                                // map iteration order feeds the first heap; the reference counts in int
-        warp_push(bp, nb, (static_cast<unsigned long long>(static_cast<unsigned>(static_cast<int>(ws.freq[i]))) << 16) | static_cast<unsigned>(i), lane);
-    int nn = n, ncur = n, nnxt = 0;
-    for (int i = lane; i < n; i += 32) cur[i + 1] = bp[i + 1];
-    __syncwarp();
-    for (int lvl = 0; lvl < kLimit; ++lvl) {
-        if (lvl + 1 < kLimit) {                                // every level but the last starts as a copy of the leaves
-            for (int i = lane; i < n; i += 32) nxt[i + 1] = bp[i + 1];
-            nnxt = n;
-            __syncwarp();
-        } else {
-            nnxt = 0;
-        }
-        while (ncur > 1) {
-            const unsigned long long a = warp_pop(cur, ncur, lane), b = warp_pop(cur, ncur, lane);
-            if (lane == 0) nodes[nn] = static_cast<uint32_t>(a & 0xFFFFu) | (static_cast<uint32_t>(b & 0xFFFFu) << 16);
-            warp_push(nxt, nnxt, ((item_w(a) + item_w(b)) << 16) | static_cast<unsigned>(nn), lane);
-            ++nn;
-        }
-        unsigned long long* sw = cur; cur = nxt; nxt = sw;
-        ncur = nnxt;
-    }
-    // ---- drain the last level: packages in pop order ----
-    int npk = 0;
-    while (ncur) {
-        const unsigned long long pk = warp_pop(cur, ncur, lane);
-        if (lane == 0) ws.root[npk] = static_cast<unsigned short>(pk & 0xFFFFu);
-        ++npk;
-    }
+    unsigned long long total = 0;
+    for (int i = lane; i < n; i += 32) total += ws.freq[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    const bool small_weights = total < (1ull << 28);           // 15 x total (the heaviest a package can get) fits 32 bits
+    int npk;
+    if (small_weights && n <= 32 && lean_ok) npk = package_merge_warp<LeanHeap<1>>(ws, nodes, n, lane);
+    else if (small_weights && n <= 64 && lean_ok) npk = package_merge_warp<LeanHeap<2>>(ws, nodes, n, lane);
+    else npk = package_merge_warp<WideHeap>(ws, nodes, n, lane);
     for (int i = lane; i < n; i += 32) { ws.cnt[i] = 0; ws.first[i] = 0xFFFFu; }
     __syncwarp();
     __threadfence_block();                                     // lane 0's node records are visible to every lane
@@ -545,7 +663,7 @@ __device__ void build_table_warp(WarpShared& ws, TableScratch& s, const uint32_t
 // parity test; -G, -Xcicc -O1 and non-inlined heap functions all gave the right tables.)
 template <bool kCooperative>
 __global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, uint32_t stats_stride, uint32_t ntables,
-                                                          TableScratch* scratch, jpgenc_huff_table* out, uint32_t* status) {
+                                                          TableScratch* scratch, jpgenc_huff_table* out, uint32_t* status, int lean_ok) {
     const uint32_t table = blockIdx.x, lane = threadIdx.x;
     if (table >= ntables) return;
     const uint32_t frame = table >> 2, t = table & 3;
@@ -561,7 +679,7 @@ __global__ void __launch_bounds__(32) build_tables_kernel(const uint8_t* stats, 
     if constexpr (kCooperative) {
         __shared__ WarpShared ws;
         __syncwarp();
-        build_table_warp(ws, s, count, first, tab, static_cast<int>(lane), status + table);
+        build_table_warp(ws, s, count, first, tab, static_cast<int>(lane), status + table, lean_ok != 0);
     } else {
         __shared__ HeapItem sh_heap[3][2 * kSharedSyms + 16];
         __shared__ Node sh_nodes[kSharedSyms * (kLimit + 2) + 16];
@@ -617,8 +735,10 @@ int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[
 int launch_build_tables(jpgenc_ctx* c, const uint8_t* d_stats, uint32_t stats_stride, uint32_t ntables, void* d_scratch,
                         jpgenc_huff_table* d_out, uint32_t* d_status) {
     static const bool serial = [] { const char* v = std::getenv("JPGENC_TABLES_SERIAL"); return v && *v && *v != '0'; }();
-    if (serial) build_tables_kernel<false><<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status);
-    else build_tables_kernel<true><<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status);
+    // JPGENC_TABLES_LEAN=0: the general heap operations for every table (A/B checks of the lean ones)
+    static const int lean = [] { const char* v = std::getenv("JPGENC_TABLES_LEAN"); return (v && *v == '0') ? 0 : 1; }();
+    if (serial) build_tables_kernel<false><<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status, lean);
+    else build_tables_kernel<true><<<ntables, 32, 0, c->stream>>>(d_stats, stats_stride, ntables, static_cast<TableScratch*>(d_scratch), d_out, d_status, lean);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return JPGENC_OK;

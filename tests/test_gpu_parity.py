@@ -419,6 +419,22 @@ def test_device_table_build_equals_host_build(encoder):
 
 
 @pytest.mark.gpu
+def test_device_table_build_small_alphabets_with_many_ties(encoder):
+    """Alphabets of up to 64 symbols with small weights take the loop-free heap operations (LeanHeap, tables_device.cu); equal
+    weights are where the heap's layout decides the result, so: tiny weight ranges, hundreds of alphabets, every size."""
+    rng = np.random.default_rng(77)
+    counts, firsts = [], []
+    for rep in range(6):
+        for nsym in range(2, 65):
+            c, f = random_symbol_stats(rng, nsym, int(rng.choice([2, 3, 4, 7, 40, 5000])))
+            counts.append(c); firsts.append(f)
+    dev = encoder.build_huffman_device(np.stack(counts), np.stack(firsts))
+    for i, (c, f) in enumerate(zip(counts, firsts)):
+        host = encoder.build_huffman([c] * 4, [f] * 4)[0]
+        assert table_fields(dev[i]) == table_fields(host), f"table {i} ({int(np.count_nonzero(c))} symbols) differs"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["synth_512", "noise_256", "odd_203x117", "one_pixel", "stripes", "maxval15"])
 def test_device_table_build_on_image_statistics(encoder, name):
     rgb, maxval = IMAGES[name]
