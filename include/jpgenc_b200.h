@@ -144,6 +144,13 @@ int jpgenc_assemble_last(jpgenc_ctx* ctx, uint8_t* dst, uint64_t cap, uint64_t* 
 /* upload + encode (host pixels in, JPEG bytes out) */
 int jpgenc_encode_rgb(jpgenc_ctx* ctx, const uint8_t* host_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval,
                       uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);
+/* Image::writeJPEG (src/Image.cpp:831-976) for an image given as the reference holds it: three row-major planes of doubles
+ * (Image::R/G/B, include/Image.hpp:104-114), `width` x `height` = the image padded to whole 16x16 MCUs (src/Image.cpp:479-530),
+ * real_w x real_h = what SOF0 reports.  ycbcr != 0: the planes already are level-shifted Y, Cb, Cr and are not converted
+ * (convertToColorSpace returns at once for them, src/Image.cpp:112-115).  Any double is accepted (edited planes, non-integral
+ * samples): every block is computed in FP64 in the reference's operation order.  Slower than the 8-bit path (~6 ms for 268 Mpx). */
+int jpgenc_encode_planes(jpgenc_ctx* ctx, const double* p0, const double* p1, const double* p2, uint32_t width, uint32_t height,
+                         uint32_t real_w, uint32_t real_h, int ycbcr, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes);
 /* main.cpp:8-32 — PPM file in, JPEG file out */
 int jpgenc_encode_ppm_file(jpgenc_ctx* ctx, const char* ppm_path, const char* jpg_path);
 

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "jpgenc_encode_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_assemble_last": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, u64p]),
+    "jpgenc_encode_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_ppm_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "jpgenc_dct_quant_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u8p, u64p]),
     "jpgenc_bind_host_to_device_numa": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -264,6 +266,17 @@ class Encoder:
                 continue
             self._check(rc)
             return out[: n.value].tobytes()
+
+    def encode_planes(self, p0: np.ndarray, p1: np.ndarray, p2: np.ndarray, real_w: int, real_h: int, ycbcr: bool = False) -> bytes:
+        """three (H16, W16) float64 planes as the reference's Image holds them -> JPEG bytes (exact FP64 path for every block)"""
+        planes = [np.ascontiguousarray(p, np.float64) for p in (p0, p1, p2)]
+        h16, w16 = planes[0].shape
+        n = C.c_uint64()
+        self._check(self.lib.jpgenc_encode_planes(self.h, planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data, w16, h16, real_w, real_h,
+                                                  1 if ycbcr else 0, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint8)
+        self._check(self.lib.jpgenc_assemble_last(self.h, out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value].tobytes()
 
     def encode_rgb_into(self, host_ptr: int, w: int, h: int, out_ptr: int, cap: int, maxval: int = 255) -> int:
         n = C.c_uint64()

@@ -1,5 +1,4 @@
-// Shared pieces of K2/K3/K4: staging MCU-ordered coefficient tiles in shared memory, the symbol-item format, CTA scan
-// and decoupled look-back.
+// Shared pieces of K2/K3/K4: staging MCU-ordered coefficient tiles in shared memory, the symbol-item format, CTA scan.
 #pragma once
 #include "common.cuh"
 
@@ -105,51 +104,6 @@ __device__ __forceinline__ uint32_t make_item(int table, int symbol, int nzrl, i
     const uint32_t cat = symbol & 15;
     const uint32_t mag = static_cast<uint32_t>(value < 0 ? value - 1 : value) & ((1u << cat) - 1u);
     return static_cast<uint32_t>(symbol) | (static_cast<uint32_t>(table) << 8) | (static_cast<uint32_t>(nzrl) << 10) | (mag << 12);
-}
-
-// ---- decoupled look-back over 64-bit status words: [63:62] state, [61:0] value ---------------------------
-constexpr unsigned long long kLbAggregate = 1ull << 62;
-constexpr unsigned long long kLbPrefix = 2ull << 62;
-constexpr unsigned long long kLbValueMask = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Called by ALL 32 lanes of one warp of tile `tile`; returns (to every lane) the exclusive prefix of `aggregate`
-// over all earlier tiles.  Each step inspects 32 predecessors at once.
-__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status, uint32_t tile,
-                                                                 unsigned long long aggregate) {
-    const int lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) lb_store(status, kLbPrefix | aggregate);
-        return 0;
-    }
-    if (lane == 0) lb_store(status + tile, kLbAggregate | aggregate);
-    unsigned long long sum = 0;
-    int64_t hi = static_cast<int64_t>(tile) - 1;     // newest predecessor not yet accounted for
-    while (true) {
-        const int64_t j = hi - lane;
-        unsigned long long s = kLbPrefix;            // lanes past tile 0 behave like an empty prefix
-        if (j >= 0) {
-            do { s = lb_load(status + j); } while ((s >> 62) == 0);
-        }
-        const unsigned prefix_lanes = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-        const int first = prefix_lanes ? __ffs(prefix_lanes) - 1 : 32;       // nearest predecessor with a full prefix
-        unsigned long long v = (lane <= first) ? (s & kLbValueMask) : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        sum += v;
-        if (prefix_lanes) break;
-        hi -= 32;
-    }
-    if (lane == 0) lb_store(status + tile, kLbPrefix | (sum + aggregate));
-    return sum;
 }
 
 // block-wide exclusive scan of one value per thread (blockDim.x <= 1024); `scratch` holds 33 words

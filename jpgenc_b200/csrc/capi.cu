@@ -943,6 +943,41 @@ int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     return assemble(c, tables, scan, dst, cap);
 }
 
+// Image::writeJPEG for an image that is not (or no longer) a set of 8-bit samples: planes a caller edited after loadPPM,
+// non-integral values, or an image that already is YCbCr (src/Image.cpp:831-846 encodes whatever the three planes hold and
+// converts only an RGB image, :112-115).  The planes are uploaded as doubles and every block takes the exact FP64 path.
+int jpgenc_encode_planes(jpgenc_ctx* c, const double* p0, const double* p1, const double* p2, uint32_t width, uint32_t height,
+                         uint32_t real_w, uint32_t real_h, int ycbcr, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) {
+    if (!c || !p0 || !p1 || !p2) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaSetDevice(c->device));
+    // the reference's stages need whole 16x16 MCUs (loadPPM pads; an Image built in memory must have such a size already)
+    if (real_w == 0 || real_h == 0 || width != ((real_w + 15u) & ~15u) || height != ((real_h + 15u) & ~15u))
+        return fail(c, JPGENC_ERR_ARG, "planes must be the image padded to whole 16x16 MCUs");
+    int rc = set_geometry(c, real_w, real_h, 255);
+    if (rc) return rc;
+    c->have_pixels = false;
+    if ((rc = ensure_coef(c))) return rc;
+    const size_t plane = static_cast<size_t>(width) * height;
+    if ((rc = ensure(c, &c->d_rgb_owned, &c->rgb_cap, 3 * plane * sizeof(double) + 16))) return rc;
+    double* d = reinterpret_cast<double*>(c->d_rgb_owned);
+    const double* src[3] = {p0, p1, p2};
+    for (int k = 0; k < 3; ++k)
+        JPGENC_CUDA(c, cudaMemcpyAsync(d + k * plane, src[k], plane * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = flush_entropy_time(c))) return rc;
+    if ((rc = launch_planes_exact(c, d, ycbcr != 0))) return rc;
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));            // the caller's planes may change as soon as we return
+    c->stats.refined_blocks = static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
+    c->have_coef = true;
+    c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
+    jpgenc_huff_table tables[4];
+    uint64_t scan = 0;
+    if ((rc = run_entropy_stages(c, tables, &scan))) return rc;
+    const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, tables, nullptr);
+    if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
+    if (!dst) return JPGENC_OK;
+    return assemble(c, tables, scan, dst, cap);
+}
+
 // main.cpp:8-32.  A binary (P6) payload is streamed: the header is parsed from the first bytes, then every band of rows is
 // read straight into pinned staging and uploaded while the next band is being read and the previous ones go through
 // K1/refinement/K2 (loadPPM's pixel path, src/Image.cpp:411-418, without ever holding the image in host memory).  ASCII

@@ -283,6 +283,7 @@ int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64
                             uint64_t* refined);
 int launch_planes_to_mcu(jpgenc_ctx* c, const int32_t* d_qy, const int32_t* d_qcb, const int32_t* d_qcr);
 int launch_refine_pending(jpgenc_ctx* c);
+int launch_planes_exact(jpgenc_ctx* c, const double* d_planes, bool ycbcr);
 // K2 over the tiles [tile0, tile0 + ntiles) of the bound image(s); `first` also clears the statistics
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
 int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid);
@@ -290,7 +291,10 @@ int launch_publish_stats(jpgenc_ctx* c);
 int launch_publish_totals(jpgenc_ctx* c);
 // batches: built tables + K2's histograms -> DeviceTables and the PassMeta block, all on the device
 int launch_finalize_tables(jpgenc_ctx* c);
-constexpr uint32_t kK4TileBytes = 16384;   // input bytes per K4 tile (entropy.cu static_asserts it)
+#ifndef JPGENC_K4_THREADS
+#define JPGENC_K4_THREADS 256
+#endif
+constexpr uint32_t kK4TileBytes = JPGENC_K4_THREADS * 16;   // input bytes per K4 tile: 16 per thread (entropy.cu)
 size_t table_scratch_bytes();
 int build_table_arrays_host(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
 int launch_build_tables(jpgenc_ctx* c, const uint8_t* d_stats, uint32_t stats_stride, uint32_t ntables, void* d_scratch,

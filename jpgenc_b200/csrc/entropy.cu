@@ -10,7 +10,7 @@
 //   K3b  one warp per range: codes assembled MSB-first in a per-warp shared-memory bit buffer and written out as whole
 //        32-bit words (only the two words a chunk shares with its neighbours use atomicOr).
 // With the offsets known up front no warp ever waits for another one: no tickets, no look-back, no block barriers.
-// K4: count FF bytes, CTA scan, decoupled look-back over per-tile status words, compact.
+// K4a/K4: FF bytes per tile; then every tile: CTA scan, output position = sum of the earlier tiles' counts, compact.
 #include <cstdlib>
 
 #include "blockwalk.cuh"
@@ -74,8 +74,7 @@ struct EntropyParams {
     const uint32_t* hdr_len;            // [nframes] bytes of JFIF header in front of the frame's scan (0: scan only)
     unsigned long long* total_bits;     // [nframes] out: bits of the scan (before padding)
     unsigned long long* ff_incl;        // [nframes] out: FF bytes K4 stuffed in frames 0..f of the pass
-    unsigned long long* k4_status;      // K4's look-back words, one per tile (all frames of the pass form ONE sequence)
-    uint32_t* counters;                 // [0] K4's tile ticket
+    uint32_t* tile_ff;                  // FF bytes per K4 tile (K4a), all frames of the pass numbered as ONE sequence
     // output as complete files (batches): every frame = header + scan + EOI, frames back to back
     const jpgenc_huff_table* built;     // [nframes * 4] tables as the device build left them (DHT segments); null = scan only
     const uint8_t* hdr_prefix;          // SOI .. SOF0, identical for every frame of the pass
@@ -123,28 +122,26 @@ constexpr int kPackThreads = 256;                       // 8 warps, one item ran
 constexpr int kPackWarps = kPackThreads / 32;
 
 // ---- K3a: bits per range (coalesced pass over the items) + housekeeping ---------------------------------------
-// Besides sizing the ranges this launch zeroes what the later kernels expect zeroed (the raw scan, K4's look-back words
-// and ticket), so that no memset sits between the host's table build and the first kernel.  Sizes are kept at three
+// Besides sizing the ranges this launch zeroes the raw scan, so that no memset sits between the host's table build and the
+// first kernel.  Sizes are kept at three
 // levels -- range, group (the 8 ranges of a CTA), super-group (256 groups, accumulated with atomics) -- so that K3b can
 // derive any range's bit offset from a few hundred values instead of waiting for a serial scan.
 __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_constant__ EntropyParams p) {
-    __shared__ uint32_t s_tab[1024], s_fast[1024];
+    __shared__ uint32_t s_len[1024];                           // bits of a symbol with its magnitude: code length + category; 0 = absent
     __shared__ uint32_t s_wbits[kPackWarps];
     if (p.hdr->error) return;                                  // the pass was refused (finalize_tables_kernel): the host re-runs it
     const uint32_t frame = blockIdx.x / p.groups_per_frame, group = blockIdx.x - frame * p.groups_per_frame;
     const DeviceTables* tables = p.tables + frame;
     for (int i = threadIdx.x; i < 1024; i += kPackThreads) {
-        s_tab[i] = (&tables->entry[0][0])[i];
-        s_fast[i] = (&tables->fast[0][0])[i];
+        const uint32_t e = (&tables->entry[0][0])[i];
+        s_len[i] = e ? (e >> 16) + (i & 15u) : 0u;
     }
     {   // housekeeping, spread over the grid
         const unsigned long long gtid = static_cast<unsigned long long>(blockIdx.x) * kPackThreads + threadIdx.x;
         const unsigned long long gsize = static_cast<unsigned long long>(gridDim.x) * kPackThreads;
-        const unsigned long long raw_words16 = p.hdr->raw_total / 16, k4_tiles = p.hdr->k4_tiles;
+        const unsigned long long raw_words16 = p.hdr->raw_total / 16;
         uint4* raw16 = reinterpret_cast<uint4*>(p.raw);
         for (unsigned long long i = gtid; i < raw_words16; i += gsize) raw16[i] = make_uint4(0, 0, 0, 0);
-        for (unsigned long long i = gtid; i < k4_tiles; i += gsize) p.k4_status[i] = 0ull;
-        if (gtid == 0) p.counters[0] = 0u;
     }
     __syncthreads();
     const uint32_t range = group * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -153,10 +150,29 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
         const size_t slab = static_cast<size_t>(frame) * p.ranges_per_frame + range;
         uint32_t n;
         const uint32_t* __restrict__ items = range_items(p, frame, range, &n);
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t item = __ldg(items + i), w = item_fast(item, s_fast);
-            bits += w ? w >> 27 : item_bits(item, s_tab);
+        // one lookup per item; a ZRL in front of it (rare) adds the ZRL code of its table
+        auto size_of = [&](uint32_t item) {
+            uint32_t b = s_len[item & 0x3FFu];
+            const uint32_t nz = (item >> 10) & 3u;
+            if (nz) b += nz * (s_len[(item & 0x300u) | 0xF0u]);            // category 0: s_len is the bare code length
+            return b;
+        };
+        uint32_t head = min(n, static_cast<uint32_t>((16u - (reinterpret_cast<uintptr_t>(items) & 15u)) & 15u) >> 2);   // items up to 16-byte alignment
+        if (lane < head) bits += size_of(__ldg(items + lane));
+        const uint4* __restrict__ q4 = reinterpret_cast<const uint4*>(items + head);
+        const uint32_t nq = (n - head) >> 2;
+        uint32_t i = lane;
+        for (; i + 32 < nq; i += 64) {                                      // two 16-byte loads in flight per lane
+            const uint4 a = __ldg(q4 + i), b = __ldg(q4 + i + 32);
+            bits += size_of(a.x) + size_of(a.y) + size_of(a.z) + size_of(a.w);
+            bits += size_of(b.x) + size_of(b.y) + size_of(b.z) + size_of(b.w);
         }
+        if (i < nq) {
+            const uint4 a = __ldg(q4 + i);
+            bits += size_of(a.x) + size_of(a.y) + size_of(a.z) + size_of(a.w);
+        }
+        const uint32_t tail0 = head + 4u * nq;
+        if (tail0 + lane < n) bits += size_of(__ldg(items + tail0 + lane));
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
         if (lane == 0) p.range_bits[slab] = bits;
@@ -225,31 +241,61 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
     uint32_t* it = s_items[warp];
     uint32_t* bitbuf = s_bits[warp];
 
+    // the rows of chunk c + 1 are requested before chunk c is processed (registers), so that a warp waits for global memory
+    // once per range, not once per chunk
+    uint32_t v[kChunkRows];
+#pragma unroll
+    for (int r = 0; r < kChunkRows; ++r) {
+        const uint32_t j = r * 32 + lane;
+        v[r] = j < n ? __ldg(items + j) : 0u;
+    }
     for (uint32_t c0 = 0; c0 < n; c0 += kChunkItems) {
         const uint32_t m = min(static_cast<uint32_t>(kChunkItems), n - c0);
         const uint32_t rows = (m + 31) >> 5;
-        if (m == kChunkItems) {                                  // full chunk: all 16 row loads in flight at once
-            uint32_t v[kChunkRows];
 #pragma unroll
-            for (int r = 0; r < kChunkRows; ++r) v[r] = __ldg(items + c0 + r * 32 + lane);
+        for (int r = 0; r < kChunkRows; ++r) it[r * 33 + lane] = v[r];
+        if (c0 + kChunkItems < n) {
 #pragma unroll
-            for (int r = 0; r < kChunkRows; ++r) it[r * 33 + lane] = v[r];
-        } else {
-#pragma unroll 4
-            for (uint32_t r = 0; r < rows; ++r) {
-                const uint32_t j = r * 32 + lane;
-                if (j < m) it[j + r] = __ldg(items + c0 + j);
+            for (int r = 0; r < kChunkRows; ++r) {
+                const uint32_t j = c0 + kChunkItems + r * 32 + lane;
+                v[r] = j < n ? __ldg(items + j) : 0u;
             }
         }
         __syncwarp();
         const uint32_t j0 = min(m, lane * rows), j1 = min(m, j0 + rows);   // this lane's consecutive items
-        // sizing pass; an item that resolves with one lookup is replaced in place by its (bit count << 27) | bits word,
-        // so the packing pass below does not touch the tables again
-        uint32_t my_bits = 0;
-        for (uint32_t j = j0; j < j1; ++j) {
-            const uint32_t at = j + (j >> 5), item = it[at], w = item_fast(item, s_fast);
-            if (w) { it[at] = w; my_bits += w >> 27; }
-            else my_bits += item_bits(item, s_tab);
+        const uint32_t lead = static_cast<uint32_t>(cur & 31);          // bits of the first word that belong to whoever came before
+        // ---- one pass over the lane's items: their codes are assembled MSB-first into a lane-local bit string whose words
+        // replace the items already consumed (word k goes to the slot of the lane's k-th item: an item yields at most 27
+        // bits on the one-lookup path, so a word is never complete before its slot is free; items that need the general
+        // path -- ZRLs in front, more than 27 bits -- may outrun their slots: then the chunk is redone the slow way) ----
+        uint32_t my_bits = 0, nw = 0;
+        bool outrun = false;
+        {
+            unsigned long long acc = 0;                                   // bit 63 = the earliest bit not yet stored
+            uint32_t fill = 0;
+            for (uint32_t j = j0; j < j1; ++j) {
+                const uint32_t item = it[j + (j >> 5)];
+                auto put = [&](uint32_t code, uint32_t len) {            // len <= 31, fill < 32
+                    acc |= static_cast<unsigned long long>(code) << (64u - fill - len);
+                    fill += len;
+                    my_bits += len;
+                    if (fill >= 32u) {
+                        if (j0 + nw <= j) { const uint32_t o = j0 + nw; it[o + (o >> 5)] = static_cast<uint32_t>(acc >> 32); }
+                        else outrun = true;
+                        ++nw;
+                        acc <<= 32;
+                        fill -= 32u;
+                    }
+                };
+                const uint32_t w = item_fast(item, s_fast);
+                if (w) put(w & 0x07FFFFFFu, w >> 27);
+                else item_codes(item, s_tab, put);
+            }
+            if (fill) {                                                   // the open word (its unused low bits are zero)
+                if (j1 > j0 && j0 + nw < j1) { const uint32_t o = j0 + nw; it[o + (o >> 5)] = static_cast<uint32_t>(acc >> 32); }
+                else outrun = true;
+                ++nw;
+            }
         }
         uint32_t inc = my_bits;
 #pragma unroll
@@ -258,17 +304,15 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
             if (lane >= d) inc += up;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t lead = static_cast<uint32_t>(cur & 31);          // bits of the first word that belong to whoever came before
-        if (lead + total <= kWarpBitWords * 32u) {
-            if (j0 < j1) {
-                BitWriter<false> bw;
-                bw.start(bitbuf, lead + inc - my_bits);
-                for (uint32_t j = j0; j < j1; ++j) {
-                    const uint32_t w = it[j + (j >> 5)];
-                    if (w >> 27) bw.put(w & 0x07FFFFFFu, w >> 27);
-                    else item_codes(w, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
-                }
-                bw.finish();
+        const bool redo = __any_sync(0xffffffffu, outrun) || lead + total > kWarpBitWords * 32u;
+        if (!redo) {
+            // every lane ORs its words into the warp's bit buffer at its place (neighbours share words: shared-memory atomics)
+            const uint32_t at = lead + inc - my_bits;
+            for (uint32_t k = 0; k < nw; ++k) {
+                const uint32_t o = j0 + k, v = it[o + (o >> 5)];
+                const uint32_t pos = at + 32u * k, sh = pos & 31u;
+                if (v >> sh) atomicOr(&bitbuf[pos >> 5], v >> sh);
+                if (sh && (v << (32u - sh))) atomicOr(&bitbuf[(pos >> 5) + 1], v << (32u - sh));
             }
             __syncwarp();
             const uint32_t nwords = (lead + total + 31) >> 5;
@@ -279,15 +323,22 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
                 if (i == 0 || i == nwords - 1) { if (v) atomicOr(&g[i], v); }
                 else g[i] = v;
             }
-        } else if (j0 < j1) {   // very dense chunk: straight to the (zeroed) global words
-            BitWriter<true> bw;
-            bw.start(p.raw, cur + inc - my_bits);
-            for (uint32_t j = j0; j < j1; ++j) {
-                const uint32_t w = it[j + (j >> 5)];
-                if (w >> 27) bw.put(w & 0x07FFFFFFu, w >> 27);
-                else item_codes(w, s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+        } else {
+            // very dense chunk: items again (the pass above has overwritten them), straight to the (zeroed) global words
+            __syncwarp();
+#pragma unroll 4
+            for (uint32_t r = 0; r < rows; ++r) {
+                const uint32_t j = r * 32 + lane;
+                if (j < m) it[j + r] = __ldg(items + c0 + j);
             }
-            bw.finish();
+            __syncwarp();
+            if (j0 < j1) {
+                BitWriter<true> bw;
+                bw.start(p.raw, cur + inc - my_bits);
+                for (uint32_t j = j0; j < j1; ++j)
+                    item_codes(it[j + (j >> 5)], s_tab, [&](uint32_t code, uint32_t len) { bw.put(code, len); });
+                bw.finish();
+            }
         }
         __syncwarp();
         cur += total;
@@ -310,7 +361,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
 // 16 input bytes (SIMD byte compare), a CTA scan + look-back give the output position, the tile's output is assembled
 // in shared memory (word stores; byte stores only at a thread's unaligned ends or where an FF actually occurs) and
 // leaves as coalesced 32-bit stores, funnel-shifted to the alignment of the global position.
-constexpr int kStuffThreads = 1024;
+constexpr int kStuffThreads = JPGENC_K4_THREADS;
 constexpr int kStuffBytesPerThread = 16;
 constexpr int kStuffTile = kStuffThreads * kStuffBytesPerThread;
 static_assert(kStuffTile == kK4TileBytes, "capi.cu numbers K4 tiles with kK4TileBytes");
@@ -346,55 +397,95 @@ __device__ __forceinline__ void write_file_header(uint8_t* dst, const EntropyPar
     }
 }
 
-__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_constant__ EntropyParams p, uint8_t* __restrict__ scan) {
-    __shared__ alignas(16) uint8_t s_out[2 * kStuffTile + 16];
-    __shared__ uint32_t s_scan[33];
-    __shared__ uint32_t s_tile, s_frame;
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x;
-    if (p.hdr->error) return;
-    if (tid == 0) {
-        // tiles are numbered frame by frame through the whole pass; tickets are handed out in start order, so every tile
-        // a look-back waits for is already running.  The grid is an upper bound (the exact count is only known on the
-        // device): surplus CTAs leave at once.
-        const uint32_t t = atomicAdd(&p.counters[0], 1u);
-        uint32_t lo = 0, hi = p.nframes;                       // frame f owns tiles [k4_tile0[f], k4_tile0[f + 1])
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (p.k4_tile0[mid] <= t) lo = mid; else hi = mid;
-        }
-        s_tile = t;
-        s_frame = lo;
+// frame that owns K4 tile `t` (frame f owns tiles [k4_tile0[f], k4_tile0[f + 1]))
+__device__ __forceinline__ uint32_t frame_of_tile(const EntropyParams& p, uint32_t t) {
+    uint32_t lo = 0, hi = p.nframes;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.k4_tile0[mid] <= t) lo = mid; else hi = mid;
     }
-    __syncthreads();
-    if (s_tile >= p.hdr->k4_tiles) return;
-    const uint32_t frame = s_frame, gtile = s_tile, tile = gtile - p.k4_tile0[frame];
-    const uint64_t nbytes = p.raw_bytes[frame];
-    const uint8_t* __restrict__ raw = reinterpret_cast<const uint8_t*>(p.raw) + p.raw_off[frame];
-    uint8_t* __restrict__ file = scan + p.file_base[frame];       // + the FFs stuffed before this frame: part of s_base
-    uint8_t* __restrict__ out = file + p.hdr_len[frame];
-    const uint64_t tile_at = static_cast<uint64_t>(tile) * kStuffTile;
-    const uint64_t at = tile_at + static_cast<uint64_t>(tid) * kStuffBytesPerThread;
+    return lo;
+}
+
+// FF bytes among a thread's 16 raw bytes at byte offset `at` of a frame's scan of `nbytes` bytes; the words (bytes past the
+// end of the scan cleared: they are not FF candidates) are returned in wv, the number of valid bytes in n
+__device__ __forceinline__ uint32_t load_and_count_ff(const uint8_t* __restrict__ raw, uint64_t at, uint64_t nbytes, uint32_t (&wv)[4], int& n) {
     uint4 q = make_uint4(0, 0, 0, 0);
-    int n = 0;
+    n = 0;
     if (at < nbytes) {
-        n = static_cast<int>(umin64(kStuffBytesPerThread, nbytes - at));
-        q = *reinterpret_cast<const uint4*>(raw + at);         // raw is padded to a multiple of 16 bytes and zero-filled
+        n = static_cast<int>(umin64(16, nbytes - at));
+        q = *reinterpret_cast<const uint4*>(raw + at);             // raw is padded to a multiple of 16 bytes and zero-filled
     }
-    uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-    if (n < 16) {                                              // bytes past the end of the scan are not FF candidates
+    wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+    if (n < 16) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             if (j >= n) wv[j >> 2] &= ~(0xFFu << (8 * (j & 3)));
     }
-    const uint32_t ff = (__popc(__vcmpeq4(wv[0], 0xFFFFFFFFu)) + __popc(__vcmpeq4(wv[1], 0xFFFFFFFFu)) +
-                         __popc(__vcmpeq4(wv[2], 0xFFFFFFFFu)) + __popc(__vcmpeq4(wv[3], 0xFFFFFFFFu))) >> 3;
-    uint32_t tile_ff;
-    const uint32_t local = block_exclusive_scan(ff, s_scan, &tile_ff);
-    if (tid >= kStuffThreads - 32) {                           // the last warp resolves the global position meanwhile
-        const unsigned long long b = lookback_exclusive(p.k4_status, gtile, tile_ff);   // FFs of all earlier tiles of the PASS
-        if (tid == kStuffThreads - 32) s_base = b;
+    return (__popc(__vcmpeq4(wv[0], 0xFFFFFFFFu)) + __popc(__vcmpeq4(wv[1], 0xFFFFFFFFu)) + __popc(__vcmpeq4(wv[2], 0xFFFFFFFFu)) +
+            __popc(__vcmpeq4(wv[3], 0xFFFFFFFFu))) >> 3;
+}
+
+// ---- K4a: FF bytes per tile.  The raw scan has just been written (it sits in L2); counting it first lets every K4 CTA
+// compute its output position by ADDING the counts of the tiles before it -- no ticket, no look-back chain in which a
+// tile waits for its predecessors (ncu on the look-back version: 47 % of K4's samples at the barrier behind the look-back).
+constexpr int kCountThreads = 256;
+__global__ void __launch_bounds__(kCountThreads) ff_count_kernel(const __grid_constant__ EntropyParams p) {
+    __shared__ uint32_t s_part[kCountThreads / 32];
+    if (p.hdr->error) return;
+    const uint32_t gtile = blockIdx.x;
+    if (gtile >= p.hdr->k4_tiles) return;                      // the grid is an upper bound (the exact count is only known on the device)
+    const uint32_t frame = frame_of_tile(p, gtile), tile = gtile - p.k4_tile0[frame];
+    const uint64_t nbytes = p.raw_bytes[frame];
+    const uint8_t* __restrict__ raw = reinterpret_cast<const uint8_t*>(p.raw) + p.raw_off[frame];
+    const uint64_t tile_at = static_cast<uint64_t>(tile) * kK4TileBytes;
+    uint32_t ff = 0;
+#pragma unroll
+    for (int r = 0; r < static_cast<int>(kK4TileBytes) / (kCountThreads * 16); ++r) {
+        uint32_t wv[4];
+        int n;
+        ff += load_and_count_ff(raw, tile_at + (static_cast<uint64_t>(r) * kCountThreads + threadIdx.x) * 16, nbytes, wv, n);
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ff += __shfl_xor_sync(0xffffffffu, ff, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ff;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t sum = 0;
+        for (int w = 0; w < kCountThreads / 32; ++w) sum += s_part[w];
+        p.tile_ff[gtile] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_constant__ EntropyParams p, uint8_t* __restrict__ scan) {
+    __shared__ alignas(16) uint8_t s_out[2 * kStuffTile + 16];
+    __shared__ uint32_t s_scan[33];
+    __shared__ unsigned long long s_before[kStuffThreads / 32];
+    const int tid = threadIdx.x;
+    if (p.hdr->error) return;
+    // tiles are numbered frame by frame through the whole pass; the grid is an upper bound: surplus CTAs leave at once
+    const uint32_t gtile = blockIdx.x;
+    if (gtile >= p.hdr->k4_tiles) return;
+    const uint32_t frame = frame_of_tile(p, gtile), tile = gtile - p.k4_tile0[frame];
+    const uint64_t nbytes = p.raw_bytes[frame];
+    const uint8_t* __restrict__ raw = reinterpret_cast<const uint8_t*>(p.raw) + p.raw_off[frame];
+    uint8_t* __restrict__ file = scan + p.file_base[frame];       // + the FFs stuffed before this frame: part of `base`
+    uint8_t* __restrict__ out = file + p.hdr_len[frame];
+    const uint64_t tile_at = static_cast<uint64_t>(tile) * kStuffTile;
+    // FFs of all earlier tiles of the PASS: a sum over K4a's counts (a few hundred to a few thousand values)
+    unsigned long long before = 0;
+    for (uint32_t i = tid; i < gtile; i += kStuffThreads) before += __ldcg(p.tile_ff + i);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+    if ((tid & 31) == 0) s_before[tid >> 5] = before;
+    uint32_t wv[4];
+    int n;
+    const uint32_t ff = load_and_count_ff(raw, tile_at + static_cast<uint64_t>(tid) * kStuffBytesPerThread, nbytes, wv, n);
+    uint32_t tile_ff;
+    const uint32_t local = block_exclusive_scan(ff, s_scan, &tile_ff);       // (its barriers also publish s_before)
+    unsigned long long base = 0;
+#pragma unroll
+    for (int w = 0; w < kStuffThreads / 32; ++w) base += s_before[w];
     // ---- assemble the tile's output at tile-relative positions ----
     uint32_t o = tid * kStuffBytesPerThread + local;
     if (ff == 0 && n == 16) {
@@ -427,7 +518,7 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_const
     // ---- copy out: global word w holds tile-relative bytes [4w - sh, 4w - sh + 4) ----
     const uint32_t in_tile = static_cast<uint32_t>(umin64(kStuffTile, nbytes - tile_at));
     const uint32_t len = in_tile + tile_ff;
-    uint8_t* g = out + tile_at + s_base;
+    uint8_t* g = out + tile_at + base;
     const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 3u);
     const uint32_t head = min(len, (4u - sh) & 3u);            // bytes before the first aligned global word
     const uint32_t nwords = (len - head) >> 2;
@@ -439,10 +530,10 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_const
     const uint32_t tail0 = head + 4 * nwords;
     if (tid < len - tail0) g[tail0 + tid] = s_out[tail0 + tid];
     if (tile_at + kStuffTile >= nbytes) {                      // the frame's last tile
-        if (tid == 0) p.ff_incl[frame] = s_base + tile_ff;
+        if (tid == 0) p.ff_incl[frame] = base + tile_ff;
         if (tid < p.tail) g[len + tid] = tid ? 0xD9 : 0xFF;   // EOI (JpegSegments.hpp:361-377)
     }
-    if (tile == 0 && p.hdr_len[frame]) write_file_header(file + s_base, p, frame, tid, kStuffThreads);
+    if (tile == 0 && p.hdr_len[frame]) write_file_header(file + base, p, frame, tid, kStuffThreads);
 }
 
 // Frame geometry (raw offsets, sizes, K4 tile numbering, output positions) is read from the PassMeta block in device
@@ -482,8 +573,7 @@ int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
     p.hdr_len = m.hdr_len;
     p.total_bits = m.total_bits;
     p.ff_incl = m.ff_incl;
-    p.k4_status = c->d_lookback;
-    p.counters = c->d_counters + kCntK4Ticket;
+    p.tile_ff = reinterpret_cast<uint32_t*>(c->d_lookback);
     if (c->file_mode) {
         p.built = c->d_built_tables;
         p.hdr_prefix = c->d_hdr_prefix;
@@ -496,10 +586,13 @@ int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
     huffman_pack_kernel<<<grid, kPackThreads, 0, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     if (k4_grid) {
+        ff_count_kernel<<<k4_grid, kCountThreads, 0, c->stream>>>(p);
+        JPGENC_CUDA(c, cudaGetLastError());
         stuff_kernel<<<k4_grid, kStuffThreads, 0, c->stream>>>(p, c->d_scan);
         JPGENC_CUDA(c, cudaGetLastError());
+        c->launches += 2;
     }
-    c->launches += 3;
+    c->launches += 2;
     if (F == 1 && !c->file_mode) return launch_publish_totals(c);    // one image: the totals go to the host's mailbox
     return JPGENC_OK;
 }

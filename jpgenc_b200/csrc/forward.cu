@@ -514,6 +514,34 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* _
                 [&](const ExactColumn& col, int r) { return exact_sample(col, real_w, real_h, r, e.scale); });
 }
 
+// Images that are not 8-bit samples: three planes of doubles as the reference holds them (Image::R/G/B after loadPPM, or
+// planes a caller computed; already YCbCr when `ycbcr`: Image::writeJPEG converts only an RGB image, src/Image.cpp:112-115,
+// 839).  Every block takes the exact path; width x height are the padded plane dimensions (multiples of 16).
+struct PlaneColumn { uint32_t x, y; int comp; };
+__global__ void __launch_bounds__(kRefineThreads) planes_exact_kernel(const double* __restrict__ p0, const double* __restrict__ p1,
+                                                                          const double* __restrict__ p2, uint32_t width, uint32_t mcu_w,
+                                                                          uint32_t nblocks, int16_t* __restrict__ coef, int ycbcr,
+                                                                          const __grid_constant__ ExactConsts e) {
+    auto pixel = [&](uint32_t x, uint32_t y, int comp) {
+        const size_t i = static_cast<size_t>(y) * width + x;
+        if (ycbcr) return (comp == 0 ? p0 : comp == 1 ? p1 : p2)[i];
+        return exact_channel(comp, p0[i], p1[i], p2[i]);
+    };
+    refine_loop(0u, nblocks, nullptr, true, coef, nblocks, e.qy, e.qc, e,
+                [&](uint32_t id, int c) {
+                    const uint32_t mcu = id / kBlocksPerMcu, k = id % kBlocksPerMcu, my = mcu / mcu_w, mx = mcu - my * mcu_w;
+                    if (k < 4) return PlaneColumn{mx * 16 + (k & 1) * 8 + c, my * 16 + (k >> 1) * 8, 0};
+                    return PlaneColumn{mx * 16 + 2 * c, my * 16, static_cast<int>(k) - 3};
+                },
+                [&](const PlaneColumn& col, int r) {
+                    if (col.comp == 0) return pixel(col.x, col.y + r, 0);
+                    const uint32_t x = col.x, y = col.y + 2 * r;                                // S420_m, src/Image.cpp:207-226
+                    const double top = dadd(dadd(0.0, pixel(x, y, col.comp)), pixel(x + 1, y, col.comp));
+                    const double bot = dadd(dadd(0.0, pixel(x, y + 1, col.comp)), pixel(x + 1, y + 1, col.comp));
+                    return dmul(dadd(top, bot), 0.25);
+                });
+}
+
 // ---------------------------------------------------------------------------------------------------
 // config-1 microbenchmark: stand-alone fp32 blocks -> dctArai -> quantize -> zigzag int16
 // ---------------------------------------------------------------------------------------------------
@@ -809,6 +837,20 @@ int launch_forward(jpgenc_ctx* c) {
 }
 
 int launch_exact_all(jpgenc_ctx* c) { return launch_refine(c, true); }
+
+// coefficients of the image bound as planes of doubles (d_planes: three planes of (mcu_w*16) x (mcu_h*16) doubles back to back)
+int launch_planes_exact(jpgenc_ctx* c, const double* d_planes, bool ycbcr) {
+    ExactConsts e;
+    fill_exact(c, c->qy, c->qc, 1.0, &e);
+    const uint32_t nblocks = c->mcu_w * c->mcu_h * kBlocksPerMcu;
+    const size_t plane = static_cast<size_t>(c->mcu_w) * 16 * c->mcu_h * 16;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(c->sm_count * 16, (static_cast<uint64_t>(nblocks) * 8 + kRefineThreads - 1) / kRefineThreads)));
+    planes_exact_kernel<<<grid, kRefineThreads, 0, c->stream>>>(d_planes, d_planes + plane, d_planes + 2 * plane, c->mcu_w * 16, c->mcu_w, nblocks, c->d_coef,
+                                                               ycbcr ? 1 : 0, e);
+    JPGENC_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return JPGENC_OK;
+}
 
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
                             uint64_t* refined) {

@@ -59,13 +59,14 @@ uint32_t frames_per_pass_cap(const jpgenc_ctx* c) {
     return static_cast<uint32_t>(std::min<size_t>(per_pass, 1024));
 }
 
-// Frames per pass.  A pass costs ~0.1 ms of launch gaps and one host wait whatever its size, and its table build (~0.35 ms,
-// independent of the number of frames) only hides behind OTHER passes' wide kernels: passes should be large, but a batch
-// should still give every slot about two of them.  Measured on 1920x1080 frames, 4 slots (frames per pass -> ms per call):
-// 1024 frames: 32 -> 9.0, 64 -> 7.6, 128 -> 6.9;  128 frames: 16 -> 1.71, 32 -> 1.26, 64 -> 1.24.
+// Frames per pass.  A pass costs ~0.1 ms of launch gaps and one host wait whatever its size, its wide kernels run the better
+// the larger they are, and its table build (~0.2 ms, independent of the number of frames) only hides behind OTHER passes' wide
+// kernels: passes should be large, but a batch should still give every slot about two of them.  Measured on 1920x1080
+// frames, 4 slots, device tables at 0.21 ms (frames per pass -> frames/s):
+// 1024 frames: 64 -> 147 k, 128 -> 159 k, 256 -> 157 k;  128 frames: 32 -> 117 k, 64 -> 120 k, 128 -> 120 k.
 uint32_t pass_frames(const jpgenc_ctx* c, uint32_t n, uint32_t slots) {
     const size_t px = static_cast<size_t>(c->mcu_w) * c->mcu_h * 256;
-    const uint32_t lo = static_cast<uint32_t>(std::max<size_t>(1, (64u << 20) / px));     // ~64 Mpx: 32 frames of 1920x1080
+    const uint32_t lo = static_cast<uint32_t>(std::max<size_t>(1, (128u << 20) / px));    // ~128 Mpx: 64 frames of 1920x1080
     const uint32_t hi = static_cast<uint32_t>(std::max<size_t>(1, (256u << 20) / px));    // ~256 Mpx: 128 such frames
     uint32_t per = std::min(hi, std::max(lo, (n + 2 * slots - 1) / (2 * slots)));
     per = env_u32("JPGENC_FRAMES_PER_PASS", per);

@@ -670,6 +670,52 @@ void jo_forward_planes(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uin
                  dct_cr, q_y, q_cb, q_cr);
 }
 
+/* Image::writeJPEG on an Image whose planes are given as doubles (Image.hpp:104-114): p0,p1,p2 are H16*W16 row-major planes,
+ * R,G,B -- converted like any pixel (Image.cpp:131-143) -- or, with ycbcr != 0, level-shifted Y,Cb,Cr that
+ * convertToColorSpace leaves alone (Image.cpp:112-115); then S420_m (Image.cpp:198-235), dctArai, quantize as above. */
+void jo_forward_from_planes(const double* p0, const double* p1, const double* p2, uint32_t W16, uint32_t H16, int ycbcr,
+                            const uint8_t qy[64], const uint8_t qc[64], int16_t* out) {
+    init_consts();
+    const uint32_t W8 = W16 / 2, mcu_w = W16 / 16, mcu_h = H16 / 16;
+    double* y = (double*)malloc(sizeof(double) * 16 * W16);
+    double* cbf = (double*)malloc(sizeof(double) * 16 * W16);
+    double* crf = (double*)malloc(sizeof(double) * 16 * W16);
+    double* cb = (double*)malloc(sizeof(double) * 8 * W8);
+    double* cr = (double*)malloc(sizeof(double) * 8 * W8);
+    double blk[64];
+    for (uint32_t my = 0; my < mcu_h; ++my) {
+        for (uint32_t r = 0; r < 16; ++r)
+            for (uint32_t x = 0; x < W16; ++x) {
+                const size_t i = ((size_t)my * 16 + r) * W16 + x;
+                if (ycbcr) { y[r * W16 + x] = p0[i]; cbf[r * W16 + x] = p1[i]; crf[r * W16 + x] = p2[i]; }
+                else rgb_to_ycc(p0[i], p1[i], p2[i], &y[r * W16 + x], &cbf[r * W16 + x], &crf[r * W16 + x]);
+            }
+        for (uint32_t r = 0; r < 8; ++r)                            /* S420_m, Image.cpp:207-226 */
+            for (uint32_t x = 0; x < W8; ++x) {
+                const double* a = cbf + (2 * r) * W16 + 2 * x;
+                double top = 0; top += 1 * a[0]; top += 1 * a[1];
+                double bot = 0; bot += 1 * a[W16]; bot += 1 * a[W16 + 1];
+                cb[r * W8 + x] = (top + bot) / 4;
+                a = crf + (2 * r) * W16 + 2 * x;
+                top = 0; top += 1 * a[0]; top += 1 * a[1];
+                bot = 0; bot += 1 * a[W16]; bot += 1 * a[W16 + 1];
+                cr[r * W8 + x] = (top + bot) / 4;
+            }
+        for (uint32_t mx = 0; mx < mcu_w; ++mx) {
+            int16_t* o = out + ((size_t)my * mcu_w + mx) * 6 * 64;
+            for (int k = 0; k < 4; ++k) {
+                block_from(y, W16, mx * 16 + (k & 1) * 8, (k >> 1) * 8, blk);
+                emit_block(blk, qy, o + k * 64, NULL, NULL, W16);
+            }
+            block_from(cb, W8, mx * 8, 0, blk);
+            emit_block(blk, qc, o + 4 * 64, NULL, NULL, W8);
+            block_from(cr, W8, mx * 8, 0, blk);
+            emit_block(blk, qc, o + 5 * 64, NULL, NULL, W8);
+        }
+    }
+    free(y); free(cbf); free(crf); free(cb); free(cr);
+}
+
 void jo_planes_to_mcu(const int32_t* q_y, const int32_t* q_cb, const int32_t* q_cr, uint32_t mcu_w, uint32_t mcu_h,
                       int16_t* out) {
     const uint32_t W16 = mcu_w * 16, W8 = mcu_w * 8;
@@ -835,6 +881,28 @@ static int encode_common(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, u
 
 int jo_encode_rgb(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uint8_t** out, size_t* out_n) {
     return encode_common(rgb, real_w, real_h, 255, out, out_n);
+}
+
+int jo_encode_planes(const double* p0, const double* p1, const double* p2, uint32_t W16, uint32_t H16, uint32_t real_w,
+                     uint32_t real_h, int ycbcr, uint8_t** out, size_t* out_n) {
+    if (W16 != jo_pad16(real_w) || H16 != jo_pad16(real_h)) return -1;
+    const uint32_t mcu_w = W16 / 16, mcu_h = H16 / 16;
+    int16_t* coef = (int16_t*)malloc(sizeof(int16_t) * (size_t)mcu_w * mcu_h * 6 * 64);
+    jo_forward_from_planes(p0, p1, p2, W16, H16, ycbcr, jo_qtable_luma, jo_qtable_chroma, coef);
+    jo_huff_table tables[4];
+    jo_bits bits;
+    jo_bits_init(&bits);
+    jo_entropy_encode(coef, mcu_w, mcu_h, tables, &bits);
+    free(coef);
+    const size_t hdr = jo_write_headers(real_w, real_h, jo_qtable_luma, jo_qtable_chroma, tables, NULL);
+    const size_t scan = jo_bits_stuffed_size(&bits);
+    uint8_t* buf = (uint8_t*)malloc(hdr + scan + 2);
+    jo_write_headers(real_w, real_h, jo_qtable_luma, jo_qtable_chroma, tables, buf);
+    jo_bits_write_stuffed(&bits, buf + hdr);
+    buf[hdr + scan] = 0xFF; buf[hdr + scan + 1] = 0xD9;                    /* sEOI */
+    jo_bits_free(&bits);
+    *out = buf; *out_n = hdr + scan + 2;
+    return 0;
 }
 
 int jo_encode_ppm(const uint8_t* file, size_t n, uint8_t** out, size_t* out_n) {

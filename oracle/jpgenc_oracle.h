@@ -97,6 +97,11 @@ void jo_forward_planes(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uin
                        double* y, double* cb, double* cr, double* dct_y, double* dct_cb, double* dct_cr,
                        int32_t* q_y, int32_t* q_cb, int32_t* q_cr);
 
+/* The same from three H16*W16 planes of doubles (an Image assembled or edited in memory): R,G,B, or with ycbcr != 0 planes that
+ * already are level-shifted Y,Cb,Cr (Image.cpp:112-115: not converted again). */
+void jo_forward_from_planes(const double* p0, const double* p1, const double* p2, uint32_t W16, uint32_t H16, int ycbcr,
+                            const uint8_t qy[64], const uint8_t qc[64], int16_t* out);
+
 /* planar natural-order int32 (the reference's QY/QCb/QCr) <-> MCU-ordered zigzag int16 */
 void jo_planes_to_mcu(const int32_t* q_y, const int32_t* q_cb, const int32_t* q_cr,
                       uint32_t mcu_w, uint32_t mcu_h, int16_t* out);
@@ -123,6 +128,9 @@ size_t jo_write_headers(uint32_t real_w, uint32_t real_h, const uint8_t qy[64], 
 int  jo_encode_ppm(const uint8_t* file, size_t n, uint8_t** out, size_t* out_n);
 /* Whole file from raw RGB (maxval 255) */
 int  jo_encode_rgb(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uint8_t** out, size_t* out_n);
+/* Whole file from planes of doubles == Image::writeJPEG on such an Image */
+int  jo_encode_planes(const double* p0, const double* p1, const double* p2, uint32_t W16, uint32_t H16, uint32_t real_w,
+                      uint32_t real_h, int ycbcr, uint8_t** out, size_t* out_n);
 void jo_free(void* p);
 
 extern const uint8_t jo_qtable_luma[64];     /* Image.cpp:850-859 */

@@ -31,7 +31,9 @@ def build(force: bool = False) -> None:
     src = HERE / "jpgenc_oracle.c"
     if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < src.stat().st_mtime:
         subprocess.run(["make", "-C", str(HERE), "-s", "-B", "liboracle.so"], check=True)
-    if Path(os.environ.get("JPGENC_REFERENCE", "/root/reference")).is_dir() and (force or not REF_SO.exists()):
+    probe = HERE / "ref_probe.cpp"
+    stale = REF_SO.exists() and REF_SO.stat().st_mtime < probe.stat().st_mtime
+    if Path(os.environ.get("JPGENC_REFERENCE", "/root/reference")).is_dir() and (force or stale or not REF_SO.exists()):
         subprocess.run(["bash", str(HERE / "build_ref.sh")], check=True)
 
 
@@ -96,6 +98,8 @@ class Oracle:
         L.jo_write_headers.restype = C.c_size_t
         L.jo_encode_ppm.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(u8p), C.POINTER(C.c_size_t)]
         L.jo_encode_rgb.argtypes = [u8p, C.c_uint32, C.c_uint32, C.POINTER(u8p), C.POINTER(C.c_size_t)]
+        L.jo_forward_from_planes.argtypes = [f64p, f64p, f64p, C.c_uint32, C.c_uint32, C.c_int, u8p, u8p, i16p]
+        L.jo_encode_planes.argtypes = [f64p, f64p, f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(u8p), C.POINTER(C.c_size_t)]
         L.jo_free.argtypes = [C.c_void_p]
         self.qy = np.ctypeslib.as_array((C.c_uint8 * 64).in_dll(L, "jo_qtable_luma")).copy()
         self.qc = np.ctypeslib.as_array((C.c_uint8 * 64).in_dll(L, "jo_qtable_chroma")).copy()
@@ -264,6 +268,28 @@ class Oracle:
         return res
 
 
+    def forward_from_planes(self, p0, p1, p2, ycbcr=False):
+        """three (H16, W16) float64 planes (Image::R/G/B, or Y/Cb/Cr with ycbcr) -> MCU-ordered zigzag int16 coefficients"""
+        pl = [np.ascontiguousarray(p, np.float64) for p in (p0, p1, p2)]
+        h16, w16 = pl[0].shape
+        out = np.empty(((h16 // 16) * (w16 // 16), 6, 64), np.int16)
+        self.L.jo_forward_from_planes(_ptr(pl[0], f64p), _ptr(pl[1], f64p), _ptr(pl[2], f64p), w16, h16, 1 if ycbcr else 0,
+                                      _ptr(self.qy, u8p), _ptr(self.qc, u8p), _ptr(out, i16p))
+        return out
+
+    def encode_planes(self, p0, p1, p2, real_w, real_h, ycbcr=False) -> bytes:
+        pl = [np.ascontiguousarray(p, np.float64) for p in (p0, p1, p2)]
+        h16, w16 = pl[0].shape
+        out, n = u8p(), C.c_size_t()
+        rc = self.L.jo_encode_planes(_ptr(pl[0], f64p), _ptr(pl[1], f64p), _ptr(pl[2], f64p), w16, h16, real_w, real_h, 1 if ycbcr else 0,
+                                     C.byref(out), C.byref(n))
+        if rc:
+            raise ValueError("planes are not the image padded to whole MCUs")
+        res = C.string_at(out, n.value)
+        self.L.jo_free(out)
+        return res
+
+
 class Reference:
     """The compiled reference (oracle/_ref).  `available()` is False when it was never built."""
 
@@ -284,6 +310,15 @@ class Reference:
         L.ref_block_symbols.argtypes = [i32p, u8p, u32p, u8p]
         L.ref_generate_huffman.argtypes = [i32p, C.c_int, u32p, u8p, u8p, u8p]
         L.ref_bitstream_pack.argtypes = [u32p, u8p, C.c_int, C.c_int, u8p, C.c_int, u32p]
+        if hasattr(L, "ref_encode_planes"):
+            L.ref_encode_planes.argtypes = [f64p, f64p, f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p]
+
+    def encode_planes(self, p0, p1, p2, real_w, real_h, ycbcr, jpg_path: str) -> int:
+        """Image::writeJPEG on an Image assembled from three (H16, W16) float64 planes"""
+        pl = [np.ascontiguousarray(p, np.float64) for p in (p0, p1, p2)]
+        h16, w16 = pl[0].shape
+        return self.L.ref_encode_planes(_ptr(pl[0], f64p), _ptr(pl[1], f64p), _ptr(pl[2], f64p), w16, h16, real_w, real_h, 1 if ycbcr else 0,
+                                        jpg_path.encode())
 
     def encode_file(self, ppm_path: str, jpg_path: str):
         lo, en = C.c_double(), C.c_double()

@@ -85,6 +85,21 @@ int ref_stage_dump(const char* ppm_path, double* rgb, double* ycc_y, double* ycc
     } catch (const std::exception&) { return -1; }
 }
 
+// Image::writeJPEG on an Image assembled in memory (Image.hpp:36, 104-114): three planes of h16*w16 doubles, taken as R,G,B
+// (ycbcr == 0) or as an image that already is YCbCr (ycbcr != 0: convertToColorSpace returns it unchanged, Image.cpp:112-115).
+int ref_encode_planes(const double* p0, const double* p1, const double* p2, unsigned w16, unsigned h16, unsigned real_w,
+                      unsigned real_h, int ycbcr, const char* jpg_path) {
+    try {
+        Image img(w16, h16, ycbcr ? Image::YCbCr : Image::RGB);
+        img.real_width = real_w;
+        img.real_height = real_h;
+        const std::size_t n = std::size_t(w16) * h16;
+        for (std::size_t i = 0; i < n; ++i) { img.R.data()[i] = p0[i]; img.G.data()[i] = p1[i]; img.B.data()[i] = p2[i]; }
+        img.writeJPEG(jpg_path);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
+
 // one 8x8 block through each DCT variant (Dct.hpp:47,238,264); mode 0=Simple 1=Matrix 2=Arai
 void ref_dct_block(const double* in, double* out, int mode) {
     matrix<double> x(8, 8), y(8, 8);

@@ -40,6 +40,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_planes():
+    """Image::writeJPEG of the compiled reference on Images assembled from planes of doubles (tests/golden/make_planes_golden.py)"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "planes.npz"))
+
+
+@pytest.fixture(scope="session")
 def encoder():
     """GPU context through the C-ABI.  Raises (does not skip) when the library or the GPU is missing."""
     from jpgenc_b200.capi import Encoder

@@ -44,3 +44,12 @@ def test_scan_is_decodable(oracle, golden):
         assert img.shape == rgb.shape
         err = np.abs(img - rgb).mean()
         assert err < (12 if name.startswith("synth") else 60), (name, err)
+
+
+def test_golden_planes_files_byte_identical(oracle, golden_planes):
+    """Image::writeJPEG on Images assembled from planes of doubles (edited samples, real-valued planes, YCbCr input): the
+    oracle's restatement (jo_encode_planes) against the compiled reference's bytes"""
+    for name in _names(golden_planes, "names"):
+        planes = golden_planes[f"{name}/planes"]
+        w, h, ycc = (int(x) for x in golden_planes[f"{name}/dims"])
+        assert oracle.encode_planes(planes[0], planes[1], planes[2], w, h, bool(ycc)) == golden_planes[f"{name}/jpg"].tobytes(), name

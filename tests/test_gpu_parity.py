@@ -642,3 +642,25 @@ def test_ppm_file_streamed_band_by_band(encoder, oracle, tmp_path):
     assert (tmp_path / "ascii.jpg").read_bytes() == oracle.encode_rgb(small)
     # the context still works for in-memory images afterwards
     assert encoder.encode_rgb(small) == oracle.encode_rgb(small)
+
+
+@pytest.mark.gpu
+def test_planes_of_doubles_byte_identical(encoder, oracle, golden_planes):
+    """jpgenc_encode_planes: an Image assembled or edited in memory (real-valued samples, edited padding, planes that already
+    are YCbCr) -- the reference's own bytes for the golden cases, the oracle's for larger ones"""
+    for name in [str(n) for n in golden_planes["names"]]:
+        planes = golden_planes[f"{name}/planes"]
+        w, h, ycc = (int(x) for x in golden_planes[f"{name}/dims"])
+        assert encoder.encode_planes(planes[0], planes[1], planes[2], w, h, bool(ycc)) == golden_planes[f"{name}/jpg"].tobytes(), name
+    rng = np.random.default_rng(31)
+    for (w, h, ycc) in [(333, 201, False), (512, 256, True)]:
+        w16, h16 = (w + 15) // 16 * 16, (h + 15) // 16 * 16
+        lo, hi = (-128, 127) if ycc else (0, 255)
+        planes = [rng.uniform(lo, hi, (h16, w16)) for _ in range(3)]
+        assert encoder.encode_planes(planes[0], planes[1], planes[2], w, h, ycc) == oracle.encode_planes(planes[0], planes[1], planes[2], w, h, ycc)
+    # 8-bit samples given as planes == the 8-bit path
+    rgb = synth_rgb(208, 120, 5)
+    pad = np.pad(rgb, ((0, 8), (0, 0), (0, 0)), mode="edge").astype(np.float64)
+    assert encoder.encode_planes(pad[..., 0], pad[..., 1], pad[..., 2], 208, 120) == encoder.encode_rgb(rgb)
+    with pytest.raises(Exception):
+        encoder.encode_planes(pad[:120, :, 0], pad[:120, :, 1], pad[:120, :, 2], 208, 120)      # not padded to whole MCUs

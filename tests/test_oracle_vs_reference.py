@@ -118,3 +118,22 @@ def test_bitstream_pack(oracle, reference):
             a, na = oracle.pack_bits(msb, nbits, msb_aligned=True, fill=fill)
             b, nb = reference.pack_bits(msb, nbits, fill=fill)
             assert na == nb and np.array_equal(a, b)
+
+
+def test_planes_path_matches_reference(oracle, reference, tmp_path):
+    """Image::writeJPEG on an Image assembled from planes of doubles (src/Image.cpp:831-846: RGB planes are converted, an
+    image that already is YCbCr is not): jo_encode_planes == the compiled reference, byte for byte"""
+    rng = np.random.default_rng(99)
+    for (w, h) in [(16, 16), (40, 24), (19, 50)]:
+        w16, h16 = (w + 15) // 16 * 16, (h + 15) // 16 * 16
+        for ycc in (False, True):
+            lo, hi = (-128, 127) if ycc else (0, 255)
+            planes = [rng.uniform(lo, hi, (h16, w16)) for _ in range(3)]
+            jpg = tmp_path / "p.jpg"
+            assert reference.encode_planes(planes[0], planes[1], planes[2], w, h, ycc, str(jpg)) == 0
+            assert oracle.encode_planes(planes[0], planes[1], planes[2], w, h, ycc) == jpg.read_bytes(), (w, h, ycc)
+    # planes that hold 8-bit samples are the ordinary path
+    from jpgenc_b200.synth import synth_rgb
+    rgb = synth_rgb(48, 32, 3)
+    planes = [rgb[..., k].astype(np.float64) for k in range(3)]
+    assert oracle.encode_planes(planes[0], planes[1], planes[2], 48, 32, False) == oracle.encode_rgb(rgb)
