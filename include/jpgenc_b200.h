@@ -87,7 +87,10 @@ int jpgenc_set_dct_constants(jpgenc_ctx* ctx, const double a[5], const double s[
 
 /* ---- input: replaces loadPPM's pixel path (src/Image.cpp:411-418, 465, 479-532) -------------------- */
 /* H2D of raw samples (P6 payload or parsed P3), maxval < 256.  Scaling by 255/maxval and the x16
- * edge-replication padding happen on the device.  host_rgb should be pinned for full PCIe speed. */
+ * edge-replication padding happen on the device.  host_rgb should be pinned for full PCIe speed.
+ * Contract: every sample <= maxval.  Host pixels are checked when maxval < 255 (JPGENC_ERR_FORMAT; the PPM readers refuse such
+ * files the same way): the reference would scale such a sample past 255, which the 8-bit path's exactness thresholds do not
+ * cover -- jpgenc_encode_planes takes that kind of data.  Device-resident pixels (bind, frames) are the caller's promise. */
 int jpgenc_upload_rgb(jpgenc_ctx* ctx, const uint8_t* host_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval);
 /* same, for pixels that already live in device memory (no copy is made; the pointer must stay valid) */
 int jpgenc_bind_device_rgb(jpgenc_ctx* ctx, const void* dev_rgb, uint32_t real_w, uint32_t real_h, uint32_t maxval);

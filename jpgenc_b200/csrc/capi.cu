@@ -347,6 +347,8 @@ int jpgenc_set_dct_constants(jpgenc_ctx* c, const double a[5], const double s[8]
 
 int jpgenc_upload_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
     if (!c || !host_rgb) return JPGENC_ERR_ARG;
+    if (maxval && maxval < 255 && !samples_within_maxval(host_rgb, static_cast<size_t>(w) * h * 3, maxval))
+        return fail(c, JPGENC_ERR_FORMAT, "a sample exceeds maxval");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
@@ -871,7 +873,7 @@ static int upload_and_forward(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w
                     JPGENC_CUDA(c, cudaEventSynchronize(c->ev_band[band - 2]));     // this slot's previous upload has left it
                 }
                 uint8_t* slot = static_cast<uint8_t*>(c->h_file_pinned) + (band & 1) * band_bytes;
-                if ((rc = (*fill)(slot, px0 * row_bytes, (px1 - px0) * row_bytes))) return fail(c, rc, "truncated PPM payload");
+                if ((rc = (*fill)(slot, px0 * row_bytes, (px1 - px0) * row_bytes))) return fail(c, rc, "truncated PPM payload, or a sample above maxval");
                 src = slot;
             }
             JPGENC_CUDA(c, cudaMemcpyAsync(c->d_rgb_owned + px0 * row_bytes, src, (px1 - px0) * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
@@ -932,6 +934,8 @@ int jpgenc_assemble_last(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jp
 int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval, uint8_t* dst,
                       uint64_t cap, uint64_t* jpeg_bytes) {
     if (!c || !host_rgb) return JPGENC_ERR_ARG;
+    if (maxval && maxval < 255 && !samples_within_maxval(host_rgb, static_cast<size_t>(w) * h * 3, maxval))
+        return fail(c, JPGENC_ERR_FORMAT, "a sample exceeds maxval");
     int rc = upload_and_forward(c, host_rgb, w, h, maxval);
     if (rc) return rc;
     jpgenc_huff_table tables[4];
@@ -1012,6 +1016,7 @@ int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_
                 }
             });
             (void)need;
+            if (!bad.load() && !samples_within_maxval(dst, n, h.maxval)) bad.store(1);     // only scans when maxval < 255
             return bad.load() ? JPGENC_ERR_FORMAT : JPGENC_OK;
         };
         if ((rc = upload_and_forward(c, nullptr, h.width, h.height, h.maxval, &fill))) return rc;
@@ -1021,7 +1026,7 @@ int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_
         closer.f = nullptr;
         if ((rc = slurp_file(ppm_path, &file))) return fail(c, rc, "Failed to open input file");
         const uint8_t* samples = nullptr;
-        if ((rc = ppm_samples(file.data(), file.size(), h, &p3, &samples))) return fail(c, rc, "truncated PPM payload");
+        if ((rc = ppm_samples(file.data(), file.size(), h, &p3, &samples))) return fail(c, rc, "truncated PPM payload, or a sample above maxval");
         if ((rc = upload_and_forward(c, samples, h.width, h.height, h.maxval))) return rc;
     }
     jpgenc_huff_table tables[4];

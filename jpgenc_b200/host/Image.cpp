@@ -145,26 +145,63 @@ Image loadPPM(std::string path) {
 // ---------------------------------------------------------------------------------------------------------------
 // the hot path: GPU
 // ---------------------------------------------------------------------------------------------------------------
-std::vector<Byte> Image::encodeJPEG() {
-    if (color_space_type != RGB) throw std::runtime_error("writeJPEG expects an RGB image (it converts itself)");
-    if (samples_.empty()) {
-        // image assembled in memory rather than loaded: the device path takes 8-bit samples
-        samples_.resize(static_cast<std::size_t>(real_width) * real_height * 3);
-        maxval_ = 255;
-        for (uint y = 0; y < real_height; ++y)
-            for (uint x = 0; x < real_width; ++x) {
-                const double c[3] = {R(y, x), G(y, x), B(y, x)};
-                for (int k = 0; k < 3; ++k) {
-                    if (c[k] < 0 || c[k] > 255 || c[k] != std::floor(c[k]))
-                        throw std::runtime_error("writeJPEG: the GPU path needs integral 8-bit samples");
-                    samples_[(static_cast<std::size_t>(y) * real_width + x) * 3 + k] = static_cast<Byte>(c[k]);
+// The 8-bit samples the planes hold, when they hold such: every real pixel k * (255 / maxval) for an integer k in
+// [0, maxval], the padding a replication of the last column / row (what loadPPM produces, src/Image.cpp:465-530).  `cached`
+// (loadPPM's copy of the file's samples) is only trusted after it has been compared with the planes: a caller may have
+// edited R/G/B since (the reference encodes the planes, src/Image.cpp:831-846).
+static bool planes_as_samples(const Image& img, const matrix<PixelDataType>* plane[3], uint maxval, std::vector<Byte>* cached) {
+    const uint rw = img.real_width, rh = img.real_height;
+    if (img.width != pad16(rw) || img.height != pad16(rh) || maxval == 0 || maxval > 255) return false;
+    for (int k = 0; k < 3; ++k)
+        if (plane[k]->size1() != img.height || plane[k]->size2() != img.width) return false;
+    const double scale = 255. / maxval;
+    const bool have = cached->size() == static_cast<std::size_t>(rw) * rh * 3;
+    if (!have) cached->assign(static_cast<std::size_t>(rw) * rh * 3, 0);
+    for (int k = 0; k < 3; ++k) {
+        const matrix<PixelDataType>& p = *plane[k];
+        for (uint y = 0; y < img.height; ++y) {
+            const uint sy = std::min(y, rh - 1);
+            for (uint x = 0; x < img.width; ++x) {
+                const uint sx = std::min(x, rw - 1);
+                const double v = p(y, x);
+                Byte& b = (*cached)[(static_cast<std::size_t>(sy) * rw + sx) * 3 + k];
+                if (y < rh && x < rw && !have) {
+                    const double q = std::floor(v / scale + 0.5);
+                    if (!(q >= 0 && q <= maxval)) return false;
+                    b = static_cast<Byte>(q);
                 }
+                if (b * scale != v) return false;              // also checks the padding against the pixel it must replicate
             }
+        }
     }
+    return true;
+}
+
+std::vector<Byte> Image::encodeJPEG() {
     jpgenc_ctx* c = g_gpu.get();
     uint64_t need = 0;
-    // upload (in bands, overlapped with the first kernel) + encode; the scan stays on the device, its size comes back
-    check(c, jpgenc_encode_rgb(c, samples_.data(), real_width, real_height, maxval_, nullptr, 0, &need));
+    const matrix<PixelDataType>* plane[3] = {&one, &two, &three};
+    bool as_samples = false;
+    if (color_space_type == RGB) {
+        as_samples = planes_as_samples(*this, plane, maxval_, &samples_);
+        if (!as_samples && !samples_.empty()) {                // the cache is stale (edited planes): one more try without it
+            samples_.clear();
+            as_samples = planes_as_samples(*this, plane, maxval_, &samples_);
+        }
+    }
+    if (as_samples) {
+        // upload (in bands, overlapped with the first kernel) + encode; the scan stays on the device, its size comes back
+        check(c, jpgenc_encode_rgb(c, samples_.data(), real_width, real_height, maxval_, nullptr, 0, &need));
+    } else {
+        // anything else the planes may hold -- edited or real-valued samples, an image that already is YCbCr (the reference
+        // converts only an RGB image, src/Image.cpp:112-115, 839): the planes themselves go to the device
+        samples_.clear();
+        if (one.size1() != height || one.size2() != width || two.size1() != height || two.size2() != width || three.size1() != height ||
+            three.size2() != width)
+            throw std::runtime_error("writeJPEG: the three planes must have the image's (padded) size");
+        check(c, jpgenc_encode_planes(c, &one.data()[0], &two.data()[0], &three.data()[0], width, height, real_width, real_height,
+                                      color_space_type == YCbCr ? 1 : 0, nullptr, 0, &need));
+    }
     std::vector<Byte> out(need);
     check(c, jpgenc_assemble_last(c, out.data(), out.size(), &need));   // headers + D2H of the scan + EOI
     return out;

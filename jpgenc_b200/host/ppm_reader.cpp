@@ -87,12 +87,19 @@ int parse_ppm_header(const uint8_t* file, size_t n, PpmHeader* h) {
     return h->payload <= n ? JPGENC_OK : JPGENC_ERR_FORMAT;
 }
 
+bool samples_within_maxval(const uint8_t* px, size_t count, uint32_t maxval) {
+    if (maxval >= 255) return true;
+    uint8_t over = 0;
+    for (size_t i = 0; i < count; ++i) over |= static_cast<uint8_t>(px[i] > maxval);
+    return over == 0;
+}
+
 int ppm_samples(const uint8_t* file, size_t n, const PpmHeader& h, std::vector<uint8_t>* storage, const uint8_t** view) {
     const size_t count = static_cast<size_t>(h.width) * h.height * 3;
     if (h.magic == 6) {                                         // loadP6PPM, src/Image.cpp:411-418
         if (h.payload + count > n) return JPGENC_ERR_FORMAT;
         *view = file + h.payload;
-        return JPGENC_OK;
+        return samples_within_maxval(*view, count, h.maxval) ? JPGENC_OK : JPGENC_ERR_FORMAT;
     }
     storage->resize(count);                                     // loadP3PPM, src/Image.cpp:393-408
     Scanner sc(file, n, h.payload);
@@ -102,6 +109,9 @@ int ppm_samples(const uint8_t* file, size_t n, const PpmHeader& h, std::vector<u
         sc.token(&b, &e);
         unsigned v = 0;                                         // fast_atoi: no checks at all (src/Image.cpp:327-333)
         for (size_t k = b; k < e && k < n; ++k) v = v * 10 + (file[k] - '0');
+        // a sample above maxval is not an image the 8-bit device path is exact for (the FP32 trust thresholds of K1 assume
+        // scaled samples of at most 255): refused, like a truncated file, instead of being encoded differently from the reference
+        if (v > h.maxval) return JPGENC_ERR_FORMAT;
         (*storage)[i] = static_cast<uint8_t>(v);
     }
     *view = storage->data();

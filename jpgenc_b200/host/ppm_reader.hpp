@@ -19,6 +19,9 @@ struct PpmHeader {
 int parse_ppm_header(const uint8_t* file, size_t n, PpmHeader* h);
 // samples -> interleaved u8 RGB.  P6: `*view` points into `file` (no copy); P3: decoded into `storage`.
 int ppm_samples(const uint8_t* file, size_t n, const PpmHeader& h, std::vector<uint8_t>* storage, const uint8_t** view);
+// false when a sample exceeds maxval (< 255): such a file is refused (JPGENC_ERR_FORMAT) -- the reference would scale the sample past 255,
+// which the 8-bit device path is not exact for; jpgenc_encode_planes takes such data as planes of doubles
+bool samples_within_maxval(const uint8_t* px, size_t count, uint32_t maxval);
 // whole file into memory; JPGENC_ERR_IO when it cannot be opened
 int slurp_file(const std::string& path, std::vector<uint8_t>* out);
 

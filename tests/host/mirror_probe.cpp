@@ -8,6 +8,8 @@
 //   huffman                     generateHuffmanCode(text) == jpgenc_build_huffman(histogram, first positions) [CPU]
 //   segments                    header bytes through the Segment:: classes == jpgenc_write_headers           [CPU]
 //   encode <in.ppm> <out.jpg>   loadPPM + Image::writeJPEG                                                    [GPU]
+//   encode_ycc / encode_edited8 / encode_edited <in.ppm> <out.jpg>   writeJPEG on an image that already is YCbCr / whose
+//                               planes were edited after loading (src/Image.cpp:831-846 encodes the planes)     [GPU]
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -175,7 +177,25 @@ int main(int argc, char** argv) {
             img.writeJPEG(argv[3]);
             return 0;
         }
-        std::cerr << "usage: mirror_probe stages|huffman|segments|encode ..." << std::endl;
+        if (mode == "encode_ycc" && argc == 4) {             // a caller converts first: writeJPEG must not convert again
+            Image img = loadPPM(argv[2]).convertToColorSpace(Image::YCbCr);
+            img.writeJPEG(argv[3]);
+            return 0;
+        }
+        if (mode == "encode_edited8" && argc == 4) {         // planes edited after loading, still 8-bit samples
+            Image img = loadPPM(argv[2]);
+            img.R(1, 2) = 255; img.G(0, 0) = 0; img.B(2, 1) = 17;
+            img.writeJPEG(argv[3]);
+            return 0;
+        }
+        if (mode == "encode_edited" && argc == 4) {          // planes edited after loading: a real-valued sample, a padding sample
+            Image img = loadPPM(argv[2]);
+            img.R(1, 2) += 0.37;
+            img.B(img.height - 1, img.width - 1) = 99.5;
+            img.writeJPEG(argv[3]);
+            return 0;
+        }
+        std::cerr << "usage: mirror_probe stages|huffman|segments|encode|encode_ycc|encode_edited8|encode_edited ..." << std::endl;
         return 2;
     } catch (const std::exception& e) {
         std::cerr << "exception: " << e.what() << std::endl;

@@ -120,6 +120,18 @@ def test_error_behaviour(encoder, tmp_path):
     with pytest.raises(JpgencError) as e:
         encoder.encode_ppm_file(str(bad), str(tmp_path / "o.jpg"))
     assert e.value.code == ERR_FORMAT and "P3 and P6" in str(e.value)
+    # a sample above maxval: refused (P6 bytes, P3 numbers, host pixels handed to the library directly)
+    over6 = tmp_path / "over6.ppm"
+    over6.write_bytes(b"P6\n2 2\n63\n" + bytes([1, 2, 3, 4, 5, 6, 7, 8, 200, 9, 10, 11]))
+    over3 = tmp_path / "over3.ppm"
+    over3.write_bytes(b"P3\n2 1\n100\n1 2 3 4 300 6\n")
+    for f in (over6, over3):
+        with pytest.raises(JpgencError) as e:
+            encoder.encode_ppm_file(str(f), str(tmp_path / "o.jpg"))
+        assert e.value.code == ERR_FORMAT, f
+    with pytest.raises(JpgencError) as e:
+        encoder.encode_rgb(np.full((16, 16, 3), 70, np.uint8), 63)
+    assert e.value.code == ERR_FORMAT
     fresh = Encoder(0)
     with pytest.raises(JpgencError) as e:
         fresh.color_dct_quant()                                     # stage called out of pipeline order

@@ -142,6 +142,21 @@ def test_ppm_rejects_what_the_reference_rejects(data):
     assert rc == capi.ERR_FORMAT          # reference: runtime_error "Only P3 and P6 format is supported!" / assert on maxval
 
 
+@pytest.mark.parametrize("data", [
+    b"P6\n2 2\n63\n" + bytes([1, 2, 3, 4, 5, 6, 7, 8, 200, 9, 10, 11]),
+    b"P3\n2 1\n100\n1 2 3 4 300 6\n",
+    b"P3\n2 1\n15\n1 2 3 4 16 6\n",
+])
+def test_ppm_samples_above_maxval_are_refused(data):
+    """the reference would scale such a sample past 255; the 8-bit device path is not exact for that, so the file is refused
+    (jpgenc_encode_planes is the entry point for data of that kind)"""
+    capi, lib = _lib()
+    rc, info = _ppm_info(lib, data)
+    assert rc == 0
+    out = np.zeros(info[1] * info[2] * 3, np.uint8)
+    assert lib.jpgenc_ppm_samples(data, len(data), out.ctypes.data_as(capi.u8p)) == capi.ERR_FORMAT
+
+
 def test_golden_ppm_headers(golden, oracle):
     capi, lib = _lib()
     for name in [str(n) for n in golden["names"]]:

@@ -155,6 +155,33 @@ def test_write_jpeg_byte_identical(probe, golden, tmp_path):
 
 
 @pytest.mark.gpu
+def test_write_jpeg_encodes_the_planes_not_the_file(probe, golden, oracle, tmp_path):
+    """Image::writeJPEG encodes what R/G/B hold when it is called (src/Image.cpp:831-846) and converts only an RGB image
+    (:112-115, 839): planes edited after loadPPM, a real-valued sample, an edited padding sample, an image converted to
+    YCbCr by the caller"""
+    for name in ("grad_26x19", "synth_64x48", "p6_max63"):
+        ppm, jpg = tmp_path / (name + ".ppm"), tmp_path / (name + ".jpg")
+        ppm.write_bytes(golden[f"{name}/ppm"].tobytes())
+        rgb, maxval = oracle.ppm_load(golden[f"{name}/ppm"].tobytes())
+        h, w, _ = rgb.shape
+        pad = np.pad(rgb, ((0, -h % 16), (0, -w % 16), (0, 0)), mode="edge").astype(np.float64) * (255. / maxval)
+        # already YCbCr: the same file as the plain encode (the conversion happened earlier, with the same arithmetic)
+        subprocess.run([probe, "encode_ycc", str(ppm), str(jpg)], check=True, capture_output=True)
+        assert jpg.read_bytes() == golden[f"{name}/jpg"].tobytes(), name
+        # edited, still 8-bit samples (takes the 8-bit path again, with the new samples)
+        p = pad.copy()
+        p[1, 2, 0] = 255; p[0, 0, 1] = 0; p[2, 1, 2] = 17
+        subprocess.run([probe, "encode_edited8", str(ppm), str(jpg)], check=True, capture_output=True)
+        assert jpg.read_bytes() == oracle.encode_planes(p[..., 0], p[..., 1], p[..., 2], w, h), name
+        # edited to something that is not an 8-bit image: the planes go to the device as doubles
+        p = pad.copy()
+        p[1, 2, 0] += 0.37
+        p[-1, -1, 2] = 99.5
+        subprocess.run([probe, "encode_edited", str(ppm), str(jpg)], check=True, capture_output=True)
+        assert jpg.read_bytes() == oracle.encode_planes(p[..., 0], p[..., 1], p[..., 2], w, h), name
+
+
+@pytest.mark.gpu
 def test_command_line_like_the_reference(golden, tmp_path):
     """jpgEnc <in.ppm> [out.jpg] (reference src/main.cpp:8-32): default output name, error on a missing file"""
     exe = os.path.join(ROOT, "jpgenc_b200", "bin", "jpgEnc")
