@@ -302,6 +302,6 @@ int launch_build_tables(jpgenc_ctx* c, const uint8_t* d_stats, uint32_t stats_st
 int launch_synth_rgb(jpgenc_ctx* c, uint8_t* d, uint32_t w, uint32_t h, uint32_t seed);
 int launch_synth_blocks(jpgenc_ctx* c, float* d, uint64_t nblocks);
 int launch_flush(jpgenc_ctx* c);
-void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out);
+void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out, double input_err);
 void default_dct_constants(double a[5], double s[8]);
 }  // namespace jpgenc

@@ -690,14 +690,17 @@ void aan2d_bounds(double err_in, Bound (&out)[64]) {
         for (int u = 0; u < 8; ++u) out[v * 8 + u] = res[u];
     }
 }
-// error of the colour conversion feeding the transform: three FMAs on magnitudes <= 383 plus the fp32 rounding of the
-// three folded constants (<= 1404 u for Y, less for Cb/Cr); the stand-alone block kernel has exact inputs
-constexpr double kColourErr = 1.0e-4;
+// error of the colour conversion feeding the transform (the reference's value is exact to ~1e-13: float constants times
+// small integers, summed in double).  maxval 255: the folded constants ARE the reference's float constants (Y) or those
+// divided by 4 (Cb, Cr, applied to the exact 2x2 sums), so only the three roundings of the FMA chain remain, each at most
+// half an ulp of a value below 128 in magnitude: 3 x 2^-18 = 1.15e-5.  Other maxvals: the constants carry the rounded
+// factor 255/maxval (<= 1404 u for Y).  The stand-alone block kernel has exact inputs.
+constexpr double kColourErr255 = 2.0e-5, kColourErrScaled = 1.0e-4;
 }  // namespace
 
-void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out) {
+void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out, double input_err) {
     Bound bound[64];
-    aan2d_bounds(kColourErr, bound);
+    aan2d_bounds(input_err, bound);
     for (int v = 0; v < 8; ++v)
         for (int u = 0; u < 8; ++u) {
             const int i = v * 8 + u;
@@ -710,9 +713,9 @@ void fill_quant_consts(const uint8_t q[64], const double s[8], QuantConsts* out)
         }
 }
 
-static void fill_quant_consts2(const uint8_t q[64], const double s[8], QuantConsts2* out) {
+static void fill_quant_consts2(const uint8_t q[64], const double s[8], QuantConsts2* out, double input_err) {
     QuantConsts c;
-    fill_quant_consts(q, s, &c);
+    fill_quant_consts(q, s, &c, input_err);
     for (int u = 0; u < 8; ++u)
         for (int qq = 0; qq < 4; ++qq) {
             const int lo = (2 * qq) * 8 + u, hi = (2 * qq + 1) * 8 + u;
@@ -770,8 +773,9 @@ static void fill_forward_params(const jpgenc_ctx* c, ForwardParams* p) {
         p->color.cb[i] = static_cast<float>(fcb[i] * scale / 4);
         p->color.cr[i] = static_cast<float>(fcr[i] * scale / 4);
     }
-    fill_quant_consts2(c->qy, c->dct_s, &p->luma);
-    fill_quant_consts2(c->qc, c->dct_s, &p->chroma);
+    const double colour_err = c->maxval == 255 ? kColourErr255 : kColourErrScaled;
+    fill_quant_consts2(c->qy, c->dct_s, &p->luma, colour_err);
+    fill_quant_consts2(c->qc, c->dct_s, &p->chroma, colour_err);
 }
 
 // exact FP64 pass over the blocks K1 flagged (all == false) or over every block (all == true)
@@ -855,7 +859,7 @@ int launch_planes_exact(jpgenc_ctx* c, const double* d_planes, bool ycbcr) {
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],
                             uint64_t* refined) {
     QuantConsts2 qc;
-    fill_quant_consts2(q, c->dct_s, &qc);
+    fill_quant_consts2(q, c->dct_s, &qc, 0.0);                 // stand-alone blocks: the samples are the inputs themselves
     ExactConsts e;
     fill_exact(c, q, q, 1.0, &e);
     JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(uint32_t), c->stream));
