@@ -300,6 +300,8 @@ void jpgenc_destroy(jpgenc_ctx* c) {
     for (cudaEvent_t ev : c->ev_band) if (ev) cudaEventDestroy(ev);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->ev_wide) cudaEventDestroy(c->ev_wide);
+    if (c->ev_fwd) cudaEventDestroy(c->ev_fwd);
+    if (c->ev_k4) cudaEventDestroy(c->ev_k4);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
     if (c->out_stream) { cudaStreamSynchronize(c->out_stream); cudaStreamDestroy(c->out_stream); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -193,7 +193,9 @@ struct jpgenc_ctx {
     uint64_t raw_limit = 0, out_limit = 0;   // what finalize_tables_kernel may use of d_raw / d_scan
     uint64_t batch_raw_per_frame = 0;     // batched calls: raw-scan bytes reserved per frame (1.5 x the largest seen so far; 0 = nothing seen yet)
     cudaEvent_t ev_done = nullptr;        // batched calls: end of the slot's current pass
-    cudaEvent_t ev_wide = nullptr;        // ... its K1/refinement/K2 are through (the next pass's wide kernels wait for it)
+    cudaEvent_t ev_wide = nullptr;        // ... its K1/refinement/K2 are through (JPGENC_STAGGER=1: the next pass's wide kernels wait for it)
+    cudaEvent_t ev_k4 = nullptr;          // ... its K4 is through (the next pass's K3 waits for it: passes finish one after the other)
+    cudaEvent_t ev_fwd = nullptr;         // ... its K1/refinement are through (JPGENC_STAGGER=2: the next pass's K1 waits for it)
     cudaEvent_t ev_copied = nullptr;      // ... its files have left d_scan (recorded on out_stream)
     cudaStream_t out_stream = nullptr;    // device-to-host copies of finished passes, beside the slot's kernels
     bool copy_pending = false;

@@ -89,6 +89,8 @@ int prepare_slot(jpgenc_ctx* root, jpgenc_ctx* l, const Job& job, const uint8_t*
     }
     if (!l->ev_done) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming));
     if (!l->ev_wide) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_wide, cudaEventDisableTiming));
+    if (!l->ev_fwd) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_fwd, cudaEventDisableTiming));
+    if (!l->ev_k4) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_k4, cudaEventDisableTiming));
     if (!l->ev_copied) JPGENC_CUDA(l, cudaEventCreateWithFlags(&l->ev_copied, cudaEventDisableTiming));
     if (!l->out_stream) JPGENC_CUDA(l, cudaStreamCreateWithFlags(&l->out_stream, cudaStreamNonBlocking));
     l->copy_pending = false;
@@ -96,7 +98,7 @@ int prepare_slot(jpgenc_ctx* root, jpgenc_ctx* l, const Job& job, const uint8_t*
 }
 
 // K3/K4 of a pass: buffers for the limits, finalize (tables -> lookup form, sizes, offsets), K3a, K3b, K4, read-back
-int enqueue_entropy(jpgenc_ctx* l, Pass& ps) {
+int enqueue_entropy(jpgenc_ctx* l, Pass& ps, cudaEvent_t prev_k4 = nullptr) {
     const uint32_t F = ps.F;
     int rc;
     const uint64_t k4_grid = l->raw_limit / kK4TileBytes + F;
@@ -107,7 +109,12 @@ int enqueue_entropy(jpgenc_ctx* l, Pass& ps) {
         l->copy_pending = false;
     }
     if ((rc = launch_finalize_tables(l))) return rc;
+    // K3/K4 of the passes run one pass after the other (each of them fills the GPU anyway): the passes then FINISH one
+    // after the other and the files of pass p travel while pass p + 1 is packed, instead of all slots' files queueing up
+    // behind the last kernel (trace of 4 slots in step: 4 x 11 MB = 0.8 ms of copies after the last K4)
+    if (prev_k4) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, prev_k4, 0));
     if ((rc = launch_entropy(l, ps.k4_grid))) return rc;
+    JPGENC_CUDA(l, cudaEventRecord(l->ev_k4, l->stream));
     uint8_t* h = static_cast<uint8_t*>(l->h_pinned) + stage_meta_off(F);
     JPGENC_CUDA(l, cudaMemcpyAsync(h, l->d_meta, pass_meta_bytes(F), cudaMemcpyDeviceToHost, l->stream));
     JPGENC_CUDA(l, cudaEventRecord(l->ev_done, l->stream));
@@ -117,7 +124,7 @@ int enqueue_entropy(jpgenc_ctx* l, Pass& ps) {
 
 // the whole chain of one pass on slot `l`; `ready` (optional): event after which the pixels are valid
 // `after` (optional): the previous pass's "wide kernels done" event (see run_passes)
-int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* dev_frames, cudaEvent_t ready, cudaEvent_t after) {
+int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* dev_frames, cudaEvent_t ready, cudaEvent_t after, cudaEvent_t prev_k4) {
     const uint32_t F = ps.F;
     int rc;
     l->nframes = F;
@@ -145,6 +152,7 @@ int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* d
     if (after) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, after, 0));
     if ((rc = launch_forward_rows(l, 0, l->mcu_h, true, true))) return rc;                       // K1 + exact refinement
     l->have_coef = true;
+    JPGENC_CUDA(l, cudaEventRecord(l->ev_fwd, l->stream));
     const size_t nblocks = static_cast<size_t>(l->mcu_w) * l->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     if ((rc = launch_symbol_stats(l, 0, static_cast<uint32_t>(tiles * F), true))) return rc;     // K2
     l->have_items = true;
@@ -167,7 +175,7 @@ int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* d
     l->raw_limit = F * raw_slot_bytes(per_frame);
     l->out_limit = F * (kMaxHeaderBytes + 2ull) + 2 * l->raw_limit;
     ps.attempts = 0;
-    return enqueue_entropy(l, ps);
+    return enqueue_entropy(l, ps, prev_k4);
 }
 
 // waits for the pass on slot `l`, re-runs its entropy stage with larger buffers if it was refused, reports sizes and sends
@@ -261,7 +269,7 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
     std::vector<Pass> pass(npasses);
     // (measured: 128 frames 1.26 -> 1.33 ms, 1024 frames 6.9 -> 7.2 ms: the cross-stream waits cost more than the earlier
     // table builds gain; kept as a switch)
-    const bool stagger = env_u32("JPGENC_STAGGER", 0) != 0;
+    const uint32_t stagger = env_u32("JPGENC_STAGGER", 0);
     rc = JPGENC_OK;
     jpgenc_ctx* failed = nullptr;
     const double t0 = trace_on() ? now_us() : 0;
@@ -284,8 +292,14 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
             // Staggering: the wide kernels of pass p (K1, refinement, K2) start when those of pass p - 1 are through.  Left
             // alone, the streams run the same stage of all passes side by side, every table build then starts at the same
             // (late) moment and nothing wide is left to run beside it.
-            cudaEvent_t after = (stagger && p > 0 && nslots > 1) ? slot[(p - 1) % nslots]->ev_wide : nullptr;
-            if (rc == JPGENC_OK) rc = enqueue_pass(c, l, pass[p], ptrs, ready, after);
+            cudaEvent_t after = nullptr;
+            if (stagger && p > 0 && nslots > 1) after = stagger == 2 ? slot[(p - 1) % nslots]->ev_fwd : slot[(p - 1) % nslots]->ev_wide;
+            // (only when files travel back: sizes-only calls are 2-5 % faster with the slots' K3/K4 side by side.  Measured,
+            // 1024 frames, in order / not: files returned 6.61 / 7.00 ms, sizes only 6.30 / 6.20 ms; JPGENC_ENTROPY_ORDER=0/1 forces)
+            static const uint32_t order_env = env_u32("JPGENC_ENTROPY_ORDER", 2);
+            const bool in_order = order_env == 2 ? (job.packed != nullptr || job.out_ptrs != nullptr) : order_env != 0;
+            cudaEvent_t prev_k4 = (in_order && p > 0 && nslots > 1) ? slot[(p - 1) % nslots]->ev_k4 : nullptr;
+            if (rc == JPGENC_OK) rc = enqueue_pass(c, l, pass[p], ptrs, ready, after, prev_k4);
             if (rc) { failed = l; break; }
         }
     }

@@ -15,7 +15,7 @@ try:
 except Exception as ex:
     print('parse failed', ex); print(open('gpurun_out/r2n${N}_bench.err').read()[-1500:])
 PY
-for fpp in 16 32 64; do
+for fpp in 32 64 128; do
   JPGENC_FRAMES_PER_PASS=$fpp timeout 300 $TR bench.py --gpus $N --workload batch1080p --steps 100 > gpurun_out/r2n${N}_batch_fpp$fpp.json 2> gpurun_out/r2n${N}_batch_fpp$fpp.err
   python - <<PY
 import json
