@@ -193,6 +193,17 @@ int jpgenc_encode_frames_packed(jpgenc_ctx* ctx, uint32_t n, const void* const* 
                                 uint32_t h, uint32_t maxval, uint8_t* out, uint64_t cap, uint64_t* offsets, uint64_t* sizes,
                                 uint64_t* total_bytes);
 
+/* ---- stage methods for the modes writeJPEG does not use ------------------------------------------ */
+/* Image::applySubsampling(mode) on one chroma plane (src/Image.cpp:198-319): `plane` = height x width doubles (host), mode =
+ * the order of Image::SubsamplingMode (0 S444, 1 S422, 2 S411, 3 S420, 4 S420_m, 5 S420_lm); `out` receives the
+ * (height / vdiv) x (width / hdiv) plane (jpgenc_stage_subsample_dims).  Same doubles as the reference, bit for bit. */
+int jpgenc_stage_subsample_dims(int mode, uint32_t width, uint32_t height, uint32_t* out_width, uint32_t* out_height);
+int jpgenc_stage_subsample(jpgenc_ctx* ctx, const double* plane, uint32_t width, uint32_t height, int mode, double* out);
+/* Image::applyDCT(mode) on one plane (src/Image.cpp:540-595): every 8x8 block through dctDirect / dctMat / dctArai
+ * (include/Dct.hpp:238-262, 264-276, 47-215; mode 0 Simple, 1 Matrix, 2 Arai = the order of Image::DCTMode).  `plane` and `out`:
+ * height x width doubles (host), sides multiples of 8.  Same doubles as the reference, bit for bit. */
+int jpgenc_stage_dct(jpgenc_ctx* ctx, const double* plane, uint32_t width, uint32_t height, int mode, double* out);
+
 /* ---- config-1 microbenchmark: dctArai + quantize + zigzag on stand-alone blocks -------------------- */
 /* dev_in: nblocks*64 fp32 samples (row-major 8x8 per block); dev_out: nblocks*64 int16 zigzag.
  * Same exactness contract as K1 (FP32 fast path + exact FP64 refinement of boundary cases). */

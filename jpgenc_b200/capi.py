@@ -78,6 +78,9 @@ _SIGNATURES = {
     "jpgenc_encode_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                        C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_ppm_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "jpgenc_stage_subsample_dims": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, u32p, u32p]),
+    "jpgenc_stage_subsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
+    "jpgenc_stage_dct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "jpgenc_dct_quant_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u8p, u64p]),
     "jpgenc_bind_host_to_device_numa": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "jpgenc_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -277,6 +280,24 @@ class Encoder:
         out = np.empty(n.value, np.uint8)
         self._check(self.lib.jpgenc_assemble_last(self.h, out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value].tobytes()
+
+    def stage_subsample(self, plane: np.ndarray, mode: int) -> np.ndarray:
+        """Image::applySubsampling(mode) on one plane of doubles (mode = order of Image::SubsamplingMode)"""
+        plane = np.ascontiguousarray(plane, np.float64)
+        h, w = plane.shape
+        ow, oh = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.jpgenc_stage_subsample_dims(mode, w, h, C.byref(ow), C.byref(oh)))
+        out = np.empty((oh.value, ow.value), np.float64)
+        self._check(self.lib.jpgenc_stage_subsample(self.h, plane.ctypes.data, w, h, mode, out.ctypes.data))
+        return out
+
+    def stage_dct(self, plane: np.ndarray, mode: int) -> np.ndarray:
+        """Image::applyDCT(mode) on one plane of doubles (mode 0 Simple, 1 Matrix, 2 Arai)"""
+        plane = np.ascontiguousarray(plane, np.float64)
+        h, w = plane.shape
+        out = np.empty_like(plane)
+        self._check(self.lib.jpgenc_stage_dct(self.h, plane.ctypes.data, w, h, mode, out.ctypes.data))
+        return out
 
     def encode_rgb_into(self, host_ptr: int, w: int, h: int, out_ptr: int, cap: int, maxval: int = 255) -> int:
         n = C.c_uint64()

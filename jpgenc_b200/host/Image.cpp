@@ -247,8 +247,26 @@ Image Image::convertToColorSpace(ColorSpace target) const {
     return out;
 }
 
+static bool g_stages_on_device = false;
+void Image::stagesOnDevice(bool on) { g_stages_on_device = on; }
+
 void Image::applySubsampling(SubsamplingMode mode) {
     if (mode == S444) return;
+    if (g_stages_on_device) {
+        // enum order == the C-ABI's mode numbers (S444, S422, S411, S420, S420_m, S420_lm)
+        jpgenc_ctx* c = g_gpu.get();
+        uint32_t ow = 0, oh = 0;
+        for (matrix<PixelDataType>* plane : {&three, &two}) {             // Cr first, then Cb, as the reference does
+            const uint32_t w = static_cast<uint32_t>(plane->size2()), h = static_cast<uint32_t>(plane->size1());
+            check(c, jpgenc_stage_subsample_dims(static_cast<int>(mode), w, h, &ow, &oh));
+            matrix<PixelDataType> small(oh, ow);
+            check(c, jpgenc_stage_subsample(c, &plane->data()[0], w, h, static_cast<int>(mode), &small.data()[0]));
+            *plane = small;
+        }
+        subsample_width = ow;
+        subsample_height = oh;
+        return;
+    }
     // horizontal step, vertical step, taps per row, whether the second row is averaged in, divisor
     int hstep = 2, vstep = 2, taps = 1;
     bool second_row = false;
@@ -291,6 +309,15 @@ void Image::applyDCT(DCTMode mode) {
     }
     const matrix<PixelDataType>* src[3] = {&one, &two, &three};
     matrix<PixelDataType>* dst[3] = {&DctY, &DctCb, &DctCr};
+    if (g_stages_on_device) {
+        jpgenc_ctx* c = g_gpu.get();
+        for (int p = 0; p < 3; ++p) {
+            *dst[p] = matrix<PixelDataType>(src[p]->size1(), src[p]->size2());
+            check(c, jpgenc_stage_dct(c, &src[p]->data()[0], static_cast<uint32_t>(src[p]->size2()), static_cast<uint32_t>(src[p]->size1()),
+                                      mode == Simple ? 0 : mode == Matrix ? 1 : 2, &dst[p]->data()[0]));
+        }
+        return;
+    }
     for (int p = 0; p < 3; ++p) {
         *dst[p] = matrix<PixelDataType>(src[p]->size1(), src[p]->size2());
         for (std::size_t y = 0; y + 8 <= src[p]->size1(); y += 8)

@@ -51,6 +51,11 @@ public:
     void doRLEandCategoryCoding();
     void doHuffmanEncoding(SymbolCodeMap& Y_DC, SymbolCodeMap& Y_AC, SymbolCodeMap& C_DC, SymbolCodeMap& C_AC);
 
+    // The stage methods applySubsampling / applyDCT are host code by default (API compatibility; they are not on the encode
+    // path).  stagesOnDevice(true) sends them -- every SubsamplingMode, every DCTMode -- through jpgenc_stage_subsample /
+    // jpgenc_stage_dct instead (same doubles, bit for bit; throws std::runtime_error without a GPU).
+    static void stagesOnDevice(bool on);
+
     // whole encode on the GPU; `file` receives a baseline JFIF file byte-identical to the reference's
     void writeJPEG(std::string file);
     // same, into memory (what writeJPEG writes)

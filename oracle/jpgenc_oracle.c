@@ -172,6 +172,8 @@ static void dct_basis(double a[64]) {           /* Dct.hpp:219-235 */
         }
 }
 
+void jo_dct_basis(double a[64]) { dct_basis(a); }
+
 void jo_dct_direct(const double in[64], double out[64]) {   /* Dct.hpp:238-262 */
     double a[64];
     dct_basis(a);
@@ -668,6 +670,56 @@ void jo_forward_planes(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uin
                        double* dct_y, double* dct_cb, double* dct_cr, int32_t* q_y, int32_t* q_cb, int32_t* q_cr) {
     forward_impl(rgb, real_w, real_h, maxval, qy, qc, 0, jo_pad16(real_h) / 16, NULL, y, cb, cr, dct_y, dct_cb,
                  dct_cr, q_y, q_cb, q_cr);
+}
+
+/* Image::subsample for every SubsamplingMode (Image.cpp:198-235, masks and divisors :237-319): mode 0 S444, 1 S422, 2 S411,
+ * 3 S420, 4 S420_m, 5 S420_lm (the enum order of Image.hpp).  in: h x w doubles; out: (h / vdiv) x (w / hdiv).  The weights
+ * are applied the way the reference applies them -- pix = 0; pix += row[m] * chan(y, x + m) for EVERY tap, zero weights
+ * included -- and the second scanline is added and divided in place. */
+void jo_subsample_dims(int mode, uint32_t w, uint32_t h, uint32_t* ow, uint32_t* oh) {
+    const int hdiv = (mode == 0) ? 1 : (mode == 2) ? 4 : 2;
+    const int vdiv = (mode >= 3) ? 2 : 1;
+    *ow = w / hdiv; *oh = h / vdiv;
+}
+
+void jo_subsample_plane(const double* in, uint32_t w, uint32_t h, int mode, double* out) {
+    if (mode == 0) { memcpy(out, in, sizeof(double) * (size_t)w * h); return; }
+    const int taps = (mode == 2) ? 4 : 2;
+    const double row[4] = {1, (mode == 4) ? 1 : 0, 0, 0};      /* {1,0} {1,0,0,0} {1,0} {1,1} {1,0} */
+    const int scanline_jump = (mode == 3), averaging = (mode == 4 || mode == 5);
+    const double div = (mode == 4) ? 4 : 2;
+    size_t pixidx = 0, pixidx2 = 0;
+    for (uint32_t y = 0; y < h; y += 2) {
+        for (uint32_t x = 0; x < w; x += taps) {
+            double pix = 0;
+            for (int m = 0; m < taps; ++m) pix += row[m] * in[(size_t)y * w + x + m];
+            out[pixidx++] = pix;
+        }
+        if (!scanline_jump) {
+            if (averaging) {
+                for (uint32_t x = 0; x < w; x += taps) {
+                    double pix = 0;
+                    for (int m = 0; m < taps; ++m) pix += row[m] * in[(size_t)(y + 1) * w + x + m];
+                    out[pixidx2] += pix;
+                    out[pixidx2] /= div;
+                    ++pixidx2;
+                }
+            } else {
+                --y;                                            /* the next scanline is an output row of its own */
+            }
+        }
+    }
+}
+
+/* Image::applyDCT on one plane (Image.cpp:540-595): every 8x8 block through dctDirect / dctMat / dctArai (mode 0 / 1 / 2) */
+void jo_dct_plane(const double* in, uint32_t w, uint32_t h, int mode, double* out) {
+    double a[64], b[64];
+    for (uint32_t by = 0; by < h; by += 8)
+        for (uint32_t bx = 0; bx < w; bx += 8) {
+            for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) a[i * 8 + j] = in[(size_t)(by + i) * w + bx + j];
+            if (mode == 0) jo_dct_direct(a, b); else if (mode == 1) jo_dct_matrix(a, b); else jo_dct_arai(a, b);
+            for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) out[(size_t)(by + i) * w + bx + j] = b[i * 8 + j];
+        }
 }
 
 /* Image::writeJPEG on an Image whose planes are given as doubles (Image.hpp:104-114): p0,p1,p2 are H16*W16 row-major planes,

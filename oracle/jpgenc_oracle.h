@@ -97,6 +97,14 @@ void jo_forward_planes(const uint8_t* rgb, uint32_t real_w, uint32_t real_h, uin
                        double* y, double* cb, double* cr, double* dct_y, double* dct_cb, double* dct_cr,
                        int32_t* q_y, int32_t* q_cb, int32_t* q_cr);
 
+/* Stage methods on one plane: Image::subsample for every SubsamplingMode (Image.cpp:198-319; mode = enum order S444, S422, S411,
+ * S420, S420_m, S420_lm) and Image::applyDCT (Image.cpp:540-595; mode 0 Simple, 1 Matrix, 2 Arai) */
+void jo_subsample_dims(int mode, uint32_t w, uint32_t h, uint32_t* ow, uint32_t* oh);
+void jo_subsample_plane(const double* in, uint32_t w, uint32_t h, int mode, double* out);
+void jo_dct_plane(const double* in, uint32_t w, uint32_t h, int mode, double* out);
+/* the 8x8 DCT basis A of Dct.hpp:217-236 (row-major) */
+void jo_dct_basis(double a[64]);
+
 /* The same from three H16*W16 planes of doubles (an Image assembled or edited in memory): R,G,B, or with ycbcr != 0 planes that
  * already are level-shifted Y,Cb,Cr (Image.cpp:112-115: not converted again). */
 void jo_forward_from_planes(const double* p0, const double* p1, const double* p2, uint32_t W16, uint32_t H16, int ycbcr,

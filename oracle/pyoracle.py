@@ -100,6 +100,10 @@ class Oracle:
         L.jo_encode_rgb.argtypes = [u8p, C.c_uint32, C.c_uint32, C.POINTER(u8p), C.POINTER(C.c_size_t)]
         L.jo_forward_from_planes.argtypes = [f64p, f64p, f64p, C.c_uint32, C.c_uint32, C.c_int, u8p, u8p, i16p]
         L.jo_encode_planes.argtypes = [f64p, f64p, f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(u8p), C.POINTER(C.c_size_t)]
+        L.jo_subsample_dims.argtypes = [C.c_int, C.c_uint32, C.c_uint32, u32p, u32p]
+        L.jo_subsample_plane.argtypes = [f64p, C.c_uint32, C.c_uint32, C.c_int, f64p]
+        L.jo_dct_plane.argtypes = [f64p, C.c_uint32, C.c_uint32, C.c_int, f64p]
+        L.jo_dct_basis.argtypes = [f64p]
         L.jo_free.argtypes = [C.c_void_p]
         self.qy = np.ctypeslib.as_array((C.c_uint8 * 64).in_dll(L, "jo_qtable_luma")).copy()
         self.qc = np.ctypeslib.as_array((C.c_uint8 * 64).in_dll(L, "jo_qtable_chroma")).copy()
@@ -268,6 +272,32 @@ class Oracle:
         return res
 
 
+    SUBSAMPLING = {"S444": 0, "S422": 1, "S411": 2, "S420": 3, "S420_m": 4, "S420_lm": 5}
+    DCT_MODES = {"simple": 0, "matrix": 1, "arai": 2}
+
+    def subsample_plane(self, plane, mode):
+        """Image::subsample (src/Image.cpp:198-319) of one plane; mode: a key of SUBSAMPLING"""
+        plane = np.ascontiguousarray(plane, np.float64)
+        h, w = plane.shape
+        ow, oh = C.c_uint32(), C.c_uint32()
+        self.L.jo_subsample_dims(self.SUBSAMPLING[mode], w, h, C.byref(ow), C.byref(oh))
+        out = np.empty((oh.value, ow.value), np.float64)
+        self.L.jo_subsample_plane(_ptr(plane, f64p), w, h, self.SUBSAMPLING[mode], _ptr(out, f64p))
+        return out
+
+    def dct_plane(self, plane, mode="arai"):
+        """Image::applyDCT (src/Image.cpp:540-595) on one plane whose sides are multiples of 8"""
+        plane = np.ascontiguousarray(plane, np.float64)
+        h, w = plane.shape
+        out = np.empty_like(plane)
+        self.L.jo_dct_plane(_ptr(plane, f64p), w, h, self.DCT_MODES[mode], _ptr(out, f64p))
+        return out
+
+    def dct_basis(self):
+        a = np.empty(64, np.float64)
+        self.L.jo_dct_basis(_ptr(a, f64p))
+        return a
+
     def forward_from_planes(self, p0, p1, p2, ycbcr=False):
         """three (H16, W16) float64 planes (Image::R/G/B, or Y/Cb/Cr with ycbcr) -> MCU-ordered zigzag int16 coefficients"""
         pl = [np.ascontiguousarray(p, np.float64) for p in (p0, p1, p2)]
@@ -310,8 +340,26 @@ class Reference:
         L.ref_block_symbols.argtypes = [i32p, u8p, u32p, u8p]
         L.ref_generate_huffman.argtypes = [i32p, C.c_int, u32p, u8p, u8p, u8p]
         L.ref_bitstream_pack.argtypes = [u32p, u8p, C.c_int, C.c_int, u8p, C.c_int, u32p]
+        if hasattr(L, "ref_subsample_plane"):
+            L.ref_subsample_plane.argtypes = [f64p, C.c_uint32, C.c_uint32, C.c_int, f64p, u32p, u32p]
+            L.ref_dct_plane.argtypes = [f64p, C.c_uint32, C.c_uint32, C.c_int, f64p]
         if hasattr(L, "ref_encode_planes"):
             L.ref_encode_planes.argtypes = [f64p, f64p, f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p]
+
+    def subsample_plane(self, plane, mode: int):
+        plane = np.ascontiguousarray(plane, np.float64)
+        h, w = plane.shape
+        out = np.empty(h * w, np.float64)
+        ow, oh = C.c_uint32(), C.c_uint32()
+        assert self.L.ref_subsample_plane(_ptr(plane, f64p), w, h, mode, _ptr(out, f64p), C.byref(ow), C.byref(oh)) == 0
+        return out[: ow.value * oh.value].reshape(oh.value, ow.value).copy()
+
+    def dct_plane(self, plane, mode: int):
+        plane = np.ascontiguousarray(plane, np.float64)
+        h, w = plane.shape
+        out = np.empty_like(plane)
+        assert self.L.ref_dct_plane(_ptr(plane, f64p), w, h, mode, _ptr(out, f64p)) == 0
+        return out
 
     def encode_planes(self, p0, p1, p2, real_w, real_h, ycbcr, jpg_path: str) -> int:
         """Image::writeJPEG on an Image assembled from three (H16, W16) float64 planes"""

@@ -100,6 +100,30 @@ int ref_encode_planes(const double* p0, const double* p1, const double* p2, unsi
     } catch (const std::exception&) { return -1; }
 }
 
+// Image::applySubsampling(mode) on an Image whose Cb plane is `in` (h x w doubles): the subsampled Cb plane comes back in `out`
+// (sized by the caller: Image.cpp:237-319 gives the divisors); mode = the enum's order S444, S422, S411, S420, S420_m, S420_lm
+int ref_subsample_plane(const double* in, unsigned w, unsigned h, int mode, double* out, unsigned* ow, unsigned* oh) {
+    try {
+        Image img(w, h, Image::YCbCr);
+        for (std::size_t i = 0; i < std::size_t(w) * h; ++i) { img.Y.data()[i] = 0; img.Cb.data()[i] = in[i]; img.Cr.data()[i] = in[i]; }
+        img.applySubsampling(static_cast<Image::SubsamplingMode>(mode));
+        *ow = static_cast<unsigned>(img.Cb.size2()); *oh = static_cast<unsigned>(img.Cb.size1());
+        copy_out(img.Cb, out);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
+
+// Image::applyDCT(mode) on an Image whose Y plane is `in` (h x w doubles, multiples of 8... the chroma planes are dummies)
+int ref_dct_plane(const double* in, unsigned w, unsigned h, int mode, double* out) {
+    try {
+        Image img(w, h, Image::YCbCr);
+        for (std::size_t i = 0; i < std::size_t(w) * h; ++i) { img.Y.data()[i] = in[i]; img.Cb.data()[i] = 0; img.Cr.data()[i] = 0; }
+        img.applyDCT(static_cast<Image::DCTMode>(mode));
+        copy_out(img.DctY, out);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
+
 // one 8x8 block through each DCT variant (Dct.hpp:47,238,264); mode 0=Simple 1=Matrix 2=Arai
 void ref_dct_block(const double* in, double* out, int mode) {
     matrix<double> x(8, 8), y(8, 8);

@@ -5,6 +5,7 @@
 //                               applyQuantization -> applyDCdifferenceCoding/doRLEandCategoryCoding/doHuffmanEncoding;
 //                               dumps Y, Cb (doubles), DctY (doubles), QY, QCb, QCr (int32, before DC differencing)
 //                               and the per-stage host scan (stuffed) for comparison with the golden vectors   [CPU]
+//   stages_device <in.ppm> <out.bin>   the same with Image::stagesOnDevice(true): applySubsampling / applyDCT on the GPU [GPU]
 //   huffman                     generateHuffmanCode(text) == jpgenc_build_huffman(histogram, first positions) [CPU]
 //   segments                    header bytes through the Segment:: classes == jpgenc_write_headers           [CPU]
 //   encode <in.ppm> <out.jpg>   loadPPM + Image::writeJPEG                                                    [GPU]
@@ -170,6 +171,10 @@ int main(int argc, char** argv) {
     try {
         const std::string mode = argc > 1 ? argv[1] : "";
         if (mode == "stages" && argc == 4) return stages(argv[2], argv[3]);
+        if (mode == "stages_device" && argc == 4) {           // the same stage sequence with applySubsampling / applyDCT on the GPU
+            Image::stagesOnDevice(true);
+            return stages(argv[2], argv[3]);
+        }
         if (mode == "huffman") return huffman();
         if (mode == "segments") return segments();
         if (mode == "encode" && argc == 4) {

@@ -676,3 +676,26 @@ def test_planes_of_doubles_byte_identical(encoder, oracle, golden_planes):
     assert encoder.encode_planes(pad[..., 0], pad[..., 1], pad[..., 2], 208, 120) == encoder.encode_rgb(rgb)
     with pytest.raises(Exception):
         encoder.encode_planes(pad[:120, :, 0], pad[:120, :, 1], pad[:120, :, 2], 208, 120)      # not padded to whole MCUs
+
+
+@pytest.mark.gpu
+def test_stage_kernels_every_subsampling_and_dct_mode(encoder, oracle):
+    """SURVEY 8(f)4: Image::applySubsampling for all six SubsamplingModes and Image::applyDCT for Simple / Matrix / Arai on whole
+    planes of doubles -- the device's planes against the oracle's (itself pinned against the compiled reference), exactly"""
+    rng = np.random.default_rng(8)
+    for (w, h) in [(16, 16), (64, 48), (256, 128), (1920, 1088)]:
+        plane = rng.uniform(-128, 127, (h, w))
+        plane[0, 0] = -0.0
+        for name, mode in oracle.SUBSAMPLING.items():
+            got, want = encoder.stage_subsample(plane, mode), oracle.subsample_plane(plane, name)
+            assert got.shape == want.shape and np.array_equal(got.view(np.uint64), want.view(np.uint64)), (name, w, h)
+        if w * h > 300000:
+            plane = plane[:64]
+        for name, mode in oracle.DCT_MODES.items():
+            got, want = encoder.stage_dct(plane, mode), oracle.dct_plane(plane, name)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (name, w, h)
+    from jpgenc_b200.capi import JpgencError
+    with pytest.raises(JpgencError):
+        encoder.stage_dct(np.zeros((12, 16)), 2)                     # sides must be multiples of 8
+    with pytest.raises(JpgencError):
+        encoder.stage_subsample(np.zeros((16, 18)), 2)               # S411 takes four columns at a time

@@ -155,6 +155,22 @@ def test_write_jpeg_byte_identical(probe, golden, tmp_path):
 
 
 @pytest.mark.gpu
+def test_stage_methods_on_the_device_match_reference_golden(probe, golden, tmp_path):
+    """Image::stagesOnDevice(true): applySubsampling / applyDCT run on the GPU (jpgenc_stage_subsample / jpgenc_stage_dct) inside the
+    reference's stage sequence; every plane that follows must still be the compiled reference's"""
+    for name in [str(n) for n in golden["names"]]:
+        ppm = tmp_path / (name + ".ppm")
+        ppm.write_bytes(golden[f"{name}/ppm"].tobytes())
+        dump = tmp_path / (name + ".bin")
+        subprocess.run([probe, "stages_device", str(ppm), str(dump)], check=True, capture_output=True)
+        y, cb, dct_y, q_y, q_cb, q_cr, scan = _read_dump(dump)
+        assert np.array_equal(q_y, golden[f"{name}/q_y"]), name
+        assert np.array_equal(q_cb, golden[f"{name}/q_cb"]) and np.array_equal(q_cr, golden[f"{name}/q_cr"]), name
+        if f"{name}/y" in golden:
+            assert np.array_equal(cb, golden[f"{name}/cb"]) and np.array_equal(dct_y, golden[f"{name}/dct_y"]), name   # doubles, exact
+
+
+@pytest.mark.gpu
 def test_write_jpeg_encodes_the_planes_not_the_file(probe, golden, oracle, tmp_path):
     """Image::writeJPEG encodes what R/G/B hold when it is called (src/Image.cpp:831-846) and converts only an RGB image
     (:112-115, 839): planes edited after loadPPM, a real-valued sample, an edited padding sample, an image converted to

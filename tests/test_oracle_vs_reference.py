@@ -137,3 +137,15 @@ def test_planes_path_matches_reference(oracle, reference, tmp_path):
     rgb = synth_rgb(48, 32, 3)
     planes = [rgb[..., k].astype(np.float64) for k in range(3)]
     assert oracle.encode_planes(planes[0], planes[1], planes[2], 48, 32, False) == oracle.encode_rgb(rgb)
+
+
+def test_stage_methods_on_planes_match_reference(oracle, reference):
+    """Image::applySubsampling for every SubsamplingMode (src/Image.cpp:198-319) and Image::applyDCT for every DCTMode
+    (src/Image.cpp:540-595, Dct.hpp:47-276) on whole planes: doubles compared exactly"""
+    rng = np.random.default_rng(123)
+    for (w, h) in [(16, 16), (32, 48), (64, 16)]:
+        plane = rng.uniform(-128, 127, (h, w))
+        for name, mode in oracle.SUBSAMPLING.items():
+            assert np.array_equal(oracle.subsample_plane(plane, name), reference.subsample_plane(plane, mode)), (name, w, h)
+        for name, mode in oracle.DCT_MODES.items():
+            assert np.array_equal(oracle.dct_plane(plane, name), reference.dct_plane(plane, mode)), (name, w, h)
