@@ -184,23 +184,26 @@ int flush_entropy_time(jpgenc_ctx* c) {
     return JPGENC_OK;
 }
 
-// Waits until the kernels of the current encode have raised mailbox word `flag_word` (K2: statistics complete, K4: scan
-// complete).  The word is written over PCIe into page-locked host memory: polling it costs a microsecond where a
-// device-to-host copy plus cudaStreamSynchronize cost 20-30.  The stream is queried every now and then so that a failed
-// launch is reported instead of waited for; long waits (the pixels of a large image still crossing PCIe) yield the core.
-int poll_mailbox(jpgenc_ctx* c, int flag_word) {
-    volatile uint32_t* flag = c->h_mailbox + flag_word;
-    const uint32_t seq = c->mailbox_seq;
+// Waits until mailbox word `word` carries the tag of the current encode's publishing kernel and returns its value.  The word
+// is written over PCIe into page-locked host memory: polling it costs a microsecond where a device-to-host copy plus
+// cudaStreamSynchronize cost 20-30.  The stream is queried every now and then so that a failed launch is reported instead
+// of waited for; long waits (the pixels of a large image still crossing PCIe) yield the core.
+int poll_mailbox(jpgenc_ctx* c, int word, unsigned long long* value) {
+    volatile unsigned long long* w = c->h_mailbox + word;
+    const unsigned long long tag = mail_tag(c->mailbox_seq);
     const double t0 = now_us();
+    unsigned long long v = 0;
     for (uint32_t spins = 1;; ++spins) {
-        if (*flag == seq) break;
+        v = *w;
+        if ((v >> kMailTagShift) == tag) break;
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
         if ((spins & 0x3FFu) == 0) {
             const cudaError_t e = cudaStreamQuery(c->stream);
             if (e == cudaSuccess) {
-                if (*flag == seq) break;
+                v = *w;
+                if ((v >> kMailTagShift) == tag) break;
                 return fail(c, JPGENC_ERR_CUDA, "the kernels finished without delivering their result");
             }
             if (e != cudaErrorNotReady) { c->error = std::string("kernel failed: ") + cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
@@ -208,6 +211,8 @@ int poll_mailbox(jpgenc_ctx* c, int flag_word) {
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    *value = v & ((1ull << kMailTagShift) - 1);
+    *w = 0;                                                          // consumed: this tag is never met again in this word
     return JPGENC_OK;
 }
 
@@ -269,8 +274,8 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
     for (cudaEvent_t* ev : {&c->ev_e0, &c->ev_e1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     // the mailbox: page-locked host memory the kernels write into directly (results of one image, a few KB)
-    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_mailbox), kMailWords * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
-    std::memset(c->h_mailbox, 0, kMailWords * sizeof(uint32_t));
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_mailbox), kMailWords64 * sizeof(unsigned long long), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    std::memset(c->h_mailbox, 0, kMailWords64 * sizeof(unsigned long long));
     if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_mailbox), c->h_mailbox, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     *out = c;
     return JPGENC_OK;
@@ -470,9 +475,21 @@ static int wait_stats(jpgenc_ctx* c) {
     c->have_items = true;
     int rc = flush_entropy_time(c);                               // the previous encode's K3/K4 time, while K2 runs
     if (rc) return rc;
-    if ((rc = poll_mailbox(c, kMailK2Flag))) return rc;          // the statistics are in the mailbox
-    c->host_hist.assign(c->h_mailbox + kMailStats, c->h_mailbox + kMailStats + 1024);
-    if (c->upload_pending || c->forward_pending) c->stats.refined_blocks = c->h_mailbox[kMailRefined];
+    unsigned long long head = 0;
+    if ((rc = poll_mailbox(c, kMailStatsHead, &head))) return rc;   // the statistics are in the mailbox
+    const uint32_t present = static_cast<uint32_t>(head & 0x7FFu);
+    std::memset(c->stat_count, 0, sizeof c->stat_count);
+    std::memset(c->stat_first, 0xFF, sizeof c->stat_first);
+    for (uint32_t k = 0; k < present; ++k) {
+        unsigned long long a = 0, b = 0;
+        if ((rc = poll_mailbox(c, kMailStatsHead + 1 + 2 * k, &a))) return rc;
+        if ((rc = poll_mailbox(c, kMailStatsHead + 2 + 2 * k, &b))) return rc;
+        const uint32_t e = static_cast<uint32_t>(a >> 32) & 1023u;
+        (&c->stat_count[0][0])[e] = static_cast<uint32_t>(a);
+        (&c->stat_first[0][0])[e] = b;
+    }
+    c->host_hist.assign(&c->stat_count[0][0], &c->stat_count[0][0] + 1024);
+    if (c->upload_pending || c->forward_pending) c->stats.refined_blocks = static_cast<uint32_t>(head >> 11);
     c->stats_pending = true;
     return JPGENC_OK;
 }
@@ -582,9 +599,9 @@ static int wait_entropy(jpgenc_ctx* c) {
     int rc = read_completed_times(c);                            // K3/K4 are running: the host has nothing else to do
     if (rc) return rc;
     c->ent_pending = true;
-    if ((rc = poll_mailbox(c, kMailK4Flag))) return rc;          // the totals are in the mailbox (launch_entropy's last kernel)
-    const volatile unsigned long long* totals = reinterpret_cast<const volatile unsigned long long*>(c->h_mailbox + kMailTotals);
-    const unsigned long long bits = totals[0], ff = totals[1];
+    unsigned long long bits = 0, ff = 0;
+    if ((rc = poll_mailbox(c, kMailTotals, &bits))) return rc;   // the totals are in the mailbox (launch_entropy's last kernel)
+    if ((rc = poll_mailbox(c, kMailTotals + 1, &ff))) return rc;
     if (bits != c->frame_bits[0]) {
         c->error = "entropy coder wrote " + std::to_string(bits) + " bits, statistics predicted " + std::to_string(c->frame_bits[0]);
         return JPGENC_ERR_ARG;
@@ -615,8 +632,8 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
     const int rc = stats_frames(c);
     if (rc) return rc;
-    std::memcpy(count, c->h_mailbox + kMailStats, 4096);
-    std::memcpy(first_pos, c->h_mailbox + kMailStats + 1024, 8192);
+    std::memcpy(count, c->stat_count, 4096);
+    std::memcpy(first_pos, c->stat_first, 8192);
     return JPGENC_OK;
 }
 
@@ -802,8 +819,8 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     }
     const double t1 = trace_on() ? now_us() : 0;
     // ---- host: the four tables ----
-    const uint32_t(*count)[256] = reinterpret_cast<const uint32_t(*)[256]>(c->h_mailbox + kMailStats);
-    const uint64_t(*first_pos)[256] = reinterpret_cast<const uint64_t(*)[256]>(c->h_mailbox + kMailStats + 1024);
+    const uint32_t(*count)[256] = c->stat_count;
+    const uint64_t(*first_pos)[256] = c->stat_first;
     if (pool) {
         if ((rc = c->pool->build(count, first_pos, tables))) return fail(c, rc, "Huffman table build failed");
     } else {

@@ -230,10 +230,12 @@ struct jpgenc_ctx {
     size_t flush_bytes = 0;
     void* h_file_pinned = nullptr;        // two band-sized pinned buffers for streamed inputs (jpgenc_encode_ppm_file)
     size_t file_pinned_bytes = 0;
-    // mailbox: mapped pinned memory the kernels of ONE image write their results into (the host polls a flag word instead of
-    // synchronising the stream): u32[3072] K2 statistics | refine count | K2 flag | pad | u64 scan bits | u64 stuffed FFs | K4 flag
-    uint32_t* h_mailbox = nullptr;        // host view
-    uint32_t* d_mailbox = nullptr;        // device view of the same memory
+    // mailbox: mapped pinned memory the kernels of ONE image write their results into (the host polls it instead of
+    // synchronising the stream); layout: kMail* below
+    unsigned long long* h_mailbox = nullptr;   // host view
+    unsigned long long* d_mailbox = nullptr;   // device view of the same memory
+    uint32_t stat_count[4][256];          // K2's statistics of the current image as last received
+    uint64_t stat_first[4][256];
     uint32_t mailbox_seq = 0;             // announced by K2 / K4 of the current encode
     void* h_pinned = nullptr;             // small pinned staging (stats, totals)
     size_t pinned_bytes = 0;
@@ -267,18 +269,24 @@ inline cudaError_t jpgenc_record(jpgenc_ctx* c, cudaEvent_t ev) {
 namespace jpgenc {
 // words of jpgenc_ctx::d_counters
 constexpr int kCntRefine = 0;      // entries in the refinement list (K1)
-constexpr int kCntK4Ticket = 2;    // K4's tile ticket (zeroed by K3a)
 constexpr int kCntRefined = 3;     // list entries already refined (band-wise encodes)
 constexpr int kCntFinalize = 4;    // finalize_tables_kernel's CTA ticket (resets itself)
 constexpr int kCntSeq = 5;         // mailbox sequence number (mailbox_publish_kernel increments it; never cleared)
 constexpr int kCounterWords = 16;
-// words of the host mailbox (jpgenc_ctx::h_mailbox)
-constexpr int kMailStats = 0;        // u32[3072]: K2's histogram and first-occurrence keys of the image
-constexpr int kMailRefined = 3072;   // K1's refinement counter
-constexpr int kMailK2Flag = 3073;    // == mailbox_seq: the statistics are complete
-constexpr int kMailTotals = 3076;    // u64 scan bits, u64 stuffed FF bytes
-constexpr int kMailK4Flag = 3080;    // == mailbox_seq: the scan is complete
-constexpr int kMailWords = 4096;
+// The host mailbox (jpgenc_ctx::h_mailbox, mapped pinned memory) as 64-bit words.  Every word carries its own validity: value
+// (42 bits) | tag << 42, tag = mail_tag(sequence number of the publishing kernel) != 0 -- an aligned 8-byte store arrives
+// whole, so the host needs no flag behind the data and the kernel no system-wide fence in front of one; the host zeroes what
+// it has consumed, so a tag is never met again.
+//   [kMailStatsHead]           n present symbols (11 bits) | K1's refinement counter << 11
+//   [kMailStatsHead + 1 + 2k]  record k: count (32 bits) | (table * 256 + symbol) << 32
+//   [kMailStatsHead + 2 + 2k]            first-occurrence key
+//   [kMailTotals], [+1]        scan bits, stuffed FF bytes (K4)
+constexpr int kMailStatsHead = 0;
+constexpr int kMailTotals = 2064;
+constexpr int kMailWords64 = 2080;
+constexpr int kMailTagShift = 42;
+__host__ __device__ inline unsigned long long mail_tag(uint32_t seq) { return static_cast<unsigned long long>(seq % 0x1FFFFFu + 1u); }
+__host__ __device__ inline unsigned long long mail_word(unsigned long long value, uint32_t seq) { return value | (mail_tag(seq) << kMailTagShift); }
 int launch_forward(jpgenc_ctx* c);
 int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, bool last);
 int launch_dct_quant_blocks(jpgenc_ctx* c, const float* in, int16_t* out, uint64_t nblocks, const uint8_t q[64],

@@ -456,7 +456,42 @@ __device__ __forceinline__ void refine_loop(uint32_t n0, uint32_t n, const uint3
     }
 }
 
+// The same with 64 threads per block (two blocks per warp).  The 8-thread form is a chain of ~800 dependent FP64
+// instructions per thread (8 samples of up to 4 pixel conversions each, two passes, 8 divisions): a small image has too few
+// flagged blocks to hide it (3840x2160: ~800 blocks, 15 us = a tenth of the encode).  Here thread (r, c) converts ONE sample and
+// quantises ONE coefficient, the two 1-D passes run on 8 of the 64 threads out of shared memory: ~180 dependent instructions,
+// and fewer warp instructions in total (the samples and divisions fill all lanes).
+template <class Locate, class Sample>
+__device__ __forceinline__ void refine_loop64(uint32_t n0, uint32_t n, const uint32_t* __restrict__ list, bool all, int16_t* __restrict__ out,
+                                              uint32_t blocks_per_frame, const uint8_t* qtab_y, const uint8_t* qtab_c, const ExactConsts& e,
+                                              Locate&& locate, Sample&& sample) {
+    __shared__ double s_x[kRefineThreads / 64][64], s_t[kRefineThreads / 64][64];
+    const int sub = threadIdx.x >> 6, t64 = threadIdx.x & 63, r = t64 >> 3, c = t64 & 7;
+    double* X = s_x[sub];
+    double* T = s_t[sub];
+    const uint32_t group = blockIdx.x * (kRefineThreads / 64) + sub, ngroups = gridDim.x * (kRefineThreads / 64);
+    const uint32_t rounds = (n - min(n0, n) + ngroups - 1) / ngroups;   // same trip count for every thread of the grid (barriers inside)
+    for (uint32_t it = 0; it < rounds; ++it) {
+        const uint32_t i = n0 + it * ngroups + group;
+        const bool valid = i < n;
+        const uint32_t id = valid ? (all ? i : list[i]) : 0;
+        const auto col = locate(id, c);
+        X[r * 8 + c] = valid ? sample(col, r) : 0.0;
+        __syncthreads();
+        if (t64 < 8) aan8_exact(X + t64, 8, T + t64 * 8, 1, e);          // column t64 of the block -> row t64 of the temporary
+        __syncthreads();
+        if (t64 < 8) aan8_exact(T + t64, 8, X + t64 * 8, 1, e);          // column t64 of the temporary -> row t64 of the result
+        __syncthreads();
+        if (valid) {
+            const uint8_t* q = ((id % blocks_per_frame) % kBlocksPerMcu) < 4 ? qtab_y : qtab_c;
+            out[static_cast<size_t>(id) * kCoefPerBlock + c_inv_zigzag[t64]] = quantize_exact(X[t64], q[t64]);
+        }
+        __syncthreads();                                                // X is overwritten by the next round's samples
+    }
+}
+
 // ids are global block indices; with `frames` (a batch) block id belongs to frame id / blocks_per_frame
+template <bool k64>
 __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* __restrict__ rgb, const uint8_t* const* __restrict__ frames,
                                                                     uint32_t blocks_per_frame, int16_t* __restrict__ coef,
                                                                     const uint32_t* __restrict__ list,
@@ -465,12 +500,13 @@ __global__ void __launch_bounds__(kRefineThreads) refine_kernel(const uint8_t* _
                                                                     uint32_t mcu_w, const __grid_constant__ ExactConsts e) {
     // count[0] = entries in the list, count[3] = entries already refined (band-wise encodes refine after every band)
     const uint32_t n = all ? nblocks : min(count[0], cap), n0 = all ? 0u : count[3];
-    refine_loop(n0, n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e,
-                [&](uint32_t id, int c) {
-                    const uint32_t f = frames ? id / blocks_per_frame : 0u;
-                    return exact_locate(frames ? frames[f] : rgb, mcu_w, id - f * blocks_per_frame, c);
-                },
-                [&](const ExactColumn& col, int r) { return exact_sample(col, real_w, real_h, r, e.scale); });
+    auto locate = [&](uint32_t id, int c) {
+        const uint32_t f = frames ? id / blocks_per_frame : 0u;
+        return exact_locate(frames ? frames[f] : rgb, mcu_w, id - f * blocks_per_frame, c);
+    };
+    auto sample = [&](const ExactColumn& col, int r) { return exact_sample(col, real_w, real_h, r, e.scale); };
+    if constexpr (k64) refine_loop64(n0, n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e, locate, sample);
+    else refine_loop(n0, n, list, all != 0, coef, blocks_per_frame, e.qy, e.qc, e, locate, sample);
 }
 
 // Images that are not 8-bit samples: three planes of doubles as the reference holds them (Image::R/G/B after loadPPM, or
@@ -745,9 +781,18 @@ static int launch_refine(jpgenc_ctx* c, bool all) {
     // grid-stride over the list; a small image does not need (and should not wait for) 2368 mostly empty CTAs
     const uint64_t total = static_cast<uint64_t>(bpf) * c->nframes;
     const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(c->sm_count, std::min<uint64_t>(c->sm_count * 16, total / 256 + 1)));
-    refine_kernel<<<grid, kRefineThreads, 0, c->stream>>>(
-        c->d_rgb, c->nframes > 1 ? c->d_frame_ptrs : nullptr, bpf, c->d_coef, c->d_refine_list, c->d_counters,
-        all ? 0u : static_cast<uint32_t>(c->refine_cap), all ? 1 : 0, bpf * c->nframes, c->real_w, c->real_h, c->mcu_w, e);
+    // 64 threads per block where the flagged blocks are few (latency: 3840x2160 15 -> 6 us), 8 per block where they are many
+    // (throughput: at 16384^2 the 64-thread form's barriers cost 42 us against 28).  JPGENC_REFINE64=0/1 forces one form.
+    static const int forced = [] { const char* v = std::getenv("JPGENC_REFINE64"); return v && *v ? (*v == '0' ? 0 : 1) : -1; }();
+    const bool wide = forced >= 0 ? forced == 1 : total < (3u << 19);
+    if (wide)
+        refine_kernel<true><<<grid, kRefineThreads, 0, c->stream>>>(
+            c->d_rgb, c->nframes > 1 ? c->d_frame_ptrs : nullptr, bpf, c->d_coef, c->d_refine_list, c->d_counters,
+            all ? 0u : static_cast<uint32_t>(c->refine_cap), all ? 1 : 0, bpf * c->nframes, c->real_w, c->real_h, c->mcu_w, e);
+    else
+        refine_kernel<false><<<grid, kRefineThreads, 0, c->stream>>>(
+            c->d_rgb, c->nframes > 1 ? c->d_frame_ptrs : nullptr, bpf, c->d_coef, c->d_refine_list, c->d_counters,
+            all ? 0u : static_cast<uint32_t>(c->refine_cap), all ? 1 : 0, bpf * c->nframes, c->real_w, c->real_h, c->mcu_w, e);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return JPGENC_OK;

@@ -30,7 +30,7 @@ int ensure_entropy_buffers(jpgenc_ctx* c, uint64_t raw_total, uint64_t out_total
 void ensure_host_pool(jpgenc_ctx* c);
 void leave_batch_state(jpgenc_ctx* c);
 int flush_entropy_time(jpgenc_ctx* c);
-int poll_mailbox(jpgenc_ctx* c, int flag_word);
+int poll_mailbox(jpgenc_ctx* c, int word, unsigned long long* value);
 
 // pinned staging of a context: [statistics F * kStatsBytes + 16][device tables F * 8 KB][PassMeta block (common.cuh)]
 size_t stage_tables_off(uint32_t F);

@@ -268,22 +268,43 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     }
 }
 
-// One image: hand results to the host through its mailbox (mapped pinned memory) -- `nwords` words from `src`, one extra
-// word, then the flag word that the host polls.  A kernel of its own, in stream order behind the producer: making the last
-// CTA of K2 do this needs a __threadfence per CTA behind its histogram atomics, which cost K2 24 us at 16384 tiles.
-// The flag value is a sequence number kept in device memory (*dseq, incremented here) and mirrored by the host
-// (jpgenc_ctx::mailbox_seq): it is not a kernel parameter, so a captured CUDA graph of the encode can be replayed as is.
-__global__ void mailbox_publish_kernel(const uint32_t* __restrict__ src, uint32_t nwords, uint32_t* mailbox, const uint32_t* extra,
-                                       uint32_t extra_word, uint32_t flag_word, uint32_t* dseq) {
-    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) mailbox[i] = __ldcg(src + i);
-    if (threadIdx.x == 0 && extra) mailbox[extra_word] = *extra;
-    __threadfence_system();
+// One image: hand the statistics to the host through its mailbox (mapped pinned memory).  A kernel of its own, in stream
+// order behind K2: making the last CTA of K2 do this needs a __threadfence per CTA behind its histogram atomics, which cost
+// K2 24 us at 16384 tiles.  Only the symbols that occur travel (a few dozen of 1024), each as two self-validating 64-bit
+// words (common.cuh: value | tag); the tag comes from a sequence number kept in device memory (*dseq, incremented here) and
+// mirrored by the host (jpgenc_ctx::mailbox_seq): it is not a kernel parameter, so a captured CUDA graph of the encode can be
+// replayed as is.  No flag word, no __threadfence_system: the first version (12 KB of statistics, a system fence, then a flag)
+// took 11 us, most of it the fence waiting for 96 PCIe writes to be acknowledged.
+__global__ void __launch_bounds__(1024) publish_stats_kernel(const uint8_t* __restrict__ stats, const uint32_t* __restrict__ refine_count,
+                                                             unsigned long long* mailbox, uint32_t* dseq) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_seq;
+    const uint32_t e = threadIdx.x, lane = e & 31, warp = e >> 5;
+    const uint32_t cnt = __ldcg(reinterpret_cast<const uint32_t*>(stats) + e);
+    const unsigned long long first = __ldcg(reinterpret_cast<const unsigned long long*>(stats + 4096) + e);
+    const unsigned present = __ballot_sync(0xffffffffu, cnt != 0);
+    if (lane == 0) s_warp[warp] = __popc(present);
+    if (e == 0) { s_seq = *dseq + 1u; *dseq = s_seq; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t seq = *dseq + 1u;
-        *dseq = seq;
-        *reinterpret_cast<volatile uint32_t*>(mailbox + flag_word) = seq;
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < 32; ++w) { const uint32_t n = s_warp[w]; if (w < warp) before += n; total += n; }
+    const uint32_t seq = s_seq;
+    volatile unsigned long long* box = mailbox + kMailStatsHead;
+    if (cnt != 0) {
+        const uint32_t k = before + __popc(present & ((1u << lane) - 1u));
+        box[1 + 2 * k] = mail_word(static_cast<unsigned long long>(cnt) | (static_cast<unsigned long long>(e) << 32), seq);
+        box[2 + 2 * k] = mail_word(first, seq);
     }
+    if (e == 0) box[0] = mail_word(static_cast<unsigned long long>(total) | (static_cast<unsigned long long>(*refine_count) << 11), seq);
+}
+
+// K4's totals of one image (scan bits, stuffed FF bytes: the results part of the PassMeta block) the same way
+__global__ void publish_totals_kernel(const unsigned long long* __restrict__ totals, unsigned long long* mailbox, uint32_t* dseq) {
+    const uint32_t seq = *dseq + 1u;
+    volatile unsigned long long* box = mailbox + kMailTotals;
+    box[0] = mail_word(__ldcg(totals), seq);
+    box[1] = mail_word(__ldcg(totals + 1), seq);
+    *dseq = seq;
 }
 
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first) {
@@ -321,21 +342,19 @@ int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool fir
     return JPGENC_OK;
 }
 
-// one image, behind its last K2 launch: statistics + K1's refinement counter into the host mailbox, then the flag
+// one image, behind its last K2 launch: the statistics of the symbols that occur + K1's refinement counter into the host mailbox
 int launch_publish_stats(jpgenc_ctx* c) {
-    mailbox_publish_kernel<<<1, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->d_stats), static_cast<uint32_t>(kStatsBytes / 4),
-                                                     c->d_mailbox, c->d_counters + kCntRefine, kMailRefined, kMailK2Flag, c->d_counters + kCntSeq);
+    publish_stats_kernel<<<1, 1024, 0, c->stream>>>(c->d_stats, c->d_counters + kCntRefine, c->d_mailbox, c->d_counters + kCntSeq);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
-    ++c->mailbox_seq;                                          // the value the kernel will announce
+    ++c->mailbox_seq;                                          // the sequence number the kernel will tag its words with
     return JPGENC_OK;
 }
 
-// one image, behind K4: scan bits and stuffed FF bytes (the results part of the PassMeta block), then the flag
+// one image, behind K4: scan bits and stuffed FF bytes
 int launch_publish_totals(jpgenc_ctx* c) {
     const PassMeta m = pass_meta_view(c->d_meta, 1);
-    mailbox_publish_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(m.total_bits), 4u, c->d_mailbox + kMailTotals, nullptr, 0u,
-                                                    kMailK4Flag - kMailTotals, c->d_counters + kCntSeq);
+    publish_totals_kernel<<<1, 1, 0, c->stream>>>(m.total_bits, c->d_mailbox, c->d_counters + kCntSeq);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     ++c->mailbox_seq;
