@@ -36,6 +36,7 @@ extern "C" {
 #define JPGENC_ERR_FORMAT    -4   /* not a P3/P6 PPM (reference: std::runtime_error, src/Image.cpp:449-450) */
 #define JPGENC_ERR_IO        -5   /* file could not be opened (reference: src/Image.cpp:427-428) */
 #define JPGENC_ERR_CAPACITY  -6   /* caller's output buffer too small */
+#define JPGENC_ERR_NOMEM     -7   /* host memory exhausted (a C++ exception was caught at the boundary; text in jpgenc_last_error) */
 
 typedef struct jpgenc_ctx jpgenc_ctx;
 

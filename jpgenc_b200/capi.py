@@ -14,7 +14,7 @@ import numpy as np
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libjpgenc_b200.so"
 
 OK = 0
-ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_FORMAT, ERR_IO, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
+ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_FORMAT, ERR_IO, ERR_CAPACITY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 
 u8p = C.POINTER(C.c_uint8)
 i16p = C.POINTER(C.c_int16)

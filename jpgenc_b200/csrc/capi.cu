@@ -318,13 +318,13 @@ const char* jpgenc_last_error(const jpgenc_ctx* c) { return c ? c->error.c_str()
 void* jpgenc_stream(jpgenc_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 uint64_t jpgenc_launch_count(const jpgenc_ctx* c) { return c ? c->launches : 0; }
 
-int jpgenc_synchronize(jpgenc_ctx* c) {
+int jpgenc_synchronize(jpgenc_ctx* c) try {
     if (!c) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_get_stats(jpgenc_ctx* c, jpgenc_stats* out) {
+int jpgenc_get_stats(jpgenc_ctx* c, jpgenc_stats* out) try {
     if (!c || !out) return JPGENC_ERR_ARG;
     const int rf = flush_entropy_time(c);
     if (rf) return rf;
@@ -332,9 +332,9 @@ int jpgenc_get_stats(jpgenc_ctx* c, jpgenc_stats* out) {
     c->stats.n_blocks = static_cast<uint64_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu;
     *out = c->stats;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_set_qtables(jpgenc_ctx* c, const uint8_t qy[64], const uint8_t qc[64]) {
+int jpgenc_set_qtables(jpgenc_ctx* c, const uint8_t qy[64], const uint8_t qc[64]) try {
     if (!c || !qy || !qc) return JPGENC_ERR_ARG;
     for (int i = 0; i < 64; ++i)
         if (qy[i] == 0 || qc[i] == 0) return fail(c, JPGENC_ERR_ARG, "quantiser entries must be >= 1");
@@ -342,17 +342,17 @@ int jpgenc_set_qtables(jpgenc_ctx* c, const uint8_t qy[64], const uint8_t qc[64]
     std::memcpy(c->qc, qc, 64);
     ++c->alloc_gen;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_set_dct_constants(jpgenc_ctx* c, const double a[5], const double s[8]) {
+int jpgenc_set_dct_constants(jpgenc_ctx* c, const double a[5], const double s[8]) try {
     if (!c || !a || !s) return JPGENC_ERR_ARG;
     std::memcpy(c->dct_a, a, sizeof c->dct_a);
     std::memcpy(c->dct_s, s, sizeof c->dct_s);
     ++c->alloc_gen;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_upload_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
+int jpgenc_upload_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval) try {
     if (!c || !host_rgb) return JPGENC_ERR_ARG;
     if (maxval && maxval < 255 && !samples_within_maxval(host_rgb, static_cast<size_t>(w) * h * 3, maxval))
         return fail(c, JPGENC_ERR_FORMAT, "a sample exceeds maxval");
@@ -369,20 +369,20 @@ int jpgenc_upload_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     c->d_rgb = c->d_rgb_owned;
     c->have_pixels = true;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_bind_device_rgb(jpgenc_ctx* c, const void* dev_rgb, uint32_t w, uint32_t h, uint32_t maxval) {
+int jpgenc_bind_device_rgb(jpgenc_ctx* c, const void* dev_rgb, uint32_t w, uint32_t h, uint32_t maxval) try {
     if (!c || !dev_rgb) return JPGENC_ERR_ARG;
     const int rc = set_geometry(c, w, h, maxval);
     if (rc) return rc;
     c->d_rgb = static_cast<const uint8_t*>(dev_rgb);
     c->have_pixels = true;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 static int enqueue_forward(jpgenc_ctx* c);
 
-int jpgenc_color_dct_quant(jpgenc_ctx* c) {
+int jpgenc_color_dct_quant(jpgenc_ctx* c) try {
     if (!c) return JPGENC_ERR_ARG;
     if (!c->have_pixels) return fail(c, JPGENC_ERR_ARG, "no pixels bound: call jpgenc_upload_rgb / jpgenc_bind_device_rgb first");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
@@ -394,9 +394,9 @@ int jpgenc_color_dct_quant(jpgenc_ctx* c) {
     c->have_coef = true;
     c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_get_coefficients(jpgenc_ctx* c, int16_t* dst) {
+int jpgenc_get_coefficients(jpgenc_ctx* c, int16_t* dst) try {
     if (!c || !dst) return JPGENC_ERR_ARG;
     if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients yet");
     const size_t bytes = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu * kBlockBytes;
@@ -406,9 +406,9 @@ int jpgenc_get_coefficients(jpgenc_ctx* c, int16_t* dst) {
     JPGENC_CUDA(c, cudaMemcpy(&refined, c->d_counters, sizeof refined, cudaMemcpyDeviceToHost));
     c->stats.refined_blocks = refined;
     return refresh_forward_stats(c);
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu_w, uint32_t mcu_h) {
+int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu_w, uint32_t mcu_h) try {
     if (!c || !coef || !mcu_w || !mcu_h) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     if (c->real_w == 0 || (c->real_w + 15) / 16 != mcu_w || (c->real_h + 15) / 16 != mcu_h) {
@@ -423,10 +423,10 @@ int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu
     c->have_coef = true;
     c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_cb, const int32_t* q_cr, uint32_t mcu_w,
-                            uint32_t mcu_h) {
+                            uint32_t mcu_h) try {
     if (!c || !q_y || !q_cb || !q_cr || !mcu_w || !mcu_h) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     if (c->real_w == 0 || (c->real_w + 15) / 16 != mcu_w || (c->real_h + 15) / 16 != mcu_h) {
@@ -449,7 +449,7 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
     c->have_coef = true;
     c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 // ---- K2 and K3/K4 for all frames bound to the context (one image = one frame) ------------------------------------
 // ---- one image: the GPU work of an encode as two enqueue-only phases (no host waits inside: they can be captured) ----
@@ -626,7 +626,7 @@ static int entropy_frames(jpgenc_ctx* c, const jpgenc_huff_table* tables) {
     return wait_entropy(c);
 }
 
-int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_pos[4][256]) {
+int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_pos[4][256]) try {
     if (!c || !count || !first_pos) return JPGENC_ERR_ARG;
     if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
     if (c->nframes != 1) return fail(c, JPGENC_ERR_ARG, "stage calls work on one image; a batch is bound");
@@ -635,7 +635,7 @@ int jpgenc_symbol_stats(jpgenc_ctx* c, uint32_t count[4][256], uint64_t first_po
     std::memcpy(count, c->stat_count, 4096);
     std::memcpy(first_pos, c->stat_first, 8192);
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 // the device build's code (array restatement of the container orders) executed on the host, no GPU involved
 int jpgenc_build_huffman_arrays(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
@@ -646,7 +646,7 @@ int jpgenc_build_huffman_arrays(const uint32_t count[256], const uint64_t first_
 // generateHuffmanCode on the device (tables_device.cu) for n independent (count, first_pos) pairs; what the batched-frame
 // calls use on hosts with few cores per GPU, exposed so that it can be checked against jpgenc_build_huffman directly
 int jpgenc_build_huffman_device(jpgenc_ctx* c, uint32_t n, const uint32_t (*count)[256], const uint64_t (*first_pos)[256],
-                                jpgenc_huff_table* out) {
+                                jpgenc_huff_table* out) try {
     if (!c || !count || !first_pos || !out || n == 0) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     const uint32_t frames = (n + 3) / 4;                       // the kernel reads K2's layout: 4 tables per frame
@@ -683,9 +683,9 @@ int jpgenc_build_huffman_device(jpgenc_ctx* c, uint32_t n, const uint32_t (*coun
         out[i] = res[i];
     }
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t* scan_bytes) {
+int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t* scan_bytes) try {
     if (!c || !tables) return JPGENC_ERR_ARG;
     if (!c->have_coef) return fail(c, JPGENC_ERR_ARG, "no coefficients: run jpgenc_color_dct_quant first");
     if (!c->have_items) return fail(c, JPGENC_ERR_ARG, "symbol statistics missing: run jpgenc_symbol_stats first");
@@ -694,9 +694,9 @@ int jpgenc_entropy_encode(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint
     if (rc) return rc;
     if (scan_bytes) *scan_bytes = c->stats.scan_bytes;
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_download_scan(jpgenc_ctx* c, uint8_t* dst, uint64_t cap) {
+int jpgenc_download_scan(jpgenc_ctx* c, uint8_t* dst, uint64_t cap) try {
     if (!c || !dst) return JPGENC_ERR_ARG;
     if (!c->have_scan) return fail(c, JPGENC_ERR_ARG, "no scan yet: run jpgenc_entropy_encode first");
     if (cap < c->stats.scan_bytes) return fail(c, JPGENC_ERR_CAPACITY, "scan buffer too small");
@@ -706,7 +706,7 @@ int jpgenc_download_scan(jpgenc_ctx* c, uint8_t* dst, uint64_t cap) {
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_d2h, c->ev_t0, c->ev_t1));
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 // K2 .. K4 on the coefficients K1 left on the device
 static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* scan) {
@@ -930,7 +930,7 @@ static int assemble(jpgenc_ctx* c, const jpgenc_huff_table tables[4], uint64_t s
     return JPGENC_OK;
 }
 
-int jpgenc_encode_bound(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) {
+int jpgenc_encode_bound(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) try {
     if (!c) return JPGENC_ERR_ARG;
     jpgenc_huff_table tables[4];
     uint64_t scan = 0;
@@ -940,18 +940,18 @@ int jpgenc_encode_bound(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpe
     if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
     if (!dst) return JPGENC_OK;                                  // device-resident run: the scan stays in HBM
     return assemble(c, tables, scan, dst, cap);
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_assemble_last(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) {
+int jpgenc_assemble_last(jpgenc_ctx* c, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) try {
     if (!c || !dst) return JPGENC_ERR_ARG;
     if (!c->have_tables || !c->have_scan) return fail(c, JPGENC_ERR_ARG, "no finished encode on this context");
     const size_t hdr = jpgenc_write_headers(c->real_w, c->real_h, c->qy, c->qc, c->last_tables, nullptr);
     if (jpeg_bytes) *jpeg_bytes = hdr + c->stats.scan_bytes + 2;
     return assemble(c, c->last_tables, c->stats.scan_bytes, dst, cap);
-}
+} JPGENC_CATCH(c)
 
 int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32_t h, uint32_t maxval, uint8_t* dst,
-                      uint64_t cap, uint64_t* jpeg_bytes) {
+                      uint64_t cap, uint64_t* jpeg_bytes) try {
     if (!c || !host_rgb) return JPGENC_ERR_ARG;
     if (maxval && maxval < 255 && !samples_within_maxval(host_rgb, static_cast<size_t>(w) * h * 3, maxval))
         return fail(c, JPGENC_ERR_FORMAT, "a sample exceeds maxval");
@@ -964,13 +964,13 @@ int jpgenc_encode_rgb(jpgenc_ctx* c, const uint8_t* host_rgb, uint32_t w, uint32
     if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
     if (!dst) return JPGENC_OK;
     return assemble(c, tables, scan, dst, cap);
-}
+} JPGENC_CATCH(c)
 
 // Image::writeJPEG for an image that is not (or no longer) a set of 8-bit samples: planes a caller edited after loadPPM,
 // non-integral values, or an image that already is YCbCr (src/Image.cpp:831-846 encodes whatever the three planes hold and
 // converts only an RGB image, :112-115).  The planes are uploaded as doubles and every block takes the exact FP64 path.
 int jpgenc_encode_planes(jpgenc_ctx* c, const double* p0, const double* p1, const double* p2, uint32_t width, uint32_t height,
-                         uint32_t real_w, uint32_t real_h, int ycbcr, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) {
+                         uint32_t real_w, uint32_t real_h, int ycbcr, uint8_t* dst, uint64_t cap, uint64_t* jpeg_bytes) try {
     if (!c || !p0 || !p1 || !p2) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     // the reference's stages need whole 16x16 MCUs (loadPPM pads; an Image built in memory must have such a size already)
@@ -999,13 +999,13 @@ int jpgenc_encode_planes(jpgenc_ctx* c, const double* p0, const double* p1, cons
     if (jpeg_bytes) *jpeg_bytes = hdr + scan + 2;
     if (!dst) return JPGENC_OK;
     return assemble(c, tables, scan, dst, cap);
-}
+} JPGENC_CATCH(c)
 
 // main.cpp:8-32.  A binary (P6) payload is streamed: the header is parsed from the first bytes, then every band of rows is
 // read straight into pinned staging and uploaded while the next band is being read and the previous ones go through
 // K1/refinement/K2 (loadPPM's pixel path, src/Image.cpp:411-418, without ever holding the image in host memory).  ASCII
 // (P3) files are parsed on the host first (src/Image.cpp:393-408) and then take the same banded upload.
-int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) {
+int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_path) try {
     if (!c || !ppm_path || !jpg_path) return JPGENC_ERR_ARG;
     std::FILE* in = std::fopen(ppm_path, "rb");
     if (!in) return fail(c, JPGENC_ERR_IO, "Failed to open input file");
@@ -1059,7 +1059,7 @@ int jpgenc_encode_ppm_file(jpgenc_ctx* c, const char* ppm_path, const char* jpg_
     const size_t wrote = std::fwrite(out.data(), 1, out.size(), f);
     std::fclose(f);
     return wrote == out.size() ? JPGENC_OK : fail(c, JPGENC_ERR_IO, "short write");
-}
+} JPGENC_CATCH(c)
 
 int jpgenc_ppm_info(const uint8_t* file, size_t n, uint32_t* width, uint32_t* height, uint32_t* maxval, int* magic,
                     size_t* payload_offset) {
@@ -1088,7 +1088,7 @@ int jpgenc_ppm_samples(const uint8_t* file, size_t n, uint8_t* dst) {
 }
 
 int jpgenc_dct_quant_blocks(jpgenc_ctx* c, const float* dev_in, int16_t* dev_out, uint64_t nblocks, const uint8_t q[64],
-                            uint64_t* refined_blocks) {
+                            uint64_t* refined_blocks) try {
     if (!c || !dev_in || !dev_out || !q || nblocks == 0 || nblocks > 0xFFFFFFFFull) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     size_t cap_bytes = c->refine_cap * sizeof(uint32_t);
@@ -1096,7 +1096,7 @@ int jpgenc_dct_quant_blocks(jpgenc_ctx* c, const float* dev_in, int16_t* dev_out
     c->refine_cap = cap_bytes / sizeof(uint32_t);
     if (rc) return rc;
     return launch_dct_quant_blocks(c, dev_in, dev_out, nblocks, q, refined_blocks);
-}
+} JPGENC_CATCH(c)
 
 // One process per GPU on a multi-socket host: pixels that cross the socket interconnect on their way to the GPU share it with
 // every other rank.  Restricting the calling thread to the CPUs of the GPU's NUMA node makes the pinned buffers it allocates
@@ -1142,58 +1142,58 @@ int jpgenc_bind_host_to_device_numa(int device, int* numa_node, int* cpus_bound)
     return JPGENC_OK;
 }
 
-int jpgenc_dev_alloc(jpgenc_ctx* c, size_t bytes, void** p) {
+int jpgenc_dev_alloc(jpgenc_ctx* c, size_t bytes, void** p) try {
     if (!c || !p) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     JPGENC_CUDA(c, cudaMalloc(p, bytes));
     return JPGENC_OK;
-}
-int jpgenc_dev_free(jpgenc_ctx* c, void* p) {
+} JPGENC_CATCH(c)
+int jpgenc_dev_free(jpgenc_ctx* c, void* p) try {
     if (!c) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaFree(p));
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 int jpgenc_host_alloc_pinned(size_t bytes, void** p) { return cudaMallocHost(p, bytes) == cudaSuccess ? JPGENC_OK : JPGENC_ERR_CUDA; }
 int jpgenc_host_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? JPGENC_OK : JPGENC_ERR_CUDA; }
-int jpgenc_memcpy_h2d(jpgenc_ctx* c, void* d, const void* h, size_t bytes) {
+int jpgenc_memcpy_h2d(jpgenc_ctx* c, void* d, const void* h, size_t bytes) try {
     if (!c) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     return JPGENC_OK;
-}
-int jpgenc_memcpy_d2h(jpgenc_ctx* c, void* h, const void* d, size_t bytes) {
+} JPGENC_CATCH(c)
+int jpgenc_memcpy_d2h(jpgenc_ctx* c, void* h, const void* d, size_t bytes) try {
     if (!c) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
     JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
     return JPGENC_OK;
-}
-int jpgenc_synth_rgb(jpgenc_ctx* c, void* dev_rgb, uint32_t w, uint32_t h, uint32_t seed) {
+} JPGENC_CATCH(c)
+int jpgenc_synth_rgb(jpgenc_ctx* c, void* dev_rgb, uint32_t w, uint32_t h, uint32_t seed) try {
     if (!c || !dev_rgb) return JPGENC_ERR_ARG;
     return launch_synth_rgb(c, static_cast<uint8_t*>(dev_rgb), w, h, seed);
-}
-int jpgenc_synth_blocks(jpgenc_ctx* c, float* dev_blocks, uint64_t nblocks) {
+} JPGENC_CATCH(c)
+int jpgenc_synth_blocks(jpgenc_ctx* c, float* dev_blocks, uint64_t nblocks) try {
     if (!c || !dev_blocks) return JPGENC_ERR_ARG;
     return launch_synth_blocks(c, dev_blocks, nblocks);
-}
-int jpgenc_flush_l2(jpgenc_ctx* c) {
+} JPGENC_CATCH(c)
+int jpgenc_flush_l2(jpgenc_ctx* c) try {
     if (!c) return JPGENC_ERR_ARG;
     if (!c->d_flush) {
         c->flush_bytes = 256ull << 20;                           // 2x the 126 MB L2
         JPGENC_CUDA(c, cudaMalloc(&c->d_flush, c->flush_bytes));
     }
     return launch_flush(c);
-}
-int jpgenc_timer_begin(jpgenc_ctx* c) {
+} JPGENC_CATCH(c)
+int jpgenc_timer_begin(jpgenc_ctx* c) try {
     if (!c) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_u0, c->stream));
     return JPGENC_OK;
-}
-int jpgenc_timer_end(jpgenc_ctx* c, float* ms) {
+} JPGENC_CATCH(c)
+int jpgenc_timer_end(jpgenc_ctx* c, float* ms) try {
     if (!c || !ms) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaEventRecord(c->ev_u1, c->stream));
     JPGENC_CUDA(c, cudaEventSynchronize(c->ev_u1));
     JPGENC_CUDA(c, cudaEventElapsedTime(ms, c->ev_u0, c->ev_u1));
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 }  // extern "C"

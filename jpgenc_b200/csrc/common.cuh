@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <exception>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -264,6 +265,17 @@ inline cudaError_t jpgenc_record(jpgenc_ctx* c, cudaEvent_t ev) {
             return JPGENC_ERR_CUDA;                                                                  \
         }                                                                                            \
     } while (0)
+
+// No exception crosses the C boundary (include/jpgenc_b200.h): every entry point that takes a context is a function-try-block
+// closed by this.  What can arrive here is std::bad_alloc / std::length_error from a host container.
+#define JPGENC_CATCH(ctx)                                                                            \
+    catch (const std::exception& ex__) {                                                             \
+        if (ctx) (ctx)->error = std::string("host exception: ") + ex__.what();                      \
+        return JPGENC_ERR_NOMEM;                                                                     \
+    } catch (...) {                                                                                  \
+        if (ctx) (ctx)->error = "host exception";                                                   \
+        return JPGENC_ERR_NOMEM;                                                                     \
+    }
 
 // launchers implemented in the kernel translation units
 namespace jpgenc {

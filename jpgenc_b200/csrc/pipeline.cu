@@ -413,25 +413,25 @@ int encode_host_frames(jpgenc_ctx* c, Job& job, const uint8_t* const* frames) {
 extern "C" {
 
 int jpgenc_encode_frames_device(jpgenc_ctx* c, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h, uint32_t maxval,
-                                uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
+                                uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) try {
     Job job;
     job.n = n; job.w = w; job.h = h; job.maxval = maxval;
     job.out_ptrs = out; job.caps = caps; job.sizes = sizes;
     const int rc = check_job(c, job, dev_frames);
     return rc ? rc : encode_device_frames(c, job, dev_frames);
-}
+} JPGENC_CATCH(c)
 
 int jpgenc_encode_frames(jpgenc_ctx* c, uint32_t n, const uint8_t* const* frames, uint32_t w, uint32_t h, uint32_t maxval,
-                         uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) {
+                         uint8_t* const* out, const uint64_t* caps, uint64_t* sizes) try {
     Job job;
     job.n = n; job.w = w; job.h = h; job.maxval = maxval;
     job.out_ptrs = out; job.caps = caps; job.sizes = sizes;
     const int rc = check_job(c, job, frames);
     return rc ? rc : encode_host_frames(c, job, frames);
-}
+} JPGENC_CATCH(c)
 
 int jpgenc_encode_frames_packed(jpgenc_ctx* c, uint32_t n, const void* const* frames, int frames_on_device, uint32_t w, uint32_t h,
-                                uint32_t maxval, uint8_t* out, uint64_t cap, uint64_t* offsets, uint64_t* sizes, uint64_t* total_bytes) {
+                                uint32_t maxval, uint8_t* out, uint64_t cap, uint64_t* offsets, uint64_t* sizes, uint64_t* total_bytes) try {
     Job job;
     job.n = n; job.w = w; job.h = h; job.maxval = maxval;
     job.packed_mode = true; job.packed = out; job.packed_cap = cap; job.offsets = offsets; job.sizes = sizes;
@@ -440,6 +440,6 @@ int jpgenc_encode_frames_packed(jpgenc_ctx* c, uint32_t n, const void* const* fr
     rc = frames_on_device ? encode_device_frames(c, job, frames) : encode_host_frames(c, job, reinterpret_cast<const uint8_t* const*>(frames));
     if (total_bytes) *total_bytes = job.packed_at;
     return rc;
-}
+} JPGENC_CATCH(c)
 
 }  // extern "C"

@@ -104,7 +104,7 @@ int jpgenc_stage_subsample_dims(int mode, uint32_t width, uint32_t height, uint3
     return JPGENC_OK;
 }
 
-int jpgenc_stage_subsample(jpgenc_ctx* c, const double* plane, uint32_t width, uint32_t height, int mode, double* out) {
+int jpgenc_stage_subsample(jpgenc_ctx* c, const double* plane, uint32_t width, uint32_t height, int mode, double* out) try {
     if (!c || !plane || !out || mode < 0 || mode > 5 || width == 0 || height == 0) return JPGENC_ERR_ARG;
     if (mode == 0) {                                             // S444: applySubsampling returns at once (src/Image.cpp:263-268)
         std::memcpy(out, plane, static_cast<size_t>(width) * height * sizeof(double));
@@ -129,9 +129,9 @@ int jpgenc_stage_subsample(jpgenc_ctx* c, const double* plane, uint32_t width, u
     cudaFree(d);
     if (e != cudaSuccess) { c->error = std::string("jpgenc_stage_subsample: ") + cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
-int jpgenc_stage_dct(jpgenc_ctx* c, const double* plane, uint32_t width, uint32_t height, int mode, double* out) {
+int jpgenc_stage_dct(jpgenc_ctx* c, const double* plane, uint32_t width, uint32_t height, int mode, double* out) try {
     if (!c || !plane || !out || mode < 0 || mode > 2) return JPGENC_ERR_ARG;
     if (width == 0 || height == 0 || width % 8 || height % 8) return fail(c, JPGENC_ERR_ARG, "plane sides must be multiples of 8");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
@@ -163,6 +163,6 @@ int jpgenc_stage_dct(jpgenc_ctx* c, const double* plane, uint32_t width, uint32_
     cudaFree(d);
     if (e != cudaSuccess) { c->error = std::string("jpgenc_stage_dct: ") + cudaGetErrorString(e); return JPGENC_ERR_CUDA; }
     return JPGENC_OK;
-}
+} JPGENC_CATCH(c)
 
 }  // extern "C"
