@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_r2n.sh N  -- default bench on N GPUs under torchrun, then the batch workload alone with a few pass sizes
+# usage: gpu_r2n.sh N ["fpp list"]  -- default bench on N GPUs under torchrun, then (optional) the batch workload alone with the given pass sizes
 N=$1
 mkdir -p gpurun_out
 nproc > gpurun_out/r2n${N}_nproc.txt; nvidia-smi topo -m > gpurun_out/r2n${N}_topo.txt 2>&1
@@ -15,7 +15,7 @@ try:
 except Exception as ex:
     print('parse failed', ex); print(open('gpurun_out/r2n${N}_bench.err').read()[-1500:])
 PY
-for fpp in 32 64 128; do
+for fpp in $2; do
   JPGENC_FRAMES_PER_PASS=$fpp timeout 300 $TR bench.py --gpus $N --workload batch1080p --steps 100 > gpurun_out/r2n${N}_batch_fpp$fpp.json 2> gpurun_out/r2n${N}_batch_fpp$fpp.err
   python - <<PY
 import json
