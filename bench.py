@@ -604,6 +604,27 @@ def extra_workloads(enc, args, peak):
         out["frame4k"] = {"ms_per_frame": round(tot / reps, 4), "mpx_per_s": round(w * h / 1e6 / (tot / reps / 1e3), 1),
                           "k1_ms": round(s.ms_k1, 4), "l2": "flushed between iterations (256 MB write)"}
         enc.dev_free(d)
+    # the high-entropy variant (uniform random u8, numpy default_rng(1)) that stresses K3/K4 -- ~37 AC symbols per
+    # block and ~3 bit/px instead of 4.2 symbols per block and 0.32 bit/px
+    w = h = 4096
+    rng = np.random.default_rng(1)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    d = enc.dev_alloc(w * h * 3)
+    enc.h2d(d, rgb)
+    enc.bind_device_rgb(d, w, h)
+    for _ in range(3):
+        nbytes = enc.encode_bound(None)
+    enc.synchronize()
+    reps = 20
+    enc.timer_begin()
+    for _ in range(reps):
+        enc.encode_bound(None)
+    ms = enc.timer_end() / reps
+    s = enc.stats()
+    out["noise4096"] = {"ms_per_image": round(ms, 4), "mpx_per_s": round(w * h / 1e6 / (ms / 1e3), 1), "jpeg_bytes": int(nbytes),
+                        "bits_per_px": round(8 * nbytes / (w * h), 3), "k1_plus_refine_ms": round(s.ms_forward, 4), "k2_ms": round(s.ms_stats, 4),
+                        "k3_k4_ms": round(s.ms_entropy, 4), "stuffed_ff": int(s.stuffed_ff)}
+    enc.dev_free(d)
     return out
 
 
