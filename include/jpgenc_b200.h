@@ -218,6 +218,9 @@ int jpgenc_dct_quant_blocks(jpgenc_ctx* ctx, const float* dev_in, int16_t* dev_o
  * *cpus_bound = CPUs in the new mask.  Call before allocating pinned memory. */
 int jpgenc_bind_host_to_device_numa(int device, int* numa_node, int* cpus_bound);
 
+/* diagnostics for tests: one of the context's device-side counters (index 6: chunks the Huffman packer took the slow way) */
+int jpgenc_debug_counter(jpgenc_ctx* ctx, int index, uint32_t* value);
+
 /* ---- plain device-memory helpers so a Python/C harness needs no other CUDA binding ---------------- */
 int jpgenc_dev_alloc(jpgenc_ctx* ctx, size_t bytes, void** dev_ptr);
 int jpgenc_dev_free(jpgenc_ctx* ctx, void* dev_ptr);

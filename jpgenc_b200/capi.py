@@ -78,6 +78,7 @@ _SIGNATURES = {
     "jpgenc_encode_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                        C.c_void_p, C.c_uint64, u64p]),
     "jpgenc_encode_ppm_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "jpgenc_debug_counter": (C.c_int, [C.c_void_p, C.c_int, u32p]),
     "jpgenc_stage_subsample_dims": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, u32p, u32p]),
     "jpgenc_stage_subsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "jpgenc_stage_dct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
@@ -280,6 +281,11 @@ class Encoder:
         out = np.empty(n.value, np.uint8)
         self._check(self.lib.jpgenc_assemble_last(self.h, out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value].tobytes()
+
+    def debug_counter(self, index: int) -> int:
+        v = C.c_uint32()
+        self._check(self.lib.jpgenc_debug_counter(self.h, index, C.byref(v)))
+        return v.value
 
     def stage_subsample(self, plane: np.ndarray, mode: int) -> np.ndarray:
         """Image::applySubsampling(mode) on one plane of doubles (mode = order of Image::SubsamplingMode)"""

@@ -1142,6 +1142,14 @@ int jpgenc_bind_host_to_device_numa(int device, int* numa_node, int* cpus_bound)
     return JPGENC_OK;
 }
 
+// diagnostics for tests: word `index` of the context's device counters (common.cuh kCnt*), after a stream synchronisation
+int jpgenc_debug_counter(jpgenc_ctx* c, int index, uint32_t* value) try {
+    if (!c || !value || index < 0 || index >= kCounterWords) return JPGENC_ERR_ARG;
+    JPGENC_CUDA(c, cudaStreamSynchronize(c->stream));
+    JPGENC_CUDA(c, cudaMemcpy(value, c->d_counters + index, sizeof *value, cudaMemcpyDeviceToHost));
+    return JPGENC_OK;
+} JPGENC_CATCH(c)
+
 int jpgenc_dev_alloc(jpgenc_ctx* c, size_t bytes, void** p) try {
     if (!c || !p) return JPGENC_ERR_ARG;
     JPGENC_CUDA(c, cudaSetDevice(c->device));

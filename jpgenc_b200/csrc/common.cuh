@@ -283,6 +283,7 @@ namespace jpgenc {
 constexpr int kCntRefine = 0;      // entries in the refinement list (K1)
 constexpr int kCntRefined = 3;     // list entries already refined (band-wise encodes)
 constexpr int kCntFinalize = 4;    // finalize_tables_kernel's CTA ticket (resets itself)
+constexpr int kCntK3Redo = 6;     // chunks K3b packed the slow way (zeroed by K3a; read by tests through jpgenc_debug_counter)
 constexpr int kCntSeq = 5;         // mailbox sequence number (mailbox_publish_kernel increments it; never cleared)
 constexpr int kCounterWords = 16;
 // The host mailbox (jpgenc_ctx::h_mailbox, mapped pinned memory) as 64-bit words.  Every word carries its own validity: value

@@ -75,6 +75,7 @@ struct EntropyParams {
     unsigned long long* total_bits;     // [nframes] out: bits of the scan (before padding)
     unsigned long long* ff_incl;        // [nframes] out: FF bytes K4 stuffed in frames 0..f of the pass
     uint32_t* tile_ff;                  // FF bytes per K4 tile (K4a), all frames of the pass numbered as ONE sequence
+    uint32_t* redo_count;               // chunks K3b had to pack the slow way (diagnostics)
     // output as complete files (batches): every frame = header + scan + EOI, frames back to back
     const jpgenc_huff_table* built;     // [nframes * 4] tables as the device build left them (DHT segments); null = scan only
     const uint8_t* hdr_prefix;          // SOI .. SOF0, identical for every frame of the pass
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
         const unsigned long long raw_words16 = p.hdr->raw_total / 16;
         uint4* raw16 = reinterpret_cast<uint4*>(p.raw);
         for (unsigned long long i = gtid; i < raw_words16; i += gsize) raw16[i] = make_uint4(0, 0, 0, 0);
+        if (gtid == 0) *p.redo_count = 0u;
     }
     __syncthreads();
     const uint32_t range = group * kPackWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(kPackThreads) huffman_pack_kernel(const __grid
             }
         } else {
             // very dense chunk: items again (the pass above has overwritten them), straight to the (zeroed) global words
+            if (lane == 0) atomicAdd(p.redo_count, 1u);
             __syncwarp();
 #pragma unroll 4
             for (uint32_t r = 0; r < rows; ++r) {
@@ -574,6 +577,7 @@ int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
     p.total_bits = m.total_bits;
     p.ff_incl = m.ff_incl;
     p.tile_ff = reinterpret_cast<uint32_t*>(c->d_lookback);
+    p.redo_count = c->d_counters + kCntK3Redo;
     if (c->file_mode) {
         p.built = c->d_built_tables;
         p.hdr_prefix = c->d_hdr_prefix;

@@ -699,3 +699,71 @@ def test_stage_kernels_every_subsampling_and_dct_mode(encoder, oracle):
         encoder.stage_dct(np.zeros((12, 16)), 2)                     # sides must be multiples of 8
     with pytest.raises(JpgencError):
         encoder.stage_subsample(np.zeros((16, 18)), 2)               # S411 takes four columns at a time
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["dense_extreme", "zrl_runs", "last_only", "mixed", "ff_rich", "outrun"])
+def test_entropy_coder_on_synthetic_coefficient_arrays(encoder, oracle, kind):
+    """K2 .. K4 on coefficient arrays no image produces: every coefficient non-zero with 15-bit magnitudes (code + magnitude
+    longer than the one-lookup path's 27 bits, chunks denser than the warp bit buffer: the straight-to-global path of K3b), runs
+    of exactly 15 / 16 / 17 / 31 / 32 / 47 / 48 / 62 zeros (ZRL boundaries), blocks whose only coefficient is the last one (no
+    EOB), and a mix; statistics, tables and the stuffed scan against the oracle's entropy coder on the same array"""
+    rng = np.random.default_rng({"dense_extreme": 1, "zrl_runs": 2, "last_only": 3, "mixed": 4, "ff_rich": 5, "outrun": 6}[kind])
+    mw, mh = (128, 128) if kind == "outrun" else (24, 20)
+    nb = mw * mh * 6
+    coef = np.zeros((nb, 64), np.int16)
+    if kind == "outrun":
+        # K3b writes a lane's completed words over the items the lane has consumed; an item of more than 64 bits that is a lane's
+        # FIRST item outruns that (its second word has no free slot) and the chunk must take the slow path.  Such an item needs
+        # three ZRLs and a 15-bit magnitude behind codes of 15-16 bits: ~100 k light blocks over ~160 symbols make the two
+        # heavy blocks' symbols that rare; the heavy blocks sit where their AC item opens a lane's items (K3 cuts this array's tiles
+        # into quarters of 287 items, 9 per lane: with the tile's first block DC-only, block 21's AC item is item 63 = 9 x 7).
+        coef[:, 0] = rng.integers(-500, 500, nb)
+        pos = np.minimum(16, rng.geometric(0.25, nb)); cat = np.minimum(10, rng.geometric(0.45, nb))
+        val = ((1 << (cat - 1)) + rng.integers(0, 1 << 14, nb) % (1 << (cat - 1))) * rng.choice([-1, 1], nb)
+        coef[np.arange(nb), pos] = val.astype(np.int16)
+        for tile in (7, 100):
+            coef[384 * tile, 1:] = 0
+            coef[384 * tile + 21, 1:] = 0
+            coef[384 * tile + 21, 63] = -30000
+    elif kind == "dense_extreme":
+        coef[:] = rng.integers(8192, 32768, (nb, 64)) * rng.choice([-1, 1], (nb, 64))
+        coef[:, 0] = rng.integers(-16000, 16000, nb)              # DC differences stay below 2^15: category 16 is outside the reference's coder
+    elif kind == "zrl_runs":
+        for b in range(nb):
+            gap = int(rng.choice([15, 16, 17, 31, 32, 47, 48, 62]))
+            coef[b, 0] = rng.integers(-300, 300)
+            coef[b, 1 + gap - 1 if gap < 63 else 63] = rng.integers(1, 40) * rng.choice([-1, 1])
+            if gap + 17 < 64 and rng.random() < 0.5:
+                coef[b, gap + 17] = rng.integers(1, 5)
+    elif kind == "last_only":
+        coef[:, 63] = rng.integers(1, 1000, nb) * rng.choice([-1, 1], nb)
+        coef[::3, 0] = rng.integers(-1000, 1000, len(coef[::3]))
+    elif kind == "ff_rich":
+        # magnitudes of all ones behind short codes: more than a quarter of the scan's bytes are FF (8 k of 29 k), runs of them across
+        # K4's 4 KB tiles and at the frame's end
+        coef[:, :8] = 1023
+    else:
+        dense = rng.random(nb) < 0.15
+        coef[dense] = (rng.integers(1, 2000, (int(dense.sum()), 64)) * rng.choice([-1, 1], (int(dense.sum()), 64))).astype(np.int16)
+        sparse = ~dense
+        mask = rng.random((nb, 64)) < 0.05
+        vals = (rng.integers(1, 30, (nb, 64)) * rng.choice([-1, 1], (nb, 64))).astype(np.int16)
+        coef[sparse] = np.where(mask[sparse], vals[sparse], 0)
+        coef[:, 0] = rng.integers(-1024, 1024, nb)
+    coef = coef.reshape(mw * mh, 6, 64)
+    encoder.set_coefficients_mcu(coef, mw, mh)
+    count, first = encoder.symbol_stats()
+    ocount, ofirst = oracle.symbol_stats(coef, mw, mh)
+    assert np.array_equal(count, ocount) and np.array_equal(first, ofirst)
+    tabs = encoder.build_huffman(count, first)
+    otabs, _, onbits, ostuffed = oracle.entropy_encode(coef, mw, mh)
+    for t in range(4):
+        assert table_fields(tabs[t]) == table_fields(otabs[t]), f"table {t}"
+    n = encoder.entropy_encode(tabs)
+    scan = encoder.download_scan()
+    assert n == ostuffed.size and np.array_equal(scan, ostuffed), kind
+    if kind == "ff_rich":
+        assert encoder.stats().stuffed_ff > 5000
+    if kind == "outrun":
+        assert encoder.debug_counter(6) >= 1, "the slow path of the Huffman packer was not exercised"
