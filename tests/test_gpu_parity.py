@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import random_symbol_stats, table_fields
-from jpgenc_b200.synth import noise_rgb, synth_rgb
+from jpgenc_b200.synth import noise_rgb, ppm_p6_bytes, synth_rgb
 
 pytestmark = pytest.mark.gpu
 
@@ -767,3 +767,44 @@ def test_entropy_coder_on_synthetic_coefficient_arrays(encoder, oracle, kind):
         assert encoder.stats().stuffed_ff > 5000
     if kind == "outrun":
         assert encoder.debug_counter(6) >= 1, "the slow path of the Huffman packer was not exercised"
+
+
+@pytest.mark.gpu
+def test_random_sizes_and_contents_byte_identical(encoder, oracle):
+    """80 images of random size (1 .. 260 pixels a side: every padding amount, single-MCU and single-row images, partial strips
+    and tiles) and random content (noise, flat, sparse spikes, saturated checkers, gradients, low maxval): whole files against the
+    oracle, through the host-pixel path and -- every fourth -- through bound device pixels"""
+    rng = np.random.default_rng(20261019)
+    for case in range(80):
+        w, h = int(rng.integers(1, 261)), int(rng.integers(1, 261))
+        kind = case % 6
+        maxval = 255
+        if kind == 0:
+            rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == 1:
+            rgb = np.full((h, w, 3), rng.integers(0, 256, 3), np.uint8)
+        elif kind == 2:
+            rgb = np.zeros((h, w, 3), np.uint8)
+            n = max(1, w * h // 50)
+            rgb[rng.integers(0, h, n), rng.integers(0, w, n)] = rng.integers(0, 256, (n, 3))
+        elif kind == 3:
+            yy, xx = np.mgrid[0:h, 0:w]
+            rgb = (((yy // int(rng.integers(1, 9)) + xx // int(rng.integers(1, 9))) % 2) * 255).astype(np.uint8)[..., None].repeat(3, 2)
+        elif kind == 4:
+            yy, xx = np.mgrid[0:h, 0:w]
+            rgb = np.stack([(xx * 255 // max(1, w - 1)), (yy * 255 // max(1, h - 1)), ((xx + yy) % 256)], -1).astype(np.uint8)
+        else:
+            maxval = int(rng.choice([1, 7, 31, 100, 200]))
+            rgb = rng.integers(0, maxval + 1, (h, w, 3), dtype=np.uint8)
+        want = oracle.encode_ppm(ppm_p6_bytes(rgb, maxval))
+        assert encoder.encode_rgb(rgb, maxval) == want, (case, w, h, kind, maxval)
+        if case % 4 == 0:
+            d = encoder.dev_alloc(rgb.size + 16)
+            try:
+                encoder.h2d(d, rgb)
+                encoder.bind_device_rgb(d, w, h, maxval)
+                out = np.empty(len(want) + 64, np.uint8)
+                n = encoder.encode_bound(out)
+                assert out[:n].tobytes() == want, (case, w, h, kind, "bound")
+            finally:
+                encoder.dev_free(d)
