@@ -67,23 +67,10 @@ __device__ __forceinline__ void warp_count(uint32_t* s_hist, uint32_t* s_first, 
 // first block, and the chroma ones are the tile's MCU numbers, once for Cb and once -- n_mcu later -- for Cr:
 //   luma    local = (text index - text index of the tile's first Y block) * 256 + position key      (< 2^24)
 //   chroma  local = (is Cr) << 30 | (MCU - first MCU of the tile) * 256 + position key
-// TileKeys converts between the two forms; to_local also maps any global key that no symbol of this tile can beat (or
-// that every symbol of it beats) to a value with exactly that effect.
+// TileKeys converts a tile-local key back to the global form when the tile flushes.
 struct TileKeys {
     unsigned long long y_base, cb_base, cr_base;          // global keys of local key 0
     static constexpr uint32_t kCr = 1u << 30, kSpan = 64u * 256u;
-    __device__ __forceinline__ uint32_t to_local(int table, unsigned long long g) const {
-        if (table < 2) {
-            if (g <= y_base) return 0u;
-            const unsigned long long d = g - y_base;
-            return d > 0xFFFFFFFEull ? 0xFFFFFFFFu : static_cast<uint32_t>(d);
-        }
-        if (g <= cb_base) return 0u;
-        if (g < cb_base + kSpan) return static_cast<uint32_t>(g - cb_base);
-        if (g <= cr_base) return kCr;
-        if (g < cr_base + kSpan) return kCr + static_cast<uint32_t>(g - cr_base);
-        return 0xFFFFFFFFu;
-    }
     __device__ __forceinline__ unsigned long long to_global(int table, uint32_t k) const {
         if (table < 2) return y_base + k;
         return ((k & kCr) ? cr_base : cb_base) + (k & (kCr - 1));
@@ -96,7 +83,7 @@ constexpr int kStatsSmem = kTileSmemBytes                // masks + dc
                            + kTileBlocks * 4             // local text key of the block
                            + kTileBlocks * 4             // first item / first AC descriptor of the block
                            + kDescCap * 4                // descriptors
-                           + 4096 + 8192 + 4096          // histogram, global keys as fetched, local first-occurrence keys
+                           + 4096 + 4096                 // histogram, local first-occurrence keys
                            + 36 * 4;                     // scan scratch
 
 __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __grid_constant__ StatsParams p) {
@@ -107,11 +94,9 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     uint32_t* s_base = reinterpret_cast<uint32_t*>(at);                       at += kTileBlocks * 4;
     uint32_t* s_desc = reinterpret_cast<uint32_t*>(at);                       at += kDescCap * 4;
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(at);                       at += 4096;
-    unsigned long long* s_first_g = reinterpret_cast<unsigned long long*>(at); at += 8192;   // offset 19200: 16-byte aligned
     uint32_t* s_first = reinterpret_cast<uint32_t*>(at);                      at += 4096;
     uint32_t* s_scan = reinterpret_cast<uint32_t*>(at);
     __shared__ uint32_t s_origin[2];                                      // MCU column / row of the tile's first MCU
-    __shared__ alignas(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t gtile = p.tile0 + blockIdx.x;
@@ -122,29 +107,24 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
     uint32_t* __restrict__ g_hist = reinterpret_cast<uint32_t*>(p.g_stats + frame * kStatsBytes);
     unsigned long long* __restrict__ g_first = reinterpret_cast<unsigned long long*>(p.g_stats + frame * kStatsBytes + 4096);
 
-    // The global minima seen so far bound what this tile can still contribute (after the first tiles of an image almost
-    // no key is smaller, so the shared-memory atomics below are rarely executed).  They are fetched by one bulk copy
-    // that runs behind the coefficient scan; a stale (larger) value only costs a redundant update.
+    // First-occurrence keys start at "none" in every tile: a symbol's first occurrence in the tile costs one shared-memory
+    // atomic (a few dozen symbols per tile), later ones none; the tile's minima meet the global ones when it flushes.  (Round 1
+    // fetched the 8 KB of global minima into every CTA and converted them to tile-local form -- 1024 conversions and 134 MB of
+    // L2 reads per image -- to save those few atomics.)
     if (tid == 0) {
-        ptx::mbar_init(&s_bar, 1);
-        ptx::mbar_init_fence();
-        ptx::mbar_expect_tx(&s_bar, 8192);
-        ptx::bulk_g2s(s_first_g, g_first, 8192, &s_bar);
         const uint32_t m0 = first / kBlocksPerMcu, y0 = m0 / p.mcu_w;  // the tile's only division
         s_origin[0] = m0 - y0 * p.mcu_w;
         s_origin[1] = y0;
     }
-    for (int i = tid; i < 1024; i += kTileBlocks) s_hist[i] = 0;
+    for (int i = tid; i < 1024; i += kTileBlocks) { s_hist[i] = 0; s_first[i] = 0xFFFFFFFFu; }
     scan_tile(tv, coef + static_cast<size_t>(first) * kCoefPerBlock, nb, tid, kTileBlocks);
     __syncthreads();
-    ptx::mbar_wait(&s_bar, 0);
     const uint32_t m_first = first / kBlocksPerMcu;
     const uint32_t y_text0 = (s_origin[1] * 2u) * (2u * p.mcu_w) + s_origin[0] * 2u;     // text index of the tile's first Y block
     TileKeys tk;
     tk.y_base = 256ull * y_text0;
     tk.cb_base = 256ull * m_first;
     tk.cr_base = 256ull * (static_cast<unsigned long long>(p.n_mcu) + m_first);
-    for (int i = tid; i < 1024; i += kTileBlocks) s_first[i] = tk.to_local(i >> 8, s_first_g[i]);   // visible after the scan's barrier below
 
     // ---- per block: mask, DC difference, text key, item counts ----
     const bool live = tid < nb;
