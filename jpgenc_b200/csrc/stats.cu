@@ -16,6 +16,8 @@
 // consecutive non-zero COEFFICIENTS: no lane ever loops over zeros, the work per lane is equal whatever the blocks look
 // like, the loop body is branch-free and the item stores are coalesced.  The DC and EOB symbols
 // exist exactly once (at most once) per block and stay with the block's own thread.
+#include <cstdlib>
+
 #include "blockwalk.cuh"
 #include "ptx.cuh"
 
@@ -86,6 +88,7 @@ constexpr int kStatsSmem = kTileSmemBytes                // masks + dc
                            + 4096 + 4096                 // histogram, local first-occurrence keys
                            + 36 * 4;                     // scan scratch
 
+template <bool kAggregateAc>
 __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __grid_constant__ StatsParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const TileView tv = tile_view(smem);
@@ -163,7 +166,12 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
         out[base] = make_item(tdc, dcat, 0, diff);
         if (eob) out[base + count - 1] = make_item(tdc + 1, 0, 0, 0);
     }
-    warp_count(s_hist, s_first, live, tdc * 256 + dcat, key);
+    if constexpr (kAggregateAc) {
+        warp_count(s_hist, s_first, live, tdc * 256 + dcat, key);
+    } else if (live) {
+        atomicAdd(&s_hist[tdc * 256 + dcat], 1u);
+        if (key < s_first[tdc * 256 + dcat]) atomicMin(&s_first[tdc * 256 + dcat], key);
+    }
     {
         const bool ey = eob && k < 4, ec = eob && k >= 4;
         const unsigned by = __ballot_sync(0xffffffffu, ey), bc = __ballot_sync(0xffffffffu, ec);
@@ -224,7 +232,12 @@ __global__ void __launch_bounds__(kTileBlocks, 5) symbol_stats_kernel(const __gr
                 const uint32_t sb = s_base[b];
                 out[(sb & 0xFFFFu) + 1u + (win + j - (sb >> 16))] = make_item(table, symbol, nzrl, value);
             }
-            warp_count(s_hist, s_first, has, idx, ikey);
+            if constexpr (kAggregateAc) {
+                warp_count(s_hist, s_first, has, idx, ikey);
+            } else if (has) {                                            // plain shared-memory atomics: same-address lanes are serialised by the LSU
+                atomicAdd(&s_hist[idx], 1u);
+                if (ikey < s_first[idx]) atomicMin(&s_first[idx], ikey);
+            }
             if (__any_sync(0xffffffffu, nzrl != 0)) {                   // ZRLs (runs of 16 zeros) are rare
                 if (nzrl) {
                     const int zi = table * 256 + 0xF0;
@@ -313,10 +326,14 @@ int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool fir
     p.refine_count = c->d_counters;
     p.refine_copy = reinterpret_cast<uint32_t*>(c->d_stats + c->nframes * kStatsBytes);
     if (!c->k2_configured) {                                   // (the first encode of a context is never graph-captured)
-        JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
+        JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
+        JPGENC_CUDA(c, cudaFuncSetAttribute(symbol_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatsSmem));
         c->k2_configured = true;
     }
-    symbol_stats_kernel<<<ntiles, kTileBlocks, kStatsSmem, c->stream>>>(p);
+    // JPGENC_K2_AGG=1: MATCH.ANY-grouped histogram updates (round 1) instead of plain shared-memory atomics
+    static const bool aggregate = [] { const char* v = std::getenv("JPGENC_K2_AGG"); return v && *v == '1'; }();
+    if (aggregate) symbol_stats_kernel<true><<<ntiles, kTileBlocks, kStatsSmem, c->stream>>>(p);
+    else symbol_stats_kernel<false><<<ntiles, kTileBlocks, kStatsSmem, c->stream>>>(p);
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return JPGENC_OK;
