@@ -174,9 +174,11 @@ int jpgenc_batch_encode(jpgenc_batch* batch, uint32_t n, const uint8_t* const* f
 int jpgenc_batch_encode_device(jpgenc_batch* batch, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h,
                                uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
 
-/* all frames TOGETHER through every kernel on one context (one launch of each kernel per pass instead of per frame; the
- * 4*n Huffman tables are built in parallel on host threads).  Frames must have one size and live in device memory;
- * out may be NULL (sizes only).  Results are byte-identical to encoding the frames one by one. */
+/* all frames TOGETHER through every kernel on one context: the batch is cut into passes of 64-128 Mpx-sized groups of frames,
+ * each pass one asynchronous chain K1 > K2 > device table build > device sizes/offsets > K3 > K4 with ONE host wait (the 4*n
+ * Huffman tables are built on the device, same tables as jpgenc_build_huffman), the passes rotating over four streams driven
+ * by the calling thread alone.  Frames must have one size and live in device memory; out may be NULL (sizes only).  Results
+ * are byte-identical to encoding the frames one by one. */
 int jpgenc_encode_frames_device(jpgenc_ctx* ctx, uint32_t n, const void* const* dev_frames, uint32_t w, uint32_t h,
                                 uint32_t maxval, uint8_t* const* out, const uint64_t* caps, uint64_t* sizes);
 /* the same for frames in host memory (pinned for full PCIe speed): uploads of the next slice of the batch overlap the
