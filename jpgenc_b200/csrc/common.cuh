@@ -311,7 +311,6 @@ int launch_planes_exact(jpgenc_ctx* c, const double* d_planes, bool ycbcr);
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
 int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid);
 int launch_publish_stats(jpgenc_ctx* c);
-int launch_publish_totals(jpgenc_ctx* c);
 // batches: built tables + K2's histograms -> DeviceTables and the PassMeta block, all on the device
 int launch_finalize_tables(jpgenc_ctx* c);
 #ifndef JPGENC_K4_THREADS

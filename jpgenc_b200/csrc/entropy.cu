@@ -76,6 +76,8 @@ struct EntropyParams {
     unsigned long long* ff_incl;        // [nframes] out: FF bytes K4 stuffed in frames 0..f of the pass
     uint32_t* tile_ff;                  // FF bytes per K4 tile (K4a), all frames of the pass numbered as ONE sequence
     uint32_t* redo_count;               // chunks K3b had to pack the slow way (diagnostics)
+    unsigned long long* mailbox;        // one image: the host's mailbox (common.cuh kMail*); K4's last tile reports the totals there
+    uint32_t* dseq;                     // ... tagged with the next sequence number
     // output as complete files (batches): every frame = header + scan + EOI, frames back to back
     const jpgenc_huff_table* built;     // [nframes * 4] tables as the device build left them (DHT segments); null = scan only
     const uint8_t* hdr_prefix;          // SOI .. SOF0, identical for every frame of the pass
@@ -533,7 +535,18 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_const
     const uint32_t tail0 = head + 4 * nwords;
     if (tid < len - tail0) g[tail0 + tid] = s_out[tail0 + tid];
     if (tile_at + kStuffTile >= nbytes) {                      // the frame's last tile
-        if (tid == 0) p.ff_incl[frame] = base + tile_ff;
+        if (tid == 0) {
+            p.ff_incl[frame] = base + tile_ff;
+            if (p.mailbox) {
+                // one image: scan bits (K3b wrote them, a kernel ago) and stuffed FF bytes go straight to the host's mailbox as
+                // self-validating words -- no publishing kernel behind K4
+                const uint32_t seq = *p.dseq + 1u;
+                volatile unsigned long long* box = p.mailbox + kMailTotals;
+                box[0] = mail_word(__ldcg(p.total_bits + frame), seq);
+                box[1] = mail_word(base + tile_ff, seq);
+                *p.dseq = seq;
+            }
+        }
         if (tid < p.tail) g[len + tid] = tid ? 0xD9 : 0xFF;   // EOI (JpegSegments.hpp:361-377)
     }
     if (tile == 0 && p.hdr_len[frame]) write_file_header(file + base, p, frame, tid, kStuffThreads);
@@ -578,6 +591,11 @@ int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
     p.ff_incl = m.ff_incl;
     p.tile_ff = reinterpret_cast<uint32_t*>(c->d_lookback);
     p.redo_count = c->d_counters + kCntK3Redo;
+    if (F == 1 && !c->file_mode && k4_grid) {                    // one image: K4's last tile writes the totals into the host's mailbox
+        p.mailbox = c->d_mailbox;
+        p.dseq = c->d_counters + kCntSeq;
+        ++c->mailbox_seq;                                        // the sequence number those words will be tagged with
+    }
     if (c->file_mode) {
         p.built = c->d_built_tables;
         p.hdr_prefix = c->d_hdr_prefix;
@@ -597,7 +615,6 @@ int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid) {
         c->launches += 2;
     }
     c->launches += 2;
-    if (F == 1 && !c->file_mode) return launch_publish_totals(c);    // one image: the totals go to the host's mailbox
     return JPGENC_OK;
 }
 

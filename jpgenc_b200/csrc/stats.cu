@@ -292,15 +292,6 @@ __global__ void __launch_bounds__(1024) publish_stats_kernel(const uint8_t* __re
     if (e == 0) box[0] = mail_word(static_cast<unsigned long long>(total) | (static_cast<unsigned long long>(*refine_count) << 11), seq);
 }
 
-// K4's totals of one image (scan bits, stuffed FF bytes: the results part of the PassMeta block) the same way
-__global__ void publish_totals_kernel(const unsigned long long* __restrict__ totals, unsigned long long* mailbox, uint32_t* dseq) {
-    const uint32_t seq = *dseq + 1u;
-    volatile unsigned long long* box = mailbox + kMailTotals;
-    box[0] = mail_word(__ldcg(totals), seq);
-    box[1] = mail_word(__ldcg(totals + 1), seq);
-    *dseq = seq;
-}
-
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
     const unsigned tiles = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
@@ -346,16 +337,6 @@ int launch_publish_stats(jpgenc_ctx* c) {
     JPGENC_CUDA(c, cudaGetLastError());
     c->launches += 1;
     ++c->mailbox_seq;                                          // the sequence number the kernel will tag its words with
-    return JPGENC_OK;
-}
-
-// one image, behind K4: scan bits and stuffed FF bytes
-int launch_publish_totals(jpgenc_ctx* c) {
-    const PassMeta m = pass_meta_view(c->d_meta, 1);
-    publish_totals_kernel<<<1, 1, 0, c->stream>>>(m.total_bits, c->d_mailbox, c->d_counters + kCntSeq);
-    JPGENC_CUDA(c, cudaGetLastError());
-    c->launches += 1;
-    ++c->mailbox_seq;
     return JPGENC_OK;
 }
 
