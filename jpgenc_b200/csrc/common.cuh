@@ -193,6 +193,7 @@ struct jpgenc_ctx {
     uint32_t hdr_prefix_len = 0;
     uint64_t raw_limit = 0, out_limit = 0;   // what finalize_tables_kernel may use of d_raw / d_scan
     uint64_t batch_raw_per_frame = 0;     // batched calls: raw-scan bytes reserved per frame (1.5 x the largest seen so far; 0 = nothing seen yet)
+    uint32_t batch_geom_w = 0, batch_geom_h = 0;   // ... the frame size that figure was learnt on (kept across calls of one size)
     cudaEvent_t ev_done = nullptr;        // batched calls: end of the slot's current pass
     cudaEvent_t ev_wide = nullptr;        // ... its K1/refinement/K2 are through (JPGENC_STAGGER=1: the next pass's wide kernels wait for it)
     cudaEvent_t ev_k4 = nullptr;          // ... its K4 is through (the next pass's K3 waits for it: passes finish one after the other)

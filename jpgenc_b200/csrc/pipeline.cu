@@ -338,7 +338,9 @@ int encode_device_frames(jpgenc_ctx* c, Job& job, const void* const* dev_frames)
     int rc = set_geometry(c, job.w, job.h, job.maxval);
     if (rc) return rc;
     if (job.n == 0) return JPGENC_OK;
-    c->batch_raw_per_frame = 0;
+    // what earlier calls learnt about the size of such frames' scans stays valid (a later frame that needs more is refused on the
+    // device and re-run, finish_pass); a new frame size starts from the guess again
+    if (c->batch_geom_w != job.w || c->batch_geom_h != job.h) { c->batch_raw_per_frame = 0; c->batch_geom_w = job.w; c->batch_geom_h = job.h; }
     const uint32_t nslots0 = std::min(kMaxSlots, env_u32("JPGENC_SLOTS", env_u32("JPGENC_LANES", kDefaultSlots)));
     const uint32_t per_pass = pass_frames(c, job.n, std::max(1u, nslots0));
     const uint32_t nslots = slots_for(job.n, per_pass);
@@ -359,7 +361,9 @@ int encode_host_frames(jpgenc_ctx* c, Job& job, const uint8_t* const* frames) {
     int rc = set_geometry(c, job.w, job.h, job.maxval);
     if (rc) return rc;
     if (job.n == 0) return JPGENC_OK;
-    c->batch_raw_per_frame = 0;
+    // what earlier calls learnt about the size of such frames' scans stays valid (a later frame that needs more is refused on the
+    // device and re-run, finish_pass); a new frame size starts from the guess again
+    if (c->batch_geom_w != job.w || c->batch_geom_h != job.h) { c->batch_raw_per_frame = 0; c->batch_geom_w = job.w; c->batch_geom_h = job.h; }
     const uint32_t nslots0 = std::min(kMaxSlots, env_u32("JPGENC_SLOTS", env_u32("JPGENC_LANES", kDefaultSlots)));
     const uint32_t per_pass = pass_frames(c, job.n, std::max(1u, nslots0));
     const uint32_t nslots = slots_for(job.n, per_pass);
