@@ -32,6 +32,34 @@ namespace {
 constexpr uint32_t kDefaultSlots = 4, kMaxSlots = 6;
 constexpr uint32_t kMaxHeaderBytes = 2 + 18 + 2 * 69 + 19 + 4 * (21 + 256) + 14;   // SOI APP0 DQTx2 SOF0 DHTx4 SOS
 
+// JPGENC_TRACE=2: a device-side timeline of the call -- timing events between the stages of every pass, printed relative to
+// the first one when the call ends (development aid; the extra event records cost a few microseconds per pass)
+struct Timeline {
+    struct Mark { cudaEvent_t ev; uint32_t pass; const char* what; };
+    std::vector<Mark> marks;
+    bool on = false;
+    void mark(jpgenc_ctx* l, uint32_t pass, const char* what) {
+        if (!on) return;
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        cudaEventRecord(ev, l->stream);
+        marks.push_back({ev, pass, what});
+    }
+    void print() {
+        if (marks.empty()) return;
+        cudaEventSynchronize(marks.back().ev);
+        for (const Mark& m : marks) {
+            float ms = 0;
+            cudaEventSynchronize(m.ev);
+            cudaEventElapsedTime(&ms, marks.front().ev, m.ev);
+            std::fprintf(stderr, "[jpgenc timeline] pass %u %-10s %8.1f us\n", m.pass, m.what, ms * 1e3);
+        }
+        for (const Mark& m : marks) cudaEventDestroy(m.ev);
+        marks.clear();
+    }
+};
+Timeline g_timeline;
+
 struct Job {
     uint32_t n = 0;
     uint32_t w = 0, h = 0, maxval = 255;
@@ -113,7 +141,9 @@ int enqueue_entropy(jpgenc_ctx* l, Pass& ps, cudaEvent_t prev_k4 = nullptr) {
     // after the other and the files of pass p travel while pass p + 1 is packed, instead of all slots' files queueing up
     // behind the last kernel (trace of 4 slots in step: 4 x 11 MB = 0.8 ms of copies after the last K4)
     if (prev_k4) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, prev_k4, 0));
+    g_timeline.mark(l, ps.f0, "finalize");
     if ((rc = launch_entropy(l, ps.k4_grid))) return rc;
+    g_timeline.mark(l, ps.f0, "K3+K4");
     JPGENC_CUDA(l, cudaEventRecord(l->ev_k4, l->stream));
     uint8_t* h = static_cast<uint8_t*>(l->h_pinned) + stage_meta_off(F);
     JPGENC_CUDA(l, cudaMemcpyAsync(h, l->d_meta, pass_meta_bytes(F), cudaMemcpyDeviceToHost, l->stream));
@@ -150,12 +180,15 @@ int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* d
     JPGENC_CUDA(l, cudaMemcpyAsync(l->d_frame_ptrs, l->h_pinned, F * sizeof(void*), cudaMemcpyHostToDevice, l->stream));
     if (ready) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, ready, 0));
     if (after) JPGENC_CUDA(l, cudaStreamWaitEvent(l->stream, after, 0));
+    g_timeline.mark(l, ps.f0, "start");
     if ((rc = launch_forward_rows(l, 0, l->mcu_h, true, true))) return rc;                       // K1 + exact refinement
+    g_timeline.mark(l, ps.f0, "K1+refine");
     l->have_coef = true;
     JPGENC_CUDA(l, cudaEventRecord(l->ev_fwd, l->stream));
     const size_t nblocks = static_cast<size_t>(l->mcu_w) * l->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
     if ((rc = launch_symbol_stats(l, 0, static_cast<uint32_t>(tiles * F), true))) return rc;     // K2
     l->have_items = true;
+    g_timeline.mark(l, ps.f0, "K2");
     JPGENC_CUDA(l, cudaEventRecord(l->ev_wide, l->stream));
     const uint32_t nt = 4 * F;
     if ((rc = ensure(l, reinterpret_cast<uint8_t**>(&l->d_tab_scratch), &l->tab_scratch_cap, nt * table_scratch_bytes()))) return rc;
@@ -167,6 +200,7 @@ int enqueue_pass(jpgenc_ctx* root, jpgenc_ctx* l, Pass& ps, const void* const* d
         if ((rc = launch_build_tables(l, l->d_stats, static_cast<uint32_t>(kStatsBytes), nt, l->d_tab_scratch, l->d_built_tables,
                                       reinterpret_cast<uint32_t*>(l->d_built_tables + nt)))) return rc;
     l->debug_tables_valid = nt;
+    g_timeline.mark(l, ps.f0, "tables");
     // how much raw scan / output the pass may use: 1.5 x the largest frame the batch has produced so far
     // (root->batch_raw_per_frame), before the first pass has finished a guess of 12 bytes per block; a pass that needs more
     // is refused by finalize_tables_kernel and its entropy stage re-run with what it asked for (finish_pass)
@@ -269,10 +303,14 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
     std::vector<Pass> pass(npasses);
     // (measured: 128 frames 1.26 -> 1.33 ms, 1024 frames 6.9 -> 7.2 ms: the cross-stream waits cost more than the earlier
     // table builds gain; kept as a switch)
-    const uint32_t stagger = env_u32("JPGENC_STAGGER", 0);
+    // default: the streams run side by side, except for a call of exactly two passes -- there nothing else will ever run beside
+    // the table builds, and letting pass 1's K1 start when pass 0's K1 is through (mode 2) puts pass 0's table build beside pass 1's
+    // wide kernels (timeline, 128 frames: 1.057 -> 1.014 ms; 256 and 1024 frames are 2-4 % slower staggered)
+    const uint32_t stagger = env_u32("JPGENC_STAGGER", npasses == 2 ? 2u : 0u);
     rc = JPGENC_OK;
     jpgenc_ctx* failed = nullptr;
     const double t0 = trace_on() ? now_us() : 0;
+    g_timeline.on = env_u32("JPGENC_TRACE", 0) >= 2;
     for (uint32_t p = 0; p < npasses + nslots && rc == JPGENC_OK; ++p) {
         if (p >= nslots) {                                          // the slot's previous pass: results, files, slot free again
             const uint32_t q = p - nslots;
@@ -310,6 +348,7 @@ int run_passes(jpgenc_ctx* c, Job& job, uint32_t per_pass, uint32_t nslots, Fram
         slot[k]->copy_pending = false;
         if (e != cudaSuccess && rc == JPGENC_OK) { rc = JPGENC_ERR_CUDA; c->error = std::string("batched pass: ") + cudaGetErrorString(e); }
     }
+    g_timeline.print();
     if (failed && failed != c) c->error = failed->error;
     for (uint32_t k = 1; k < nslots; ++k) {
         c->launches += slot[k]->launches;
