@@ -808,3 +808,39 @@ def test_random_sizes_and_contents_byte_identical(encoder, oracle):
                 assert out[:n].tobytes() == want, (case, w, h, kind, "bound")
             finally:
                 encoder.dev_free(d)
+
+
+@pytest.mark.gpu
+def test_batched_calls_of_changing_frame_sizes_on_one_context(oracle):
+    """One context, batched calls of different frame sizes and contents in a row: what a call learnt about scan sizes (buffer
+    reservations, K4 grids) is reused for the same size and dropped for another; a later, much denser batch of a known size is
+    refused on the device and re-run; n = 1 and n = 0 are batches too"""
+    from jpgenc_b200.capi import Encoder
+    enc = Encoder(0)
+    try:
+        def run(frames):
+            n = len(frames)
+            h, w, _ = frames[0].shape if n else (16, 16, 3)
+            fb = w * h * 3
+            d = enc.dev_alloc(max(1, n) * fb + 16)
+            try:
+                for k, f in enumerate(frames):
+                    enc.h2d(d + k * fb, np.ascontiguousarray(f))
+                want = [oracle.encode_rgb(f) for f in frames]
+                cap = sum(len(x) for x in want) + 4096
+                out = np.zeros(cap, np.uint8)
+                offs, sizes, total = enc.encode_frames_packed([d + k * fb for k in range(n)], w, h, out.ctypes.data, out.size)
+                assert sizes == [len(x) for x in want] and total == sum(sizes)
+                for k in range(n):
+                    assert out[offs[k]: offs[k] + sizes[k]].tobytes() == want[k], (w, h, k)
+            finally:
+                enc.dev_free(d)
+        smooth = [synth_rgb(320, 240, k) for k in range(20)]
+        run(smooth)
+        run(smooth[:7])                                             # same size again: the learnt reservation is reused
+        run([noise_rgb(208, 120, k) for k in range(9)])             # another size
+        run([noise_rgb(320, 240, 100 + k) for k in range(20)])      # the first size again, ~10x the scan bytes: refused and re-run
+        run(smooth[:1])
+        run([])
+    finally:
+        enc.close()
