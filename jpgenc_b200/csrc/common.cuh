@@ -216,6 +216,11 @@ struct jpgenc_ctx {
     std::vector<uint32_t> host_hist;      // K2's histograms as last read back, [nframes][4][256]
     std::vector<uint64_t> frame_bits, frame_out_off, frame_ff;   // per frame after K3/K4: scan bits, byte offset of its stuffed scan in d_scan, stuffed FFs
     bool k2_configured = false;
+    // launch_forward_rows(first) clears K1's counters AND what K2 / K3a accumulate into in one kernel; launch_symbol_stats(first)
+    // then skips its own clears -- valid while no buffer was reallocated and the frame count is the same
+    bool stats_clear_valid = false;
+    uint64_t stats_clear_gen = 0;
+    uint32_t stats_clear_frames = 0;
     void* d_tab_scratch = nullptr;        // device-side table build (tables_device.cu): work space, one slab per table
     size_t tab_scratch_cap = 0;
     jpgenc_huff_table* d_built_tables = nullptr;   // ... its results [4 * nframes], and one status word per table behind them
@@ -310,6 +315,8 @@ int launch_refine_pending(jpgenc_ctx* c);
 int launch_planes_exact(jpgenc_ctx* c, const double* d_planes, bool ycbcr);
 // K2 over the tiles [tile0, tile0 + ntiles) of the bound image(s); `first` also clears the statistics
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first);
+// K1's counters, the statistics of all frames bound and K3a's sums in one launch (false: the statistics' buffers do not exist yet)
+bool launch_encode_clear(jpgenc_ctx* c);
 int launch_entropy(jpgenc_ctx* c, uint32_t k4_grid);
 int launch_publish_stats(jpgenc_ctx* c);
 // batches: built tables + K2's histograms -> DeviceTables and the PassMeta block, all on the device

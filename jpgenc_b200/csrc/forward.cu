@@ -810,7 +810,8 @@ int launch_forward_rows(jpgenc_ctx* c, uint32_t y0, uint32_t rows, bool first, b
         static const int ahead = [] { const char* v = std::getenv("JPGENC_K1_PREFETCH"); return v && *v ? std::atoi(v) : 256; }();
         p.prefetch_ahead = static_cast<uint32_t>(ahead);
     }
-    if (first) JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(uint32_t), c->stream));   // list length .. refined so far
+    if (first && !launch_encode_clear(c))                                                          // counters + K2's / K3a's accumulators in one kernel
+        JPGENC_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(uint32_t), c->stream));          // (no statistics buffers yet) list length .. refined so far
     bool aligned = (c->real_w % 16 == 0) && (reinterpret_cast<uintptr_t>(c->d_rgb) % 16 == 0);
     if (c->nframes > 1) aligned = (c->real_w % 16 == 0) && c->frames_aligned;
     // (strips of 24 and of 40 MCUs, which divide 1920- and 3840-pixel rows evenly, were measured: no gain on those frames

@@ -16,6 +16,7 @@
 // consecutive non-zero COEFFICIENTS: no lane ever loops over zeros, the work per lane is equal whatever the blocks look
 // like, the loop body is branch-free and the item stores are coalesced.  The DC and EOB symbols
 // exist exactly once (at most once) per block and stay with the block's own thread.
+#include <algorithm>
 #include <cstdlib>
 
 #include "blockwalk.cuh"
@@ -292,15 +293,44 @@ __global__ void __launch_bounds__(1024) publish_stats_kernel(const uint8_t* __re
     if (e == 0) box[0] = mail_word(static_cast<unsigned long long>(total) | (static_cast<unsigned long long>(*refine_count) << 11), seq);
 }
 
+// Everything an encode accumulates into, cleared by ONE kernel in front of K1 (four memset nodes before: one ahead of K1, three
+// between the refinement and K2, each a link of a few microseconds in the chain of a small frame): K1's counters, per frame
+// histogram = 0 and first-occurrence keys = all ones, K3a's group / super-group sums = 0.
+__global__ void encode_clear_kernel(uint32_t* counters, uint32_t* stats, uint32_t stat_words, unsigned long long* range_base, uint32_t range_words) {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+    for (uint32_t i = i0; i < stat_words; i += step) stats[i] = (i % (kStatsBytes / 4)) < 1024u ? 0u : 0xFFFFFFFFu;
+    for (uint32_t i = i0; i < range_words; i += step) range_base[i] = 0ull;
+    if (i0 < 4) counters[i0] = 0u;                             // refinement list length .. entries refined so far
+}
+
+bool launch_encode_clear(jpgenc_ctx* c) {
+    const size_t stat_bytes = static_cast<size_t>(c->nframes) * kStatsBytes;
+    if (!c->d_stats || !c->d_range_base || c->stats_cap < stat_bytes || stat_bytes / 4 > 0xFFFFFFFFull || c->range_base_cap / 8 > 0xFFFFFFFFull) return false;
+    const uint32_t stat_words = static_cast<uint32_t>(stat_bytes / 4), range_words = static_cast<uint32_t>(c->range_base_cap / 8);
+    const uint32_t work = std::max(stat_words, range_words);
+    encode_clear_kernel<<<std::max(1u, std::min(296u, (work + 1023u) / 1024u)), 256, 0, c->stream>>>(c->d_counters, reinterpret_cast<uint32_t*>(c->d_stats), stat_words,
+                                                                                                 c->d_range_base, range_words);
+    if (cudaGetLastError() != cudaSuccess) return false;
+    c->launches += 1;
+    c->stats_clear_valid = true;
+    c->stats_clear_gen = c->alloc_gen;
+    c->stats_clear_frames = c->nframes;
+    return true;
+}
+
 int launch_symbol_stats(jpgenc_ctx* c, uint32_t tile0, uint32_t ntiles, bool first) {
     const uint64_t n_mcu = static_cast<uint64_t>(c->mcu_w) * c->mcu_h, nblocks = n_mcu * kBlocksPerMcu;
     const unsigned tiles = static_cast<unsigned>((nblocks + kTileBlocks - 1) / kTileBlocks);
     if (first) {
-        // per frame: histogram = 0, first-occurrence keys = all ones
-        JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats, kStatsBytes, 0, 4096, c->nframes, c->stream));
-        JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats + 4096, kStatsBytes, 0xFF, 8192, c->nframes, c->stream));
-        // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base; clear it off the critical path
-        JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, c->range_base_cap, c->stream));
+        if (!(c->stats_clear_valid && c->stats_clear_gen == c->alloc_gen && c->stats_clear_frames == c->nframes)) {
+            // (no K1 in front of this K2 -- coefficients set by a test hook, planes, a second K2 over the same coefficients)
+            // per frame: histogram = 0, first-occurrence keys = all ones
+            JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats, kStatsBytes, 0, 4096, c->nframes, c->stream));
+            JPGENC_CUDA(c, cudaMemset2DAsync(c->d_stats + 4096, kStatsBytes, 0xFF, 8192, c->nframes, c->stream));
+            // K3a accumulates bit counts per group of 8 tiles and per 256 groups into d_range_base
+            JPGENC_CUDA(c, cudaMemsetAsync(c->d_range_base, 0, c->range_base_cap, c->stream));
+        }
+        c->stats_clear_valid = false;
         c->entropy_runs = 0;
     }
     if (ntiles == 0) return JPGENC_OK;
