@@ -500,8 +500,9 @@ def batch_section(enc, rank, world, barrier, max_over_ranks, reps=3, frames_tota
     mpx = frames_total * w * h / 1e6
     sec = {"resident": dt_res, "files_returned": dt_files, "e2e": dt_e2e}
     res = {"frames": frames_total, "frames_per_gpu": nf, "width": w, "height": h, "n_gpus": world, "scaling": "strong",
-           "mode": "passes of ~32 frames, each one asynchronous chain K1 > K2 > device table build > device sizes/offsets > K3 > K4 (files "
-                   "assembled on the device), rotating over 4 streams driven by one host thread; one host synchronisation per pass",
+           "mode": "passes of 64-128 frames (the library picks the size from the shard), each one asynchronous chain K1 > K2 > device table "
+                   "build > device sizes/offsets > K3 > K4 (files assembled on the device), rotating over 4 streams driven by one host "
+                   "thread; one host synchronisation per pass",
            "timing": f"host wall clock around one synchronous call per rank, barrier before, max over ranks, mean of {reps}",
            "gpu_launches_per_call": int(launches), "jpeg_bytes_total_this_rank": int(total), "parity": parity}
     for k, dt in sec.items():

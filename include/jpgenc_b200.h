@@ -116,6 +116,9 @@ int jpgenc_symbol_stats(jpgenc_ctx* ctx, uint32_t count[4][256], uint64_t first_
 
 /* ---- host: generateHuffmanCode from the statistics (src/Huffman.cpp:3-66, Huffman.hpp:114-174) ----- */
 int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
+/* the same tables from the plain statement of the algorithm (one std container per container of the reference, one vector
+ * per package-merge level): the anchor jpgenc_build_huffman (allocation-free queues) and the device build are tested against */
+int jpgenc_build_huffman_containers(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
 
 /* the same on the device, n tables at once (one warp per table; libstdc++'s container orders restated on arrays).  The
  * batched-frame calls use it when the process has few host cores for its GPU (8-GPU boxes); identical results. */

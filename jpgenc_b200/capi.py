@@ -65,6 +65,7 @@ _SIGNATURES = {
     "jpgenc_set_coefficients_mcu": (C.c_int, [C.c_void_p, i16p, C.c_uint32, C.c_uint32]),
     "jpgenc_symbol_stats": (C.c_int, [C.c_void_p, u32p, u64p]),
     "jpgenc_build_huffman": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
+    "jpgenc_build_huffman_containers": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_build_huffman_arrays": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_build_huffman_device": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_entropy_encode": (C.c_int, [C.c_void_p, C.POINTER(HuffTable), u64p]),

@@ -80,7 +80,177 @@ void assign_codes(const std::vector<std::vector<int>>& per_length, jpgenc_huff_t
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The build the encode path calls.  Same containers for the two library-defined orders (std::unordered_map for the
+// symbol and code-length maps, std::push_heap / std::pop_heap for the package queues), but no allocation per level:
+// a queue item is ONE 64-bit word (weight << 13 | arena index, compared on the weight alone, so the heap algorithms
+// make exactly the moves they make on the reference's items; pop_heap is written out, see PackedLevel::pop), the queues are fixed arrays and a level starts as a
+// memcpy of the heapified leaves.  For the 28-symbol luma AC table of a 3840x2160 frame this is the host time between
+// K2 and K3 of a single image -- 21 us with one vector per level, see DESIGN.md 3.
+namespace {
+
+constexpr int kNodeBits = 13;                                  // 256 leaves + 15 levels of < 256 packages < 8192 arena nodes
+constexpr uint64_t kNodeMask = (1ull << kNodeBits) - 1;
+struct PackedHeavierFirstOut {
+    bool operator()(uint64_t a, uint64_t b) const { return (a >> kNodeBits) > (b >> kNodeBits); }
+};
+struct PackedNode { int16_t left, right, symbol; };
+struct SymbolSet { uint64_t w[4]; };
+
+struct PackedLevel {
+    uint64_t v[2 * 256 + 8];
+    int n = 0;
+    void push(uint64_t weight, int node) {
+        v[n++] = weight << kNodeBits | static_cast<uint64_t>(node);
+        std::push_heap(v, v + n, PackedHeavierFirstOut());
+    }
+    // top() + std::pop_heap + pop_back.  pop_heap is libstdc++'s __adjust_heap written out (the hole at the root walks down
+    // to the bottom, always to the lighter child, the right one on a tie; the former last item is then sifted up from
+    // there) with the child choice as arithmetic instead of a branch: the choice is a coin flip for the predictor.
+    uint64_t pop() {
+        const uint64_t top = v[0];
+        const int len = n - 1;
+        if (len > 0) {
+            const uint64_t val = v[len];
+            int hole = 0, child = 0;
+            const int last_parent = (len - 1) / 2;
+            while (child < last_parent) {
+                child = 2 * (child + 1);
+                child -= (v[child] >> kNodeBits) > (v[child - 1] >> kNodeBits);
+                v[hole] = v[child];
+                hole = child;
+            }
+            if ((len & 1) == 0 && child == (len - 2) / 2) {
+                child = 2 * (child + 1);
+                v[hole] = v[child - 1];
+                hole = child - 1;
+            }
+            int parent = (hole - 1) / 2;
+            while (hole > 0 && (v[parent] >> kNodeBits) > (val >> kNodeBits)) {
+                v[hole] = v[parent];
+                hole = parent;
+                parent = (hole - 1) / 2;
+            }
+            v[hole] = val;
+        }
+        n = len;
+        return top;
+    }
+    void start_as(const PackedLevel& o) { std::memcpy(v, o.v, sizeof(uint64_t) * o.n); n = o.n; }
+};
+
+}  // namespace
+
+static int build_huffman_packed(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
+
 extern "C" int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
+    if (!count || !first_pos || !out) return JPGENC_ERR_ARG;
+    for (int s = 0; s < 256; ++s)
+        if (count[s] >> 31) return jpgenc_build_huffman_containers(count, first_pos, out);   // int overflow of the reference's counter: its arithmetic, not ours
+    return build_huffman_packed(count, first_pos, out);
+}
+
+static int build_huffman_packed(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
+    std::memset(out, 0, sizeof *out);
+    int appearance[256], n = 0;
+    for (int s = 0; s < 256; ++s)
+        if (count[s]) appearance[n++] = s;
+    if (n == 0) return JPGENC_ERR_ARG;
+    std::sort(appearance, appearance + n, [&](int a, int b) { return first_pos[a] < first_pos[b]; });
+    std::unordered_map<int, int> freq;
+    for (int i = 0; i < n; ++i) freq[appearance[i]] = static_cast<int>(count[appearance[i]]);
+    out->nsymbols = n;
+
+    uint8_t per_length[18][256];
+    int per_length_n[18] = {};
+    auto emit = [&] {                                          // generateCodes, src/Huffman.cpp:50-66
+        uint32_t code = 0;
+        int k = 0;
+        for (int len = 1; len <= 16; ++len) {
+            out->counts[len - 1] = static_cast<uint8_t>(per_length_n[len]);
+            for (int i = 0; i < per_length_n[len]; ++i) {
+                const int s = per_length[len][i];
+                out->code_msb[s] = code << (32 - len);
+                out->length[s] = static_cast<uint8_t>(len);
+                out->symbols[k++] = static_cast<uint8_t>(s);
+                ++code;
+            }
+            code <<= 1;
+        }
+    };
+    if (n == 1) {
+        per_length[1][per_length_n[1]++] = static_cast<uint8_t>(appearance[0]);
+        emit();
+        return JPGENC_OK;
+    }
+
+    constexpr int kLimit = 15;
+    constexpr int kArena = 256 * (kLimit + 1) + 8;
+    PackedNode nodes[kArena];
+    SymbolSet sets[kArena];                                    // the symbols among a node's leaves
+    int nn = 0;
+    PackedLevel blueprint, a, b;
+    for (const auto& kv : freq) {
+        nodes[nn] = {-1, -1, static_cast<int16_t>(kv.first)};
+        sets[nn] = SymbolSet{};
+        sets[nn].w[kv.first >> 6] = 1ull << (kv.first & 63);
+        blueprint.push(static_cast<uint64_t>(kv.second), nn++);
+    }
+    PackedLevel *current = &a, *next = &b;
+    current->start_as(blueprint);
+    for (int lvl = 0; lvl < kLimit; ++lvl) {
+        if (lvl + 1 < kLimit) next->start_as(blueprint); else next->n = 0;
+        while (current->n > 1) {
+            const uint64_t x = current->pop();
+            const uint64_t y = current->pop();
+            const int xn = static_cast<int>(x & kNodeMask), yn = static_cast<int>(y & kNodeMask);
+            nodes[nn] = {static_cast<int16_t>(xn), static_cast<int16_t>(yn), -1};
+            for (int w = 0; w < 4; ++w) sets[nn].w[w] = sets[xn].w[w] | sets[yn].w[w];
+            next->push((x >> kNodeBits) + (y >> kNodeBits), nn++);
+        }
+        std::swap(current, next);
+    }
+    // Drain the last level.  The reference walks every surviving package, sorts its symbols and bumps a map entry per
+    // occurrence; what that fixes is (a) the ORDER in which symbols enter the lengths map -- package by package in pop
+    // order, ascending inside a package: read off the packages' symbol sets -- and (b) how often each symbol occurs in
+    // all of them: one pass down the arena, a package handing its multiplicity to its two children (children always
+    // have lower indices than their package).
+    std::unordered_map<int, int> code_lengths;
+    uint16_t times[kArena];
+    std::memset(times, 0, sizeof(uint16_t) * nn);
+    uint64_t entered[4] = {0, 0, 0, 0};
+    while (current->n) {
+        const int root = static_cast<int>(current->pop() & kNodeMask);
+        ++times[root];
+        for (int w = 0; w < 4; ++w) {
+            uint64_t fresh = sets[root].w[w] & ~entered[w];
+            entered[w] |= fresh;
+            for (; fresh; fresh &= fresh - 1) code_lengths.emplace(w * 64 + __builtin_ctzll(fresh), 0);
+        }
+    }
+    for (int k = nn - 1; k >= n; --k) {
+        times[nodes[k].left] += times[k];
+        times[nodes[k].right] += times[k];
+    }
+    uint16_t length_of[256];
+    for (int k = 0; k < n; ++k) length_of[nodes[k].symbol] = times[k];
+    for (const auto& kv : code_lengths) {
+        const int len = length_of[kv.first];
+        per_length[len][per_length_n[len]++] = static_cast<uint8_t>(kv.first);
+    }
+
+    int deepest = 16;                                          // preventOnlyOnesCode, src/Huffman.cpp:37-48
+    while (deepest > 0 && per_length_n[deepest] == 0) --deepest;
+    const int moved = per_length[deepest][--per_length_n[deepest]];
+    per_length[deepest + 1][per_length_n[deepest + 1]++] = static_cast<uint8_t>(moved);
+    emit();
+    return JPGENC_OK;
+}
+
+// The straightforward statement: one container per thing the reference has one for.  Kept as the anchor the other
+// builds (packed above, array restatement on the device) are tested against; itself pinned against the compiled
+// reference in tests/test_oracle_vs_reference.py.
+extern "C" int jpgenc_build_huffman_containers(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
     if (!count || !first_pos || !out) return JPGENC_ERR_ARG;
     std::memset(out, 0, sizeof *out);
 

@@ -73,9 +73,11 @@ def test_host_huffman_build_matches_oracle(oracle):
         first = np.full(256, np.iinfo(np.uint64).max, np.uint64)
         for pos in range(n - 1, -1, -1):
             first[text[pos]] = pos * 64
-        tab = capi.HuffTable()
-        assert lib.jpgenc_build_huffman(count.ctypes.data_as(capi.u32p), first.ctypes.data_as(capi.u64p), C.byref(tab)) == 0
-        assert table_fields(tab) == table_fields(oracle.huffman_from_text(text)), trial
+        want = table_fields(oracle.huffman_from_text(text))
+        for build in (lib.jpgenc_build_huffman, lib.jpgenc_build_huffman_containers):
+            tab = capi.HuffTable()
+            assert build(count.ctypes.data_as(capi.u32p), first.ctypes.data_as(capi.u64p), C.byref(tab)) == 0
+            assert table_fields(tab) == want, trial
 
 
 def test_host_huffman_golden(golden):
@@ -169,8 +171,9 @@ def test_golden_ppm_headers(golden, oracle):
 def test_array_restatement_of_the_table_build_equals_the_container_driven_build():
     """The device-side table build (csrc/tables_device.cu) restates libstdc++'s unordered_map iteration order and heap
     order on plain arrays.  Its code also runs on the host (jpgenc_build_huffman_arrays): every alphabet size, tie-heavy,
-    geometric (length limit binds) and maximally deep weight patterns must give the tables of jpgenc_build_huffman, which
-    drives the real containers and is itself pinned against the reference (test_oracle_vs_reference)."""
+    geometric (length limit binds) and maximally deep weight patterns must give the tables of jpgenc_build_huffman_containers,
+    which drives the real containers and is itself pinned against the reference (test_oracle_vs_reference) -- and so must
+    jpgenc_build_huffman, the allocation-free build the encode path calls."""
     import ctypes as C
     import numpy as np
     from conftest import random_symbol_stats, table_fields
@@ -180,10 +183,18 @@ def test_array_restatement_of_the_table_build_equals_the_container_driven_build(
     sizes = list(range(1, 70)) + [100, 127, 128, 129, 161, 162, 200, 255, 256] + [int(x) for x in rng.integers(1, 257, 700)]
     for n in sizes:
         c, f = random_symbol_stats(rng, n, int(rng.choice([5, 1000, 10 ** 6, 2 ** 31 - 1])))
-        a, b = HuffTable(), HuffTable()
-        assert lib.jpgenc_build_huffman(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(a)) == 0
+        a, b, p = HuffTable(), HuffTable(), HuffTable()
+        assert lib.jpgenc_build_huffman_containers(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(a)) == 0
         assert lib.jpgenc_build_huffman_arrays(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(b)) == 0
+        assert lib.jpgenc_build_huffman(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(p)) == 0
         assert table_fields(a) == table_fields(b) and a.nsymbols == b.nsymbols, f"{n} symbols: {c[c > 0].tolist()}"
+        assert table_fields(a) == table_fields(p) and a.nsymbols == p.nsymbols, f"{n} symbols: {c[c > 0].tolist()}"
+    # a count past INT_MAX wraps in the reference's int counter: the packed build hands such input to the plain one
+    c, f = random_symbol_stats(rng, 9, 1000)
+    c[np.flatnonzero(c)[0]] = 2 ** 31 + 5
+    a, p = HuffTable(), HuffTable()
+    assert lib.jpgenc_build_huffman_containers(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(a)) == lib.jpgenc_build_huffman(_np_ptr(c, u32p), _np_ptr(f, u64p), C.byref(p))
+    assert table_fields(a) == table_fields(p)
     empty = np.zeros(256, np.uint32)
     none = np.full(256, np.iinfo(np.uint64).max, np.uint64)
     assert lib.jpgenc_build_huffman_arrays(_np_ptr(empty, u32p), _np_ptr(none, u64p), C.byref(HuffTable())) != 0
