@@ -279,8 +279,12 @@ def run_ours(args):
     enc.synchronize()
 
     # ---- device-resident: K steps of the whole encode, pixels in HBM, scan left in HBM -------------------
+    # The library's event records between the kernels cost ~3 us each inside the replayed graphs (include/jpgenc_b200.h,
+    # jpgenc_set_stage_timing), so the timed region carries only the two around the roofline kernel (level 1: K1's launch
+    # duration is measured over exactly these K steps); the other stage times come from a second loop of K steps at level 2.
     sampler = ClockSampler(local)
     sampler.start()                                   # samples from the first warm-up step to the end of the timed steps
+    enc.set_stage_timing(1)
     for _ in range(args.warmup):
         jpeg_bytes = enc.encode_bound(None)
     barrier()
@@ -292,14 +296,34 @@ def run_ours(args):
     ms_total = enc.timer_end()
     s1 = enc.stats()
     n_timed = max(1, s1.timed_encodes - s0.timed_encodes)
-    k1_ms = [(s1.sum_ms_k1 - s0.sum_ms_k1) / n_timed]; fwd_ms = [(s1.sum_ms_forward - s0.sum_ms_forward) / n_timed]
-    st_ms = [(s1.sum_ms_stats - s0.sum_ms_stats) / n_timed]; en_ms = [(s1.sum_ms_entropy - s0.sum_ms_entropy) / n_timed]
+    k1_ms = [(s1.sum_ms_k1 - s0.sum_ms_k1) / n_timed]
     launches = enc.launch_count() - launches0
     barrier()
     clocks = sampler.summary()
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     value = world * npx / 1e6 / (ms_step / 1e3)
+    # the same K steps with every stage's events on (stage_ms), and with none (what a caller gets by default)
+    enc.set_stage_timing(2)
+    for _ in range(3):
+        enc.encode_bound(None)
+    s0 = enc.stats()
+    enc.timer_begin()
+    for _ in range(args.steps):
+        enc.encode_bound(None)
+    ms_step_all_events = max_over_ranks(enc.timer_end()) / args.steps
+    s1 = enc.stats()
+    n_timed = max(1, s1.timed_encodes - s0.timed_encodes)
+    fwd_ms = [(s1.sum_ms_forward - s0.sum_ms_forward) / n_timed]
+    st_ms = [(s1.sum_ms_stats - s0.sum_ms_stats) / n_timed]; en_ms = [(s1.sum_ms_entropy - s0.sum_ms_entropy) / n_timed]
+    enc.set_stage_timing(0)
+    for _ in range(3):
+        enc.encode_bound(None)
+    enc.timer_begin()
+    for _ in range(args.steps):
+        enc.encode_bound(None)
+    ms_step_no_events = max_over_ranks(enc.timer_end()) / args.steps
+    barrier()
     stats = enc.stats()
 
     # ---- end to end: pinned host pixels in, JPEG bytes out in pinned host memory ---------------------------
@@ -395,7 +419,12 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "stage_ms": {"k1_forward": round(k1, 4), "k1_plus_refine": round(sum(fwd_ms) / len(fwd_ms), 4),
-                     "k2_stats": round(sum(st_ms) / len(st_ms), 4), "k3_k4_entropy": round(sum(en_ms) / len(en_ms), 4)},
+                     "k2_stats": round(sum(st_ms) / len(st_ms), 4), "k3_k4_entropy": round(sum(en_ms) / len(en_ms), 4),
+                     "how": "k1_forward: event records around K1 inside the timed region (stage timing level 1); the others from a "
+                            "second loop of the same K steps with every stage's records on (level 2)"},
+        "stage_event_cost": {"ms_per_step_k1_events_only": round(ms_step, 4), "ms_per_step_all_stage_events": round(ms_step_all_events, 4),
+                             "ms_per_step_no_events": round(ms_step_no_events, 4),
+                             "note": "jpgenc_set_stage_timing: the library's default is no event records; each one is a graph node of ~3 us"},
         "jpeg_bytes": int(jpeg_bytes), "refined_blocks": int(stats.refined_blocks), "n_blocks": int(stats.n_blocks),
         "whole_encode_gbps_irreducible": round((npx * 3 + jpeg_bytes) / (ms_step / 1e3) / 1e9, 1),
     }
@@ -601,9 +630,20 @@ def extra_workloads(enc, args, peak):
             enc.timer_begin()
             enc.encode_bound(None)
             tot += enc.timer_end()
+        enc.timer_begin()
+        for _ in range(200):
+            enc.encode_bound(None)
+        warm = enc.timer_end() / 200
+        enc.set_stage_timing(2)
+        for _ in range(4):
+            enc.flush_l2()
+            enc.encode_bound(None)
         s = enc.stats()
+        enc.set_stage_timing(0)
         out["frame4k"] = {"ms_per_frame": round(tot / reps, 4), "mpx_per_s": round(w * h / 1e6 / (tot / reps / 1e3), 1),
-                          "k1_ms": round(s.ms_k1, 4), "l2": "flushed between iterations (256 MB write)"}
+                          "ms_per_frame_l2_warm": round(warm, 4),
+                          "k1_ms": round(s.ms_k1, 4), "l2": "flushed between iterations (256 MB write); l2_warm: 200 encodes back to back",
+                          "stage_timing": "off in the timed loops (library default); k1_ms from separate encodes with it on"}
         enc.dev_free(d)
     # the high-entropy variant (uniform random u8, numpy default_rng(1)) that stresses K3/K4 -- ~37 AC symbols per
     # block and ~3 bit/px instead of 4.2 symbols per block and 0.32 bit/px
@@ -621,7 +661,11 @@ def extra_workloads(enc, args, peak):
     for _ in range(reps):
         enc.encode_bound(None)
     ms = enc.timer_end() / reps
+    enc.set_stage_timing(2)
+    for _ in range(4):
+        enc.encode_bound(None)
     s = enc.stats()
+    enc.set_stage_timing(0)
     out["noise4096"] = {"ms_per_image": round(ms, 4), "mpx_per_s": round(w * h / 1e6 / (ms / 1e3), 1), "jpeg_bytes": int(nbytes),
                         "bits_per_px": round(8 * nbytes / (w * h), 3), "k1_plus_refine_ms": round(s.ms_forward, 4), "k2_ms": round(s.ms_stats, 4),
                         "k3_k4_ms": round(s.ms_entropy, 4), "stuffed_ff": int(s.stuffed_ff)}

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "jpgenc_set_coefficients": (C.c_int, [C.c_void_p, i32p, i32p, i32p, C.c_uint32, C.c_uint32]),
     "jpgenc_set_coefficients_mcu": (C.c_int, [C.c_void_p, i16p, C.c_uint32, C.c_uint32]),
     "jpgenc_symbol_stats": (C.c_int, [C.c_void_p, u32p, u64p]),
+    "jpgenc_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "jpgenc_build_huffman": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_build_huffman_containers": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
     "jpgenc_build_huffman_arrays": (C.c_int, [u32p, u64p, C.POINTER(HuffTable)]),
@@ -168,6 +169,11 @@ class Encoder:
             raise JpgencError(rc, (self.lib.jpgenc_last_error(self.h) or b"").decode())
 
     # ---- parameters -----------------------------------------------------------------------------
+    def set_stage_timing(self, level: int):
+        """0: no event records between the kernels (default); 1: around the K1 fast kernel; 2: around every stage -- what fills
+        stats().ms_k1 / ms_forward / ms_stats / ms_entropy and their running sums"""
+        self._check(self.lib.jpgenc_set_stage_timing(self.h, int(level)))
+
     def set_qtables(self, qy, qc):
         qy = np.ascontiguousarray(qy, np.uint8).reshape(64)
         qc = np.ascontiguousarray(qc, np.uint8).reshape(64)

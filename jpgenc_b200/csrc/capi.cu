@@ -88,8 +88,9 @@ int ensure_pinned(jpgenc_ctx* c, size_t bytes) {
 // after the stream has been synchronised past K1: event times and the refine counter
 int refresh_forward_stats(jpgenc_ctx* c) {
     if (!c->forward_pending) return JPGENC_OK;
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_k1, c->ev_k0, c->ev_k1));
+    c->stats.ms_forward = c->stats.ms_k1 = 0;
+    if (c->fwd_timed >= 2) JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_forward, c->ev_a, c->ev_b));
+    if (c->fwd_timed >= 1) JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_k1, c->ev_k0, c->ev_k1));
     c->forward_pending = false;
     return JPGENC_OK;
 }
@@ -172,8 +173,11 @@ size_t stage_bytes(uint32_t F) { return stage_meta_off(F) + pass_meta_bytes(F) +
 // when that encode went through all four stages, add its stage times to the running sums
 int flush_entropy_time(jpgenc_ctx* c) {
     if (!c->ent_pending) return JPGENC_OK;
-    JPGENC_CUDA(c, cudaEventSynchronize(c->ev_e1));
-    JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_e0, c->ev_e1));
+    c->stats.ms_entropy = 0;
+    if (c->ent_timed >= 2) {
+        JPGENC_CUDA(c, cudaEventSynchronize(c->ev_e1));
+        JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_entropy, c->ev_e0, c->ev_e1));
+    }
     c->ent_pending = false;
     if (c->last_whole) {
         c->stats.sum_ms_k1 += c->last_k1; c->stats.sum_ms_forward += c->last_fwd;
@@ -256,6 +260,7 @@ int jpgenc_create(int device, jpgenc_ctx** out) {
         return JPGENC_ERR_NO_DEVICE;
     }
     c->sm_count = prop.multiProcessorCount;
+    c->stage_timing = static_cast<int>(std::min(2u, env_u32("JPGENC_STAGE_TIMING", 0)));    // jpgenc_set_stage_timing
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (cudaEvent_t& ev : c->ev_band)
@@ -334,6 +339,12 @@ int jpgenc_get_stats(jpgenc_ctx* c, jpgenc_stats* out) try {
     return JPGENC_OK;
 } JPGENC_CATCH(c)
 
+int jpgenc_set_stage_timing(jpgenc_ctx* c, int level) try {
+    if (!c || level < 0 || level > 2) return JPGENC_ERR_ARG;
+    c->stage_timing = level;                                     // part of the graph keys (run_pipeline): the phases are captured again
+    return JPGENC_OK;
+} JPGENC_CATCH(c)
+
 int jpgenc_set_qtables(jpgenc_ctx* c, const uint8_t qy[64], const uint8_t qc[64]) try {
     if (!c || !qy || !qc) return JPGENC_ERR_ARG;
     for (int i = 0; i < 64; ++i)
@@ -391,6 +402,7 @@ int jpgenc_color_dct_quant(jpgenc_ctx* c) try {
     if ((rc = flush_entropy_time(c))) return rc;
     if ((rc = enqueue_forward(c))) return rc;
     c->forward_pending = true;
+    c->fwd_timed = c->stage_timing;
     c->have_coef = true;
     c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
@@ -455,19 +467,19 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
 // ---- one image: the GPU work of an encode as two enqueue-only phases (no host waits inside: they can be captured) ----
 // K1 + exact refinement, between the forward-stage events
 static int enqueue_forward(jpgenc_ctx* c) {
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_a));
+    JPGENC_CUDA(c, stage_record(c, c->ev_a, 2));
     const int rc = launch_forward(c);
     if (rc) return rc;
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_b));
+    JPGENC_CUDA(c, stage_record(c, c->ev_b, 2));
     return JPGENC_OK;
 }
 // K2 over the tiles [done, tiles) and the hand-over of the statistics to the host's mailbox
 static int enqueue_stats(jpgenc_ctx* c, uint32_t done) {
     const size_t nblocks = static_cast<size_t>(c->mcu_w) * c->mcu_h * kBlocksPerMcu, tiles = (nblocks + 383) / 384;
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_t0));
+    JPGENC_CUDA(c, stage_record(c, c->ev_t0, 2));
     int rc = launch_symbol_stats(c, done, static_cast<uint32_t>(tiles) - done, done == 0);
     if (rc) return rc;
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_t1));
+    JPGENC_CUDA(c, stage_record(c, c->ev_t1, 2));
     return launch_publish_stats(c);
 }
 // the host's half: wait for the mailbox, take the histogram
@@ -491,6 +503,7 @@ static int wait_stats(jpgenc_ctx* c) {
     c->host_hist.assign(&c->stat_count[0][0], &c->stat_count[0][0] + 1024);
     if (c->upload_pending || c->forward_pending) c->stats.refined_blocks = static_cast<uint32_t>(head >> 11);
     c->stats_pending = true;
+    c->stats_timed = c->stage_timing;
     return JPGENC_OK;
 }
 
@@ -521,8 +534,11 @@ static int read_completed_times(jpgenc_ctx* c) {
     }
     if (c->forward_pending && (rc = refresh_forward_stats(c))) return rc;
     if (c->stats_pending) {
-        JPGENC_CUDA(c, cudaEventSynchronize(c->ev_t1));            // recorded right behind K2, whose flag the host has seen long ago
-        JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_stats, c->ev_t0, c->ev_t1));
+        c->stats.ms_stats = 0;
+        if (c->stats_timed >= 2) {
+            JPGENC_CUDA(c, cudaEventSynchronize(c->ev_t1));        // recorded right behind K2, whose flag the host has seen long ago
+            JPGENC_CUDA(c, cudaEventElapsedTime(&c->stats.ms_stats, c->ev_t0, c->ev_t1));
+        }
         c->stats_pending = false;
     }
     c->last_whole = whole;
@@ -588,10 +604,10 @@ static int enqueue_entropy_phase(jpgenc_ctx* c, uint32_t k4_grid) {
     // (Measured and rejected: passing the 8 KB of tables as kernel parameters instead -- the launches get slower and the
     // per-thread reads of the parameter bank serialise; K3+K4 went from 185 to 212 us.)
     JPGENC_CUDA(c, cudaMemcpyAsync(c->d_tables, h + stage_tables_off(1), sizeof(DeviceTables) + pass_meta_input_bytes(1), cudaMemcpyHostToDevice, c->stream));
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_e0));
+    JPGENC_CUDA(c, stage_record(c, c->ev_e0, 2));
     const int rc = launch_entropy(c, k4_grid);
     if (rc) return rc;
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_e1));
+    JPGENC_CUDA(c, stage_record(c, c->ev_e1, 2));
     return JPGENC_OK;
 }
 // the host's half: stage times that are final by now, then the totals from the mailbox
@@ -599,6 +615,7 @@ static int wait_entropy(jpgenc_ctx* c) {
     int rc = read_completed_times(c);                            // K3/K4 are running: the host has nothing else to do
     if (rc) return rc;
     c->ent_pending = true;
+    c->ent_timed = c->stage_timing;
     unsigned long long bits = 0, ff = 0;
     if ((rc = poll_mailbox(c, kMailTotals, &bits))) return rc;   // the totals are in the mailbox (launch_entropy's last kernel)
     if ((rc = poll_mailbox(c, kMailTotals + 1, &ff))) return rc;
@@ -799,7 +816,8 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     const double t0 = trace_on() ? now_us() : 0;
     // ---- phase A: K1, refinement, K2, statistics into the mailbox ----
     c->k2_tiles_done = 0;
-    const uint64_t key_a[5] = {c->alloc_gen, reinterpret_cast<uint64_t>(c->d_rgb), (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, c->maxval, 1};
+    const uint64_t key_a[5] = {c->alloc_gen, reinterpret_cast<uint64_t>(c->d_rgb), (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, c->maxval,
+                               1u | static_cast<uint64_t>(c->stage_timing) << 8};
     const bool pool = c->parallel_tables;
     if (pool) {
         if (!c->pool) c->pool = new TablePool();
@@ -810,6 +828,7 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
         return r ? r : enqueue_stats(c, 0);
     });
     c->forward_pending = true;
+    c->fwd_timed = c->stage_timing;
     c->have_coef = true;
     c->have_scan = false;
     if (!rc) rc = wait_stats(c);
@@ -832,7 +851,7 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     uint32_t k4_tiles = 0;
     if ((rc = prepare_entropy(c, tables, &k4_tiles))) return rc;
     const uint32_t k4_grid = static_cast<uint32_t>(c->raw_cap / kK4TileBytes + 1);      // >= k4_tiles: the raw buffer holds the scan
-    const uint64_t key_b[5] = {c->alloc_gen, k4_grid, (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, 0, 1};
+    const uint64_t key_b[5] = {c->alloc_gen, k4_grid, (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, 0, 1u | static_cast<uint64_t>(c->stage_timing) << 8};
     if ((rc = run_phase(c, c->graph_b, key_b, [&]() -> int { return enqueue_entropy_phase(c, k4_grid); }))) return rc;
     const double t3 = trace_on() ? now_us() : 0;
     if ((rc = wait_entropy(c))) return rc;

@@ -148,6 +148,10 @@ struct jpgenc_ctx {
     // K3/K4 of one image: the time of encode N is read while K2 of encode N + 1 runs (or by jpgenc_get_stats)
     cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;
     bool ent_pending = false, stats_pending = false, last_whole = false;
+    // Event records between the kernels of an image (jpgenc_set_stage_timing): 0 none -- inside the replayed graphs every
+    // record is a node of its own, ~3 us each, 22 us per image with all eight --, 1 around the K1 fast kernel alone (the
+    // roofline kernel), 2 around every stage.  *_timed: the level the events of the encode in flight were recorded at.
+    int stage_timing = 0, fwd_timed = 0, stats_timed = 0, ent_timed = 0;
     float last_k1 = 0, last_fwd = 0, last_st = 0;
     std::string error;
     int sm_count = 148;
@@ -261,6 +265,11 @@ struct jpgenc_ctx {
 // only marks a dependency and leaves an event that cannot be waited for or timed)
 inline cudaError_t jpgenc_record(jpgenc_ctx* c, cudaEvent_t ev) {
     return cudaEventRecordWithFlags(ev, c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
+// an event of the per-stage timing: recorded only when stage timing is on at `level` or above
+inline cudaError_t stage_record(jpgenc_ctx* c, cudaEvent_t ev, int level) {
+    return c->stage_timing >= level ? jpgenc_record(c, ev) : cudaSuccess;
 }
 
 #define JPGENC_CUDA(ctx, expr)                                                                       \

@@ -837,11 +837,11 @@ int launch_refine_pending(jpgenc_ctx* c) {
 }
 
 int launch_forward(jpgenc_ctx* c) {
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_k0));
+    JPGENC_CUDA(c, stage_record(c, c->ev_k0, 1));
     // the fast kernel alone is timed (ev_k0..ev_k1): it is the roofline kernel; the refinement follows
     const int rc = launch_forward_rows(c, 0, c->mcu_h, true, false);
     if (rc) return rc;
-    JPGENC_CUDA(c, jpgenc_record(c, c->ev_k1));
+    JPGENC_CUDA(c, stage_record(c, c->ev_k1, 1));
     return launch_refine(c, false);
 }
 

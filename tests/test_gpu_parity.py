@@ -608,6 +608,41 @@ def test_repeated_encodes_of_bound_pixels_replay_graphs(oracle, monkeypatch, gra
         enc.close()
 
 
+def test_stage_timing_levels_change_times_not_bytes(oracle):
+    """jpgenc_set_stage_timing: the event records between the kernels are off by default (stats' stage times stay 0), level 1
+    times the K1 fast kernel, level 2 every stage; switching in the middle of a run of encodes re-captures the graphs and
+    never changes a byte"""
+    from jpgenc_b200.capi import Encoder
+    enc = Encoder(0)
+    try:
+        w, h = 624, 416
+        rgb = synth_rgb(w, h, 3)
+        want = oracle.encode_rgb(rgb)
+        d = enc.dev_alloc(w * h * 3)
+        out = np.zeros(len(want) + 64, np.uint8)
+        try:
+            enc.h2d(d, rgb)
+            enc.bind_device_rgb(d, w, h)
+            for level in (0, 2, 1, 0, 2):
+                enc.set_stage_timing(level)
+                for _ in range(4):                                # plain launches, capture, replays
+                    n = enc.encode_bound(out)
+                    assert out[:n].tobytes() == want
+                s = enc.stats()
+                if level == 0:
+                    assert s.ms_k1 == 0 and s.ms_forward == 0 and s.ms_stats == 0 and s.ms_entropy == 0
+                elif level == 1:
+                    assert s.ms_k1 > 0 and s.ms_forward == 0 and s.ms_stats == 0 and s.ms_entropy == 0
+                else:
+                    assert 0 < s.ms_k1 <= s.ms_forward and s.ms_stats > 0 and s.ms_entropy > 0
+            with pytest.raises(Exception):
+                enc.set_stage_timing(3)
+        finally:
+            enc.dev_free(d)
+    finally:
+        enc.close()
+
+
 def test_entropy_stage_can_run_twice_on_a_large_image(encoder, oracle):
     """K3a accumulates bit counts per 256 groups with atomics into words that K2's launch cleared: a second
     jpgenc_entropy_encode over the same symbol items (here: the same tables again) must not see them doubled.  4096x2304

@@ -6,6 +6,7 @@ from jpgenc_b200.capi import Encoder, pinned_empty
 w, h = 1920, 1080
 fb = w * h * 3
 enc = Encoder(0)
+enc.set_stage_timing(2)
 for nf in (64, 256, 1024):
     d = enc.dev_alloc(nf * fb)
     for k in range(nf):

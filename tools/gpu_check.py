@@ -8,6 +8,7 @@ from oracle.pyoracle import Oracle
 
 O = Oracle()
 E = Encoder(0)
+E.set_stage_timing(2)
 
 
 def check_image(name, rgb, maxval=255):

@@ -4,6 +4,7 @@ sys.path.insert(0, ".")
 from jpgenc_b200.capi import Encoder
 w = h = 16384
 enc = Encoder(0)
+enc.set_stage_timing(2)
 d = enc.dev_alloc(w * h * 3)
 enc.synth_rgb(d, w, h, 0)
 enc.bind_device_rgb(d, w, h)

@@ -4,6 +4,7 @@ sys.path.insert(0, ".")
 import numpy as np
 from jpgenc_b200.capi import Encoder
 enc = Encoder(0)
+enc.set_stage_timing(2)
 w = h = 8192
 yy, xx = np.mgrid[0:16, 0:16]
 cell = np.stack([(xx * 16) % 256, (yy * 9) % 256, ((xx + yy) * 7) % 256], -1).astype(np.uint8)

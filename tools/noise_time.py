@@ -3,6 +3,7 @@ sys.path.insert(0, ".")
 from jpgenc_b200.capi import Encoder
 from jpgenc_b200.synth import noise_rgb
 E = Encoder(0)
+E.set_stage_timing(2)
 for n in (4096,):
     rgb = noise_rgb(n, n, 3)
     E.upload_rgb(rgb)

@@ -13,6 +13,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--dct-blocks", type=int, default=0)
 a = ap.parse_args()
 E = Encoder(0)
+E.set_stage_timing(2)
 d = E.dev_alloc(a.w * a.h * 3)
 E.synth_rgb(d, a.w, a.h, 0)
 E.bind_device_rgb(d, a.w, a.h)

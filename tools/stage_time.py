@@ -3,6 +3,7 @@ import sys
 sys.path.insert(0, ".")
 from jpgenc_b200.capi import Encoder
 enc = Encoder(0)
+enc.set_stage_timing(2)
 for w, h in ((16384, 16384), (3840, 2160)):
     d = enc.dev_alloc(w * h * 3)
     enc.synth_rgb(d, w, h, 0)
