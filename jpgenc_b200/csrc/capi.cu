@@ -850,7 +850,12 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
     // ---- phase B: tables to the device, K3a, K3b, K4, totals into the mailbox ----
     uint32_t k4_tiles = 0;
     if ((rc = prepare_entropy(c, tables, &k4_tiles))) return rc;
-    const uint32_t k4_grid = static_cast<uint32_t>(c->raw_cap / kK4TileBytes + 1);      // >= k4_tiles: the raw buffer holds the scan
+    // K4's grid is part of the captured graph, the number of tiles is not (K4 reads it from device memory; surplus CTAs leave at
+    // once): an upper bound that follows the images seen -- half as much again as the last one that did not fit, given up
+    // when an image needs less than a quarter of it (a context that once encoded 16384^2 would otherwise launch 2 x 2700
+    // CTAs for the 83 tiles of every 3840x2160 frame: 10 us), never more than the raw buffer holds
+    if (k4_tiles > c->k4_grid_hint || k4_tiles < c->k4_grid_hint / 4) c->k4_grid_hint = k4_tiles + k4_tiles / 2 + 8;
+    const uint32_t k4_grid = std::min(c->k4_grid_hint, static_cast<uint32_t>(c->raw_cap / kK4TileBytes + 1));   // raw_cap holds the scan: >= k4_tiles
     const uint64_t key_b[5] = {c->alloc_gen, k4_grid, (static_cast<uint64_t>(c->real_w) << 32) | c->real_h, 0, 1u | static_cast<uint64_t>(c->stage_timing) << 8};
     if ((rc = run_phase(c, c->graph_b, key_b, [&]() -> int { return enqueue_entropy_phase(c, k4_grid); }))) return rc;
     const double t3 = trace_on() ? now_us() : 0;

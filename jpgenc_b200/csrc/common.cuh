@@ -152,6 +152,7 @@ struct jpgenc_ctx {
     // record is a node of its own, ~3 us each, 22 us per image with all eight --, 1 around the K1 fast kernel alone (the
     // roofline kernel), 2 around every stage.  *_timed: the level the events of the encode in flight were recorded at.
     int stage_timing = 0, fwd_timed = 0, stats_timed = 0, ent_timed = 0;
+    uint32_t k4_grid_hint = 0;            // single image: the grid K4a / K4 are captured with (run_pipeline)
     float last_k1 = 0, last_fwd = 0, last_st = 0;
     std::string error;
     int sm_count = 148;
