@@ -761,7 +761,7 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
 // their events, phase B 5 (tables upload, K3a, K3b, K4, publish); at ~4-5 us of host time per call the GPU waits for its
 // next kernel (3840x2160: 35 us of enqueueing in front of 38 us of K3/K4).  Nothing in either phase depends on the
 // content of the image: sizes that do (scan length, number of K4 tiles) are read from device memory by the kernels, the
-// mailbox sequence number lives in device memory, K4's grid is the upper bound the raw buffer allows.  So a phase is
+// mailbox sequence number lives in device memory, K4's grid is an upper bound (run_pipeline: k4_grid_hint).  So a phase is
 // captured once per configuration (pixels pointer, geometry, buffers: the key) and replayed with one launch.  A
 // configuration is captured when it is encoded the second time in a row; JPGENC_GRAPHS=0 disables it.
 static bool graphs_enabled() {

@@ -20,3 +20,7 @@ JPGENC_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none --laun
 python tools/one_batch.py 1024 1 > /dev/null &&
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1096 --launch-count 72 --csv --log-file gpurun_out/r2z_launches_batch1024.csv python tools/one_batch.py 1024 1 > /dev/null 2>&1
 ls -la gpurun_out/r2z*
+# small frames: warm encodes at the library default (no stage events) and with all of them
+for sz in "3840 2160 400" "1920 1080 400" "512 512 400"; do python tools/one_image.py $sz 0; python tools/one_image.py $sz 2; done | tee gpurun_out/r2z_small_frames.txt
+python tools/one_image.py 3840 2160 3 > /dev/null 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 18 --launch-count 9 --csv --log-file gpurun_out/r2z_launches4k.csv python tools/one_image.py 3840 2160 1 > /dev/null 2>&1
