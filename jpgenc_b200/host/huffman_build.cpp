@@ -143,11 +143,14 @@ struct PackedLevel {
 
 static int build_huffman_packed(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out);
 
-extern "C" int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
+// (no exception crosses the C boundary: the maps allocate)
+extern "C" int jpgenc_build_huffman(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) try {
     if (!count || !first_pos || !out) return JPGENC_ERR_ARG;
     for (int s = 0; s < 256; ++s)
         if (count[s] >> 31) return jpgenc_build_huffman_containers(count, first_pos, out);   // int overflow of the reference's counter: its arithmetic, not ours
     return build_huffman_packed(count, first_pos, out);
+} catch (...) {
+    return JPGENC_ERR_NOMEM;
 }
 
 static int build_huffman_packed(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
@@ -250,7 +253,7 @@ static int build_huffman_packed(const uint32_t count[256], const uint64_t first_
 // The straightforward statement: one container per thing the reference has one for.  Kept as the anchor the other
 // builds (packed above, array restatement on the device) are tested against; itself pinned against the compiled
 // reference in tests/test_oracle_vs_reference.py.
-extern "C" int jpgenc_build_huffman_containers(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) {
+extern "C" int jpgenc_build_huffman_containers(const uint32_t count[256], const uint64_t first_pos[256], jpgenc_huff_table* out) try {
     if (!count || !first_pos || !out) return JPGENC_ERR_ARG;
     std::memset(out, 0, sizeof *out);
 
@@ -312,4 +315,6 @@ extern "C" int jpgenc_build_huffman_containers(const uint32_t count[256], const 
 
     assign_codes(per_length, out);
     return JPGENC_OK;
+} catch (...) {
+    return JPGENC_ERR_NOMEM;
 }
