@@ -163,6 +163,13 @@ void ensure_host_pool(jpgenc_ctx* c) {
     c->owns_host_pool = true;
 }
 
+// threads beside the caller that build the four tables of a single image (TablePool): ONE -- it takes the two DC tables and
+// chroma AC while the caller builds luma AC, which is about the same work (a photograph: 3 + 3 + 3 us against 10; noise: both AC
+// tables are large and the same holds).  Measured against a thread per table (3840x2160 / 16384^2 / 2048^2 noise, all 16 cores
+// and pinned to 4): 0.0887 / 0.6787 / 0.1529 ms against 0.0913 / 0.6806 / 0.1540 -- fewer threads to wake and to wait for, and
+// a process that shares its host with seven other ranks keeps two of its four cores.  JPGENC_TABLE_THREADS (1..3) overrides.
+static int table_workers() { return static_cast<int>(std::min(3u, std::max(1u, env_u32("JPGENC_TABLE_THREADS", 1u)))); }
+
 // pinned staging: [statistics F * kStatsBytes + 16][device tables F * 8 KB][PassMeta block (common.cuh)]
 size_t stage_tables_off(uint32_t F) { return ((F * kStatsBytes + 16 + 255) / 256) * 256; }
 size_t stage_meta_off(uint32_t F) { return stage_tables_off(F) + F * sizeof(DeviceTables); }
@@ -738,7 +745,7 @@ static int run_entropy_stages(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64
         for (int t = 0; t < 4; ++t)
             if ((rc = jpgenc_build_huffman(count[t], first_pos[t], &tables[t]))) return fail(c, rc, "Huffman table build failed");
     } else {
-        if (!c->pool) c->pool = new TablePool();
+        if (!c->pool) c->pool = new TablePool(table_workers());
         c->pool->arm();                                             // the workers wake up while K2 runs
         if ((rc = jpgenc_symbol_stats(c, count, first_pos))) {
             c->pool->build(nullptr, nullptr, nullptr);              // release them again
@@ -820,7 +827,7 @@ static int run_pipeline(jpgenc_ctx* c, jpgenc_huff_table tables[4], uint64_t* sc
                                1u | static_cast<uint64_t>(c->stage_timing) << 8};
     const bool pool = c->parallel_tables;
     if (pool) {
-        if (!c->pool) c->pool = new TablePool();
+        if (!c->pool) c->pool = new TablePool(table_workers());
         c->pool->arm();                                             // the table builders wake up while K1 / K2 run
     }
     rc = run_phase(c, c->graph_a, key_a, [&]() -> int {

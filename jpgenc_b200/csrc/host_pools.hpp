@@ -16,8 +16,8 @@
 namespace jpgenc {
 
 // The four Huffman tables of an image are independent and the build is sequential host work (tens of microseconds
-// for a dozen symbols, half a millisecond for a full AC alphabet) during which the GPU has nothing to do.  Three
-// worker threads plus the calling thread build them side by side.  Waking a sleeping thread costs about as much as a
+// for a dozen symbols, half a millisecond for a full AC alphabet) during which the GPU has nothing to do.  A worker
+// thread (up to three) and the calling thread build them side by side.  Waking a sleeping thread costs about as much as a
 // small table, so the workers are ARMED (woken, then spinning) when the statistics kernel is launched and find the
 // histogram as soon as it arrives; they go back to sleep after every image.
 // parallel_for over n jobs on persistent host threads (the 4 * F table builds of a batch of F frames).  One pool serves
@@ -97,8 +97,12 @@ private:
 
 class TablePool {
 public:
-    TablePool() {
-        for (int i = 0; i < 3; ++i) workers_[i] = std::thread([this, i] { run(i); });
+    // `workers` 1..3 threads beside the caller.  The caller always builds the luma AC table (normally the largest alphabet:
+    // 10 us against 3 us for each of the others on a photograph); with three workers each of the other tables has a thread
+    // of its own, with one worker that thread builds all three one after the other -- about as long as the luma AC table
+    // takes, with one spinning thread instead of three (the default, capi.cu: table_workers).
+    explicit TablePool(int workers = 1) : nworkers_(workers < 1 ? 1 : workers > 3 ? 3 : workers) {
+        for (int i = 0; i < nworkers_; ++i) workers_[i] = std::thread([this, i] { run(i); });
     }
     ~TablePool() {
         {
@@ -106,7 +110,7 @@ public:
             quit_ = true;
         }
         cv_.notify_all();
-        for (std::thread& t : workers_) t.join();
+        for (int i = 0; i < nworkers_; ++i) workers_[i].join();
     }
     void arm() {
         {
@@ -123,7 +127,7 @@ public:
         published_.store(armed_, std::memory_order_release);
         static const int kMine = 1;                                   // Y_AC: normally the largest alphabet
         if (count) rc_[kMine] = jpgenc_build_huffman(count[kMine], first[kMine], &tables[kMine]);
-        while (done_.load(std::memory_order_acquire) != 3) cpu_relax();
+        while (done_.load(std::memory_order_acquire) != nworkers_) cpu_relax();
         for (int r : rc_) if (r) return r;
         return JPGENC_OK;
     }
@@ -135,7 +139,7 @@ private:
 #endif
     }
     void run(int idx) {
-        static const int kTable[3] = {0, 2, 3};
+        static const int kTable[3] = {0, 2, 3};                       // Y_DC, C_DC, C_AC
         uint64_t seen = 0;
         for (;;) {
             {
@@ -145,11 +149,15 @@ private:
                 seen = armed_;
             }
             while (published_.load(std::memory_order_acquire) != seen) cpu_relax();
-            const int t = kTable[idx];
-            if (count_) rc_[t] = jpgenc_build_huffman(count_[t], first_[t], &tables_[t]);
+            if (count_)
+                for (int k = idx; k < 3; k += nworkers_) {            // worker idx of n takes tables idx, idx + n, ...
+                    const int t = kTable[k];
+                    rc_[t] = jpgenc_build_huffman(count_[t], first_[t], &tables_[t]);
+                }
             done_.fetch_add(1, std::memory_order_release);
         }
     }
+    const int nworkers_;
     std::thread workers_[3];
     std::mutex m_;
     std::condition_variable cv_;
