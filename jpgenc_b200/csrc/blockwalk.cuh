@@ -9,8 +9,9 @@ constexpr int kTileBlocks = 384;                       // 64 MCUs; one thread pe
 // 8-bit non-zero flags of one 16-byte chunk (bit j = coefficient j of the chunk != 0).  Branch-free: VIMNMX.U16x2
 // turns every halfword into a 0/1 flag.
 __device__ __forceinline__ uint32_t chunk_flags(const uint4& q) {
-    const uint32_t f = __vminu2(q.x, 0x00010001u) | (__vminu2(q.y, 0x00010001u) << 2) | (__vminu2(q.z, 0x00010001u) << 4) |
-                       (__vminu2(q.w, 0x00010001u) << 6);
+    // the four 0/1 pairs never overlap, so the shifts and ORs are three multiply-adds
+    const uint32_t f = (__vminu2(q.w, 0x00010001u) * 4u + __vminu2(q.z, 0x00010001u)) * 16u +
+                       (__vminu2(q.y, 0x00010001u) * 4u + __vminu2(q.x, 0x00010001u));
     return (f | (f >> 15)) & 0xFFu;                 // even bits: low halfwords, odd bits: high halfwords
 }
 
