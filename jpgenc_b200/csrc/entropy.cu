@@ -166,12 +166,14 @@ __global__ void __launch_bounds__(kPackThreads) range_bits_kernel(const __grid_c
         const uint4* __restrict__ q4 = reinterpret_cast<const uint4*>(items + head);
         const uint32_t nq = (n - head) >> 2;
         uint32_t i = lane;
-        for (; i + 32 < nq; i += 64) {                                      // two 16-byte loads in flight per lane
-            const uint4 a = __ldg(q4 + i), b = __ldg(q4 + i + 32);
+        for (; i + 96 < nq; i += 128) {                                     // four 16-byte loads in flight per lane
+            const uint4 a = __ldg(q4 + i), b = __ldg(q4 + i + 32), c = __ldg(q4 + i + 64), d = __ldg(q4 + i + 96);
             bits += size_of(a.x) + size_of(a.y) + size_of(a.z) + size_of(a.w);
             bits += size_of(b.x) + size_of(b.y) + size_of(b.z) + size_of(b.w);
+            bits += size_of(c.x) + size_of(c.y) + size_of(c.z) + size_of(c.w);
+            bits += size_of(d.x) + size_of(d.y) + size_of(d.z) + size_of(d.w);
         }
-        if (i < nq) {
+        for (; i < nq; i += 32) {
             const uint4 a = __ldg(q4 + i);
             bits += size_of(a.x) + size_of(a.y) + size_of(a.z) + size_of(a.w);
         }
