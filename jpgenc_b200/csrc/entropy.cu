@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kCountThreads) ff_count_kernel(const __grid_co
     }
 }
 
-__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(const __grid_constant__ EntropyParams p, uint8_t* __restrict__ scan) {
+__global__ void __launch_bounds__(kStuffThreads, 6) stuff_kernel(const __grid_constant__ EntropyParams p, uint8_t* __restrict__ scan) {
     __shared__ alignas(16) uint8_t s_out[2 * kStuffTile + 16];
     __shared__ uint32_t s_scan[33];
     __shared__ unsigned long long s_before[kStuffThreads / 32];
