@@ -221,3 +221,23 @@ def test_bench_reference_arm_prints_one_json_line(tmp_path):
     sys.path.insert(0, ROOT)
     import bench
     assert d["config"] == bench.headline_config("image16k", 1)
+
+
+@pytest.mark.parametrize("workers", [1, 2, 3])
+def test_table_pool_handover_under_stress(tmp_path_factory, workers):
+    """TablePool (csrc/host_pools.hpp) hands the four histograms of an image to its worker thread(s) through an armed /
+    published / done handshake with spinning waits: thousands of cycles on random, tie-heavy histograms, the release-without-
+    work path in between, every table compared with a direct build (tests/host/table_pool_probe.cu; clean under
+    -fsanitize=thread as well)"""
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    libdir = os.path.join(ROOT, "jpgenc_b200", "lib")
+    exe = str(tmp_path_factory.getbasetemp() / "table_pool_probe")
+    if not os.path.exists(exe):
+        subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                        os.path.join(ROOT, "tests", "host", "table_pool_probe.cu"), "-o", exe, "-L" + libdir, "-ljpgenc_b200",
+                        "-Xlinker", "-rpath", "-Xlinker", libdir], check=True)
+    r = subprocess.run([exe, str(workers), "2000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
