@@ -241,3 +241,21 @@ def test_table_pool_handover_under_stress(tmp_path_factory, workers):
                         "-Xlinker", "-rpath", "-Xlinker", libdir], check=True)
     r = subprocess.run([exe, str(workers), "2000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_host_pool_parallel_for_under_stress(tmp_path_factory):
+    """HostPool::parallel_for with several callers at once on one pool (the lanes of a threaded batch, the band reader of
+    jpgenc_encode_ppm_file): every job runs exactly once, a call returns only after its last job
+    (tests/host/host_pool_probe.cu; clean under -fsanitize=thread as well)"""
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    libdir = os.path.join(ROOT, "jpgenc_b200", "lib")
+    exe = str(tmp_path_factory.getbasetemp() / "host_pool_probe")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                    os.path.join(ROOT, "tests", "host", "host_pool_probe.cu"), "-o", exe, "-L" + libdir, "-ljpgenc_b200",
+                    "-Xlinker", "-rpath", "-Xlinker", libdir], check=True)
+    for workers, callers in ((3, 4), (1, 6), (7, 2)):
+        r = subprocess.run([exe, str(workers), str(callers), "1000"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
