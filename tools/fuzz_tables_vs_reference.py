@@ -2,7 +2,8 @@
 (oracle/_ref, i.e. only where /root/reference is mounted) on random symbol texts of five families:
     python tools/fuzz_tables_vs_reference.py <seed> <texts>
 30 000 texts (seeds 1-6 x 5000): 0 mismatches."""
-import sys, time
+import os
+import sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import ctypes as C
 import numpy as np
