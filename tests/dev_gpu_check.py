@@ -1,4 +1,5 @@
-"""Stage-by-stage GPU-vs-oracle diagnostics (development aid; the real parity tests live in tests/)."""
+"""Stage-by-stage GPU-vs-oracle diagnostics (development aid, run from the repository root: python tests/dev_gpu_check.py; the
+parity tests proper are the test_*.py files).  Lives under tests/ because it uses the oracle."""
 import sys, time, traceback
 import numpy as np
 sys.path.insert(0, ".")

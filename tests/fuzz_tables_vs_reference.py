@@ -1,6 +1,6 @@
 """The product's host table builder (jpgenc_build_huffman) against the COMPILED REFERENCE's generateHuffmanCode
 (oracle/_ref, i.e. only where /root/reference is mounted) on random symbol texts of five families:
-    python tools/fuzz_tables_vs_reference.py <seed> <texts>
+    python tests/fuzz_tables_vs_reference.py <seed> <texts>
 30 000 texts (seeds 1-6 x 5000): 0 mismatches."""
 import os
 import sys
