@@ -70,6 +70,7 @@ int set_geometry(jpgenc_ctx* c, uint32_t w, uint32_t h, uint32_t maxval) {
     c->real_w = w; c->real_h = h; c->maxval = maxval;
     c->mcu_w = (w + 15) / 16; c->mcu_h = (h + 15) / 16;        // src/Image.cpp:479-489
     c->nframes = 1;
+    c->have_pixels = false;                                      // whoever changes the geometry binds its pixels afterwards
     c->have_coef = c->have_scan = c->have_items = false; c->k2_tiles_done = 0;
     return JPGENC_OK;
 }
@@ -432,6 +433,7 @@ int jpgenc_set_coefficients_mcu(jpgenc_ctx* c, const int16_t* coef, uint32_t mcu
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     if (c->real_w == 0 || (c->real_w + 15) / 16 != mcu_w || (c->real_h + 15) / 16 != mcu_h) {
         c->real_w = mcu_w * 16; c->real_h = mcu_h * 16; c->maxval = 255;
+        c->have_pixels = false;                                   // pixels bound earlier belong to another geometry: K1 must not read them with this one
     }
     c->mcu_w = mcu_w; c->mcu_h = mcu_h;
     int rc = ensure_coef(c);
@@ -450,6 +452,7 @@ int jpgenc_set_coefficients(jpgenc_ctx* c, const int32_t* q_y, const int32_t* q_
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     if (c->real_w == 0 || (c->real_w + 15) / 16 != mcu_w || (c->real_h + 15) / 16 != mcu_h) {
         c->real_w = mcu_w * 16; c->real_h = mcu_h * 16; c->maxval = 255;
+        c->have_pixels = false;                                   // pixels bound earlier belong to another geometry: K1 must not read them with this one
     }
     c->mcu_w = mcu_w; c->mcu_h = mcu_h;
     int rc = ensure_coef(c);

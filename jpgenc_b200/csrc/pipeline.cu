@@ -373,10 +373,11 @@ int check_job(jpgenc_ctx* c, const Job& job, const void* frames) {
 }
 
 int encode_device_frames(jpgenc_ctx* c, Job& job, const void* const* dev_frames) {
+    // an empty batch is legal and touches nothing: an image bound to the context keeps its geometry
+    if (job.n == 0) return (job.w && job.h && job.maxval && job.maxval <= 255) ? JPGENC_OK : fail(c, JPGENC_ERR_ARG, "width/height/maxval out of range");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, job.w, job.h, job.maxval);
     if (rc) return rc;
-    if (job.n == 0) return JPGENC_OK;
     // what earlier calls learnt about the size of such frames' scans stays valid (a later frame that needs more is refused on the
     // device and re-run, finish_pass); a new frame size starts from the guess again
     if (c->batch_geom_w != job.w || c->batch_geom_h != job.h) { c->batch_raw_per_frame = 0; c->batch_geom_w = job.w; c->batch_geom_h = job.h; }
@@ -396,10 +397,11 @@ int encode_device_frames(jpgenc_ctx* c, Job& job, const void* const* dev_frames)
 // of device memory, always a few passes ahead of the kernels; when pass p is finished its slice is re-filled with the
 // frames of pass p + ring.
 int encode_host_frames(jpgenc_ctx* c, Job& job, const uint8_t* const* frames) {
+    // an empty batch is legal and touches nothing: an image bound to the context keeps its geometry
+    if (job.n == 0) return (job.w && job.h && job.maxval && job.maxval <= 255) ? JPGENC_OK : fail(c, JPGENC_ERR_ARG, "width/height/maxval out of range");
     JPGENC_CUDA(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, job.w, job.h, job.maxval);
     if (rc) return rc;
-    if (job.n == 0) return JPGENC_OK;
     // what earlier calls learnt about the size of such frames' scans stays valid (a later frame that needs more is refused on the
     // device and re-run, finish_pass); a new frame size starts from the guess again
     if (c->batch_geom_w != job.w || c->batch_geom_h != job.h) { c->batch_raw_per_frame = 0; c->batch_geom_w = job.w; c->batch_geom_h = job.h; }

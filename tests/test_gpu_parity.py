@@ -879,3 +879,42 @@ def test_batched_calls_of_changing_frame_sizes_on_one_context(oracle):
         run([])
     finally:
         enc.close()
+
+
+def test_empty_batches_and_geometry_changes_leave_no_stale_binding(oracle):
+    """An empty batch is legal, reports nothing and leaves an image bound to the context alone (its geometry included);
+    the coefficient test hook with ANOTHER geometry unbinds the pixels instead of letting K1 read them with the wrong size."""
+    from jpgenc_b200.capi import Encoder, JpgencError
+    enc = Encoder(0)
+    try:
+        w, h = 336, 208
+        rgb = synth_rgb(w, h, 4)
+        want = oracle.encode_rgb(rgb)
+        d = enc.dev_alloc(w * h * 3)
+        out = np.zeros(len(want) + 64, np.uint8)
+        try:
+            enc.h2d(d, rgb)
+            enc.bind_device_rgb(d, w, h)
+            n = enc.encode_bound(out)
+            assert out[:n].tobytes() == want
+            # empty batches of a LARGER geometry, in all three forms
+            assert enc.encode_frames_device([], 4096, 4096) == []
+            assert enc.encode_frames_device([], 4096, 4096, host_frames=True) == []
+            assert enc.encode_frames_packed([], 4096, 4096, None, 0) == ([], [], 0)
+            with pytest.raises(JpgencError):
+                enc.encode_frames_device([], 0, 16)
+            for _ in range(3):
+                n = enc.encode_bound(out)
+                assert out[:n].tobytes() == want
+            # coefficients of another geometry through the test hook: the bound pixels no longer apply
+            coef = oracle.forward(synth_rgb(64, 48, 1))
+            enc.set_coefficients_mcu(coef, 4, 3)
+            with pytest.raises(JpgencError):
+                enc.encode_bound(out)
+            enc.bind_device_rgb(d, w, h)
+            n = enc.encode_bound(out)
+            assert out[:n].tobytes() == want
+        finally:
+            enc.dev_free(d)
+    finally:
+        enc.close()
